@@ -1,0 +1,136 @@
+/* panda_validity.h -- C-ABI of libpanda_validity.so (sm_100a CUDA kernels behind plain C entry points).
+ *
+ * This is the drop-in boundary for the reference's motion-planning hot path.  Each entry point names
+ * the reference interface it replaces (file:line under /root/reference/code).  No torch / C++ types in
+ * any signature: plain pointers and sizes.  Pointers named d_* are DEVICE pointers (the caller owns the
+ * buffers, e.g. torch tensors handed over as data_ptr()); pointers named h_* are HOST pointers.
+ * `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Device-pointer calls
+ * are asynchronous on `stream`; host-pointer calls return when the result is in the host buffer.
+ *
+ * Every function returns 0 on success or a negative PV_ERR_* code; pv_last_error() gives the message.
+ * One handle per device; a handle is not thread-safe.
+ *
+ * Layouts
+ *   configuration, SoA:  d_qA[i] = float4(q1,q2,q3,q4), d_qB[i] = float4(q5,q6,q7,q8), d_q9[i] = q9
+ *                        (d_q9 == NULL means q9 = q8: symmetric gripper)
+ *   configuration, AoS:  h_q[i*9 + j], j = 0..8 -- the qpos vectors the reference passes around
+ *                        (planning.py:131-135, shape (n_qs,) = (9,))
+ *   verdict bits:        bit (i & 31) of word (i >> 5); 1 = valid.  ceil(n/32) words, tail bits 0.
+ *   scene box (OBB):     16 floats: centre xyz, half extents xyz, world-from-box rotation (row-major 9),
+ *                        1 pad float (overwritten with the bounding radius).
+ */
+#ifndef PANDA_VALIDITY_H
+#define PANDA_VALIDITY_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PV_MAX_OBB 32
+
+#define PV_OK 0
+#define PV_ERR_BAD_HANDLE (-1)
+#define PV_ERR_BAD_ARG (-2)
+#define PV_ERR_CUDA (-3)
+#define PV_ERR_NO_DEVICE (-4)
+#define PV_ERR_NO_SCENE (-5)
+
+/* validity rule switches */
+#define PV_FLAG_SELF 1u   /* robot-vs-robot pairs on (Genesis enable_self_collision) */
+#define PV_FLAG_LIMITS 2u /* also require lower <= q <= upper (planning.py:139-150, 165-173) */
+
+typedef struct PvHandle PvHandle;
+
+/* Library/handle life cycle.  Replaces PlannerInterface.__init__ (planning.py:24-30): binds the frozen
+ * Panda model to one CUDA device.  Fails with PV_ERR_NO_DEVICE when no sm_100 device is visible --
+ * there is no CPU fallback. */
+int pv_create(int device, PvHandle **out);
+void pv_destroy(PvHandle *h);
+const char *pv_last_error(const PvHandle *h); /* h may be NULL: last pv_create error */
+const char *pv_version(void);
+
+/* Model constants the host side needs (frozen with the kernels). */
+int pv_model_info(int *n_spheres, int *n_boxes, int *n_ss_pairs, int *n_sb_pairs);
+int pv_joint_limits(float lower[9], float upper[9]); /* robot.q_limit, planning.py:139-140 */
+
+/* Scene snapshot: what robot.detect_collision() sees through Genesis (planning.py:211): the block
+ * entities (scenes.py:52-83), the ground plane (scenes.py:49) and the robot base pose (scenes.py:29-34).
+ * h_obb is [n_obb][16] on the host. */
+int pv_set_scene(PvHandle *h, const float *h_obb, int n_obb, float table_z, const float base_xyz[3]);
+
+/* self.attached_object = attached_object (planning.py:153): scene-box index whose contacts with hand /
+ * left_finger / right_finger are forgiven (planning.py:221-230); -1 = none. */
+int pv_set_attached(PvHandle *h, int obb_index);
+int pv_set_flags(PvHandle *h, unsigned flags);
+
+/* robot.set_qpos(q) -> link poses (planning.py:210; Genesis FK).  d_pose_out is [n][11][12]:
+ * per link position xyz then rotation row-major. */
+int pv_fk(PvHandle *h, const float *d_qA, const float *d_qB, const float *d_q9, int64_t n,
+          float *d_pose_out, void *stream);
+
+/* _is_ompl_state_valid(state) for n states at once (planning.py:209-219). */
+int pv_check_states(PvHandle *h, const float *d_qA, const float *d_qB, const float *d_q9, int64_t n,
+                    uint32_t *d_bits, void *stream);
+
+/* Same rule, reporting the signed clearance in metres (valid iff >= 0) and, optionally, a culprit code
+ * (diagnose_valid_violation, planning.py:43-57).  culprit = kind << 16 | a << 8 | b with kind 1 = table
+ * (a = link), 2 = scene box (a = link, b = box), 3 = self (a, b = links), 4 = joint limit (a = joint);
+ * 0 = none.  d_culprit may be NULL. */
+int pv_state_margins(PvHandle *h, const float *d_qA, const float *d_qB, const float *d_q9, int64_t n,
+                     float *d_margin, int32_t *d_culprit, void *stream);
+
+/* si.checkMotion(a, b) for n edges at once (OMPL DiscreteMotionValidator installed by SimpleSetup,
+ * planning.py:151-156).  States q(t) = a + t (b - a), t = k/nd, k = 1..nd (a is assumed valid).
+ * n_steps > 0: nd = n_steps for every edge.  n_steps == 0: nd = ceil(|b - a|_2 / resolution). */
+int pv_check_edges(PvHandle *h, const float *d_aA, const float *d_aB, const float *d_a9,
+                   const float *d_bA, const float *d_bB, const float *d_b9, int64_t n_edges, int n_steps,
+                   float resolution, uint32_t *d_bits, void *stream);
+int pv_edge_margins(PvHandle *h, const float *d_aA, const float *d_aB, const float *d_a9,
+                    const float *d_bA, const float *d_bB, const float *d_b9, int64_t n_edges, int n_steps,
+                    float resolution, float *d_margin, void *stream);
+
+/* Host-buffer forms of the two checks (the call a reference-side binding makes): AoS qpos rows in,
+ * verdict bits out, host<->device copies pipelined inside.  h_q* may be pinned or pageable. */
+int pv_check_states_host(PvHandle *h, const float *h_q, int64_t n, uint32_t *h_bits);
+int pv_check_edges_host(PvHandle *h, const float *h_qa, const float *h_qb, int64_t n_edges, int n_steps,
+                        float resolution, uint32_t *h_bits);
+
+/* Device-generated sweep (BASELINE config 5): configs first .. first+n-1 of the counter-based stream
+ * `seed` (Philox-4x32-10; q_j = fma(u_j, upper_j - lower_j, lower_j)), checked in place.
+ * d_bits gets ceil(n/32) words; *d_n_valid (device, may be NULL) is incremented by the valid count.
+ * `first` must be a multiple of 32.  d_q_out (may be NULL) receives the configs as AoS [n][9]. */
+int pv_sweep(PvHandle *h, uint64_t first, int64_t n, uint32_t seed, int fingers_open, uint32_t *d_bits,
+             unsigned long long *d_n_valid, float *d_q_out, void *stream);
+
+/* Batched multi-query RRT-Connect (og.RRTConnect + ss.solve, planning.py:156,190), one warp per query,
+ * trees and paths in device memory.  See PvRrtcParams. */
+typedef struct {
+    float range;         /* RRTConnect range; <= 0 -> 0.2 * extent (OMPL default) */
+    float resolution;    /* motion-validity resolution; <= 0 -> 0.01 * extent */
+    int max_iters;       /* iteration cap per query */
+    int max_nodes;       /* per tree */
+    int max_path;        /* capacity of one output path (states) */
+    uint32_t seed;
+    int replicas;        /* independent searches per (start, goal); the first to connect wins */
+    int shortcut_passes; /* deterministic shortcutting passes after the solve (simplifySolution) */
+} PvRrtcParams;
+
+/* h_starts/h_goals: [n_queries][9] host AoS.  h_path_out: [n_queries][max_path][9]; h_path_len: states
+ * per path (0 = no solution); h_iters: iterations used; h_checks: state checks issued (may be NULL). */
+int pv_rrtc_batch(PvHandle *h, const float *h_starts, const float *h_goals, int n_queries,
+                  const PvRrtcParams *params, float *h_path_out, int *h_path_len, int *h_iters,
+                  long long *h_checks);
+
+/* FP32 FMA issue-rate micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP32 entry).
+ * Returns achieved TFLOP/s over `iters` unrolled FFMA rounds; ms (may be NULL) gets the kernel time. */
+int pv_fp32_peak(PvHandle *h, int iters, double *tflops, float *ms);
+
+/* Number of kernel launches issued through this handle since creation (bench.py's gpu_launches). */
+long long pv_launch_count(const PvHandle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

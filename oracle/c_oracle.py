@@ -1,0 +1,117 @@
+"""ctypes front end of the C oracle (oracle/panda_oracle.c).  Test infrastructure, NOT product code:
+only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libpanda_oracle.so")
+
+FLAG_SELF = 1
+FLAG_LIMITS = 2
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(_HERE, f) for f in ("panda_oracle.c", "panda_oracle_impl.h")]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
+        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    return LIB_PATH
+
+
+def _model_struct(real):
+    class Model(C.Structure):
+        _fields_ = [
+            ("n_spheres", C.c_int), ("sphere_link", C.POINTER(C.c_int)),
+            ("sphere_center", C.POINTER(real)), ("sphere_radius", C.POINTER(real)),
+            ("n_boxes", C.c_int), ("box_link", C.POINTER(C.c_int)),
+            ("box_center", C.POINTER(real)), ("box_half", C.POINTER(real)),
+            ("n_ss", C.c_int), ("ss_pairs", C.POINTER(C.c_int)),
+            ("n_sb", C.c_int), ("sb_pairs", C.POINTER(C.c_int)),
+            ("q_lower", C.POINTER(real)), ("q_upper", C.POINTER(real)),
+        ]
+    return Model
+
+
+class COracle:
+    """precision: 'f64' or 'f32'."""
+
+    def __init__(self, model: dict, precision: str = "f64"):
+        self.lib = C.CDLL(build())
+        self.sfx = "_" + precision
+        self.np_t = np.float64 if precision == "f64" else np.float32
+        self.c_t = C.c_double if precision == "f64" else C.c_float
+        self._keep = {}
+        Model = _model_struct(self.c_t)
+        m = Model()
+
+        def arr(name, dtype):
+            a = np.ascontiguousarray(model[name], dtype=dtype)
+            self._keep[name] = a
+            return a
+
+        def fp(a):
+            return a.ctypes.data_as(C.POINTER(self.c_t))
+
+        def ip(a):
+            return a.ctypes.data_as(C.POINTER(C.c_int))
+
+        m.n_spheres = len(model["sphere_link"])
+        m.sphere_link = ip(arr("sphere_link", np.int32))
+        m.sphere_center = fp(arr("sphere_center", self.np_t))
+        m.sphere_radius = fp(arr("sphere_radius", self.np_t))
+        m.n_boxes = len(model["box_link"])
+        m.box_link = ip(arr("box_link", np.int32))
+        m.box_center = fp(arr("box_center", self.np_t))
+        m.box_half = fp(arr("box_half", self.np_t))
+        m.n_ss = len(model["ss_pairs"])
+        m.ss_pairs = ip(arr("ss_pairs", np.int32))
+        m.n_sb = len(model["sb_pairs"])
+        m.sb_pairs = ip(arr("sb_pairs", np.int32))
+        m.q_lower = fp(arr("q_lower", self.np_t))
+        m.q_upper = fp(arr("q_upper", self.np_t))
+        self.model = m
+
+    def _p(self, a):
+        return a.ctypes.data_as(C.POINTER(self.c_t))
+
+    def fk(self, q, base=(0.0, 0.0, 0.01)):
+        q = np.ascontiguousarray(np.atleast_2d(q), dtype=self.np_t)
+        n = q.shape[0]
+        R = np.empty((n, 11, 3, 3), dtype=self.np_t)
+        p = np.empty((n, 11, 3), dtype=self.np_t)
+        b = np.asarray(base, dtype=self.np_t)
+        getattr(self.lib, "po_fk" + self.sfx)(self._p(q), C.c_long(n), self._p(b), self._p(R), self._p(p))
+        return R, p
+
+    def state_margin(self, q, scene, attached=-1, flags=FLAG_SELF, base=(0.0, 0.0, 0.01), nthreads=0):
+        q = np.ascontiguousarray(np.atleast_2d(q), dtype=self.np_t)
+        n = q.shape[0]
+        obb = np.ascontiguousarray(scene["obb"], dtype=self.np_t).reshape(-1, 16)
+        out = np.empty(n, dtype=self.np_t)
+        b = np.asarray(base, dtype=self.np_t)
+        getattr(self.lib, "po_state_margin" + self.sfx)(
+            C.byref(self.model), self._p(obb), C.c_int(obb.shape[0]), self.c_t(scene["table_z"]), self._p(b),
+            C.c_int(attached), C.c_int(flags), self._p(q), C.c_long(n), self._p(out),
+            C.c_int(nthreads or os.cpu_count() or 1))
+        return out
+
+    def edge_margin(self, qa, qb, scene, n_steps=0, resolution=0.13037159046356686, attached=-1,
+                    flags=FLAG_SELF, base=(0.0, 0.0, 0.01), early_exit=False, nthreads=0, return_count=False):
+        qa = np.ascontiguousarray(np.atleast_2d(qa), dtype=self.np_t)
+        qb = np.ascontiguousarray(np.atleast_2d(qb), dtype=self.np_t)
+        n = qa.shape[0]
+        obb = np.ascontiguousarray(scene["obb"], dtype=self.np_t).reshape(-1, 16)
+        out = np.empty(n, dtype=self.np_t)
+        b = np.asarray(base, dtype=self.np_t)
+        cnt = C.c_long(0)
+        getattr(self.lib, "po_edge_margin" + self.sfx)(
+            C.byref(self.model), self._p(obb), C.c_int(obb.shape[0]), self.c_t(scene["table_z"]), self._p(b),
+            C.c_int(attached), C.c_int(flags), self._p(qa), self._p(qb), C.c_long(n), C.c_int(n_steps),
+            self.c_t(resolution), C.c_int(1 if early_exit else 0), self._p(out), C.byref(cnt),
+            C.c_int(nthreads or os.cpu_count() or 1))
+        return (out, cnt.value) if return_count else out

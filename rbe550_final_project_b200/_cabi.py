@@ -1,0 +1,123 @@
+"""ctypes binding of libpanda_validity.so (include/panda_validity.h) and its build recipe.
+
+The library is built IN-TREE (csrc/libpanda_validity.so) for sm_100a only.  There is no CPU fallback:
+`load()` raises if the shared object is missing, and `pv_create` fails on a machine without a B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from typing import List
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libpanda_validity.so")
+SOURCES = ["pv_kernels.cu", "pv_rrtc.cu"]
+HEADERS = ["pv_device.cuh", "pv_handle.h", "panda_model_gen.h", os.path.join("..", "..", "include", "panda_validity.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "--threads", "4",
+]
+
+# every symbol include/panda_validity.h declares
+EXPORTS = [
+    "pv_create", "pv_destroy", "pv_last_error", "pv_version", "pv_model_info", "pv_joint_limits",
+    "pv_set_scene", "pv_set_attached", "pv_set_flags", "pv_fk", "pv_check_states", "pv_state_margins",
+    "pv_check_edges", "pv_edge_margins", "pv_check_states_host", "pv_check_edges_host", "pv_sweep",
+    "pv_rrtc_batch", "pv_fp32_peak", "pv_launch_count",
+]
+
+
+class PvRrtcParams(C.Structure):
+    _fields_ = [
+        ("range", C.c_float), ("resolution", C.c_float), ("max_iters", C.c_int), ("max_nodes", C.c_int),
+        ("max_path", C.c_int), ("seed", C.c_uint32), ("replicas", C.c_int), ("shortcut_passes", C.c_int),
+    ]
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; cannot build libpanda_validity.so")
+    return exe
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a into csrc/libpanda_validity.so (nvcc cross-compiles without a GPU)."""
+    from . import panda_model
+
+    panda_model.write_header()
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = _nvcc()
+    objs: List[str] = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode:
+            print(out)
+        if p.returncode:
+            raise RuntimeError(f"nvcc failed on {src}")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs + ["-lcudart"], cwd=CSRC, check=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the in-tree library and declare prototypes.  Raises (no fallback) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "The validity path has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, fp, u32p, i32p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    lib.pv_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.pv_destroy.argtypes = [vp]
+    lib.pv_destroy.restype = None
+    lib.pv_last_error.argtypes = [vp]
+    lib.pv_last_error.restype = C.c_char_p
+    lib.pv_version.restype = C.c_char_p
+    lib.pv_model_info.argtypes = [C.POINTER(C.c_int)] * 4
+    lib.pv_joint_limits.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.pv_set_scene.argtypes = [vp, C.POINTER(C.c_float), C.c_int, C.c_float, C.POINTER(C.c_float)]
+    lib.pv_set_attached.argtypes = [vp, C.c_int]
+    lib.pv_set_flags.argtypes = [vp, C.c_uint]
+    lib.pv_set_culling.argtypes = [vp, C.c_int]
+    lib.pv_fk.argtypes = [vp, fp, fp, fp, C.c_int64, fp, vp]
+    lib.pv_check_states.argtypes = [vp, fp, fp, fp, C.c_int64, u32p, vp]
+    lib.pv_state_margins.argtypes = [vp, fp, fp, fp, C.c_int64, fp, i32p, vp]
+    lib.pv_check_edges.argtypes = [vp, fp, fp, fp, fp, fp, fp, C.c_int64, C.c_int, C.c_float, u32p, vp]
+    lib.pv_edge_margins.argtypes = [vp, fp, fp, fp, fp, fp, fp, C.c_int64, C.c_int, C.c_float, fp, vp]
+    lib.pv_check_states_host.argtypes = [vp, fp, C.c_int64, u32p]
+    lib.pv_check_edges_host.argtypes = [vp, fp, fp, C.c_int64, C.c_int, C.c_float, u32p]
+    lib.pv_sweep.argtypes = [vp, C.c_uint64, C.c_int64, C.c_uint32, C.c_int, u32p, vp, fp, vp]
+    lib.pv_rrtc_batch.argtypes = [vp, fp, fp, C.c_int, C.POINTER(PvRrtcParams), fp, i32p, i32p, vp]
+    lib.pv_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    lib.pv_launch_count.argtypes = [vp]
+    lib.pv_launch_count.restype = C.c_longlong
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int or name in ("pv_create",):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib

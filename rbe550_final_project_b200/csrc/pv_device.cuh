@@ -1,0 +1,459 @@
+// pv_device.cuh -- device-side Panda state validity: FK + primitive tests, specialised at compile time
+// to the frozen model in panda_model_gen.h.  sm_100a, FP32 CUDA-core work (no dense contraction, so no
+// tensor cores).  One thread evaluates one configuration; all robot primitives live in registers.
+//
+// Verdict rule restated from the reference: planning.py:209-219 (_is_ompl_state_valid: any robot
+// contact invalidates), planning.py:221-230 (contacts of hand/fingers with the attached box are
+// forgiven), planning.py:139-150 (joint limits), Genesis pair filter as in SURVEY.md App. C.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "panda_model_gen.h"
+
+#ifndef PV_MAX_OBB
+#define PV_MAX_OBB 32
+#endif
+#define PV_FLAG_SELF 1u
+#define PV_FLAG_LIMITS 2u
+
+// Scene snapshot, passed to every kernel BY VALUE as a __grid_constant__ parameter: it then lives in
+// the constant bank, every thread reads the same box at the same time (constant-cache broadcast, or a
+// uniform-register load), and concurrent streams / handles never share mutable state.
+struct PvScene {
+    float obb[PV_MAX_OBB][16];  // c.xyz, half.xyz, R row-major (world-from-box), bounding radius
+    float table_z;
+    float base[3];
+    int n_obb;
+    int attached;  // scene-box index forgiven for hand / fingers, -1 = none
+    unsigned flags;
+    unsigned yaw_only_mask;  // bit b: box b is rotated about world z only
+};
+
+enum { PV_MODE_BITS = 0, PV_MODE_MARGIN = 1 };
+enum { PV_EXIT_NONE = 0, PV_EXIT_ALL = 1, PV_EXIT_ANY = 2 };
+
+#define PV_CODE(kind, a, b) (((kind) << 16) | ((a) << 8) | (b))
+
+template <int MODE>
+struct PvAcc;
+template <>
+struct PvAcc<PV_MODE_BITS> {
+    bool hit = false;
+};
+template <>
+struct PvAcc<PV_MODE_MARGIN> {
+    float m = 1e30f;
+    int code = 0;
+    __device__ __forceinline__ void take(float g, int c) {
+        if (g < m) {
+            m = g;
+            code = c;
+        }
+    }
+};
+
+// ---- small vector helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ float3 v_sub(float3 a, float3 b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 v_neg(float3 a) { return make_float3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float v_dot(float3 a, float3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+// a * s + b
+__device__ __forceinline__ float3 v_fma(float3 a, float s, float3 b) {
+    return make_float3(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z));
+}
+// joint rotation about the (pre-rotated) z axis:  X = c Xp + s Yp,  Y = c Yp - s Xp
+__device__ __forceinline__ void v_rotz(float3 Xp, float3 Yp, float c, float s, float3& X, float3& Y) {
+    X = make_float3(fmaf(s, Yp.x, c * Xp.x), fmaf(s, Yp.y, c * Xp.y), fmaf(s, Yp.z, c * Xp.z));
+    Y = make_float3(fmaf(-s, Xp.x, c * Yp.x), fmaf(-s, Xp.y, c * Yp.y), fmaf(-s, Xp.z, c * Yp.z));
+}
+
+// sin/cos for joint angles (|x| of a few rad; still correct to ~1e-7 up to |x| ~ 1e4): Cody-Waite
+// reduction by pi/2 and the classic single-precision minimax polynomials on [-pi/4, pi/4].
+__device__ __forceinline__ void pv_sincos(float x, float& s, float& c) {
+    float kf = rintf(x * 0.63661977236758134f);
+    int k = (int)kf;
+    float r = fmaf(kf, -1.5707962512969971f, x);
+    r = fmaf(kf, -7.5497894158615964e-08f, r);
+    r = fmaf(kf, -5.3903029534742384e-15f, r);
+    float r2 = r * r;
+    float sp = fmaf(fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f), r2 * r, r);
+    float cp = fmaf(fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f),
+                    r2 * r2, fmaf(-0.5f, r2, 1.0f));
+    float a = (k & 1) ? cp : sp;
+    float b = (k & 1) ? sp : cp;
+    s = (k & 2) ? -a : a;
+    c = ((k + 1) & 2) ? -b : b;
+}
+
+// ---- primitive tests ---------------------------------------------------------------------------------
+// sphere (centre c, radius r) vs box (centre oc, half oh, box axes in world = columns of R)
+template <int MODE>
+__device__ __forceinline__ void pv_sphere_box(PvAcc<MODE>& acc, float3 c, float r, float r2, float3 oc, float3 oh,
+                                              float3 ax, float3 ay, float3 az, int code) {
+    float3 d = v_sub(c, oc);
+    float ex = fabsf(v_dot(d, ax)) - oh.x;
+    float ey = fabsf(v_dot(d, ay)) - oh.y;
+    float ez = fabsf(v_dot(d, az)) - oh.z;
+    float px = fmaxf(ex, 0.f), py = fmaxf(ey, 0.f), pz = fmaxf(ez, 0.f);
+    float s2 = fmaf(pz, pz, fmaf(py, py, px * px));
+    if constexpr (MODE == PV_MODE_BITS) {
+        acc.hit |= (s2 < r2);
+    } else {
+        float g = (s2 > 0.f ? sqrtf(s2) : fmaxf(ex, fmaxf(ey, ez))) - r;
+        acc.take(g, code);
+    }
+}
+
+// sphere vs a box rotated about world z only: axes (cy, sy, 0), (-sy, cy, 0), (0, 0, 1)
+template <int MODE>
+__device__ __forceinline__ void pv_sphere_box_yaw(PvAcc<MODE>& acc, float3 c, float r, float r2, float3 oc, float3 oh,
+                                                  float cy, float sy, int code) {
+    float dx = c.x - oc.x, dy = c.y - oc.y, dz = c.z - oc.z;
+    float ex = fabsf(fmaf(dy, sy, dx * cy)) - oh.x;
+    float ey = fabsf(fmaf(dy, cy, -dx * sy)) - oh.y;
+    float ez = fabsf(dz) - oh.z;
+    float px = fmaxf(ex, 0.f), py = fmaxf(ey, 0.f), pz = fmaxf(ez, 0.f);
+    float s2 = fmaf(pz, pz, fmaf(py, py, px * px));
+    if constexpr (MODE == PV_MODE_BITS) {
+        acc.hit |= (s2 < r2);
+    } else {
+        float g = (s2 > 0.f ? sqrtf(s2) : fmaxf(ex, fmaxf(ey, ez))) - r;
+        acc.take(g, code);
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void pv_sphere_sphere(PvAcc<MODE>& acc, float3 a, float3 b, float rr2, float rr, int code) {
+    float3 d = v_sub(a, b);
+    float d2 = v_dot(d, d);
+    if constexpr (MODE == PV_MODE_BITS) {
+        acc.hit |= (d2 < rr2);
+    } else {
+        acc.take(sqrtf(d2) - rr, code);
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void pv_plane(PvAcc<MODE>& acc, float lowest, float table_z, int code) {
+    float g = lowest - table_z;
+    if constexpr (MODE == PV_MODE_BITS) {
+        acc.hit |= (g < 0.f);
+    } else {
+        acc.take(g, code);
+    }
+}
+
+// box A (centre ca, half ha, axes AX/AY/AZ) vs box B (centre cb, half hb, axes BX/BY/BZ): 15-axis SAT.
+// Gap = largest normalised separation; cross axes with |a_i x b_j|^2 <= 1e-4 are skipped.
+template <int MODE>
+__device__ __noinline__ void pv_box_box(PvAcc<MODE>& acc, float3 ca, float3 ha, float3 AX, float3 AY, float3 AZ,
+                                        float3 cb, float3 hb, float3 BX, float3 BY, float3 BZ, int code) {
+    float Rm[3][3], A[3][3], t[3], h_a[3] = {ha.x, ha.y, ha.z}, h_b[3] = {hb.x, hb.y, hb.z};
+    float3 d = v_sub(cb, ca);
+    const float3 Aax[3] = {AX, AY, AZ}, Bax[3] = {BX, BY, BZ};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            Rm[i][j] = v_dot(Aax[i], Bax[j]);
+            A[i][j] = fabsf(Rm[i][j]);
+        }
+        t[i] = v_dot(Aax[i], d);
+    }
+    float best = -1e30f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float rb = fmaf(A[i][2], h_b[2], fmaf(A[i][1], h_b[1], A[i][0] * h_b[0]));
+        best = fmaxf(best, fabsf(t[i]) - h_a[i] - rb);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float ra = fmaf(A[2][j], h_a[2], fmaf(A[1][j], h_a[1], A[0][j] * h_a[0]));
+        float tl = fmaf(t[2], Rm[2][j], fmaf(t[1], Rm[1][j], t[0] * Rm[0][j]));
+        best = fmaxf(best, fabsf(tl) - ra - h_b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            float len2 = fmaf(-Rm[i][j], Rm[i][j], 1.0f);
+            float ra = fmaf(h_a[i2], A[i1][j], h_a[i1] * A[i2][j]);
+            float rb = fmaf(h_b[j2], A[i][j1], h_b[j1] * A[i][j2]);
+            float tl = fabsf(fmaf(t[i2], Rm[i1][j], -t[i1] * Rm[i2][j]));
+            float g = tl - ra - rb;
+            if constexpr (MODE == PV_MODE_MARGIN) g = g * rsqrtf(fmaxf(len2, 1e-4f));
+            if (len2 > 1e-4f) best = fmaxf(best, g);
+        }
+    }
+    if constexpr (MODE == PV_MODE_BITS) {
+        acc.hit |= (best < 0.f);
+    } else {
+        acc.take(best, code);
+    }
+}
+
+// ---- forward kinematics --------------------------------------------------------------------------------
+// Frames of link1..link7, hand; fingers share the hand's axes.  Chain constants: SURVEY.md App. A
+// (Menagerie panda.xml, scenes.py:85); the six +-90 deg x pre-rotations are axis permutations.
+struct PvFrames {
+    float3 p[11];
+    float3 X[9], Y[9], Z[9];  // links 0..8 (fingers: axes of link 8; right finger has X, Y negated)
+};
+
+// Visitor-driven FK: `on_link(l, p, X, Y, Z)` is called as soon as link l's frame exists, so callers
+// that only need sphere centres never keep more than one frame live.
+template <class F>
+__device__ __forceinline__ void pv_fk_visit(const float* q, float bx, float by, float bz, F&& on_link) {
+    float s, c;
+    float3 p = make_float3(bx, by, bz);
+    float3 X = make_float3(1.f, 0.f, 0.f), Y = make_float3(0.f, 1.f, 0.f), Z = make_float3(0.f, 0.f, 1.f);
+    on_link(std::integral_constant<int, 0>{}, p, X, Y, Z);
+    // link1: pos (0,0,0.333), no pre-rotation
+    pv_sincos(q[0], s, c);
+    p.z += 0.333f;
+    X = make_float3(c, s, 0.f);
+    Y = make_float3(-s, c, 0.f);
+    on_link(std::integral_constant<int, 1>{}, p, X, Y, Z);
+    float3 Xp, Yp, Zp;
+    // link2: pos 0, Rx(-90): X' = X, Y' = -Z, Z' = Y
+    pv_sincos(q[1], s, c);
+    {
+        float3 X1 = X, Y1 = Y;
+        X = make_float3(c * X1.x, c * X1.y, -s);
+        Y = make_float3(-s * X1.x, -s * X1.y, -c);
+        Z = Y1;
+    }
+    on_link(std::integral_constant<int, 2>{}, p, X, Y, Z);
+    // link3: pos (0,-0.316,0), Rx(+90): X' = X, Y' = Z, Z' = -Y
+    pv_sincos(q[2], s, c);
+    p = v_fma(Y, -0.316f, p);
+    Xp = X; Yp = Z; Zp = v_neg(Y);
+    v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
+    on_link(std::integral_constant<int, 3>{}, p, X, Y, Z);
+    // link4: pos (0.0825,0,0), Rx(+90)
+    pv_sincos(q[3], s, c);
+    p = v_fma(X, 0.0825f, p);
+    Xp = X; Yp = Z; Zp = v_neg(Y);
+    v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
+    on_link(std::integral_constant<int, 4>{}, p, X, Y, Z);
+    // link5: pos (-0.0825,0.384,0), Rx(-90): X' = X, Y' = -Z, Z' = Y
+    pv_sincos(q[4], s, c);
+    p = v_fma(Y, 0.384f, v_fma(X, -0.0825f, p));
+    Xp = X; Yp = v_neg(Z); Zp = Y;
+    v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
+    on_link(std::integral_constant<int, 5>{}, p, X, Y, Z);
+    // link6: pos 0, Rx(+90)
+    pv_sincos(q[5], s, c);
+    Xp = X; Yp = Z; Zp = v_neg(Y);
+    v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
+    on_link(std::integral_constant<int, 6>{}, p, X, Y, Z);
+    // link7: pos (0.088,0,0), Rx(+90)
+    pv_sincos(q[6], s, c);
+    p = v_fma(X, 0.088f, p);
+    Xp = X; Yp = Z; Zp = v_neg(Y);
+    v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
+    on_link(std::integral_constant<int, 7>{}, p, X, Y, Z);
+    // hand: pos (0,0,0.107), fixed rotation about z by -45 deg
+    p = v_fma(Z, 0.107f, p);
+    Xp = X; Yp = Y;
+    v_rotz(Xp, Yp, PV_HAND_COS, PV_HAND_SIN, X, Y);
+    on_link(std::integral_constant<int, 8>{}, p, X, Y, Z);
+    // fingers: pos (0,0,0.0584), slide along own +y; right finger frame is the hand's turned 180 deg about z
+    float3 pf = v_fma(Z, 0.0584f, p);
+    on_link(std::integral_constant<int, 9>{}, v_fma(Y, q[7], pf), X, Y, Z);
+    on_link(std::integral_constant<int, 10>{}, v_fma(Y, -q[8], pf), v_neg(X), v_neg(Y), Z);
+}
+
+// ---- the state check ----------------------------------------------------------------------------------
+// Returns through `acc`.  All 32 lanes of a warp must call this together when EXIT != PV_EXIT_NONE.
+template <int MODE, bool CULL, int EXIT>
+__device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S, PvAcc<MODE>& acc) {
+    const unsigned FULL = 0xffffffffu;
+#define PV_EARLY_EXIT()                                                              \
+    if constexpr (MODE == PV_MODE_BITS && EXIT != PV_EXIT_NONE) {                    \
+        bool h_ = acc.hit;                                                           \
+        if (EXIT == PV_EXIT_ALL ? __all_sync(FULL, h_) : __any_sync(FULL, h_)) return; \
+    }
+
+    if (S.flags & PV_FLAG_LIMITS) {
+        const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            bool out = (q[j] < lo[j]) || (q[j] > hi[j]);
+            if constexpr (MODE == PV_MODE_BITS) {
+                acc.hit |= out;
+            } else if (out) {
+                acc.take(-1e30f, PV_CODE(4, j, 0));
+            }
+        }
+    }
+
+    // FK -> sphere centres (registers) + gripper boxes
+    float3 s[PV_N_SPHERES];
+    float3 hX, hY, hZ, bc[3];
+    pv_fk_visit(q, S.base[0], S.base[1], S.base[2], [&](auto lc, float3 p, float3 X, float3 Y, float3 Z) {
+        constexpr int l = decltype(lc)::value;
+        if constexpr (l == 0) { PV_PLACE_LINK0(s, p, X, Y, Z) }
+        if constexpr (l == 1) { PV_PLACE_LINK1(s, p, X, Y, Z) }
+        if constexpr (l == 2) { PV_PLACE_LINK2(s, p, X, Y, Z) }
+        if constexpr (l == 3) { PV_PLACE_LINK3(s, p, X, Y, Z) }
+        if constexpr (l == 4) { PV_PLACE_LINK4(s, p, X, Y, Z) }
+        if constexpr (l == 5) { PV_PLACE_LINK5(s, p, X, Y, Z) }
+        if constexpr (l == 6) { PV_PLACE_LINK6(s, p, X, Y, Z) }
+        if constexpr (l == 7) { PV_PLACE_LINK7(s, p, X, Y, Z) }
+        if constexpr (l == 8) { hX = X; hY = Y; hZ = Z; }
+#define PV_BOX_PLACE(k, link, cx, cy, cz, hx, hy, hz, br) \
+    if constexpr (l == link) bc[k] = v_fma(Z, cz, v_fma(Y, cy, v_fma(X, cx, p)));
+        PV_BOXES(PV_BOX_PLACE)
+#undef PV_BOX_PLACE
+    });
+    const float bh[3][3] = {
+#define PV_BOX_HALF(k, link, cx, cy, cz, hx, hy, hz, br) {hx, hy, hz},
+        PV_BOXES(PV_BOX_HALF)
+#undef PV_BOX_HALF
+    };
+    const float bbr[3] = {
+#define PV_BOX_BR(k, link, cx, cy, cz, hx, hy, hz, br) br,
+        PV_BOXES(PV_BOX_BR)
+#undef PV_BOX_BR
+    };
+    const int blink[3] = {
+#define PV_BOX_LK(k, link, cx, cy, cz, hx, hy, hz, br) link,
+        PV_BOXES(PV_BOX_LK)
+#undef PV_BOX_LK
+    };
+
+    // ---- robot vs ground plane (link0 is fixed to the world: pair filtered) -------------
+    const float tz = S.table_z;
+#define PV_TABLE_SPHERE(i, link, cx, cy, cz, r) \
+    if (link != 0) pv_plane<MODE>(acc, s[i].z - r, tz, PV_CODE(1, link, 0));
+    PV_SPHERES(PV_TABLE_SPHERE)
+#undef PV_TABLE_SPHERE
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float ext = fmaf(fabsf(hZ.z), bh[k][2], fmaf(fabsf(hY.z), bh[k][1], fabsf(hX.z) * bh[k][0]));
+        pv_plane<MODE>(acc, bc[k].z - ext, tz, PV_CODE(1, blink[k], 0));
+    }
+    PV_EARLY_EXIT()
+
+    // ---- self collision ------------------------------------------------------------------------------
+    if (S.flags & PV_FLAG_SELF) {
+#define PV_SS(a, b, rr2, rr) pv_sphere_sphere<MODE>(acc, s[a], s[b], rr2, rr, PV_CODE(3, a, b));
+#define PV_LP(la, lb, ca, cb, cull2)                         \
+    {                                                        \
+        float3 d_ = v_sub(s[ca], s[cb]);                     \
+        if (!CULL || v_dot(d_, d_) < cull2) {                \
+            PV_SS_PAIRS_##la##_##lb(PV_SS)                   \
+        }                                                    \
+    }
+        PV_SS_LINKPAIRS(PV_LP)
+#undef PV_LP
+#undef PV_SS
+        PV_EARLY_EXIT()
+#define PV_SB(a, k, r2, r)                                                                                  \
+    pv_sphere_box<MODE>(acc, s[a], r, r2, bc[k], make_float3(bh[k][0], bh[k][1], bh[k][2]), hX, hY, hZ, \
+                        PV_CODE(3, a, 33 + k));
+#define PV_LB(la, k, ca, cull2)                              \
+    {                                                        \
+        float3 d_ = v_sub(s[ca], bc[k]);                     \
+        if (!CULL || v_dot(d_, d_) < cull2) {                \
+            PV_SB_PAIRS_##la##_##k(PV_SB)                    \
+        }                                                    \
+    }
+        PV_SB_LINKBOX(PV_LB)
+#undef PV_LB
+#undef PV_SB
+        PV_EARLY_EXIT()
+    }
+
+    // ---- robot vs scene boxes ------------------------------------------------------------------------
+    const int nb = S.n_obb;
+    for (int b = 0; b < nb; ++b) {
+        const float3 oc = make_float3(S.obb[b][0], S.obb[b][1], S.obb[b][2]);
+        const float3 oh = make_float3(S.obb[b][3], S.obb[b][4], S.obb[b][5]);
+        const float obr = S.obb[b][15];
+        const float3 BX = make_float3(S.obb[b][6], S.obb[b][9], S.obb[b][12]);
+        const float3 BY = make_float3(S.obb[b][7], S.obb[b][10], S.obb[b][13]);
+        const float3 BZ = make_float3(S.obb[b][8], S.obb[b][11], S.obb[b][14]);
+        const bool yaw_only = (S.yaw_only_mask >> b) & 1u;
+#define PV_ENV_SPHERE(i, link, cx, cy, cz, r)                                                      \
+    if (yaw_only)                                                                                  \
+        pv_sphere_box_yaw<MODE>(acc, s[i], r, (r) * (r), oc, oh, BX.x, BX.y, PV_CODE(2, link, b)); \
+    else                                                                                           \
+        pv_sphere_box<MODE>(acc, s[i], r, (r) * (r), oc, oh, BX, BY, BZ, PV_CODE(2, link, b));
+#define PV_ENV_GROUP(l, cs, br)                                 \
+    {                                                           \
+        float3 d_ = v_sub(s[cs], oc);                           \
+        float rr_ = (br + PV_CULL_SLACK) + obr;                 \
+        if (!CULL || v_dot(d_, d_) < rr_ * rr_) {               \
+            PV_SPHERES_LINK##l(PV_ENV_SPHERE)                   \
+        }                                                       \
+    }
+        PV_LINK_GROUPS(PV_ENV_GROUP)
+#undef PV_ENV_GROUP
+#undef PV_ENV_SPHERE
+        if (b != S.attached) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float3 d_ = v_sub(bc[k], oc);
+                float rr_ = (bbr[k] + PV_CULL_SLACK) + obr;
+                if (!CULL || v_dot(d_, d_) < rr_ * rr_) {
+                    pv_box_box<MODE>(acc, bc[k], make_float3(bh[k][0], bh[k][1], bh[k][2]), hX, hY, hZ, oc, oh, BX, BY,
+                                     BZ, PV_CODE(2, blink[k], b));
+                }
+            }
+        }
+        PV_EARLY_EXIT()
+    }
+#undef PV_EARLY_EXIT
+}
+
+// ---- config loads ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pv_load_soa(const float4* __restrict__ qA, const float4* __restrict__ qB,
+                                            const float* __restrict__ q9, int64_t i, float* q) {
+    float4 a = __ldg(qA + i), b = __ldg(qB + i);
+    q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w;
+    q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+    q[8] = q9 ? __ldg(q9 + i) : b.w;
+}
+__device__ __forceinline__ void pv_load_aos(const float* __restrict__ qa, int64_t i, float* q) {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) q[j] = __ldg(qa + 9 * i + j);
+}
+
+// ---- Philox-4x32-10 (counter-based RNG for the device-generated sweeps) ---------------------------------
+__device__ __forceinline__ uint4 pv_philox(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ void pv_sweep_config(uint64_t i, unsigned seed, bool fingers_open, float* q) {
+    const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
+    float u[12];
+    const uint2 key = make_uint2(seed, 0x50414E44u);
+#pragma unroll
+    for (int blk = 0; blk < 3; ++blk) {
+        uint4 r = pv_philox(make_uint4((unsigned)(i & 0xffffffffull), (unsigned)(i >> 32), blk, 0u), key);
+        u[4 * blk + 0] = (float)(r.x >> 8) * 5.9604644775390625e-08f;
+        u[4 * blk + 1] = (float)(r.y >> 8) * 5.9604644775390625e-08f;
+        u[4 * blk + 2] = (float)(r.z >> 8) * 5.9604644775390625e-08f;
+        u[4 * blk + 3] = (float)(r.w >> 8) * 5.9604644775390625e-08f;
+    }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) q[j] = __fmaf_rn(u[j], hi[j] - lo[j], lo[j]);
+    if (fingers_open) {
+        q[7] = 0.04f;
+        q[8] = 0.04f;
+    }
+}

@@ -1,0 +1,29 @@
+// pv_handle.h -- the opaque handle behind the C-ABI (shared by pv_kernels.cu and pv_rrtc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pv_device.cuh"
+
+#define PV_HANDLE_MAGIC 0x50564831u
+#define PV_N_STREAMS 3
+#define PV_HOST_CHUNK (1 << 18)  // configs per pipelined chunk of the host-buffer entry points
+
+struct PvHandle {
+    uint32_t magic;
+    int device;
+    int sm_count;
+    int has_scene;
+    int cull;
+    long long launches;
+    PvScene scene;
+    cudaStream_t streams[PV_N_STREAMS];
+    float* stage_q[PV_N_STREAMS];
+    float* stage_q2[PV_N_STREAMS];
+    uint32_t* stage_bits[PV_N_STREAMS];
+    void* rrtc_buf;
+    size_t rrtc_bytes;
+    char err[512];
+};
+
+int pv_grid_for(PvHandle* h, const void* kernel, int threads, int64_t warps_needed);

@@ -1,0 +1,608 @@
+// pv_kernels.cu -- sm_100a kernels + the C-ABI of include/panda_validity.h (state / edge validity, FK,
+// device-generated sweeps, FP32 peak probe).  The batched RRT-Connect lives in pv_rrtc.cu.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/panda_validity.h"
+#include "pv_device.cuh"
+#include "pv_handle.h"
+
+#ifndef PV_THREADS
+#define PV_THREADS 128
+#endif
+#ifndef PV_MIN_BLOCKS
+#define PV_MIN_BLOCKS 3
+#endif
+
+static char g_create_error[512] = "";
+
+#define PV_CUDA(h, expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            snprintf((h)->err, sizeof((h)->err), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                                             \
+            return PV_ERR_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+
+// =========================================================================================================
+// kernels
+// =========================================================================================================
+
+// K2: one thread per configuration, warp-ballot bit packing.  Persistent warps, warp-stride over words.
+template <bool AOS, bool CULL>
+__global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
+    pv_state_bits_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA,
+                         const float4* __restrict__ qB, const float* __restrict__ q9,
+                         const float* __restrict__ q_aos, int64_t n, uint32_t* __restrict__ bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_words = (n + 31) >> 5;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = warp0; w < n_words; w += n_warps) {
+        const int64_t i = (w << 5) + lane;
+        const bool in = i < n;
+        const int64_t ii = in ? i : n - 1;
+        float q[9];
+        if (AOS) pv_load_aos(q_aos, ii, q);
+        else pv_load_soa(qA, qB, q9, ii, q);
+        PvAcc<PV_MODE_BITS> acc;
+        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_ALL>(q, S, acc);
+        const unsigned word = __ballot_sync(0xffffffffu, in && !acc.hit);
+        if (lane == 0) bits[w] = word;
+    }
+}
+
+template <bool CULL>
+__global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
+    pv_state_margin_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA,
+                           const float4* __restrict__ qB, const float* __restrict__ q9, int64_t n,
+                           float* __restrict__ margin, int32_t* __restrict__ culprit) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float q[9];
+        pv_load_soa(qA, qB, q9, i, q);
+        PvAcc<PV_MODE_MARGIN> acc;
+        pv_check_config<PV_MODE_MARGIN, CULL, PV_EXIT_NONE>(q, S, acc);
+        margin[i] = acc.m;
+        if (culprit) culprit[i] = acc.m < 0.f ? acc.code : 0;
+    }
+}
+
+// K1: forward kinematics only; [n][11][12] = position then row-major rotation per link.
+__global__ void __launch_bounds__(128)
+    pv_fk_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA, const float4* __restrict__ qB,
+                 const float* __restrict__ q9, int64_t n, float* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float q[9];
+        pv_load_soa(qA, qB, q9, i, q);
+        float* o = out + i * 132;
+        pv_fk_visit(q, S.base[0], S.base[1], S.base[2], [&](auto lc, float3 p, float3 X, float3 Y, float3 Z) {
+            constexpr int l = decltype(lc)::value;
+            float* r = o + 12 * l;
+            r[0] = p.x; r[1] = p.y; r[2] = p.z;
+            r[3] = X.x; r[4] = Y.x; r[5] = Z.x;
+            r[6] = X.y; r[7] = Y.y; r[8] = Z.y;
+            r[9] = X.z; r[10] = Y.z; r[11] = Z.z;
+        });
+    }
+}
+
+// K3: one warp per edge, lanes = interpolation states, coarse-to-fine rounds, any-hit early exit.
+// Each warp owns 32 consecutive edges and emits one verdict word.
+template <bool CULL, int MODE>
+__global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
+    pv_edge_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ aA, const float4* __restrict__ aB,
+                   const float* __restrict__ a9, const float4* __restrict__ bA, const float4* __restrict__ bB,
+                   const float* __restrict__ b9, const float* __restrict__ a_aos, const float* __restrict__ b_aos,
+                   int64_t n_edges, int n_steps, float resolution, uint32_t* __restrict__ bits,
+                   float* __restrict__ margin) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t n_words = (n_edges + 31) >> 5;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = warp0; w < n_words; w += n_warps) {
+        const int64_t e_lane = (w << 5) + lane;
+        const int64_t ee = e_lane < n_edges ? e_lane : n_edges - 1;
+        float qa[9], qb[9];
+        if (a_aos) {
+            pv_load_aos(a_aos, ee, qa);
+            pv_load_aos(b_aos, ee, qb);
+        } else {
+            pv_load_soa(aA, aB, a9, ee, qa);
+            pv_load_soa(bA, bB, b9, ee, qb);
+        }
+        unsigned word = 0;
+        const int n_here = (int)min((int64_t)32, n_edges - (w << 5));
+        for (int j = 0; j < n_here; ++j) {
+            float ea[9], de[9], eb[9];
+            float d2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                ea[k] = __shfl_sync(FULL, qa[k], j);
+                eb[k] = __shfl_sync(FULL, qb[k], j);
+                de[k] = eb[k] - ea[k];
+                d2 = fmaf(de[k], de[k], d2);
+            }
+            int nd = n_steps;
+            if (nd <= 0) nd = max(1, (int)ceilf(sqrtf(d2) / resolution));
+            const int rounds = (nd + 31) >> 5;
+            const float inv_nd = 1.0f / (float)nd;
+            bool edge_hit = false;
+            float edge_m = 1e30f;
+            for (int r = 0; r < rounds; ++r) {
+                int k = nd - (lane * rounds + r);
+                const bool active = k >= 1;
+                if (!active) k = nd;  // idle lanes re-check the end point so the warp stays converged
+                const float t = (float)k * inv_nd;
+                float q[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, de[c], ea[c]);
+                PvAcc<MODE> acc;
+                pv_check_config<MODE, CULL, (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE)>(q, S, acc);
+                if constexpr (MODE == PV_MODE_BITS) {
+                    if (__any_sync(FULL, acc.hit)) {
+                        edge_hit = true;
+                        break;
+                    }
+                } else {
+                    edge_m = fminf(edge_m, acc.m);
+                }
+            }
+            if constexpr (MODE == PV_MODE_BITS) {
+                word |= (edge_hit ? 0u : 1u) << j;
+            } else {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) edge_m = fminf(edge_m, __shfl_xor_sync(FULL, edge_m, o));
+                if (lane == 0) margin[(w << 5) + j] = edge_m;
+            }
+        }
+        if constexpr (MODE == PV_MODE_BITS) {
+            if (lane == 0) bits[w] = word;
+        }
+    }
+}
+
+// Config-5 sweep: configurations generated on device from a counter-based RNG, checked, bit-packed, counted.
+template <bool CULL>
+__global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
+    pv_sweep_kernel(const __grid_constant__ PvScene S, uint64_t first, int64_t n, unsigned seed, int fingers_open,
+                    uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid,
+                    float* __restrict__ q_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_words = (n + 31) >> 5;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    unsigned long long count = 0;
+    for (int64_t w = warp0; w < n_words; w += n_warps) {
+        const int64_t i = (w << 5) + lane;
+        const bool in = i < n;
+        float q[9];
+        pv_sweep_config(first + (uint64_t)(in ? i : n - 1), seed, fingers_open != 0, q);
+        if (q_out && in) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) q_out[9 * i + j] = q[j];
+        }
+        PvAcc<PV_MODE_BITS> acc;
+        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_ALL>(q, S, acc);
+        const unsigned word = __ballot_sync(0xffffffffu, in && !acc.hit);
+        if (lane == 0) {
+            bits[w] = word;
+            count += __popc(word);
+        }
+    }
+    if (n_valid && lane == 0 && count) atomicAdd(n_valid, count);
+}
+
+// FP32 issue-rate probe: 8 independent FFMA chains per thread.
+__global__ void __launch_bounds__(256) pv_fp32_peak_kernel(int iters, float seed, float* out) {
+    float a0 = seed, a1 = seed + 1.f, a2 = seed + 2.f, a3 = seed + 3.f;
+    float a4 = seed + 4.f, a5 = seed + 5.f, a6 = seed + 6.f, a7 = seed + 7.f;
+    const float m = 0.999f + 1e-6f * (float)threadIdx.x, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456f) out[0] = r;  // never true in practice; keeps the chains alive
+}
+
+// =========================================================================================================
+// host side
+// =========================================================================================================
+static int pv_check_handle(const PvHandle* h) { return (h && h->magic == PV_HANDLE_MAGIC) ? 0 : PV_ERR_BAD_HANDLE; }
+
+int pv_grid_for(PvHandle* h, const void* kernel, int threads, int64_t warps_needed) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0) != cudaSuccess || occ < 1) occ = 1;
+    int64_t blocks = (int64_t)h->sm_count * occ;
+    const int64_t need = (warps_needed * 32 + threads - 1) / threads;
+    if (need < blocks) blocks = need;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+extern "C" {
+
+const char* pv_version(void) { return "panda_validity 0.1 (sm_100a)"; }
+
+const char* pv_last_error(const PvHandle* h) { return (h && h->magic == PV_HANDLE_MAGIC) ? h->err : g_create_error; }
+
+long long pv_launch_count(const PvHandle* h) { return pv_check_handle(h) ? -1 : h->launches; }
+
+int pv_model_info(int* n_spheres, int* n_boxes, int* n_ss_pairs, int* n_sb_pairs) {
+    if (n_spheres) *n_spheres = PV_N_SPHERES;
+    if (n_boxes) *n_boxes = PV_N_BOXES;
+    if (n_ss_pairs) *n_ss_pairs = PV_N_SS_PAIRS;
+    if (n_sb_pairs) *n_sb_pairs = PV_N_SB_PAIRS;
+    return PV_OK;
+}
+
+int pv_joint_limits(float lower[9], float upper[9]) {
+    const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
+    if (!lower || !upper) return PV_ERR_BAD_ARG;
+    memcpy(lower, lo, sizeof(lo));
+    memcpy(upper, hi, sizeof(hi));
+    return PV_OK;
+}
+
+int pv_create(int device, PvHandle** out) {
+    if (!out) return PV_ERR_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        snprintf(g_create_error, sizeof(g_create_error), "no CUDA device visible (%s); there is no CPU fallback",
+                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return PV_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        snprintf(g_create_error, sizeof(g_create_error), "device %d out of range (0..%d)", device, count - 1);
+        return PV_ERR_BAD_ARG;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        snprintf(g_create_error, sizeof(g_create_error), "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+        return PV_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        snprintf(g_create_error, sizeof(g_create_error),
+                 "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+        return PV_ERR_NO_DEVICE;
+    }
+    PvHandle* h = new PvHandle();
+    memset(h, 0, sizeof(*h));
+    h->magic = PV_HANDLE_MAGIC;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->scene.attached = -1;
+    h->scene.flags = PV_FLAG_SELF;
+    h->scene.base[2] = 0.01f;
+    h->cull = 1;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        snprintf(g_create_error, sizeof(g_create_error), "cudaSetDevice: %s", cudaGetErrorString(e));
+        delete h;
+        return PV_ERR_CUDA;
+    }
+    for (int i = 0; i < PV_N_STREAMS; ++i) {
+        if ((e = cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking)) != cudaSuccess) {
+            snprintf(g_create_error, sizeof(g_create_error), "cudaStreamCreate: %s", cudaGetErrorString(e));
+            delete h;
+            return PV_ERR_CUDA;
+        }
+    }
+    *out = h;
+    return PV_OK;
+}
+
+void pv_destroy(PvHandle* h) {
+    if (pv_check_handle(h)) return;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < PV_N_STREAMS; ++i) {
+        if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+        if (h->stage_q[i]) cudaFree(h->stage_q[i]);
+        if (h->stage_q2[i]) cudaFree(h->stage_q2[i]);
+        if (h->stage_bits[i]) cudaFree(h->stage_bits[i]);
+    }
+    if (h->rrtc_buf) cudaFree(h->rrtc_buf);
+    h->magic = 0;
+    delete h;
+}
+
+int pv_set_scene(PvHandle* h, const float* h_obb, int n_obb, float table_z, const float base_xyz[3]) {
+    if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
+    if (n_obb < 0 || n_obb > PV_MAX_OBB || (n_obb > 0 && !h_obb)) {
+        snprintf(h->err, sizeof(h->err), "pv_set_scene: n_obb=%d outside 0..%d (or null buffer)", n_obb, PV_MAX_OBB);
+        return PV_ERR_BAD_ARG;
+    }
+    PvScene& S = h->scene;
+    memset(S.obb, 0, sizeof(S.obb));
+    S.yaw_only_mask = 0;
+    for (int b = 0; b < n_obb; ++b) {
+        const float* o = h_obb + 16 * b;
+        for (int k = 0; k < 15; ++k) {
+            if (!isfinite(o[k])) {
+                snprintf(h->err, sizeof(h->err), "pv_set_scene: box %d has a non-finite entry", b);
+                return PV_ERR_BAD_ARG;
+            }
+            S.obb[b][k] = o[k];
+        }
+        if (!(o[3] > 0.f && o[4] > 0.f && o[5] > 0.f)) {
+            snprintf(h->err, sizeof(h->err), "pv_set_scene: box %d has non-positive half extents", b);
+            return PV_ERR_BAD_ARG;
+        }
+        S.obb[b][15] = sqrtf(o[3] * o[3] + o[4] * o[4] + o[5] * o[5]);
+        const float* R = o + 6;
+        if (R[2] == 0.f && R[5] == 0.f && R[6] == 0.f && R[7] == 0.f && R[8] == 1.f) S.yaw_only_mask |= 1u << b;
+    }
+    S.n_obb = n_obb;
+    S.table_z = table_z;
+    if (base_xyz) {
+        S.base[0] = base_xyz[0];
+        S.base[1] = base_xyz[1];
+        S.base[2] = base_xyz[2];
+    }
+    if (S.attached >= n_obb) S.attached = -1;
+    h->has_scene = 1;
+    return PV_OK;
+}
+
+int pv_set_attached(PvHandle* h, int obb_index) {
+    if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
+    if (obb_index < -1 || obb_index >= h->scene.n_obb) {
+        snprintf(h->err, sizeof(h->err), "pv_set_attached: index %d outside -1..%d", obb_index, h->scene.n_obb - 1);
+        return PV_ERR_BAD_ARG;
+    }
+    h->scene.attached = obb_index;
+    return PV_OK;
+}
+
+int pv_set_flags(PvHandle* h, unsigned flags) {
+    if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
+    h->scene.flags = flags & (PV_FLAG_SELF | PV_FLAG_LIMITS);
+    return PV_OK;
+}
+
+// test / profiling hook: 0 = brute force (no bounding-ball culling), 1 = culling (default)
+int pv_set_culling(PvHandle* h, int on) {
+    if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
+    h->cull = on ? 1 : 0;
+    return PV_OK;
+}
+
+#define PV_PRECHECK(h, n)                                                   \
+    if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;                       \
+    if (!(h)->has_scene) {                                                  \
+        snprintf((h)->err, sizeof((h)->err), "no scene set (pv_set_scene)"); \
+        return PV_ERR_NO_SCENE;                                             \
+    }                                                                       \
+    if ((n) < 0) {                                                          \
+        snprintf((h)->err, sizeof((h)->err), "negative count");             \
+        return PV_ERR_BAD_ARG;                                              \
+    }                                                                       \
+    if ((n) == 0) return PV_OK;                                             \
+    PV_CUDA(h, cudaSetDevice((h)->device));
+
+int pv_fk(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9, int64_t n, float* d_pose_out,
+          void* stream) {
+    PV_PRECHECK(h, n);
+    if (!d_qA || !d_qB || !d_pose_out) return PV_ERR_BAD_ARG;
+    const int threads = 128;
+    int64_t blocks = (n + threads - 1) / threads;
+    if (blocks > (int64_t)h->sm_count * 16) blocks = (int64_t)h->sm_count * 16;
+    pv_fk_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(h->scene, (const float4*)d_qA, (const float4*)d_qB,
+                                                                    d_q9, n, d_pose_out);
+    h->launches++;
+    PV_CUDA(h, cudaGetLastError());
+    return PV_OK;
+}
+
+static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9,
+                                const float* d_aos, int64_t n, uint32_t* d_bits, cudaStream_t st) {
+    const int64_t words = (n + 31) / 32;
+#define PV_LAUNCH_SB(AOS, CULL)                                                                               \
+    {                                                                                                         \
+        int grid = pv_grid_for(h, (const void*)pv_state_bits_kernel<AOS, CULL>, PV_THREADS, words);           \
+        pv_state_bits_kernel<AOS, CULL><<<grid, PV_THREADS, 0, st>>>(h->scene, (const float4*)d_qA,           \
+                                                                     (const float4*)d_qB, d_q9, d_aos, n, d_bits); \
+    }
+    if (d_aos) {
+        if (h->cull) PV_LAUNCH_SB(true, true) else PV_LAUNCH_SB(true, false)
+    } else {
+        if (h->cull) PV_LAUNCH_SB(false, true) else PV_LAUNCH_SB(false, false)
+    }
+#undef PV_LAUNCH_SB
+    h->launches++;
+    PV_CUDA(h, cudaGetLastError());
+    return PV_OK;
+}
+
+int pv_check_states(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9, int64_t n,
+                    uint32_t* d_bits, void* stream) {
+    PV_PRECHECK(h, n);
+    if (!d_qA || !d_qB || !d_bits) return PV_ERR_BAD_ARG;
+    return pv_launch_state_bits(h, d_qA, d_qB, d_q9, nullptr, n, d_bits, (cudaStream_t)stream);
+}
+
+int pv_state_margins(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9, int64_t n,
+                     float* d_margin, int32_t* d_culprit, void* stream) {
+    PV_PRECHECK(h, n);
+    if (!d_qA || !d_qB || !d_margin) return PV_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        // margins are a diagnostic: always brute force (culling only guarantees that contacts are never
+        // missed, it may skip the far-away primitive that defines a positive clearance)
+        int grid = pv_grid_for(h, (const void*)pv_state_margin_kernel<false>, PV_THREADS, (n + 31) / 32);
+        pv_state_margin_kernel<false><<<grid, PV_THREADS, 0, st>>>(h->scene, (const float4*)d_qA, (const float4*)d_qB,
+                                                                   d_q9, n, d_margin, d_culprit);
+    }
+    h->launches++;
+    PV_CUDA(h, cudaGetLastError());
+    return PV_OK;
+}
+
+static int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* a9, const float* bA,
+                           const float* bB, const float* b9, const float* a_aos, const float* b_aos, int64_t n,
+                           int n_steps, float resolution, uint32_t* d_bits, float* d_margin, cudaStream_t st) {
+    if (n_steps < 0 || (n_steps == 0 && !(resolution > 0.f))) {
+        snprintf(h->err, sizeof(h->err), "edge check needs n_steps > 0 or resolution > 0");
+        return PV_ERR_BAD_ARG;
+    }
+    const int64_t words = (n + 31) / 32;
+#define PV_LAUNCH_E(CULL, MODE)                                                                                \
+    {                                                                                                          \
+        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE>, PV_THREADS, words);                 \
+        pv_edge_kernel<CULL, MODE><<<grid, PV_THREADS, 0, st>>>(h->scene, (const float4*)aA, (const float4*)aB, a9, \
+                                                                (const float4*)bA, (const float4*)bB, b9, a_aos, b_aos, \
+                                                                n, n_steps, resolution, d_bits, d_margin);     \
+    }
+    if (d_bits) {
+        if (h->cull) PV_LAUNCH_E(true, PV_MODE_BITS) else PV_LAUNCH_E(false, PV_MODE_BITS)
+    } else {
+        PV_LAUNCH_E(false, PV_MODE_MARGIN)  // margins: always brute force
+    }
+#undef PV_LAUNCH_E
+    h->launches++;
+    PV_CUDA(h, cudaGetLastError());
+    return PV_OK;
+}
+
+int pv_check_edges(PvHandle* h, const float* d_aA, const float* d_aB, const float* d_a9, const float* d_bA,
+                   const float* d_bB, const float* d_b9, int64_t n_edges, int n_steps, float resolution,
+                   uint32_t* d_bits, void* stream) {
+    PV_PRECHECK(h, n_edges);
+    if (!d_aA || !d_aB || !d_bA || !d_bB || !d_bits) return PV_ERR_BAD_ARG;
+    return pv_launch_edges(h, d_aA, d_aB, d_a9, d_bA, d_bB, d_b9, nullptr, nullptr, n_edges, n_steps, resolution,
+                           d_bits, nullptr, (cudaStream_t)stream);
+}
+
+int pv_edge_margins(PvHandle* h, const float* d_aA, const float* d_aB, const float* d_a9, const float* d_bA,
+                    const float* d_bB, const float* d_b9, int64_t n_edges, int n_steps, float resolution,
+                    float* d_margin, void* stream) {
+    PV_PRECHECK(h, n_edges);
+    if (!d_aA || !d_aB || !d_bA || !d_bB || !d_margin) return PV_ERR_BAD_ARG;
+    return pv_launch_edges(h, d_aA, d_aB, d_a9, d_bA, d_bB, d_b9, nullptr, nullptr, n_edges, n_steps, resolution,
+                           nullptr, d_margin, (cudaStream_t)stream);
+}
+
+// ---- host-buffer entry points: chunked H2D -> kernel -> D2H pipeline over PV_N_STREAMS streams -----------
+static int pv_ensure_stage(PvHandle* h) {
+    for (int i = 0; i < PV_N_STREAMS; ++i) {
+        if (!h->stage_q[i]) PV_CUDA(h, cudaMalloc(&h->stage_q[i], (size_t)PV_HOST_CHUNK * 9 * sizeof(float)));
+        if (!h->stage_q2[i]) PV_CUDA(h, cudaMalloc(&h->stage_q2[i], (size_t)PV_HOST_CHUNK * 9 * sizeof(float)));
+        if (!h->stage_bits[i]) PV_CUDA(h, cudaMalloc(&h->stage_bits[i], (size_t)(PV_HOST_CHUNK / 32) * sizeof(uint32_t)));
+    }
+    return PV_OK;
+}
+
+int pv_check_states_host(PvHandle* h, const float* h_q, int64_t n, uint32_t* h_bits) {
+    PV_PRECHECK(h, n);
+    if (!h_q || !h_bits) return PV_ERR_BAD_ARG;
+    int rc = pv_ensure_stage(h);
+    if (rc) return rc;
+    // chunk size: whole input for small batches, else PV_HOST_CHUNK (multiple of 32) so copies overlap compute
+    int64_t done = 0;
+    int slot = 0;
+    while (done < n) {
+        const int64_t m = (n - done < PV_HOST_CHUNK) ? (n - done) : PV_HOST_CHUNK;
+        cudaStream_t st = h->streams[slot];
+        PV_CUDA(h, cudaMemcpyAsync(h->stage_q[slot], h_q + done * 9, (size_t)m * 9 * sizeof(float),
+                                   cudaMemcpyHostToDevice, st));
+        rc = pv_launch_state_bits(h, nullptr, nullptr, nullptr, h->stage_q[slot], m, h->stage_bits[slot], st);
+        if (rc) return rc;
+        PV_CUDA(h, cudaMemcpyAsync(h_bits + done / 32, h->stage_bits[slot], (size_t)((m + 31) / 32) * sizeof(uint32_t),
+                                   cudaMemcpyDeviceToHost, st));
+        done += m;
+        slot = (slot + 1) % PV_N_STREAMS;
+    }
+    for (int i = 0; i < PV_N_STREAMS; ++i) PV_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+    return PV_OK;
+}
+
+int pv_check_edges_host(PvHandle* h, const float* h_qa, const float* h_qb, int64_t n_edges, int n_steps,
+                        float resolution, uint32_t* h_bits) {
+    PV_PRECHECK(h, n_edges);
+    if (!h_qa || !h_qb || !h_bits) return PV_ERR_BAD_ARG;
+    int rc = pv_ensure_stage(h);
+    if (rc) return rc;
+    int64_t done = 0;
+    int slot = 0;
+    while (done < n_edges) {
+        const int64_t m = (n_edges - done < PV_HOST_CHUNK) ? (n_edges - done) : PV_HOST_CHUNK;
+        cudaStream_t st = h->streams[slot];
+        PV_CUDA(h, cudaMemcpyAsync(h->stage_q[slot], h_qa + done * 9, (size_t)m * 9 * sizeof(float),
+                                   cudaMemcpyHostToDevice, st));
+        PV_CUDA(h, cudaMemcpyAsync(h->stage_q2[slot], h_qb + done * 9, (size_t)m * 9 * sizeof(float),
+                                   cudaMemcpyHostToDevice, st));
+        rc = pv_launch_edges(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, h->stage_q[slot],
+                             h->stage_q2[slot], m, n_steps, resolution, h->stage_bits[slot], nullptr, st);
+        if (rc) return rc;
+        PV_CUDA(h, cudaMemcpyAsync(h_bits + done / 32, h->stage_bits[slot], (size_t)((m + 31) / 32) * sizeof(uint32_t),
+                                   cudaMemcpyDeviceToHost, st));
+        done += m;
+        slot = (slot + 1) % PV_N_STREAMS;
+    }
+    for (int i = 0; i < PV_N_STREAMS; ++i) PV_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+    return PV_OK;
+}
+
+int pv_sweep(PvHandle* h, uint64_t first, int64_t n, uint32_t seed, int fingers_open, uint32_t* d_bits,
+             unsigned long long* d_n_valid, float* d_q_out, void* stream) {
+    PV_PRECHECK(h, n);
+    if (!d_bits || (first & 31ull)) {
+        snprintf(h->err, sizeof(h->err), "pv_sweep: null bits buffer or `first` not a multiple of 32");
+        return PV_ERR_BAD_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t words = (n + 31) / 32;
+    if (h->cull) {
+        int grid = pv_grid_for(h, (const void*)pv_sweep_kernel<true>, PV_THREADS, words);
+        pv_sweep_kernel<true><<<grid, PV_THREADS, 0, st>>>(h->scene, first, n, seed, fingers_open, d_bits, d_n_valid, d_q_out);
+    } else {
+        int grid = pv_grid_for(h, (const void*)pv_sweep_kernel<false>, PV_THREADS, words);
+        pv_sweep_kernel<false><<<grid, PV_THREADS, 0, st>>>(h->scene, first, n, seed, fingers_open, d_bits, d_n_valid, d_q_out);
+    }
+    h->launches++;
+    PV_CUDA(h, cudaGetLastError());
+    return PV_OK;
+}
+
+int pv_fp32_peak(PvHandle* h, int iters, double* tflops, float* ms_out) {
+    if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
+    if (iters < 1 || !tflops) return PV_ERR_BAD_ARG;
+    PV_CUDA(h, cudaSetDevice(h->device));
+    float* d_out = nullptr;
+    PV_CUDA(h, cudaMalloc(&d_out, sizeof(float)));
+    cudaEvent_t e0, e1;
+    PV_CUDA(h, cudaEventCreate(&e0));
+    PV_CUDA(h, cudaEventCreate(&e1));
+    const int threads = 256, blocks = h->sm_count * 8;
+    cudaStream_t st = h->streams[0];
+    pv_fp32_peak_kernel<<<blocks, threads, 0, st>>>(iters / 8 + 1, 1.0f, d_out);  // warm-up
+    PV_CUDA(h, cudaEventRecord(e0, st));
+    pv_fp32_peak_kernel<<<blocks, threads, 0, st>>>(iters, 1.0f, d_out);
+    PV_CUDA(h, cudaEventRecord(e1, st));
+    PV_CUDA(h, cudaEventSynchronize(e1));
+    h->launches += 2;
+    float ms = 0.f;
+    PV_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 128.0 * (double)iters * (double)threads * (double)blocks;
+    *tflops = flops / ((double)ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return PV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+"""Drop-in for the reference's `planning.py`: `PlannerInterface(robot, scene).plan_path(...)`.
+
+Same constructor, same `plan_path` signature, same return convention and the same soft/hard error
+behaviour as planning.py:24-242 -- but every validity query (planning.py:209-219) is answered by the
+sm_100a kernels behind `libpanda_validity.so`, and the RRT-Connect solve, shortcutting and edge checks
+run as one device kernel instead of one Python callback per sampled state.  `motion_primitives.py` uses
+it unchanged (`from planning import PlannerInterface`, motion_primitives.py:9).
+
+Differences that are deliberate and visible:
+  * the simulated robot is never moved during planning (the reference poses it for every state and
+    restores it at planning.py:205); `robot.set_qpos(qpos_cur)` is still issued at exit when the robot
+    offers it, so callers relying on that side effect see the same final state;
+  * only RRTConnect is implemented on the device; the other seven names of planning.py:108-117 are accepted
+    by the guard and rejected with a clear error instead of being silently mapped;
+  * there is no CPU fallback: without the CUDA library / a B200 the constructor raises.
+"""
+from __future__ import annotations
+
+import logging
+import time
+from typing import Any, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import panda_model as pm
+from .pathutil import interpolate
+from .robot_adapter import RobotAdapter
+from .scenes import SceneSnapshot, snapshot_from_sim
+from .validity import PandaValidity, decode_culprit
+
+logger = logging.getLogger("panda_validity.planning")
+
+SUPPORTED_PLANNERS = ["PRM", "RRT", "RRTConnect", "RRTstar", "EST", "FMT", "BITstar", "ABITstar"]  # planning.py:108-117
+DEVICE_PLANNERS = ["RRTConnect"]
+
+
+class PlanningError(Exception):
+    """Raised where the reference calls gs.raise_exception (planning.py:106,119,122,125,135)."""
+
+
+def tensor_to_array(x) -> np.ndarray:
+    """genesis.utils.misc.tensor_to_array as used at planning.py:131-132."""
+    if torch.is_tensor(x):
+        return x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+def _ensure_adapter(robot: Any, scene: Any) -> RobotAdapter:
+    # planning.py:14-22
+    return robot if isinstance(robot, RobotAdapter) else RobotAdapter(robot, scene)
+
+
+class StateValidityChecker:
+    """Callable with the shape OMPL's `ob.StateValidityCheckerFn` expects (planning.py:155): `state[i]`
+    indexable for i < 9 -> bool.  One state per call goes through the host entry point of the C-ABI;
+    batches should use `PandaValidity.check_states` directly."""
+
+    def __init__(self, validity: PandaValidity, n_qs: int = pm.N_Q):
+        self.validity = validity
+        self.n_qs = n_qs
+        self.calls = 0
+
+    def __call__(self, state) -> bool:
+        self.calls += 1
+        q = np.array([float(state[i]) for i in range(self.n_qs)], dtype=np.float32)
+        return self.validity.is_state_valid(q)
+
+
+class PlannerInterface:
+    def __init__(self, robot: Any, scene: Any, device: int = 0, validity: Optional[PandaValidity] = None):
+        self.robot = _ensure_adapter(robot, scene)
+        self.scene = scene
+        self.attached_object = None
+        self.validity = validity if validity is not None else PandaValidity(device)
+        self._snapshot: Optional[SceneSnapshot] = None
+        self.rng_seed = 1
+        self.replicas = 32          # independent device searches per plan; the first to connect wins
+        self.last_stats: dict = {}
+
+    # ---- scene --------------------------------------------------------------------------------------
+    def refresh_scene(self) -> SceneSnapshot:
+        """Freeze the block poses for this plan (they do not move inside plan_path)."""
+        snap = self.scene if isinstance(self.scene, SceneSnapshot) else snapshot_from_sim(self.scene, self.robot)
+        self.validity.set_scene(snap)
+        self._snapshot = snap
+        return snap
+
+    def _attached_index(self, attached_object) -> int:
+        if attached_object is None:
+            return -1
+        if isinstance(attached_object, (int, np.integer)):
+            return int(attached_object)
+        idx = getattr(attached_object, "idx", None)
+        if idx is None:
+            raise PlanningError("attached_object has no .idx (planning.py:226)")
+        return self._snapshot.index_of_entity(int(idx))
+
+    # ---- diagnostics (planning.py:32-57) ----------------------------------------------------------------
+    def diagnose_bounds_violation(self, state, lower=None, upper=None):
+        lower = pm.Q_LOWER if lower is None else lower
+        upper = pm.Q_UPPER if upper is None else upper
+        violated = [(i, float(state[i]), float(lower[i]), float(upper[i]))
+                    for i in range(self.robot.n_qs) if state[i] < lower[i] or state[i] > upper[i]]
+        logger.warning(f"State violates bounds on joints: {violated}")
+        return violated
+
+    def diagnose_valid_violation(self, state):
+        q = np.array([float(state[i]) for i in range(pm.N_Q)], dtype=np.float32)
+        m, cu = self.validity.state_margins(torch.as_tensor(q[None], device=self.validity.device), want_culprit=True)
+        culprit = decode_culprit(int(cu[0].item()))
+        logger.warning(f"State causes collisions: {culprit} (clearance {float(m[0].item()):.4f} m)")
+        return culprit
+
+    # ---- the validity callback (planning.py:209-219) ---------------------------------------------------------
+    def _is_ompl_state_valid(self, state) -> bool:
+        if self._snapshot is None:
+            self.refresh_scene()
+        q = np.array([float(state[i]) for i in range(pm.N_Q)], dtype=np.float32)
+        return self.validity.is_state_valid(q)
+
+    def state_validity_checker(self) -> StateValidityChecker:
+        if self._snapshot is None:
+            self.refresh_scene()
+        return StateValidityChecker(self.validity, self.robot.n_qs)
+
+    def check_motion(self, qa: Sequence[float], qb: Sequence[float]) -> bool:
+        """si.checkMotion(a, b) with the DiscreteMotionValidator defaults."""
+        w = self.validity.check_edges_host(np.asarray(qa, np.float32)[None], np.asarray(qb, np.float32)[None], n_steps=0)
+        return bool(w[0] & 1)
+
+    # ---- plan_path (planning.py:59-207) ---------------------------------------------------------------------
+    def plan_path(self, qpos_goal, qpos_start=None, timeout=5.0, smooth_path=True, num_waypoints=100,
+                  attached_object=None, planner="RRTConnect") -> List[torch.Tensor]:
+        if planner not in SUPPORTED_PLANNERS:
+            raise PlanningError(f"Planner {planner} is not supported. Supported planners: {SUPPORTED_PLANNERS}.")
+        if planner not in DEVICE_PLANNERS:
+            raise PlanningError(f"Planner {planner} has no device implementation; available: {DEVICE_PLANNERS}.")
+        solver = getattr(self.robot, "_solver", None)
+        if solver is not None and getattr(solver, "n_envs", 0) > 0:
+            raise PlanningError("Motion planning is not supported for batched envs (yet).")
+        if self.robot.n_qs != self.robot.n_dofs:
+            raise PlanningError("Motion planning is not yet supported for rigid entities with free joints.")
+
+        qpos_cur = self.robot.get_qpos()
+        if qpos_start is None:
+            qpos_start = qpos_cur
+        qpos_start = np.asarray(tensor_to_array(qpos_start), dtype=np.float64)
+        qpos_goal = np.asarray(tensor_to_array(qpos_goal), dtype=np.float64)
+        if qpos_start.shape != (self.robot.n_qs,) or qpos_goal.shape != (self.robot.n_qs,):
+            raise PlanningError("Invalid shape for `qpos_start` or `qpos_goal`.")
+        if self.robot.n_qs != pm.N_Q:
+            raise PlanningError(f"the device kernels are specialised to the {pm.N_Q}-DoF Panda; robot has {self.robot.n_qs}")
+
+        # joint limits come from the robot (planning.py:139-140); the kernels carry the frozen Panda limits
+        lower, upper = pm.Q_LOWER, pm.Q_UPPER
+        q_limit = getattr(self.robot, "q_limit", None)
+        if q_limit is not None:
+            lo_r = np.asarray(tensor_to_array(q_limit[0]), dtype=float)
+            hi_r = np.asarray(tensor_to_array(q_limit[1]), dtype=float)
+            if np.abs(lo_r - lower).max() > 1e-4 or np.abs(hi_r - upper).max() > 1e-4:
+                logger.warning("robot.q_limit differs from the frozen Panda limits the kernels sample in")
+
+        t0 = time.perf_counter()
+        snap = self.refresh_scene()
+        self.attached_object = attached_object  # planning.py:153
+        self.validity.set_attached(self._attached_index(attached_object))
+        self.validity.set_flags(True, False)
+
+        # diagnostics on start / goal (planning.py:163-183): log, keep going
+        eps = np.finfo(np.float64).eps
+        start_in = bool(np.all((qpos_start - eps <= upper) & (qpos_start + eps >= lower)))
+        goal_in = bool(np.all((qpos_goal - eps <= upper) & (qpos_goal + eps >= lower)))
+        if not start_in:
+            logger.warning("OMPL start state out of bounds")
+            self.diagnose_bounds_violation(qpos_start, lower, upper)
+        if not goal_in:
+            logger.warning("OMPL goal state out of bounds")
+            self.diagnose_bounds_violation(qpos_goal, lower, upper)
+        sg = np.stack([qpos_start, qpos_goal]).astype(np.float32)
+        w = self.validity.check_states_host(sg)
+        start_valid, goal_valid = bool(w[0] & 1), bool(w[0] & 2)
+        if not start_valid:
+            logger.warning("OMPL start state invalid")
+            self.diagnose_valid_violation(qpos_start)
+        if not goal_valid:
+            logger.warning("OMPL goal state invalid")
+            self.diagnose_valid_violation(qpos_goal)
+
+        waypoints: List[torch.Tensor] = []
+        stats = {"solved": False, "iters": 0, "state_checks": 0, "attempts": 0, "n_obb": snap.n_obb}
+        # OMPL drops out-of-bounds / invalid starts and goals at intake -> "no solution" 
+        if start_in and goal_in and start_valid and goal_valid:
+            path = None
+            attempt = 0
+            while path is None:
+                paths, plen, iters, checks = self.validity.rrtc_batch(
+                    sg[0:1], sg[1:2], max_iters=2000, max_nodes=2048, max_path=256,
+                    seed=self.rng_seed + 7919 * attempt, replicas=self.replicas,
+                    shortcut_passes=2 if smooth_path else 0)
+                attempt += 1
+                stats["attempts"] = attempt
+                stats["iters"] += int(iters[0])
+                stats["state_checks"] += int(checks[0])
+                if plen[0] > 0:
+                    path = paths[0, : plen[0]].astype(np.float64)
+                elif time.perf_counter() - t0 > timeout:
+                    break
+            self.rng_seed += 1
+            if path is not None:
+                logger.info("Path solution found successfully.")
+                path[0], path[-1] = qpos_start, qpos_goal  # exact end points, as OMPL keeps them in fp64
+                if num_waypoints is not None:
+                    path = interpolate(path, int(num_waypoints))
+                print("Number of waypoints in path:", len(path))  # planning.py:199
+                waypoints = [torch.tensor(p, dtype=torch.float32) for p in path]
+                stats["solved"] = True
+        if not waypoints:
+            logger.warning("Path planning failed. Returning empty path.")
+        stats["plan_ms"] = (time.perf_counter() - t0) * 1e3
+        self.last_stats = stats
+
+        # restore original state (planning.py:205) -- a no-op for us, kept for side-effect parity
+        if hasattr(self.robot, "set_qpos"):
+            try:
+                self.robot.set_qpos(qpos_cur)
+            except Exception:  # a stub robot without a simulator behind it
+                pass
+        return waypoints
+
+    # ---- batched front end (BASELINE config 4) -------------------------------------------------------------
+    def plan_paths_batch(self, starts: np.ndarray, goals: np.ndarray, max_iters: int = 2000, max_nodes: int = 2048,
+                         smooth_path: bool = True, seed: int = 1, replicas: int = 1, max_path: int = 128):
+        """Many independent (start, goal) queries in one kernel launch.  Returns (paths, lengths, iters, checks)."""
+        if self._snapshot is None:
+            self.refresh_scene()
+        return self.validity.rrtc_batch(starts, goals, max_iters=max_iters, max_nodes=max_nodes, max_path=max_path,
+                                        seed=seed, replicas=replicas, shortcut_passes=2 if smooth_path else 0)
+
+    # planning.py:232-242
+    def _ompl_state_to_tensor(self, state) -> torch.Tensor:
+        return torch.tensor([float(state[i]) for i in range(self.robot.n_qs)], dtype=torch.float32)
+
+    def _ompl_states_to_tensor_list(self, states) -> List[torch.Tensor]:
+        return [self._ompl_state_to_tensor(s) for s in states]

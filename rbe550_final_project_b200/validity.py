@@ -1,0 +1,246 @@
+"""PandaValidity: Python face of the C-ABI handle (one per GPU).
+
+PyTorch is used only for device buffers and streams; every computation is a hand-written sm_100a
+kernel reached through ctypes.  There is no CPU path: constructing a PandaValidity without the built
+library or without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi
+from . import panda_model as pm
+from .scenes import SceneSnapshot
+
+FLAG_SELF = 1
+FLAG_LIMITS = 2
+
+CULPRIT_KINDS = {0: "none", 1: "table", 2: "scene_box", 3: "self", 4: "joint_limit"}
+
+
+class PandaValidityError(RuntimeError):
+    pass
+
+
+def soa_from_aos(q: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """(n, 9) float32 -> planes A (n, 4), B (n, 4), q9 (n,) as the kernels read them."""
+    q = q.to(torch.float32)
+    return q[:, 0:4].contiguous(), q[:, 4:8].contiguous(), q[:, 8].contiguous()
+
+
+class PandaValidity:
+    def __init__(self, device: int = 0):
+        self.lib = _cabi.load()
+        self._h = C.c_void_p()
+        rc = self.lib.pv_create(int(device), C.byref(self._h))
+        if rc != 0:
+            raise PandaValidityError(f"pv_create failed ({rc}): {self.lib.pv_last_error(None).decode()}")
+        self.device = torch.device("cuda", int(device))
+        self.scene: Optional[SceneSnapshot] = None
+        self.attached = -1
+        self.flags = FLAG_SELF
+
+    # -- plumbing -------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.pv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int, what: str):
+        if rc != 0:
+            raise PandaValidityError(f"{what} failed ({rc}): {self.lib.pv_last_error(self._h).decode()}")
+
+    @staticmethod
+    def _stream(stream) -> C.c_void_p:
+        if stream is None:
+            stream = torch.cuda.current_stream()
+        return C.c_void_p(stream.cuda_stream)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.pv_launch_count(self._h))
+
+    # -- configuration --------------------------------------------------------------------------------
+    def set_scene(self, scene: SceneSnapshot):
+        obb = np.ascontiguousarray(scene.obb, dtype=np.float32).reshape(-1, 16)
+        base = (C.c_float * 3)(*[float(v) for v in scene.base])
+        self._ck(self.lib.pv_set_scene(self._h, obb.ctypes.data_as(C.POINTER(C.c_float)), obb.shape[0],
+                                       float(scene.table_z), base), "pv_set_scene")
+        self.scene = scene
+        self.attached = -1
+
+    def set_attached(self, obb_index: int):
+        self._ck(self.lib.pv_set_attached(self._h, int(obb_index)), "pv_set_attached")
+        self.attached = int(obb_index)
+
+    def set_flags(self, self_collision: bool = True, joint_limits: bool = False):
+        self.flags = (FLAG_SELF if self_collision else 0) | (FLAG_LIMITS if joint_limits else 0)
+        self._ck(self.lib.pv_set_flags(self._h, self.flags), "pv_set_flags")
+
+    def set_culling(self, on: bool):
+        self._ck(self.lib.pv_set_culling(self._h, 1 if on else 0), "pv_set_culling")
+
+    # -- device-buffer calls --------------------------------------------------------------------------
+    def _planes(self, q) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], int]:
+        if isinstance(q, (tuple, list)) and len(q) in (2, 3) and torch.is_tensor(q[0]) and q[0].dim() == 2 \
+                and q[0].shape[1] == 4:
+            A, B = q[0], q[1]
+            q9 = q[2] if len(q) == 3 else None
+        else:
+            qt = torch.as_tensor(q, dtype=torch.float32, device=self.device)
+            if qt.dim() == 1:
+                qt = qt[None]
+            A, B, q9 = soa_from_aos(qt)
+        for t in (A, B) + ((q9,) if q9 is not None else ()):
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise PandaValidityError("config planes must be contiguous float32 tensors on the handle's device")
+        return A, B, q9, int(A.shape[0])
+
+    def check_states(self, q, out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
+        """Verdict bit words (int32 tensor viewed as uint32 bits) for n configurations."""
+        A, B, q9, n = self._planes(q)
+        words = (n + 31) // 32
+        if out is None:
+            out = torch.empty(words, dtype=torch.int32, device=self.device)
+        self._ck(self.lib.pv_check_states(self._h, A.data_ptr(), B.data_ptr(), q9.data_ptr() if q9 is not None else None,
+                                          n, out.data_ptr(), self._stream(stream)), "pv_check_states")
+        return out
+
+    def state_margins(self, q, want_culprit: bool = False, stream=None):
+        A, B, q9, n = self._planes(q)
+        m = torch.empty(n, dtype=torch.float32, device=self.device)
+        cu = torch.empty(n, dtype=torch.int32, device=self.device) if want_culprit else None
+        self._ck(self.lib.pv_state_margins(self._h, A.data_ptr(), B.data_ptr(), q9.data_ptr() if q9 is not None else None,
+                                           n, m.data_ptr(), cu.data_ptr() if cu is not None else None,
+                                           self._stream(stream)), "pv_state_margins")
+        return (m, cu) if want_culprit else m
+
+    def fk(self, q, stream=None) -> torch.Tensor:
+        """(n, 11, 12): per link position xyz then row-major rotation."""
+        A, B, q9, n = self._planes(q)
+        out = torch.empty((n, 11, 12), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.pv_fk(self._h, A.data_ptr(), B.data_ptr(), q9.data_ptr() if q9 is not None else None, n,
+                                out.data_ptr(), self._stream(stream)), "pv_fk")
+        return out
+
+    def check_edges(self, qa, qb, n_steps: int = 0, resolution: float = pm.VALIDITY_RESOLUTION,
+                    out: Optional[torch.Tensor] = None, stream=None) -> torch.Tensor:
+        aA, aB, a9, n = self._planes(qa)
+        bA, bB, b9, nb = self._planes(qb)
+        if n != nb:
+            raise PandaValidityError("qa and qb must hold the same number of configurations")
+        if out is None:
+            out = torch.empty((n + 31) // 32, dtype=torch.int32, device=self.device)
+        self._ck(self.lib.pv_check_edges(self._h, aA.data_ptr(), aB.data_ptr(), a9.data_ptr() if a9 is not None else None,
+                                         bA.data_ptr(), bB.data_ptr(), b9.data_ptr() if b9 is not None else None, n,
+                                         int(n_steps), float(resolution), out.data_ptr(), self._stream(stream)),
+                 "pv_check_edges")
+        return out
+
+    def edge_margins(self, qa, qb, n_steps: int = 0, resolution: float = pm.VALIDITY_RESOLUTION, stream=None):
+        aA, aB, a9, n = self._planes(qa)
+        bA, bB, b9, nb = self._planes(qb)
+        if n != nb:
+            raise PandaValidityError("qa and qb must hold the same number of configurations")
+        m = torch.empty(n, dtype=torch.float32, device=self.device)
+        self._ck(self.lib.pv_edge_margins(self._h, aA.data_ptr(), aB.data_ptr(), a9.data_ptr() if a9 is not None else None,
+                                          bA.data_ptr(), bB.data_ptr(), b9.data_ptr() if b9 is not None else None, n,
+                                          int(n_steps), float(resolution), m.data_ptr(), self._stream(stream)),
+                 "pv_edge_margins")
+        return m
+
+    def sweep(self, first: int, n: int, seed: int, fingers_open: bool = True, want_configs: bool = False, stream=None):
+        words = (n + 31) // 32
+        bits = torch.empty(words, dtype=torch.int32, device=self.device)
+        count = torch.zeros(1, dtype=torch.int64, device=self.device)
+        qo = torch.empty((n, 9), dtype=torch.float32, device=self.device) if want_configs else None
+        self._ck(self.lib.pv_sweep(self._h, int(first), int(n), int(seed) & 0xFFFFFFFF, 1 if fingers_open else 0,
+                                   bits.data_ptr(), count.data_ptr(), qo.data_ptr() if qo is not None else None,
+                                   self._stream(stream)), "pv_sweep")
+        return (bits, count, qo) if want_configs else (bits, count)
+
+    # -- host-buffer calls (what a reference-side binding uses) ----------------------------------------------
+    def check_states_host(self, q: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """q: (n, 9) float32 host array (numpy, or a pinned torch tensor's .numpy()).  Returns uint32 words."""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, 9)
+        n = q.shape[0]
+        if out is None:
+            out = np.empty((n + 31) // 32, dtype=np.uint32)
+        self._ck(self.lib.pv_check_states_host(self._h, q.ctypes.data, n, out.ctypes.data), "pv_check_states_host")
+        return out
+
+    def check_edges_host(self, qa: np.ndarray, qb: np.ndarray, n_steps: int = 0,
+                         resolution: float = pm.VALIDITY_RESOLUTION, out: Optional[np.ndarray] = None) -> np.ndarray:
+        qa = np.ascontiguousarray(qa, dtype=np.float32).reshape(-1, 9)
+        qb = np.ascontiguousarray(qb, dtype=np.float32).reshape(-1, 9)
+        n = qa.shape[0]
+        if qb.shape[0] != n:
+            raise PandaValidityError("qa and qb must hold the same number of configurations")
+        if out is None:
+            out = np.empty((n + 31) // 32, dtype=np.uint32)
+        self._ck(self.lib.pv_check_edges_host(self._h, qa.ctypes.data, qb.ctypes.data, n, int(n_steps), float(resolution),
+                                              out.ctypes.data), "pv_check_edges_host")
+        return out
+
+    def is_state_valid(self, q: Sequence[float]) -> bool:
+        """One state through the host entry point (the shape of planning.py:209 `_is_ompl_state_valid`)."""
+        w = self.check_states_host(np.asarray(q, dtype=np.float32).reshape(1, 9))
+        return bool(w[0] & 1)
+
+    def rrtc_batch(self, starts: np.ndarray, goals: np.ndarray, max_iters: int = 2000, max_nodes: int = 2048,
+                   max_path: int = 128, seed: int = 1, replicas: int = 1, shortcut_passes: int = 2,
+                   rrt_range: float = 0.0, resolution: float = 0.0):
+        starts = np.ascontiguousarray(starts, dtype=np.float32).reshape(-1, 9)
+        goals = np.ascontiguousarray(goals, dtype=np.float32).reshape(-1, 9)
+        nq = starts.shape[0]
+        if goals.shape[0] != nq:
+            raise PandaValidityError("starts and goals must have the same length")
+        prm = _cabi.PvRrtcParams(float(rrt_range), float(resolution), int(max_iters), int(max_nodes), int(max_path),
+                                 int(seed) & 0xFFFFFFFF, int(replicas), int(shortcut_passes))
+        paths = np.zeros((nq, max_path, 9), dtype=np.float32)
+        plen = np.zeros(nq, dtype=np.int32)
+        iters = np.zeros(nq, dtype=np.int32)
+        checks = np.zeros(nq, dtype=np.int64)
+        self._ck(self.lib.pv_rrtc_batch(self._h, starts.ctypes.data, goals.ctypes.data, nq, C.byref(prm),
+                                        paths.ctypes.data, plen.ctypes.data, iters.ctypes.data, checks.ctypes.data),
+                 "pv_rrtc_batch")
+        return paths, plen, iters, checks
+
+    def fp32_peak(self, iters: int = 4096) -> Tuple[float, float]:
+        tf, ms = C.c_double(0), C.c_float(0)
+        self._ck(self.lib.pv_fp32_peak(self._h, int(iters), C.byref(tf), C.byref(ms)), "pv_fp32_peak")
+        return tf.value, ms.value
+
+
+def unpack_bits(words, n: int) -> np.ndarray:
+    """uint32 verdict words -> bool[n] (bit i&31 of word i>>5)."""
+    if torch.is_tensor(words):
+        words = words.detach().cpu().numpy()
+    w = np.asarray(words).view(np.uint32)
+    b = (w[:, None] >> np.arange(32, dtype=np.uint32)) & np.uint32(1)
+    return b.reshape(-1)[:n].astype(bool)
+
+
+def decode_culprit(code: int) -> str:
+    kind, a, b = (code >> 16) & 0xFF, (code >> 8) & 0xFF, code & 0xFF
+    if kind == 1:
+        return f"{pm.LINK_NAMES[a]} vs ground plane"
+    if kind == 2:
+        return f"{pm.LINK_NAMES[a]} vs scene box {b}"
+    if kind == 3:
+        la = pm.LINK_NAMES[int(pm.SPHERE_LINK[a])]
+        lb = pm.LINK_NAMES[int(pm.BOX_LINK[b - 33])] if b >= 33 else pm.LINK_NAMES[int(pm.SPHERE_LINK[b])]
+        return f"{la} vs {lb}"
+    if kind == 4:
+        return f"joint {a + 1} outside its limits"
+    return "none"

@@ -1,0 +1,218 @@
+"""GPU parity tests: CUDA kernels (through the C-ABI) vs the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): FK poses within 1e-5 m / 1e-5 rad; collision verdicts identical for
+every configuration more than 1e-4 m from contact (|oracle margin| > 1e-4); bit packing exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import random_configs
+from oracle import panda_oracle as po
+from rbe550_final_project_b200 import panda_model as pm
+from rbe550_final_project_b200 import scenes as sc
+from rbe550_final_project_b200.validity import unpack_bits
+
+pytestmark = pytest.mark.gpu
+
+BAND = 1e-4
+SCENES = ["goal1_scattered", "goal4_task1_pentagon", "goal3_tower"]
+
+
+def _dev(q):
+    return torch.as_tensor(q, device="cuda")
+
+
+def _assert_verdicts(gpu_valid, margin, what):
+    ora_valid = margin >= 0
+    far = np.abs(margin) > BAND
+    bad = np.nonzero((gpu_valid != ora_valid) & far)[0]
+    assert bad.size == 0, f"{what}: {bad.size} verdict mismatches outside the 1e-4 band, first {bad[:5]}, margins {margin[bad[:5]]}"
+    return int((~far).sum()), int(((gpu_valid != ora_valid) & ~far).sum())
+
+
+def test_fk_parity(pv, c64):
+    pv.set_scene(sc.goal1_scattered())
+    q = random_configs(50000, 11, fingers="random")
+    q[0] = 0
+    q[1] = pm.Q_SAFE_HOME
+    q[2] = pm.Q_SCENE_INIT
+    out = pv.fk(_dev(q)).cpu().numpy()
+    R, p = c64.fk(q.astype(np.float64))
+    assert np.abs(out[:, :, 0:3] - p).max() < 2e-6  # bar: 1e-5 m
+    Rg = out[:, :, 3:12].reshape(-1, 11, 3, 3)
+    # rotation angle between the two frames: bar 1e-5 rad
+    # (sin of the relative angle from the skew part: arccos of the trace is ill-conditioned near 0)
+    rel = np.einsum("nlij,nlik->nljk", R, Rg.astype(np.float64))
+    skew = 0.5 * (rel - np.swapaxes(rel, 2, 3))
+    ang = np.arcsin(np.clip(np.sqrt((skew ** 2).sum((2, 3)) / 2), 0, 1))
+    assert np.abs(Rg - R).max() < 2e-6
+    assert ang.max() < 1e-5
+    # analytic known answers (base lift 0.01 included)
+    assert np.allclose(out[0, 7, 0:3], [0.088, 0, 1.043], atol=2e-6)
+    assert np.allclose(out[0, 8, 0:3], [0.088, 0, 0.936], atol=2e-6)
+    assert np.allclose(out[1, 8, 0:3], [0.30702, 0, 0.60027], atol=1e-5)
+
+
+@pytest.mark.parametrize("scene_name", SCENES)
+@pytest.mark.parametrize("attached", [-1, 3])
+def test_state_verdicts(pv, c64, scene_name, attached):
+    scene = sc.FIXTURES[scene_name]()
+    pv.set_scene(scene)
+    pv.set_flags(True, False)
+    pv.set_attached(attached)
+    n = 200_003  # ragged tail on purpose
+    q = random_configs(n, 5 + attached, fingers="random" if attached >= 0 else "open")
+    bits = pv.check_states(_dev(q))
+    torch.cuda.synchronize()
+    gpu_valid = unpack_bits(bits, n)
+    margin = c64.state_margin(q.astype(np.float64), scene.as_oracle_scene(), attached=attached)
+    in_band, flips = _assert_verdicts(gpu_valid, margin, scene_name)
+    assert in_band < n * 2e-3
+    # tail bits of the last word are zero
+    w = bits.cpu().numpy().view(np.uint32)
+    assert (w[-1] >> np.uint32(n & 31)) == 0
+    pv.set_attached(-1)
+
+
+def test_state_margins_and_culprits(pv, c64):
+    scene = sc.goal4_task1_pentagon()
+    pv.set_scene(scene)
+    pv.set_flags(True, False)
+    q = random_configs(100_000, 21, fingers="random")
+    m, cu = pv.state_margins(_dev(q), want_culprit=True)
+    m = m.cpu().numpy()
+    ref = c64.state_margin(q.astype(np.float64), scene.as_oracle_scene())
+    assert np.abs(m - ref).max() < 1e-5
+    cu = cu.cpu().numpy()
+    assert ((cu != 0) == (m < 0)).all()
+    # bits and margins agree with each other away from contact
+    bits = unpack_bits(pv.check_states(_dev(q)), len(q))
+    far = np.abs(ref) > BAND
+    assert (bits[far] == (m[far] >= 0)).all()
+
+
+def test_flags_self_and_limits(pv, c64):
+    from oracle.c_oracle import FLAG_LIMITS, FLAG_SELF
+    scene = sc.goal1_scattered()
+    pv.set_scene(scene)
+    q = random_configs(60_000, 31, fingers="random")
+    q[::7, 3] += 3.2  # push joint 4 out of its limits on every 7th config
+    q[::11, 8] = 0.0405
+    for self_on, lim_on in [(False, False), (True, True), (False, True)]:
+        pv.set_flags(self_on, lim_on)
+        gpu = unpack_bits(pv.check_states(_dev(q)), len(q))
+        fl = (FLAG_SELF if self_on else 0) | (FLAG_LIMITS if lim_on else 0)
+        margin = c64.state_margin(q.astype(np.float64), scene.as_oracle_scene(), flags=fl)
+        _assert_verdicts(gpu, margin, f"flags {self_on} {lim_on}")
+    pv.set_flags(True, False)
+
+
+def test_culling_is_exact(pv):
+    for name in SCENES:
+        pv.set_scene(sc.FIXTURES[name]())
+        q = _dev(random_configs(300_000, 77, fingers="random"))
+        pv.set_culling(True)
+        a = pv.check_states(q).cpu().numpy()
+        pv.set_culling(False)
+        b = pv.check_states(q).cpu().numpy()
+        pv.set_culling(True)
+        assert (a == b).all(), name
+
+
+@pytest.mark.parametrize("n_steps", [64, 0])
+def test_edge_verdicts(pv, c64, n_steps):
+    scene = sc.goal4_task1_pentagon()
+    pv.set_scene(scene)
+    pv.set_flags(True, False)
+    n = 20_001
+    qa = random_configs(n, 41)
+    rng = np.random.default_rng(42)
+    qb = np.clip(qa + rng.normal(0, 0.3, qa.shape), pm.Q_LOWER, pm.Q_UPPER).astype(np.float32)
+    qb[:, 7:] = 0.04
+    bits = pv.check_edges(_dev(qa), _dev(qb), n_steps=n_steps)
+    gpu = unpack_bits(bits, n)
+    ref = c64.edge_margin(qa.astype(np.float64), qb.astype(np.float64), scene.as_oracle_scene(), n_steps=n_steps)
+    _assert_verdicts(gpu, ref, f"edges n_steps={n_steps}")
+    m = pv.edge_margins(_dev(qa), _dev(qb), n_steps=n_steps).cpu().numpy()
+    assert np.abs(m - ref).max() < 2e-5
+    # property: an edge verdict is the AND of its state verdicts (64-step form)
+    if n_steps == 64:
+        k = 2000
+        t = (np.arange(1, 65, dtype=np.float32) / np.float32(64))[None, :, None]
+        states = qa[:k, None, :] + t * (qb[:k, None, :] - qa[:k, None, :])
+        states[:, -1, :] = qb[:k]
+        sm = pv.state_margins(_dev(states.reshape(-1, 9))).cpu().numpy().reshape(k, 64).min(1)
+        far = np.abs(sm) > BAND
+        assert (gpu[:k][far] == (sm[far] >= 0)).all()
+
+
+def test_edge_long_edges_resolution_mode(pv, c64):
+    """uniform-pair edges are long (nd up to ~60): exercises the multi-round coarse-to-fine path"""
+    scene = sc.goal3_tower()
+    pv.set_scene(scene)
+    n = 5000
+    qa, qb = random_configs(n, 51), random_configs(n, 52)
+    gpu = unpack_bits(pv.check_edges(_dev(qa), _dev(qb), n_steps=0), n)
+    ref = c64.edge_margin(qa.astype(np.float64), qb.astype(np.float64), scene.as_oracle_scene(), n_steps=0)
+    _assert_verdicts(gpu, ref, "long edges")
+
+
+def test_host_entry_points_match_device(pv):
+    scene = sc.goal1_scattered()
+    pv.set_scene(scene)
+    n = 600_011  # > 2 pipeline chunks, ragged
+    q = random_configs(n, 61)
+    dev = pv.check_states(_dev(q)).cpu().numpy().view(np.uint32)
+    host = pv.check_states_host(q)
+    assert (dev == host).all()
+    pinned = torch.from_numpy(q).pin_memory()
+    host2 = pv.check_states_host(pinned.numpy())
+    assert (dev == host2).all()
+    assert pv.is_state_valid(pm.Q_SAFE_HOME) is True
+    ne = 40_000
+    qb = np.clip(q[:ne] + 0.2, pm.Q_LOWER, pm.Q_UPPER).astype(np.float32)
+    d = pv.check_edges(_dev(q[:ne]), _dev(qb), n_steps=16).cpu().numpy().view(np.uint32)
+    hh = pv.check_edges_host(q[:ne], qb, n_steps=16)
+    assert (d == hh).all()
+
+
+def test_sweep_matches_oracle_stream(pv, c64, model):
+    scene = sc.goal1_scattered()
+    pv.set_scene(scene)
+    first, n, seed = 64 * 1000, 100_000, 20251212
+    for fingers_open in (True, False):
+        bits, count, qd = pv.sweep(first, n, seed, fingers_open=fingers_open, want_configs=True)
+        qo = po.sweep_configs(first, n, seed, model, fingers_open=fingers_open)
+        assert np.array_equal(qd.cpu().numpy().view(np.uint32), qo.view(np.uint32)), "device RNG stream differs"
+        gpu = unpack_bits(bits, n)
+        assert int(count.item()) == int(gpu.sum())
+        margin = c64.state_margin(qo.astype(np.float64), scene.as_oracle_scene())
+        _assert_verdicts(gpu, margin, "sweep")
+
+
+def test_acceptance_poses(pv):
+    """App. F: the poses the reference plans from are valid in every scene; a deep table hit is not."""
+    for name, f in sc.FIXTURES.items():
+        pv.set_scene(f())
+        q = np.stack([pm.Q_SAFE_HOME, pm.Q_SAFE_HOME_039, pm.Q_SCENE_INIT]).astype(np.float32)
+        v = unpack_bits(pv.check_states(_dev(q)), 3)
+        assert v.all(), name
+    bad = np.array([[0, 1.7, 0, -0.1, 0, 0.5, 0, 0.04, 0.04]], dtype=np.float32)
+    assert not unpack_bits(pv.check_states(_dev(bad)), 1)[0]
+
+
+def test_error_paths(pv):
+    from rbe550_final_project_b200.validity import PandaValidity, PandaValidityError
+    h = PandaValidity(0)
+    with pytest.raises(PandaValidityError):
+        h.check_states(_dev(random_configs(8, 1)))  # no scene yet
+    big = sc.goal1_scattered()
+    big.obb = np.repeat(big.obb, 6, axis=0)  # 36 boxes > PV_MAX_OBB
+    with pytest.raises(PandaValidityError):
+        h.set_scene(big)
+    h.set_scene(sc.goal1_scattered())
+    with pytest.raises(PandaValidityError):
+        h.set_attached(17)
+    assert h.check_states(_dev(np.zeros((0, 9), np.float32))).numel() == 0
+    h.close()

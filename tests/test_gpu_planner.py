@@ -1,0 +1,143 @@
+"""GPU tests of the drop-in planner: PlannerInterface.plan_path contract and the batched
+RRT-Connect front end.  Paths are re-validated with the edge kernel AND the CPU oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import random_configs
+from rbe550_final_project_b200 import panda_model as pm
+from rbe550_final_project_b200 import scenes as sc
+from rbe550_final_project_b200.planning import PlannerInterface, PlanningError, SUPPORTED_PLANNERS
+from rbe550_final_project_b200.sim_stub import create_scene
+from rbe550_final_project_b200.validity import unpack_bits
+
+pytestmark = pytest.mark.gpu
+
+GOALS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "goal_configs.json")))
+
+
+def _path_ok(pv, c64, scene, path, attached=-1):
+    """every state valid, every segment valid at OMPL's resolution -- on the GPU and in the oracle"""
+    p = np.asarray(path, dtype=np.float32)
+    w = pv.check_states_host(p)
+    assert unpack_bits(w, len(p)).all()
+    e = pv.check_edges_host(p[:-1], p[1:], n_steps=0)
+    assert unpack_bits(e, len(p) - 1).all()
+    m = c64.edge_margin(p[:-1].astype(np.float64), p[1:].astype(np.float64), scene.as_oracle_scene(), n_steps=0,
+                        attached=attached)
+    assert (m > -1e-4).all()
+
+
+def test_plan_path_contract(pv, c64):
+    scene, franka, blocks = create_scene("goal1_scattered")
+    franka.set_qpos(pm.Q_SAFE_HOME)
+    planner = PlannerInterface(franka, scene, validity=pv)
+    calls_before = franka.raw.set_qpos_calls
+    for name in ("approach_r", "grasp_r", "approach_c"):
+        goal = np.array(GOALS["goal1_scattered"][name]["q"])
+        path = planner.plan_path(qpos_goal=goal, num_waypoints=150, attached_object=None, timeout=10.0)
+        assert isinstance(path, list) and len(path) == 150
+        assert all(isinstance(w, torch.Tensor) and w.device.type == "cpu" and w.dtype == torch.float32
+                   and w.shape == (9,) for w in path)
+        arr = np.stack([w.numpy() for w in path])
+        assert np.allclose(arr[0], pm.Q_SAFE_HOME, atol=1e-6) and np.allclose(arr[-1], goal, atol=1e-6)
+        # caller-side conversions of motion_primitives.py:164-176 work
+        assert np.array(path[-1], dtype=float).shape == (9,)
+        _path_ok(pv, c64, sc.goal1_scattered(), arr)
+        assert planner.last_stats["solved"]
+    # the robot is put back where it was (planning.py:205) and never moved in between
+    assert franka.raw.set_qpos_calls == calls_before + 3
+    assert np.allclose(franka.get_qpos(), pm.Q_SAFE_HOME)
+
+
+def test_plan_path_soft_failures_return_empty(pv):
+    scene, franka, _ = create_scene("goal1_scattered")
+    franka.set_qpos(pm.Q_SAFE_HOME)
+    planner = PlannerInterface(franka, scene, validity=pv)
+    in_table = np.array([0, 1.7, 0, -0.1, 0, 0.5, 0, 0.04, 0.04])
+    assert planner.plan_path(qpos_goal=in_table, timeout=1.0) == []
+    out_of_bounds = pm.Q_SAFE_HOME.copy()
+    out_of_bounds[7:] = 0.0405  # the README's finger-drift case: start above the 0.04 limit
+    assert planner.plan_path(qpos_goal=pm.Q_SCENE_INIT, qpos_start=out_of_bounds, timeout=1.0) == []
+
+
+def test_plan_path_hard_errors(pv):
+    scene, franka, _ = create_scene("goal1_scattered")
+    planner = PlannerInterface(franka, scene, validity=pv)
+    with pytest.raises(PlanningError):
+        planner.plan_path(qpos_goal=pm.Q_SAFE_HOME, planner="LazyPRM")
+    with pytest.raises(PlanningError):
+        planner.plan_path(qpos_goal=pm.Q_SAFE_HOME[:7])
+    franka.raw._solver.n_envs = 4
+    with pytest.raises(PlanningError):
+        planner.plan_path(qpos_goal=pm.Q_SAFE_HOME)
+    franka.raw._solver.n_envs = 0
+    assert "RRTConnect" in SUPPORTED_PLANNERS
+
+
+def test_attached_object_forgiveness(pv, c64):
+    """planning.py:221-230: hand/finger contacts with the attached block are forgiven, nothing else."""
+    scene, franka, blocks = create_scene("goal1_scattered")
+    franka.set_qpos(pm.Q_SAFE_HOME)
+    planner = PlannerInterface(franka, scene, validity=pv)
+    planner.refresh_scene()
+    # grasp pose with the fingers closed onto block r (idx 1): fingers penetrate the block
+    q = np.array(GOALS["goal1_scattered"]["grasp_r"]["q"])
+    q[7:] = 0.015
+    pv.set_attached(-1)
+    assert not pv.is_state_valid(q)
+    pv.set_attached(planner._snapshot.index_of_entity(blocks["r"].idx))
+    assert pv.is_state_valid(q)
+    pv.set_attached(planner._snapshot.index_of_entity(blocks["g"].idx))
+    assert not pv.is_state_valid(q)
+    pv.set_attached(-1)
+    # and through plan_path: planning away from that pose only works with the block attached
+    assert planner.plan_path(qpos_goal=pm.Q_SAFE_HOME, qpos_start=q, timeout=1.0) == []
+    path = planner.plan_path(qpos_goal=pm.Q_SAFE_HOME, qpos_start=q, attached_object=blocks["r"], timeout=10.0,
+                             num_waypoints=50)
+    assert len(path) == 50
+    _path_ok(pv, c64, sc.goal1_scattered(), np.stack([w.numpy() for w in path]), attached=0)
+
+
+def test_validity_callback_shape(pv):
+    scene, franka, _ = create_scene("goal3_tower")
+    planner = PlannerInterface(franka, scene, validity=pv)
+    chk = planner.state_validity_checker()
+    assert chk(list(pm.Q_SAFE_HOME)) is True
+    assert planner._is_ompl_state_valid(pm.Q_SAFE_HOME) is True
+    assert chk([0, 1.7, 0, -0.1, 0, 0.5, 0, 0.04, 0.04]) is False
+    assert chk.calls == 2
+    assert planner.check_motion(pm.Q_SAFE_HOME, pm.Q_SCENE_INIT) in (True, False)
+
+
+def test_batched_rrtc_tower_scene(pv, c64):
+    """BASELINE config 4 in miniature: many start/goal pairs in the tall-tower scene."""
+    snap = sc.goal3_tower()
+    pv.set_scene(snap)
+    pv.set_attached(-1)
+    cand = random_configs(4000, 123)
+    ok = unpack_bits(pv.check_states_host(cand), len(cand))
+    valid = cand[ok]
+    nq = 512
+    starts, goals = valid[:nq], valid[nq:2 * nq]
+    paths, plen, iters, checks = pv.rrtc_batch(starts, goals, max_iters=2000, max_nodes=2048, max_path=128, seed=5,
+                                               replicas=1, shortcut_passes=2)
+    solved = plen > 0
+    assert solved.mean() > 0.9, f"success rate {solved.mean():.3f}"
+    assert (checks[solved] > 0).all() and (iters[solved] >= 1).all()
+    for k in np.nonzero(solved)[0][:64]:
+        p = paths[k, : plen[k]]
+        assert np.array_equal(p[0], starts[k]) and np.array_equal(p[-1], goals[k])
+        _path_ok(pv, c64, snap, p)
+    # determinism with replicas = 1
+    paths2, plen2, _, _ = pv.rrtc_batch(starts, goals, max_iters=2000, max_nodes=2048, max_path=128, seed=5,
+                                        replicas=1, shortcut_passes=2)
+    assert np.array_equal(plen, plen2) and np.array_equal(paths, paths2)
+    # replicas: OR-parallel searches still return valid paths
+    paths3, plen3, _, _ = pv.rrtc_batch(starts[:64], goals[:64], seed=9, replicas=8)
+    assert (plen3 > 0).mean() >= solved[:64].mean() - 0.05
+    for k in np.nonzero(plen3 > 0)[0][:16]:
+        _path_ok(pv, c64, snap, paths3[k, : plen3[k]])
