@@ -30,9 +30,8 @@ def ik(pos, quat=(0.0, 1.0, 0.0, 0.0), seed=pm.Q_SAFE_HOME, fingers=0.04):
         q = np.concatenate([x, [fingers, fingers]])
         R, p = po.fk(q[None])
         e_p = p[0, 8] - pos
-        Re = R[0, 8].T @ Rt
-        e_r = 0.5 * np.array([Re[2, 1] - Re[1, 2], Re[0, 2] - Re[2, 0], Re[1, 0] - Re[0, 1]])
-        return np.concatenate([e_p, 0.3 * e_r])
+        e_r = (R[0, 8] - Rt).ravel()  # full matrix difference: no spurious minimum at a half-turn
+        return np.concatenate([e_p, 0.2 * e_r])
 
     best = None
     rng = np.random.default_rng(0)
