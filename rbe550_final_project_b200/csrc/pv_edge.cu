@@ -1,0 +1,162 @@
+// pv_edge.cu -- K3 motion-validity kernels (fused interpolation + state check + any-hit early exit) and
+// their C-ABI entry points.  Split from pv_kernels.cu so the two translation units compile in parallel.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/panda_validity.h"
+#include "pv_device.cuh"
+#include "pv_handle.h"
+
+#ifndef PV_THREADS
+#define PV_THREADS 128
+#endif
+#ifndef PV_MIN_BLOCKS
+#define PV_MIN_BLOCKS 3
+#endif
+
+#define PV_CUDA(h, expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            snprintf((h)->err, sizeof((h)->err), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                                             \
+            return PV_ERR_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+
+#define PV_PRECHECK(h, n)                                                   \
+    if (!(h) || (h)->magic != PV_HANDLE_MAGIC) return PV_ERR_BAD_HANDLE;    \
+    if (!(h)->has_scene) {                                                  \
+        snprintf((h)->err, sizeof((h)->err), "no scene set (pv_set_scene)"); \
+        return PV_ERR_NO_SCENE;                                             \
+    }                                                                       \
+    if ((n) < 0) {                                                          \
+        snprintf((h)->err, sizeof((h)->err), "negative count");             \
+        return PV_ERR_BAD_ARG;                                              \
+    }                                                                       \
+    if ((n) == 0) return PV_OK;                                             \
+    PV_CUDA(h, cudaSetDevice((h)->device));
+
+// K3: one warp per edge, lanes = interpolation states, coarse-to-fine rounds, any-hit early exit.
+// Each warp owns 32 consecutive edges and emits one verdict word.
+template <bool CULL, int MODE>
+__global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
+    pv_edge_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ aA, const float4* __restrict__ aB,
+                   const float* __restrict__ a9, const float4* __restrict__ bA, const float4* __restrict__ bB,
+                   const float* __restrict__ b9, const float* __restrict__ a_aos, const float* __restrict__ b_aos,
+                   int64_t n_edges, int n_steps, float resolution, uint32_t* __restrict__ bits,
+                   float* __restrict__ margin) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t n_words = (n_edges + 31) >> 5;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = warp0; w < n_words; w += n_warps) {
+        const int64_t e_lane = (w << 5) + lane;
+        const int64_t ee = e_lane < n_edges ? e_lane : n_edges - 1;
+        float qa[9], qb[9];
+        if (a_aos) {
+            pv_load_aos(a_aos, ee, qa);
+            pv_load_aos(b_aos, ee, qb);
+        } else {
+            pv_load_soa(aA, aB, a9, ee, qa);
+            pv_load_soa(bA, bB, b9, ee, qb);
+        }
+        unsigned word = 0;
+        const int n_here = (int)min((int64_t)32, n_edges - (w << 5));
+        for (int j = 0; j < n_here; ++j) {
+            float ea[9], de[9], eb[9];
+            float d2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                ea[k] = __shfl_sync(FULL, qa[k], j);
+                eb[k] = __shfl_sync(FULL, qb[k], j);
+                de[k] = eb[k] - ea[k];
+                d2 = fmaf(de[k], de[k], d2);
+            }
+            int nd = n_steps;
+            if (nd <= 0) nd = max(1, (int)ceilf(sqrtf(d2) / resolution));
+            const int rounds = (nd + 31) >> 5;
+            const float inv_nd = 1.0f / (float)nd;
+            bool edge_hit = false;
+            float edge_m = 1e30f;
+            for (int r = 0; r < rounds; ++r) {
+                int k = nd - (lane * rounds + r);
+                const bool active = k >= 1;
+                if (!active) k = nd;  // idle lanes re-check the end point so the warp stays converged
+                const float t = (float)k * inv_nd;
+                float q[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, de[c], ea[c]);
+                PvAcc<MODE> acc;
+                pv_check_config<MODE, CULL, (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE)>(q, S, acc);
+                if constexpr (MODE == PV_MODE_BITS) {
+                    if (__any_sync(FULL, acc.hit)) {
+                        edge_hit = true;
+                        break;
+                    }
+                } else {
+                    edge_m = fminf(edge_m, acc.m);
+                }
+            }
+            if constexpr (MODE == PV_MODE_BITS) {
+                word |= (edge_hit ? 0u : 1u) << j;
+            } else {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) edge_m = fminf(edge_m, __shfl_xor_sync(FULL, edge_m, o));
+                if (lane == 0) margin[(w << 5) + j] = edge_m;
+            }
+        }
+        if constexpr (MODE == PV_MODE_BITS) {
+            if (lane == 0) bits[w] = word;
+        }
+    }
+}
+
+
+int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* a9, const float* bA,
+                           const float* bB, const float* b9, const float* a_aos, const float* b_aos, int64_t n,
+                           int n_steps, float resolution, uint32_t* d_bits, float* d_margin, cudaStream_t st) {
+    if (n_steps < 0 || (n_steps == 0 && !(resolution > 0.f))) {
+        snprintf(h->err, sizeof(h->err), "edge check needs n_steps > 0 or resolution > 0");
+        return PV_ERR_BAD_ARG;
+    }
+    const int64_t words = (n + 31) / 32;
+#define PV_LAUNCH_E(CULL, MODE)                                                                                \
+    {                                                                                                          \
+        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE>, PV_THREADS, words);                 \
+        pv_edge_kernel<CULL, MODE><<<grid, PV_THREADS, 0, st>>>(h->scene, (const float4*)aA, (const float4*)aB, a9, \
+                                                                (const float4*)bA, (const float4*)bB, b9, a_aos, b_aos, \
+                                                                n, n_steps, resolution, d_bits, d_margin);     \
+    }
+    if (d_bits) {
+        PV_LAUNCH_E(true, PV_MODE_BITS)
+    } else {
+        PV_LAUNCH_E(false, PV_MODE_MARGIN)  // margins: always brute force
+    }
+#undef PV_LAUNCH_E
+    h->launches++;
+    PV_CUDA(h, cudaGetLastError());
+    return PV_OK;
+}
+
+extern "C" int pv_check_edges(PvHandle* h, const float* d_aA, const float* d_aB, const float* d_a9, const float* d_bA,
+                   const float* d_bB, const float* d_b9, int64_t n_edges, int n_steps, float resolution,
+                   uint32_t* d_bits, void* stream) {
+    PV_PRECHECK(h, n_edges);
+    if (!d_aA || !d_aB || !d_bA || !d_bB || !d_bits) return PV_ERR_BAD_ARG;
+    return pv_launch_edges(h, d_aA, d_aB, d_a9, d_bA, d_bB, d_b9, nullptr, nullptr, n_edges, n_steps, resolution,
+                           d_bits, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int pv_edge_margins(PvHandle* h, const float* d_aA, const float* d_aB, const float* d_a9, const float* d_bA,
+                    const float* d_bB, const float* d_b9, int64_t n_edges, int n_steps, float resolution,
+                    float* d_margin, void* stream) {
+    PV_PRECHECK(h, n_edges);
+    if (!d_aA || !d_aB || !d_bA || !d_bB || !d_margin) return PV_ERR_BAD_ARG;
+    return pv_launch_edges(h, d_aA, d_aB, d_a9, d_bA, d_bB, d_b9, nullptr, nullptr, n_edges, n_steps, resolution,
+                           nullptr, d_margin, (cudaStream_t)stream);
+}
+

@@ -94,82 +94,6 @@ __global__ void __launch_bounds__(128)
     }
 }
 
-// K3: one warp per edge, lanes = interpolation states, coarse-to-fine rounds, any-hit early exit.
-// Each warp owns 32 consecutive edges and emits one verdict word.
-template <bool CULL, int MODE>
-__global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
-    pv_edge_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ aA, const float4* __restrict__ aB,
-                   const float* __restrict__ a9, const float4* __restrict__ bA, const float4* __restrict__ bB,
-                   const float* __restrict__ b9, const float* __restrict__ a_aos, const float* __restrict__ b_aos,
-                   int64_t n_edges, int n_steps, float resolution, uint32_t* __restrict__ bits,
-                   float* __restrict__ margin) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int64_t n_words = (n_edges + 31) >> 5;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t w = warp0; w < n_words; w += n_warps) {
-        const int64_t e_lane = (w << 5) + lane;
-        const int64_t ee = e_lane < n_edges ? e_lane : n_edges - 1;
-        float qa[9], qb[9];
-        if (a_aos) {
-            pv_load_aos(a_aos, ee, qa);
-            pv_load_aos(b_aos, ee, qb);
-        } else {
-            pv_load_soa(aA, aB, a9, ee, qa);
-            pv_load_soa(bA, bB, b9, ee, qb);
-        }
-        unsigned word = 0;
-        const int n_here = (int)min((int64_t)32, n_edges - (w << 5));
-        for (int j = 0; j < n_here; ++j) {
-            float ea[9], de[9], eb[9];
-            float d2 = 0.f;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                ea[k] = __shfl_sync(FULL, qa[k], j);
-                eb[k] = __shfl_sync(FULL, qb[k], j);
-                de[k] = eb[k] - ea[k];
-                d2 = fmaf(de[k], de[k], d2);
-            }
-            int nd = n_steps;
-            if (nd <= 0) nd = max(1, (int)ceilf(sqrtf(d2) / resolution));
-            const int rounds = (nd + 31) >> 5;
-            const float inv_nd = 1.0f / (float)nd;
-            bool edge_hit = false;
-            float edge_m = 1e30f;
-            for (int r = 0; r < rounds; ++r) {
-                int k = nd - (lane * rounds + r);
-                const bool active = k >= 1;
-                if (!active) k = nd;  // idle lanes re-check the end point so the warp stays converged
-                const float t = (float)k * inv_nd;
-                float q[9];
-#pragma unroll
-                for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, de[c], ea[c]);
-                PvAcc<MODE> acc;
-                pv_check_config<MODE, CULL, (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE)>(q, S, acc);
-                if constexpr (MODE == PV_MODE_BITS) {
-                    if (__any_sync(FULL, acc.hit)) {
-                        edge_hit = true;
-                        break;
-                    }
-                } else {
-                    edge_m = fminf(edge_m, acc.m);
-                }
-            }
-            if constexpr (MODE == PV_MODE_BITS) {
-                word |= (edge_hit ? 0u : 1u) << j;
-            } else {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) edge_m = fminf(edge_m, __shfl_xor_sync(FULL, edge_m, o));
-                if (lane == 0) margin[(w << 5) + j] = edge_m;
-            }
-        }
-        if constexpr (MODE == PV_MODE_BITS) {
-            if (lane == 0) bits[w] = word;
-        }
-    }
-}
-
 // Config-5 sweep: configurations generated on device from a counter-based RNG, checked, bit-packed, counted.
 template <bool CULL>
 __global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
@@ -353,6 +277,31 @@ int pv_set_scene(PvHandle* h, const float* h_obb, int n_obb, float table_z, cons
         S.base[2] = base_xyz[2];
     }
     if (S.attached >= n_obb) S.attached = -1;
+    // static reach masks: which link groups / gripper boxes can touch which scene box at all
+    {
+        const float link_reach[8] = PV_LINK_REACH, box_reach[3] = PV_BOX_REACH;
+        const float slack = 1e-3f;
+        const float sx = S.base[0], sy = S.base[1], sz = S.base[2] + 0.333f;
+        for (int b = 0; b < PV_MAX_OBB; ++b) S.reach_mask[b] = 0;
+        for (int b = 0; b < n_obb; ++b) {
+            const float* o = S.obb[b];
+            const float dx = o[0] - sx, dy = o[1] - sy, dz = o[2] - sz;
+            const float dist = sqrtf(dx * dx + dy * dy + dz * dz) - o[15];
+            unsigned m = 0;
+            for (int l = 1; l < 8; ++l)
+                if (dist < link_reach[l] + slack) m |= 1u << l;
+            for (int k = 0; k < 3; ++k)
+                if (dist < box_reach[k] + slack) m |= 1u << (8 + k);
+#define PV_L0_REACH(i, link, cx, cy, cz, r)                                                         \
+    {                                                                                               \
+        const float ex = o[0] - (S.base[0] + cx), ey = o[1] - (S.base[1] + cy), ez = o[2] - (S.base[2] + cz); \
+        if (sqrtf(ex * ex + ey * ey + ez * ez) < (r) + o[15] + slack) m |= 1u;                      \
+    }
+            PV_SPHERES_LINK0(PV_L0_REACH)
+#undef PV_L0_REACH
+            S.reach_mask[b] = (unsigned short)m;
+        }
+    }
     h->has_scene = 1;
     return PV_OK;
 }
@@ -451,50 +400,6 @@ int pv_state_margins(PvHandle* h, const float* d_qA, const float* d_qB, const fl
     return PV_OK;
 }
 
-static int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* a9, const float* bA,
-                           const float* bB, const float* b9, const float* a_aos, const float* b_aos, int64_t n,
-                           int n_steps, float resolution, uint32_t* d_bits, float* d_margin, cudaStream_t st) {
-    if (n_steps < 0 || (n_steps == 0 && !(resolution > 0.f))) {
-        snprintf(h->err, sizeof(h->err), "edge check needs n_steps > 0 or resolution > 0");
-        return PV_ERR_BAD_ARG;
-    }
-    const int64_t words = (n + 31) / 32;
-#define PV_LAUNCH_E(CULL, MODE)                                                                                \
-    {                                                                                                          \
-        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE>, PV_THREADS, words);                 \
-        pv_edge_kernel<CULL, MODE><<<grid, PV_THREADS, 0, st>>>(h->scene, (const float4*)aA, (const float4*)aB, a9, \
-                                                                (const float4*)bA, (const float4*)bB, b9, a_aos, b_aos, \
-                                                                n, n_steps, resolution, d_bits, d_margin);     \
-    }
-    if (d_bits) {
-        if (h->cull) PV_LAUNCH_E(true, PV_MODE_BITS) else PV_LAUNCH_E(false, PV_MODE_BITS)
-    } else {
-        PV_LAUNCH_E(false, PV_MODE_MARGIN)  // margins: always brute force
-    }
-#undef PV_LAUNCH_E
-    h->launches++;
-    PV_CUDA(h, cudaGetLastError());
-    return PV_OK;
-}
-
-int pv_check_edges(PvHandle* h, const float* d_aA, const float* d_aB, const float* d_a9, const float* d_bA,
-                   const float* d_bB, const float* d_b9, int64_t n_edges, int n_steps, float resolution,
-                   uint32_t* d_bits, void* stream) {
-    PV_PRECHECK(h, n_edges);
-    if (!d_aA || !d_aB || !d_bA || !d_bB || !d_bits) return PV_ERR_BAD_ARG;
-    return pv_launch_edges(h, d_aA, d_aB, d_a9, d_bA, d_bB, d_b9, nullptr, nullptr, n_edges, n_steps, resolution,
-                           d_bits, nullptr, (cudaStream_t)stream);
-}
-
-int pv_edge_margins(PvHandle* h, const float* d_aA, const float* d_aB, const float* d_a9, const float* d_bA,
-                    const float* d_bB, const float* d_b9, int64_t n_edges, int n_steps, float resolution,
-                    float* d_margin, void* stream) {
-    PV_PRECHECK(h, n_edges);
-    if (!d_aA || !d_aB || !d_bA || !d_bB || !d_margin) return PV_ERR_BAD_ARG;
-    return pv_launch_edges(h, d_aA, d_aB, d_a9, d_bA, d_bB, d_b9, nullptr, nullptr, n_edges, n_steps, resolution,
-                           nullptr, d_margin, (cudaStream_t)stream);
-}
-
 // ---- host-buffer entry points: chunked H2D -> kernel -> D2H pipeline over PV_N_STREAMS streams -----------
 static int pv_ensure_stage(PvHandle* h) {
     for (int i = 0; i < PV_N_STREAMS; ++i) {
@@ -565,12 +470,9 @@ int pv_sweep(PvHandle* h, uint64_t first, int64_t n, uint32_t seed, int fingers_
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t words = (n + 31) / 32;
-    if (h->cull) {
+    {
         int grid = pv_grid_for(h, (const void*)pv_sweep_kernel<true>, PV_THREADS, words);
         pv_sweep_kernel<true><<<grid, PV_THREADS, 0, st>>>(h->scene, first, n, seed, fingers_open, d_bits, d_n_valid, d_q_out);
-    } else {
-        int grid = pv_grid_for(h, (const void*)pv_sweep_kernel<false>, PV_THREADS, words);
-        pv_sweep_kernel<false><<<grid, PV_THREADS, 0, st>>>(h->scene, first, n, seed, fingers_open, d_bits, d_n_valid, d_q_out);
     }
     h->launches++;
     PV_CUDA(h, cudaGetLastError());

@@ -217,7 +217,45 @@ def _derive_pairs():
     return np.array(ss, dtype=np.int32), np.array(sb, dtype=np.int32)
 
 
-SS_PAIRS, SB_PAIRS = _derive_pairs()
+def derive_pairs_unpruned():
+    """Pair lists after the static App. C filter only (before the certified never-collide pruning)."""
+    return _derive_pairs()
+
+
+def model_fingerprint() -> str:
+    """Hash of everything the never-collide certificate depends on."""
+    import hashlib
+    h = hashlib.sha256()
+    for arr in (SPHERE_LINK, SPHERE_CENTER, SPHERE_RADIUS, BOX_LINK, BOX_CENTER, BOX_HALF, Q_LOWER, Q_UPPER,
+                np.array(BODY_POS), np.array(BODY_QUAT)):
+        h.update(np.ascontiguousarray(arr).tobytes())
+    return h.hexdigest()[:16]
+
+
+NEVER_COLLIDE_PATH = os.path.join(os.path.dirname(__file__), "data", "never_collide.json")
+
+
+def _prune_certified(ss, sb):
+    """Drop the pairs that tools/certify_never_collide.py proved can never touch within the joint limits
+    (branch-and-bound with Lipschitz bounds, certified clearance >= 2 mm).  The certificate is tied to the
+    primitive tables by a fingerprint; a stale or missing file means no pruning."""
+    import json
+    try:
+        with open(NEVER_COLLIDE_PATH) as fh:
+            cert = json.load(fh)
+    except FileNotFoundError:
+        return ss, sb, None
+    if cert.get("model_fingerprint") != model_fingerprint():
+        return ss, sb, None
+    never_ss = {tuple(p) for p in cert["never_ss"]}
+    never_sb = {tuple(p) for p in cert["never_sb"]}
+    ss2 = np.array([p for p in ss if (int(p[0]), int(p[1])) not in never_ss], dtype=np.int32).reshape(-1, 2)
+    sb2 = np.array([p for p in sb if (int(p[0]), int(p[1])) not in never_sb], dtype=np.int32).reshape(-1, 2)
+    return ss2, sb2, cert
+
+
+SS_PAIRS_UNPRUNED, SB_PAIRS_UNPRUNED = _derive_pairs()
+SS_PAIRS, SB_PAIRS, NEVER_COLLIDE_CERT = _prune_certified(SS_PAIRS_UNPRUNED, SB_PAIRS_UNPRUNED)
 N_SS_PAIRS = int(SS_PAIRS.shape[0])
 N_SB_PAIRS = int(SB_PAIRS.shape[0])
 
@@ -272,6 +310,27 @@ def link_groups():
 
 
 BOX_BOUND_RADIUS = np.linalg.norm(BOX_HALF, axis=1)
+FINGER_SLIDE_MAX = float(Q_UPPER[7])
+
+
+def static_reach():
+    """Conservative reach of each link group (links 1..7) and gripper box (hand, left, right) measured from the
+    shoulder point S0 = base + (0, 0, 0.333) (origin of link1 and link2): no point of the group can ever be
+    farther from S0, whatever the joint angles (triangle inequality over the body offsets).  pv_set_scene uses
+    it to drop (group, scene box) combinations that cannot touch -- a uniform, divergence-free cull.
+    link0 does not move at all and is tested exactly on the host."""
+    chain = np.zeros(N_LINKS)
+    for l in range(3, N_LINKS):
+        chain[l] = chain[PARENT[l]] + float(np.linalg.norm(BODY_POS[l]))
+    chain[LINK_LF] += FINGER_SLIDE_MAX
+    chain[LINK_RF] += FINGER_SLIDE_MAX
+    link_reach = np.zeros(8)
+    for l in range(1, 8):
+        idx = [i for i in range(N_SPHERES) if int(SPHERE_LINK[i]) == l]
+        link_reach[l] = chain[l] + max(float(np.linalg.norm(SPHERE_CENTER[i]) + SPHERE_RADIUS[i]) for i in idx)
+    box_reach = np.array([chain[int(BOX_LINK[k])] + float(np.linalg.norm(BOX_CENTER[k]) + BOX_BOUND_RADIUS[k])
+                          for k in range(N_BOXES)])
+    return link_reach, box_reach
 
 
 def _place_expr(c, axis):
@@ -303,6 +362,11 @@ def header_text() -> str:
     ang = 2.0 * math.atan2(hq[3], hq[0])
     a(f"#define PV_HAND_COS {_f(math.cos(ang))}")
     a(f"#define PV_HAND_SIN {_f(math.sin(ang))}")
+    lr, br_ = static_reach()
+    a("// conservative reach from the shoulder point (base + (0,0,0.333)) of link groups 0..7 (entry 0 unused:")
+    a("// link0 is fixed and tested exactly) and of the 3 gripper boxes")
+    a("#define PV_LINK_REACH {" + ", ".join(_f(v) for v in lr) + "}")
+    a("#define PV_BOX_REACH {" + ", ".join(_f(v) for v in br_) + "}")
     a("// joint limits")
     a("#define PV_Q_LOWER {" + ", ".join(_f(v) for v in Q_LOWER) + "}")
     a("#define PV_Q_UPPER {" + ", ".join(_f(v) for v in Q_UPPER) + "}")
