@@ -272,9 +272,15 @@ __device__ __forceinline__ void pv_fk_visit(const float* q, float bx, float by, 
 
 // ---- the state check ----------------------------------------------------------------------------------
 // Returns through `acc`.  All 32 lanes of a warp must call this together when EXIT != PV_EXIT_NONE.
-template <int MODE, bool CULL, int EXIT>
+// SYNC: every warp of the block calls this together and block-level barriers keep the warps within one
+// code region of each other, so the (large, straight-line) instruction stream is fetched once per SM instead
+// of once per warp (ncu showed stall_no_instruction as the top stall of the free-running version).
+template <int MODE, bool CULL, int EXIT, bool SYNC = false>
 __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S, PvAcc<MODE>& acc) {
+    static_assert(!SYNC || EXIT == PV_EXIT_NONE, "block barriers and warp-level early exit do not mix");
     const unsigned FULL = 0xffffffffu;
+#define PV_LOCKSTEP() \
+    if constexpr (SYNC) __syncthreads();
 #define PV_EARLY_EXIT()                                                              \
     if constexpr (MODE == PV_MODE_BITS && EXIT != PV_EXIT_NONE) {                    \
         bool h_ = acc.hit;                                                           \
@@ -341,6 +347,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
         pv_plane<MODE>(acc, bc[k].z - ext, tz, PV_CODE(1, blink[k], 0));
     }
     PV_EARLY_EXIT()
+    PV_LOCKSTEP()
 
     // ---- self collision ------------------------------------------------------------------------------
     if (S.flags & PV_FLAG_SELF) {
@@ -356,6 +363,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
 #undef PV_LP
 #undef PV_SS
         PV_EARLY_EXIT()
+        PV_LOCKSTEP()
 #define PV_SB(a, k, r2, r)                                                                                  \
     pv_sphere_box<MODE>(acc, s[a], r, r2, bc[k], make_float3(bh[k][0], bh[k][1], bh[k][2]), hX, hY, hZ, \
                         PV_CODE(3, a, 33 + k));
@@ -375,6 +383,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
     // ---- robot vs scene boxes ------------------------------------------------------------------------
     const int nb = S.n_obb;
     for (int b = 0; b < nb; ++b) {
+        PV_LOCKSTEP()
         const float3 oc = make_float3(S.obb[b][0], S.obb[b][1], S.obb[b][2]);
         const float3 oh = make_float3(S.obb[b][3], S.obb[b][4], S.obb[b][5]);
         const float obr = S.obb[b][15];
@@ -415,6 +424,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
         PV_EARLY_EXIT()
     }
 #undef PV_EARLY_EXIT
+#undef PV_LOCKSTEP
 }
 
 // ---- config loads ---------------------------------------------------------------------------------------

@@ -432,6 +432,41 @@ def header_text() -> str:
                 r = float(np.float32(SPHERE_RADIUS[p]))
                 a(f"  X({p}, {k}, {_f(r * r)}, {_f(r)}) \\")
         a("")
+    # ---- tables for the warp-cooperative (queue-based) narrow phase ---------------------------------------
+    a("// ===== v2 (broad phase -> shared-memory work queue -> narrow phase) tables =====")
+    a("#define PV2_SPHERE_R {" + ", ".join(_f(v) for v in SPHERE_RADIUS) + "}")
+    starts = [min([i for i in range(N_SPHERES) if int(SPHERE_LINK[i]) == l], default=0) for l in range(8)]
+    counts = [sum(1 for i in range(N_SPHERES) if int(SPHERE_LINK[i]) == l) for l in range(8)]
+    for l in range(8):
+        idx = [i for i in range(N_SPHERES) if int(SPHERE_LINK[i]) == l]
+        assert idx == list(range(starts[l], starts[l] + counts[l])), "spheres must be contiguous per link"
+    a("#define PV2_GROUP_START {" + ", ".join(str(v) for v in starts) + "}")
+    a("#define PV2_GROUP_COUNT {" + ", ".join(str(v) for v in counts) + "}")
+    ss_sorted = sorted(((int(SPHERE_LINK[p]), int(SPHERE_LINK[q]), int(p), int(q)) for p, q in SS_PAIRS))
+    a("// flat sphere-sphere pair table sorted by link pair: a | b << 8, and (ra+rb)^2")
+    a("#define PV2_SS_AB {" + ", ".join(str(p | (q << 8)) for _, _, p, q in ss_sorted) + "}")
+    a("#define PV2_SS_RR2 {" + ", ".join(
+        _f(float(np.float32(SPHERE_RADIUS[p] + SPHERE_RADIUS[q])) ** 2) for _, _, p, q in ss_sorted) + "}")
+    a("// X(la, lb, ca, cb, cull_r2, start, count): link pair -> range in the flat table")
+    a("#define PV2_LPS(X) \\")
+    for la, lb in lps:
+        rr = g[la][1] + g[lb][1] + CULL_SLACK
+        st = min(i for i, t in enumerate(ss_sorted) if (t[0], t[1]) == (la, lb))
+        cn = sum(1 for t in ss_sorted if (t[0], t[1]) == (la, lb))
+        a(f"  X({la}, {lb}, {g[la][0]}, {g[lb][0]}, {_f(rr * rr)}, {st}, {cn}) \\")
+    a("")
+    sb_sorted = sorted(((int(SPHERE_LINK[p]), int(k), int(p)) for p, k in SB_PAIRS))
+    a("// flat sphere-vs-gripper-box table sorted by (link, box): sphere index; box index")
+    a("#define PV2_SB_A {" + ", ".join(str(p) for _, _, p in sb_sorted) + "}")
+    a("#define PV2_SB_K {" + ", ".join(str(k) for _, k, _ in sb_sorted) + "}")
+    a("// X(la, k, ca, cull_r2, start, count)")
+    a("#define PV2_LBS(X) \\")
+    for la, k in lbs:
+        rr = g[la][1] + BOX_BOUND_RADIUS[k] + CULL_SLACK
+        st = min(i for i, t in enumerate(sb_sorted) if (t[0], t[1]) == (la, k))
+        cn = sum(1 for t in sb_sorted if (t[0], t[1]) == (la, k))
+        a(f"  X({la}, {k}, {g[la][0]}, {_f(rr * rr)}, {st}, {cn}) \\")
+    a("")
     return "\n".join(L) + "\n"
 
 

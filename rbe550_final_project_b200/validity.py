@@ -87,8 +87,9 @@ class PandaValidity:
         self.flags = (FLAG_SELF if self_collision else 0) | (FLAG_LIMITS if joint_limits else 0)
         self._ck(self.lib.pv_set_flags(self._h, self.flags), "pv_set_flags")
 
-    def set_culling(self, on: bool):
-        self._ck(self.lib.pv_set_culling(self._h, 1 if on else 0), "pv_set_culling")
+    def set_culling(self, mode):
+        """State-kernel variant: 0 brute force, 1 per-lane culling, 2 warp-cooperative queues (default)."""
+        self._ck(self.lib.pv_set_culling(self._h, int(mode)), "pv_set_culling")
 
     # -- device-buffer calls --------------------------------------------------------------------------
     def _planes(self, q) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], int]:

@@ -9,7 +9,7 @@ scene = sys.argv[1] if len(sys.argv) > 1 else "goal1_scattered"
 cull = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 pv = PandaValidity(0)
 pv.set_scene(sc.FIXTURES[scene]())
-pv.set_culling(bool(cull))
+pv.set_culling(cull)
 n = 1 << 20
 rng = np.random.default_rng(0)
 q = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n, 9)).astype(np.float32); q[:, 7:] = 0.04
