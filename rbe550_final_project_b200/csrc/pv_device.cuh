@@ -275,12 +275,12 @@ __device__ __forceinline__ void pv_fk_visit(const float* q, float bx, float by, 
 // SYNC: every warp of the block calls this together and block-level barriers keep the warps within one
 // code region of each other, so the (large, straight-line) instruction stream is fetched once per SM instead
 // of once per warp (ncu showed stall_no_instruction as the top stall of the free-running version).
-template <int MODE, bool CULL, int EXIT, bool SYNC = false>
+template <int MODE, bool CULL, int EXIT, int SYNC = 0>
 __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S, PvAcc<MODE>& acc) {
     static_assert(!SYNC || EXIT == PV_EXIT_NONE, "block barriers and warp-level early exit do not mix");
     const unsigned FULL = 0xffffffffu;
-#define PV_LOCKSTEP() \
-    if constexpr (SYNC) __syncthreads();
+#define PV_LOCKSTEP(level) \
+    if constexpr (SYNC >= level) __syncthreads();
 #define PV_EARLY_EXIT()                                                              \
     if constexpr (MODE == PV_MODE_BITS && EXIT != PV_EXIT_NONE) {                    \
         bool h_ = acc.hit;                                                           \
@@ -347,7 +347,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
         pv_plane<MODE>(acc, bc[k].z - ext, tz, PV_CODE(1, blink[k], 0));
     }
     PV_EARLY_EXIT()
-    PV_LOCKSTEP()
+    PV_LOCKSTEP(2)
 
     // ---- self collision ------------------------------------------------------------------------------
     if (S.flags & PV_FLAG_SELF) {
@@ -363,7 +363,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
 #undef PV_LP
 #undef PV_SS
         PV_EARLY_EXIT()
-        PV_LOCKSTEP()
+        PV_LOCKSTEP(1)
 #define PV_SB(a, k, r2, r)                                                                                  \
     pv_sphere_box<MODE>(acc, s[a], r, r2, bc[k], make_float3(bh[k][0], bh[k][1], bh[k][2]), hX, hY, hZ, \
                         PV_CODE(3, a, 33 + k));
@@ -383,7 +383,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
     // ---- robot vs scene boxes ------------------------------------------------------------------------
     const int nb = S.n_obb;
     for (int b = 0; b < nb; ++b) {
-        PV_LOCKSTEP()
+        PV_LOCKSTEP(3)
         const float3 oc = make_float3(S.obb[b][0], S.obb[b][1], S.obb[b][2]);
         const float3 oh = make_float3(S.obb[b][3], S.obb[b][4], S.obb[b][5]);
         const float obr = S.obb[b][15];

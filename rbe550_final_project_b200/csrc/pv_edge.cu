@@ -40,9 +40,15 @@
     PV_CUDA(h, cudaSetDevice((h)->device));
 
 // K3: one warp per edge, lanes = interpolation states, coarse-to-fine rounds, any-hit early exit.
-// Each warp owns 32 consecutive edges and emits one verdict word.
+// Each warp owns 32 consecutive edges at a time and emits one verdict word.  The warps of a block advance
+// ROUND by round behind a block barrier (one pv_check_config per warp per round), so the 16 warps share
+// instruction fetches exactly like the state kernel; the loop ends when __syncthreads_or says no warp has
+// work left.
+#ifndef PV_E_THREADS
+#define PV_E_THREADS 384
+#endif
 template <bool CULL, int MODE>
-__global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
+__global__ void __launch_bounds__(PV_E_THREADS, 1)
     pv_edge_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ aA, const float4* __restrict__ aB,
                    const float* __restrict__ a9, const float4* __restrict__ bA, const float4* __restrict__ bB,
                    const float* __restrict__ b9, const float* __restrict__ a_aos, const float* __restrict__ b_aos,
@@ -51,23 +57,38 @@ __global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t n_words = (n_edges + 31) >> 5;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t w = warp0; w < n_words; w += n_warps) {
-        const int64_t e_lane = (w << 5) + lane;
-        const int64_t ee = e_lane < n_edges ? e_lane : n_edges - 1;
-        float qa[9], qb[9];
-        if (a_aos) {
-            pv_load_aos(a_aos, ee, qa);
-            pv_load_aos(b_aos, ee, qb);
-        } else {
-            pv_load_soa(aA, aB, a9, ee, qa);
-            pv_load_soa(bA, bB, b9, ee, qb);
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+    // warp state machine: word w, edge j of the word, round r of the edge
+    float qa[9], qb[9];          // this lane's edge of the word (edge 32 w + lane)
+    float ea[9], eb[9], de[9];   // the edge being validated (warp-uniform)
+    int j = 0, r = 0, n_here = 0, nd = 1, rounds = 1;
+    float inv_nd = 1.f, edge_m = 1e30f;
+    unsigned word = 0;
+    bool need_word = true, need_edge = true;
+
+    for (;;) {
+        const bool have = w < n_words;
+        if (!__syncthreads_or(have ? 1 : 0)) break;
+        if (!have) continue;
+        if (need_word) {
+            const int64_t e_lane = (w << 5) + lane;
+            const int64_t ee = e_lane < n_edges ? e_lane : n_edges - 1;
+            if (a_aos) {
+                pv_load_aos(a_aos, ee, qa);
+                pv_load_aos(b_aos, ee, qb);
+            } else {
+                pv_load_soa(aA, aB, a9, ee, qa);
+                pv_load_soa(bA, bB, b9, ee, qb);
+            }
+            n_here = (int)min((int64_t)32, n_edges - (w << 5));
+            word = 0;
+            j = 0;
+            need_word = false;
+            need_edge = true;
         }
-        unsigned word = 0;
-        const int n_here = (int)min((int64_t)32, n_edges - (w << 5));
-        for (int j = 0; j < n_here; ++j) {
-            float ea[9], de[9], eb[9];
+        if (need_edge) {
             float d2 = 0.f;
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
@@ -76,45 +97,55 @@ __global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
                 de[k] = eb[k] - ea[k];
                 d2 = fmaf(de[k], de[k], d2);
             }
-            int nd = n_steps;
+            nd = n_steps;
             if (nd <= 0) nd = max(1, (int)ceilf(sqrtf(d2) / resolution));
-            const int rounds = (nd + 31) >> 5;
-            const float inv_nd = 1.0f / (float)nd;
-            bool edge_hit = false;
-            float edge_m = 1e30f;
-            for (int r = 0; r < rounds; ++r) {
-                int k = nd - (lane * rounds + r);
-                const bool active = k >= 1;
-                if (!active) k = nd;  // idle lanes re-check the end point so the warp stays converged
-                const float t = (float)k * inv_nd;
-                float q[9];
+            rounds = (nd + 31) >> 5;
+            inv_nd = 1.0f / (float)nd;
+            r = 0;
+            edge_m = 1e30f;
+            need_edge = false;
+        }
+        // one round: lane -> state k (coarse to fine; idle lanes re-check the end point)
+        int k = nd - (lane * rounds + r);
+        if (k < 1) k = nd;
+        const float t = (float)k * inv_nd;
+        float q[9];
 #pragma unroll
-                for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, de[c], ea[c]);
-                PvAcc<MODE> acc;
-                pv_check_config<MODE, CULL, (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE)>(q, S, acc);
-                if constexpr (MODE == PV_MODE_BITS) {
-                    if (__any_sync(FULL, acc.hit)) {
-                        edge_hit = true;
-                        break;
-                    }
-                } else {
-                    edge_m = fminf(edge_m, acc.m);
-                }
-            }
-            if constexpr (MODE == PV_MODE_BITS) {
-                word |= (edge_hit ? 0u : 1u) << j;
-            } else {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) edge_m = fminf(edge_m, __shfl_xor_sync(FULL, edge_m, o));
-                if (lane == 0) margin[(w << 5) + j] = edge_m;
-            }
+        for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, de[c], ea[c]);
+        PvAcc<MODE> acc;
+        pv_check_config<MODE, CULL, (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE)>(q, S, acc);
+        bool edge_done;
+        bool edge_hit = false;
+        if constexpr (MODE == PV_MODE_BITS) {
+            edge_hit = __any_sync(FULL, acc.hit);
+            edge_done = edge_hit || (r + 1 >= rounds);
+        } else {
+            edge_m = fminf(edge_m, acc.m);
+            edge_done = (r + 1 >= rounds);
+        }
+        if (!edge_done) {
+            ++r;
+            continue;
         }
         if constexpr (MODE == PV_MODE_BITS) {
-            if (lane == 0) bits[w] = word;
+            word |= (edge_hit ? 0u : 1u) << j;
+        } else {
+            float m = edge_m;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, o));
+            if (lane == 0) margin[(w << 5) + j] = m;
+        }
+        ++j;
+        need_edge = true;
+        if (j >= n_here) {
+            if constexpr (MODE == PV_MODE_BITS) {
+                if (lane == 0) bits[w] = word;
+            }
+            w += n_warps;
+            need_word = true;
         }
     }
 }
-
 
 int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* a9, const float* bA,
                            const float* bB, const float* b9, const float* a_aos, const float* b_aos, int64_t n,
@@ -126,8 +157,8 @@ int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* 
     const int64_t words = (n + 31) / 32;
 #define PV_LAUNCH_E(CULL, MODE)                                                                                \
     {                                                                                                          \
-        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE>, PV_THREADS, words);                 \
-        pv_edge_kernel<CULL, MODE><<<grid, PV_THREADS, 0, st>>>(h->scene, (const float4*)aA, (const float4*)aB, a9, \
+        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE>, PV_E_THREADS, words);                 \
+        pv_edge_kernel<CULL, MODE><<<grid, PV_E_THREADS, 0, st>>>(h->scene, (const float4*)aA, (const float4*)aB, a9, \
                                                                 (const float4*)bA, (const float4*)bB, b9, a_aos, b_aos, \
                                                                 n, n_steps, resolution, d_bits, d_margin);     \
     }

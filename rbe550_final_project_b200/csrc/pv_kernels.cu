@@ -37,9 +37,17 @@ static char g_create_error[512] = "";
 
 // K2: one thread per configuration, warp-ballot bit packing.  Persistent blocks; the warps of a block walk the
 // verdict words in lockstep (block barriers inside pv_check_config) so they share instruction fetches.
-#define PV_SB_THREADS 384
+#ifndef PV_SB_THREADS
+#define PV_SB_THREADS 512  // 16 warps in lockstep, 127 registers, no spills (swept 128..1024: profiles/r1_notes.md)
+#endif
+#ifndef PV_SB_SYNC
+#define PV_SB_SYNC 0
+#endif
+#ifndef PV_SB_MINB
+#define PV_SB_MINB 1
+#endif
 template <bool AOS, bool CULL>
-__global__ void __launch_bounds__(PV_SB_THREADS, 1)
+__global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     pv_state_bits_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA,
                          const float4* __restrict__ qB, const float* __restrict__ q9,
                          const float* __restrict__ q_aos, int64_t n, uint32_t* __restrict__ bits) {
@@ -56,8 +64,9 @@ __global__ void __launch_bounds__(PV_SB_THREADS, 1)
         float q[9];
         if (AOS) pv_load_aos(q_aos, ii, q);
         else pv_load_soa(qA, qB, q9, ii, q);
+        if (PV_SB_SYNC >= 0) __syncthreads();
         PvAcc<PV_MODE_BITS> acc;
-        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, true>(q, S, acc);
+        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, PV_SB_SYNC>(q, S, acc);
         const unsigned word = __ballot_sync(0xffffffffu, in && !acc.hit);
         if (lane == 0 && w < n_words) bits[w] = word;
     }
@@ -130,16 +139,17 @@ __global__ void __launch_bounds__(128)
 
 // Config-5 sweep: configurations generated on device from a counter-based RNG, checked, bit-packed, counted.
 template <bool CULL>
-__global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
+__global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     pv_sweep_kernel(const __grid_constant__ PvScene S, uint64_t first, int64_t n, unsigned seed, int fingers_open,
                     uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid,
                     float* __restrict__ q_out) {
     const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
     const int64_t n_words = (n + 31) >> 5;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     unsigned long long count = 0;
-    for (int64_t w = warp0; w < n_words; w += n_warps) {
+    for (int64_t wb = (int64_t)blockIdx.x * warps_per_block; wb < n_words; wb += (int64_t)gridDim.x * warps_per_block) {
+        const int64_t w = wb + warp_in_block;
         const int64_t i = (w << 5) + lane;
         const bool in = i < n;
         float q[9];
@@ -148,10 +158,11 @@ __global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
 #pragma unroll
             for (int j = 0; j < 9; ++j) q_out[9 * i + j] = q[j];
         }
+        __syncthreads();  // lockstep: the warps of the block share instruction fetches
         PvAcc<PV_MODE_BITS> acc;
-        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_ALL>(q, S, acc);
+        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, 0>(q, S, acc);
         const unsigned word = __ballot_sync(0xffffffffu, in && !acc.hit);
-        if (lane == 0) {
+        if (lane == 0 && w < n_words) {
             bits[w] = word;
             count += __popc(word);
         }
@@ -526,8 +537,8 @@ int pv_sweep(PvHandle* h, uint64_t first, int64_t n, uint32_t seed, int fingers_
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t words = (n + 31) / 32;
     {
-        int grid = pv_grid_for(h, (const void*)pv_sweep_kernel<true>, PV_THREADS, words);
-        pv_sweep_kernel<true><<<grid, PV_THREADS, 0, st>>>(h->scene, first, n, seed, fingers_open, d_bits, d_n_valid, d_q_out);
+        int grid = pv_grid_for(h, (const void*)pv_sweep_kernel<true>, PV_SB_THREADS, words);
+        pv_sweep_kernel<true><<<grid, PV_SB_THREADS, 0, st>>>(h->scene, first, n, seed, fingers_open, d_bits, d_n_valid, d_q_out);
     }
     h->launches++;
     PV_CUDA(h, cudaGetLastError());
