@@ -176,13 +176,26 @@ def main():
     # device-resident inputs (SoA float4 planes), distinct per rank and per rotation slot
     host_batches = [make_batch(SEED + 1000 * rank + r, n) for r in range(N_ROT)]
     planes = [soa_from_aos(torch.as_tensor(b, device="cuda")) for b in host_batches]
-    bits = torch.empty(words, dtype=torch.int32, device="cuda")
-    gathered = torch.empty(words * world, dtype=torch.int32, device="cuda") if world > 1 else None
+    bits2 = [torch.empty(words, dtype=torch.int32, device="cuda") for _ in range(2)]
+    bits = bits2[0]
+    gathered = [torch.empty(words * world, dtype=torch.int32, device="cuda") for _ in range(2)] if world > 1 else None
+    pending = [None, None]
 
     def step(i):
-        pv.check_states(planes[i % N_ROT], out=bits)
+        # double-buffered: the NCCL all-gather of step i's verdict words overlaps step i+1's kernel
+        k = i & 1
+        if pending[k] is not None:
+            pending[k].wait()
+            pending[k] = None
+        pv.check_states(planes[i % N_ROT], out=bits2[k])
         if world > 1:
-            dist.all_gather_into_tensor(gathered, bits)
+            pending[k] = dist.all_gather_into_tensor(gathered[k], bits2[k], async_op=True)
+
+    def drain():
+        for k in range(2):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     def barrier():
         if world > 1:
@@ -192,6 +205,7 @@ def main():
     fp32_peak_tflops, _ = pv.fp32_peak(8192)
     for i in range(args.warmup):
         step(i)
+    drain()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -200,6 +214,7 @@ def main():
     e0.record()
     for i in range(args.steps):
         step(i)
+    drain()
     e1.record()
     barrier()
     launches = pv.launch_count - launches0
@@ -207,7 +222,7 @@ def main():
     # keep the GPU busy a little longer so the clock sampler sees the loaded state even for short runs
     t_end = time.perf_counter() + 0.25
     while time.perf_counter() < t_end:
-        step(0)
+        pv.check_states(planes[0], out=bits2[0])
     torch.cuda.synchronize()
     clocks = sampler.stop()
     if world > 1:
@@ -251,6 +266,11 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    executed = None
+    try:
+        executed = json.load(open(os.path.join(ROOT, "profiles", "executed_flops.json")))
+    except Exception:
+        pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     bytes_per_check = 32.0 + 1.0 / 8.0
     hbm_achieved = bytes_per_check * per_gpu_rate / 1e9
@@ -259,9 +279,18 @@ def main():
         executed = json.load(open(os.path.join(ROOT, "profiles", "executed_flops.json")))
     except Exception:
         pass
+    algorithmic_tflops = achieved_tflops
+    if executed and executed.get("fp32_flops_per_check"):
+        # achieved = FP32 FLOPs the kernel really executes per check (ncu thread-level FFMA*2 + FADD + FMUL counts of the
+        # same kernel on the same workload, committed under profiles/) x the rate measured live in this run
+        achieved_tflops = float(executed["fp32_flops_per_check"]) * per_gpu_rate / 1e12
     roofline = {
         "bound": "fp32", "kernel": "pv_state_bits_kernel", "achieved": achieved_tflops, "peak": fp32_peak_tflops,
         "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
+        "achieved_definition": ("executed FP32 FLOPs/check from profiles/executed_flops.json x live checks/s"
+                                if executed and executed.get("fp32_flops_per_check") else
+                                "algorithmic brute-force FLOPs/check x live checks/s"),
+        "algorithmic_bruteforce_equiv_tflops": algorithmic_tflops,
         "peak_source": "measured in this run by pv_fp32_peak (unrolled independent FFMA); MEASURED_PEAKS.json has no FP32 entry",
         "flops_per_check": flops_per_check,
         "flops_model": "algorithmic no-early-exit count of SURVEY.md 8d: F_fk + S(F_place + B F_sb + F_plane) + "
@@ -274,6 +303,15 @@ def main():
     }
     if executed:
         roofline["executed"] = executed
+        if executed.get("warp_inst_per_32_checks"):
+            # the binding limit of this kernel is instruction issue (ncu: issue-active ~62 %), not FLOPs or HBM:
+            # 4 schedulers/SM x 1 warp-instruction/cycle at the SM clock sampled during the run
+            mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
+            peak_issue = 148 * 4 * mhz * 1e6
+            rate = executed["warp_inst_per_32_checks"] * per_gpu_rate / 32.0
+            roofline["issue"] = {"bound": "warp-instruction issue", "achieved": rate, "peak": peak_issue,
+                                 "unit": "warp-inst/s", "frac": rate / peak_issue,
+                                 "lane_utilisation": executed["thread_inst_per_check"] * 32.0 / (32.0 * executed["warp_inst_per_32_checks"])}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
