@@ -17,7 +17,7 @@ FLAG_LIMITS = 2
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("panda_oracle.c", "panda_oracle_impl.h")]
+    src = [os.path.join(_HERE, f) for f in ("panda_oracle.c", "panda_oracle_impl.h", "rrtc_oracle_impl.h")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
     return LIB_PATH
@@ -115,3 +115,23 @@ class COracle:
             self.c_t(resolution), C.c_int(1 if early_exit else 0), self._p(out), C.byref(cnt),
             C.c_int(nthreads or os.cpu_count() or 1))
         return (out, cnt.value) if return_count else out
+
+    def rrtc(self, start, goal, scene, seed=1, search=0, max_iters=2000, max_nodes=2048, max_path=128,
+             shortcut_passes=2, rrt_range=2.6074318092713376, resolution=0.13037159046356686, attached=-1,
+             flags=FLAG_SELF, base=(0.0, 0.0, 0.01)):
+        """CPU restatement of one device RRT-Connect search (fp32 only).  Returns (path (len, 9), iters, checks)."""
+        assert self.np_t is np.float32, "the planner restatement mirrors the device arithmetic: use precision 'f32'"
+        s = np.ascontiguousarray(start, dtype=np.float32).reshape(9)
+        g = np.ascontiguousarray(goal, dtype=np.float32).reshape(9)
+        obb = np.ascontiguousarray(scene["obb"], dtype=np.float32).reshape(-1, 16)
+        b = np.asarray(base, dtype=np.float32)
+        path = np.zeros((max_path, 9), dtype=np.float32)
+        iters, checks = C.c_int(0), C.c_longlong(0)
+        fn = self.lib.po_rrtc_f32
+        fn.restype = C.c_int
+        n = fn(C.byref(self.model), self._p(obb), C.c_int(obb.shape[0]), C.c_float(scene["table_z"]), self._p(b),
+               C.c_int(attached), C.c_int(flags), self._p(s), self._p(g), C.c_float(np.float32(rrt_range)),
+               C.c_float(np.float32(resolution)), C.c_int(max_iters), C.c_int(max_nodes), C.c_int(max_path),
+               C.c_uint32(seed & 0xFFFFFFFF), C.c_uint32(search), C.c_int(shortcut_passes), self._p(path),
+               C.byref(iters), C.byref(checks))
+        return path[:n].copy(), iters.value, checks.value

@@ -31,3 +31,5 @@ static const int PO_JIDX[11] = {-1, 0, 1, 2, 3, 4, 5, 6, -1, 7, 8};
 #include "panda_oracle_impl.h"
 #undef REAL
 #undef SUFFIX
+
+#include "rrtc_oracle_impl.h"

@@ -23,6 +23,8 @@ struct PvHandle {
     uint32_t* stage_bits[PV_N_STREAMS];
     void* rrtc_buf;
     size_t rrtc_bytes;
+    void* rrtc_host;  // pinned mirror of the RRT result block
+    size_t rrtc_host_bytes;
     char err[512];
 };
 

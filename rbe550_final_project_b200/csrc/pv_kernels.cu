@@ -284,6 +284,7 @@ void pv_destroy(PvHandle* h) {
         if (h->stage_bits[i]) cudaFree(h->stage_bits[i]);
     }
     if (h->rrtc_buf) cudaFree(h->rrtc_buf);
+    if (h->rrtc_host) cudaFreeHost(h->rrtc_host);
     h->magic = 0;
     delete h;
 }

@@ -371,34 +371,44 @@ extern "C" int pv_rrtc_batch(PvHandle* h, const float* h_starts, const float* h_
     a.tree_q = (float*)p; p += b_tree;
     a.parent = (int*)p; p += b_par;
     a.path_tmp = (float*)p; p += b_ptmp;
-    a.path_out = (float*)p; p += b_pout;
+    // results are contiguous so that one memset clears them and one D2H fetches them
+    char* res0 = p;
     a.path_len = (int*)p; p += b_i;
     a.iters_out = (int*)p; p += b_i;
-    a.winner = (int*)p; p += b_i;
     a.checks = (long long*)p; p += b_ll;
+    a.path_out = (float*)p; p += b_pout;
+    const size_t res_bytes = (size_t)(p - res0);
+    a.winner = (int*)p; p += b_i;
     a.starts = d_starts;
     a.goals = d_goals;
+
+    // pinned host mirror of the result block (grow-only)
+    if (res_bytes > h->rrtc_host_bytes) {
+        if (h->rrtc_host) cudaFreeHost(h->rrtc_host);
+        h->rrtc_host = nullptr;
+        h->rrtc_host_bytes = 0;
+        RR_CUDA(cudaMallocHost(&h->rrtc_host, res_bytes));
+        h->rrtc_host_bytes = res_bytes;
+    }
 
     cudaStream_t st = h->streams[0];
     RR_CUDA(cudaMemcpyAsync(d_starts, h_starts, (size_t)n_queries * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
     RR_CUDA(cudaMemcpyAsync(d_goals, h_goals, (size_t)n_queries * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
-    RR_CUDA(cudaMemsetAsync(a.path_len, 0, b_i, st));
-    RR_CUDA(cudaMemsetAsync(a.iters_out, 0, b_i, st));
+    RR_CUDA(cudaMemsetAsync(a.path_len, 0, 2 * b_i + b_ll, st));  // path_len, iters, checks
     RR_CUDA(cudaMemsetAsync(a.winner, 0xFF, b_i, st));
-    RR_CUDA(cudaMemsetAsync(a.checks, 0, b_ll, st));
     const int warps_per_block = RRTC_THREADS / 32;
     const int grid = (int)((n_search + warps_per_block - 1) / warps_per_block);
     pv_rrtc_kernel<<<grid, RRTC_THREADS, 0, st>>>(h->scene, a);
     h->launches++;
     RR_CUDA(cudaGetLastError());
-    RR_CUDA(cudaMemcpyAsync(h_path_len, a.path_len, (size_t)n_queries * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (h_iters)
-        RR_CUDA(cudaMemcpyAsync(h_iters, a.iters_out, (size_t)n_queries * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (h_checks)
-        RR_CUDA(cudaMemcpyAsync(h_checks, a.checks, (size_t)n_queries * sizeof(long long), cudaMemcpyDeviceToHost, st));
-    RR_CUDA(cudaMemcpyAsync(h_path_out, a.path_out, (size_t)n_queries * a.max_path * 9 * sizeof(float),
-                            cudaMemcpyDeviceToHost, st));
+    // small batches: one packed copy; large batches: skip the unused tail of each path? (paths are max_path long)
+    RR_CUDA(cudaMemcpyAsync(h->rrtc_host, res0, res_bytes, cudaMemcpyDeviceToHost, st));
     RR_CUDA(cudaStreamSynchronize(st));
+    const char* hp = (const char*)h->rrtc_host;
+    memcpy(h_path_len, hp, (size_t)n_queries * sizeof(int));
+    if (h_iters) memcpy(h_iters, hp + b_i, (size_t)n_queries * sizeof(int));
+    if (h_checks) memcpy(h_checks, hp + 2 * b_i, (size_t)n_queries * sizeof(long long));
+    memcpy(h_path_out, hp + 2 * b_i + b_ll, (size_t)n_queries * a.max_path * 9 * sizeof(float));
     return PV_OK;
 #undef RR_CUDA
 }

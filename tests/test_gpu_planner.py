@@ -141,3 +141,28 @@ def test_batched_rrtc_tower_scene(pv, c64):
     assert (plen3 > 0).mean() >= solved[:64].mean() - 0.05
     for k in np.nonzero(plen3 > 0)[0][:16]:
         _path_ok(pv, c64, snap, paths3[k, : plen3[k]])
+
+
+def test_device_rrtc_follows_the_oracle_planner(pv, c32):
+    """Same seeds, same sample stream, same tie breaks: the device planner and the CPU restatement must take the same
+    decisions, so paths are bit-identical unless a state inside the 1e-4 m contact band flipped a verdict."""
+    snap = sc.goal3_tower()
+    pv.set_scene(snap)
+    pv.set_attached(-1)
+    pv.set_flags(True, False)
+    cand = random_configs(3000, 321)
+    valid = cand[unpack_bits(pv.check_states_host(cand), len(cand))]
+    nq = 160
+    starts, goals = valid[:nq], valid[nq:2 * nq]
+    paths, plen, iters, checks = pv.rrtc_batch(starts, goals, max_iters=500, max_nodes=1024, max_path=128, seed=11,
+                                               replicas=1, shortcut_passes=2)
+    same, solved_both = 0, 0
+    for k in range(nq):
+        p, it, ch = c32.rrtc(starts[k], goals[k], snap.as_oracle_scene(), seed=11, search=k, max_iters=500,
+                             max_nodes=1024, max_path=128, shortcut_passes=2)
+        if len(p) == plen[k] and np.array_equal(p, paths[k, : plen[k]]) and it == iters[k] and ch == checks[k]:
+            same += 1
+        if len(p) > 0 and plen[k] > 0:
+            solved_both += 1
+    assert same >= int(0.97 * nq), f"only {same}/{nq} searches identical to the oracle planner"
+    assert solved_both >= int(0.9 * nq)
