@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpanda_validity.so")
 SOURCES = ["pv_kernels.cu", "pv_edge.cu", "pv_rrtc.cu"]
-HEADERS = ["pv_device.cuh", "pv_device_v2.cuh", "pv_handle.h", "panda_model_gen.h", os.path.join("..", "..", "include", "panda_validity.h")]
+HEADERS = ["pv_device.cuh", "pv_handle.h", "panda_model_gen.h", os.path.join("..", "..", "include", "panda_validity.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--threads", "4",

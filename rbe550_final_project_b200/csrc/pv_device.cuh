@@ -126,6 +126,23 @@ __device__ __forceinline__ void pv_sphere_box_yaw(PvAcc<MODE>& acc, float3 c, fl
     }
 }
 
+// sphere already expressed in the box's frame (loc = R^T (c - origin)) vs a box with centre bcl in that frame
+template <int MODE>
+__device__ __forceinline__ void pv_sphere_box_local(PvAcc<MODE>& acc, float3 loc, float r, float r2, float3 bcl, float3 oh,
+                                                    int code) {
+    float ex = fabsf(loc.x - bcl.x) - oh.x;
+    float ey = fabsf(loc.y - bcl.y) - oh.y;
+    float ez = fabsf(loc.z - bcl.z) - oh.z;
+    float px = fmaxf(ex, 0.f), py = fmaxf(ey, 0.f), pz = fmaxf(ez, 0.f);
+    float s2 = fmaf(pz, pz, fmaf(py, py, px * px));
+    if constexpr (MODE == PV_MODE_BITS) {
+        acc.hit |= (s2 < r2);
+    } else {
+        float g = (s2 > 0.f ? sqrtf(s2) : fmaxf(ex, fmaxf(ey, ez))) - r;
+        acc.take(g, code);
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void pv_sphere_sphere(PvAcc<MODE>& acc, float3 a, float3 b, float rr2, float rr, int code) {
     float3 d = v_sub(a, b);
@@ -302,7 +319,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
 
     // FK -> sphere centres (registers) + gripper boxes
     float3 s[PV_N_SPHERES];
-    float3 hX, hY, hZ, bc[3];
+    float3 hX, hY, hZ, hP, bc[3];
     pv_fk_visit(q, S.base[0], S.base[1], S.base[2], [&](auto lc, float3 p, float3 X, float3 Y, float3 Z) {
         constexpr int l = decltype(lc)::value;
         if constexpr (l == 0) { PV_PLACE_LINK0(s, p, X, Y, Z) }
@@ -313,7 +330,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
         if constexpr (l == 5) { PV_PLACE_LINK5(s, p, X, Y, Z) }
         if constexpr (l == 6) { PV_PLACE_LINK6(s, p, X, Y, Z) }
         if constexpr (l == 7) { PV_PLACE_LINK7(s, p, X, Y, Z) }
-        if constexpr (l == 8) { hX = X; hY = Y; hZ = Z; }
+        if constexpr (l == 8) { hX = X; hY = Y; hZ = Z; hP = p; }
 #define PV_BOX_PLACE(k, link, cx, cy, cz, hx, hy, hz, br) \
     if constexpr (l == link) bc[k] = v_fma(Z, cz, v_fma(Y, cy, v_fma(X, cx, p)));
         PV_BOXES(PV_BOX_PLACE)
@@ -364,19 +381,35 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
 #undef PV_SS
         PV_EARLY_EXIT()
         PV_LOCKSTEP(1)
-#define PV_SB(a, k, r2, r)                                                                                  \
-    pv_sphere_box<MODE>(acc, s[a], r, r2, bc[k], make_float3(bh[k][0], bh[k][1], bh[k][2]), hX, hY, hZ, \
-                        PV_CODE(3, a, 33 + k));
-#define PV_LB(la, k, ca, cull2)                              \
-    {                                                        \
-        float3 d_ = v_sub(s[ca], bc[k]);                     \
-        if (!CULL || v_dot(d_, d_) < cull2) {                \
-            PV_SB_PAIRS_##la##_##k(PV_SB)                    \
-        }                                                    \
+        // sphere-vs-gripper pairs: the three gripper boxes share the hand's axes, so each proximal sphere is moved
+        // into the hand frame once (12 instr.) and then meets axis-aligned boxes (10 instr. each)
+        float3 bcl[3], bhl[3];
+#define PV_BOX_HF(k, cx, cy0, cz, sgn, qi, hx, hy, hz) \
+    bcl[k] = make_float3(cx, fmaf(sgn, q[qi], cy0), cz); \
+    bhl[k] = make_float3(hx, hy, hz);
+        PV_BOXES_HANDFRAME(PV_BOX_HF)
+#undef PV_BOX_HF
+        float3 loc_;
+        float lr_, lr2_;
+#define PV_SBH_S(a, r, r2)                                              \
+    {                                                                   \
+        float3 d_ = v_sub(s[a], hP);                                    \
+        loc_ = make_float3(v_dot(d_, hX), v_dot(d_, hY), v_dot(d_, hZ)); \
+        lr_ = r;                                                        \
+        lr2_ = r2;                                                      \
     }
-        PV_SB_LINKBOX(PV_LB)
+#define PV_SBH_B(a, k) pv_sphere_box_local<MODE>(acc, loc_, lr_, lr2_, bcl[k], bhl[k], PV_CODE(3, a, 33 + k));
+#define PV_LB(la, ca, c0, c1, c2)                                                                       \
+    {                                                                                                   \
+        float3 d0_ = v_sub(s[ca], bc[0]), d1_ = v_sub(s[ca], bc[1]), d2_ = v_sub(s[ca], bc[2]);         \
+        if (!CULL || v_dot(d0_, d0_) < c0 || v_dot(d1_, d1_) < c1 || v_dot(d2_, d2_) < c2) {            \
+            PV_SBH_##la(PV_SBH_S, PV_SBH_B)                                                             \
+        }                                                                                               \
+    }
+        PV_SBH_LINKS(PV_LB)
 #undef PV_LB
-#undef PV_SB
+#undef PV_SBH_B
+#undef PV_SBH_S
         PV_EARLY_EXIT()
     }
 

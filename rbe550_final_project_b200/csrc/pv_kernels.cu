@@ -9,7 +9,6 @@
 
 #include "../../include/panda_validity.h"
 #include "pv_device.cuh"
-#include "pv_device_v2.cuh"
 #include "pv_handle.h"
 
 #ifndef PV_THREADS
@@ -69,35 +68,6 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, PV_SB_SYNC>(q, S, acc);
         const unsigned word = __ballot_sync(0xffffffffu, in && !acc.hit);
         if (lane == 0 && w < n_words) bits[w] = word;
-    }
-}
-
-// K2, warp-cooperative form (default): broad phase per lane, shared-memory queues, warp-wide narrow phase.
-#define PV2_SMEM_BYTES (((sizeof(Pv2Tables) + 15) & ~(size_t)15) + PV2_WARPS * sizeof(Pv2Warp))
-template <bool AOS>
-__global__ void __launch_bounds__(PV2_WARPS * 32, 3)
-    pv_state_bits_v2_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA,
-                            const float4* __restrict__ qB, const float* __restrict__ q9,
-                            const float* __restrict__ q_aos, int64_t n, uint32_t* __restrict__ bits) {
-    extern __shared__ __align__(16) unsigned char pv2_smem[];
-    Pv2Tables& T = *reinterpret_cast<Pv2Tables*>(pv2_smem);
-    Pv2Warp* Ws = reinterpret_cast<Pv2Warp*>(pv2_smem + ((sizeof(Pv2Tables) + 15) & ~(size_t)15));
-    pv2_load_tables(T, S);
-    Pv2Warp& W = Ws[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const int64_t n_words = (n + 31) >> 5;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t w = warp0; w < n_words; w += n_warps) {
-        const int64_t i = (w << 5) + lane;
-        const bool in = i < n;
-        const int64_t ii = in ? i : n - 1;
-        float q[9];
-        if (AOS) pv_load_aos(q_aos, ii, q);
-        else pv_load_soa(qA, qB, q9, ii, q);
-        const bool hit = pv2_check_warp<PV_EXIT_NONE>(q, S, W, T, lane);
-        const unsigned word = __ballot_sync(0xffffffffu, in && !hit);
-        if (lane == 0) bits[w] = word;
     }
 }
 
@@ -368,11 +338,11 @@ int pv_set_flags(PvHandle* h, unsigned flags) {
     return PV_OK;
 }
 
-// test / profiling hook for the state kernel: 0 = thread-per-config brute force, 1 = thread-per-config with
-// per-lane bounding-ball culling, 2 = warp-cooperative broad/narrow phase with shared-memory queues (default)
+// test / profiling hook for the state kernel: 0 = brute force (every kept pair tested), 1 = per-lane
+// bounding-ball culling in front of each block of tests (default).  Verdicts are bit-identical.
 int pv_set_culling(PvHandle* h, int on) {
     if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
-    h->cull = on < 0 ? 0 : (on > 2 ? 2 : on);
+    h->cull = on ? 1 : 0;
     return PV_OK;
 }
 
@@ -412,31 +382,11 @@ static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_q
         pv_state_bits_kernel<AOS, CULL><<<grid, PV_SB_THREADS, 0, st>>>(h->scene, (const float4*)d_qA,        \
                                                                      (const float4*)d_qB, d_q9, d_aos, n, d_bits); \
     }
-#define PV_LAUNCH_V2(AOS)                                                                                       \
-    {                                                                                                         \
-        static bool attr_set_##AOS = false;                                                                   \
-        if (!attr_set_##AOS) {                                                                                \
-            PV_CUDA(h, cudaFuncSetAttribute(pv_state_bits_v2_kernel<AOS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            (int)PV2_SMEM_BYTES));                                            \
-            attr_set_##AOS = true;                                                                            \
-        }                                                                                                     \
-        int occ = 0;                                                                                          \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pv_state_bits_v2_kernel<AOS>, PV2_WARPS * 32,  \
-                                                          PV2_SMEM_BYTES) != cudaSuccess || occ < 1) occ = 1;   \
-        int64_t grid = (int64_t)h->sm_count * occ;                                                            \
-        const int64_t need = (words + PV2_WARPS - 1) / PV2_WARPS;                                             \
-        if (need < grid) grid = need;                                                                         \
-        pv_state_bits_v2_kernel<AOS><<<(int)grid, PV2_WARPS * 32, PV2_SMEM_BYTES, st>>>(                       \
-            h->scene, (const float4*)d_qA, (const float4*)d_qB, d_q9, d_aos, n, d_bits);                      \
-    }
-    if (h->cull >= 2) {
-        if (d_aos) PV_LAUNCH_V2(true) else PV_LAUNCH_V2(false)
-    } else if (d_aos) {
+    if (d_aos) {
         if (h->cull) PV_LAUNCH_SB(true, true) else PV_LAUNCH_SB(true, false)
     } else {
         if (h->cull) PV_LAUNCH_SB(false, true) else PV_LAUNCH_SB(false, false)
     }
-#undef PV_LAUNCH_V2
 #undef PV_LAUNCH_SB
     h->launches++;
     PV_CUDA(h, cudaGetLastError());

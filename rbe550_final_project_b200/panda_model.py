@@ -432,41 +432,45 @@ def header_text() -> str:
                 r = float(np.float32(SPHERE_RADIUS[p]))
                 a(f"  X({p}, {k}, {_f(r * r)}, {_f(r)}) \\")
         a("")
-    # ---- tables for the warp-cooperative (queue-based) narrow phase ---------------------------------------
-    a("// ===== v2 (broad phase -> shared-memory work queue -> narrow phase) tables =====")
-    a("#define PV2_SPHERE_R {" + ", ".join(_f(v) for v in SPHERE_RADIUS) + "}")
-    starts = [min([i for i in range(N_SPHERES) if int(SPHERE_LINK[i]) == l], default=0) for l in range(8)]
-    counts = [sum(1 for i in range(N_SPHERES) if int(SPHERE_LINK[i]) == l) for l in range(8)]
-    for l in range(8):
-        idx = [i for i in range(N_SPHERES) if int(SPHERE_LINK[i]) == l]
-        assert idx == list(range(starts[l], starts[l] + counts[l])), "spheres must be contiguous per link"
-    a("#define PV2_GROUP_START {" + ", ".join(str(v) for v in starts) + "}")
-    a("#define PV2_GROUP_COUNT {" + ", ".join(str(v) for v in counts) + "}")
-    ss_sorted = sorted(((int(SPHERE_LINK[p]), int(SPHERE_LINK[q]), int(p), int(q)) for p, q in SS_PAIRS))
-    a("// flat sphere-sphere pair table sorted by link pair: a | b << 8, and (ra+rb)^2")
-    a("#define PV2_SS_AB {" + ", ".join(str(p | (q << 8)) for _, _, p, q in ss_sorted) + "}")
-    a("#define PV2_SS_RR2 {" + ", ".join(
-        _f(float(np.float32(SPHERE_RADIUS[p] + SPHERE_RADIUS[q])) ** 2) for _, _, p, q in ss_sorted) + "}")
-    a("// X(la, lb, ca, cb, cull_r2, start, count): link pair -> range in the flat table")
-    a("#define PV2_LPS(X) \\")
-    for la, lb in lps:
-        rr = g[la][1] + g[lb][1] + CULL_SLACK
-        st = min(i for i, t in enumerate(ss_sorted) if (t[0], t[1]) == (la, lb))
-        cn = sum(1 for t in ss_sorted if (t[0], t[1]) == (la, lb))
-        a(f"  X({la}, {lb}, {g[la][0]}, {g[lb][0]}, {_f(rr * rr)}, {st}, {cn}) \\")
+    # ---- sphere-vs-gripper self pairs evaluated in the hand frame ---------------------------------------------
+    a("// gripper boxes in the HAND frame: X(k, cx, cy0, cz, slide_sign, finger_q_index, hx, hy, hz); the centre's y is")
+    a("// cy0 + slide_sign * q[finger_q_index] (hand: sign 0).  All three boxes share the hand's axes.")
+    a("#define PV_BOXES_HANDFRAME(X) \\")
+    for k in range(N_BOXES):
+        c, h = BOX_CENTER[k], BOX_HALF[k]
+        if k == 0:
+            a(f"  X(0, {_f(c[0])}, {_f(c[1])}, {_f(c[2])}, 0.0f, 7, {_f(h[0])}, {_f(h[1])}, {_f(h[2])}) \\")
+        else:
+            sign = 1.0 if k == 1 else -1.0  # right finger frame = hand frame turned half a turn about z
+            off = np.array(BODY_POS[int(BOX_LINK[k])])
+            a(f"  X({k}, {_f(sign * c[0] + off[0])}, {_f(sign * c[1] + off[1])}, {_f(c[2] + off[2])}, {_f(sign)}, {6 + k}, "
+              f"{_f(h[0])}, {_f(h[1])}, {_f(h[2])}) \\")
     a("")
-    sb_sorted = sorted(((int(SPHERE_LINK[p]), int(k), int(p)) for p, k in SB_PAIRS))
-    a("// flat sphere-vs-gripper-box table sorted by (link, box): sphere index; box index")
-    a("#define PV2_SB_A {" + ", ".join(str(p) for _, _, p in sb_sorted) + "}")
-    a("#define PV2_SB_K {" + ", ".join(str(k) for _, k, _ in sb_sorted) + "}")
-    a("// X(la, k, ca, cull_r2, start, count)")
-    a("#define PV2_LBS(X) \\")
-    for la, k in lbs:
-        rr = g[la][1] + BOX_BOUND_RADIUS[k] + CULL_SLACK
-        st = min(i for i, t in enumerate(sb_sorted) if (t[0], t[1]) == (la, k))
-        cn = sum(1 for t in sb_sorted if (t[0], t[1]) == (la, k))
-        a(f"  X({la}, {k}, {g[la][0]}, {_f(rr * rr)}, {st}, {cn}) \\")
+    a("// LB(la, ca, cull0, cull1, cull2): link la's block runs when its bounding ball (centre s[ca]) reaches the")
+    a("// bounding ball of gripper box k for any k (cull_k = squared reach, 0 when the link has no pair with box k)")
+    a("#define PV_SBH_LINKS(LB) \\")
+    sb_links = sorted({int(SPHERE_LINK[p]) for p, _ in SB_PAIRS})
+    for la in sb_links:
+        culls = []
+        for k in range(N_BOXES):
+            if any(int(SPHERE_LINK[p]) == la and int(kk) == k for p, kk in SB_PAIRS):
+                rr = g[la][1] + BOX_BOUND_RADIUS[k] + CULL_SLACK
+                culls.append(_f(rr * rr))
+            else:
+                culls.append("0.0f")
+        a(f"  LB({la}, {g[la][0]}, {', '.join(culls)}) \\")
     a("")
+    a("// per link: S(a, r, r2) brings sphere a into the hand frame, B(a, k) tests it against gripper box k")
+    for la in sb_links:
+        a(f"#define PV_SBH_{la}(S, B) \\")
+        for sp in sorted({int(p) for p, _ in SB_PAIRS if int(SPHERE_LINK[p]) == la}):
+            r = float(np.float32(SPHERE_RADIUS[sp]))
+            line = f"  S({sp}, {_f(r)}, {_f(r * r)})"
+            for p, kk in SB_PAIRS:
+                if int(p) == sp:
+                    line += f" B({sp}, {int(kk)})"
+            a(line + " \\")
+        a("")
     return "\n".join(L) + "\n"
 
 

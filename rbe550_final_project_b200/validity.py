@@ -88,7 +88,7 @@ class PandaValidity:
         self._ck(self.lib.pv_set_flags(self._h, self.flags), "pv_set_flags")
 
     def set_culling(self, mode):
-        """State-kernel variant: 0 brute force, 1 per-lane culling, 2 warp-cooperative queues (default)."""
+        """State-kernel variant: 0 brute force, 1 per-lane bounding-ball culling (default); bit-identical verdicts."""
         self._ck(self.lib.pv_set_culling(self._h, int(mode)), "pv_set_culling")
 
     # -- device-buffer calls --------------------------------------------------------------------------

@@ -23,11 +23,11 @@ A, B, q9 = soa_from_aos(torch.as_tensor(q, device="cuda"))
 out = torch.empty(n // 32, dtype=torch.int32, device="cuda")
 for name in ("goal1_scattered", "goal4_task1_pentagon", "goal3_tower"):
     pv.set_scene(sc.FIXTURES[name]())
-    for cull in (2, 1, 0):
+    for cull in (1, 0):
         pv.set_culling(cull)
         ms = timeit(lambda: pv.check_states((A, B, q9), out=out))
         print(f"{name:22s} cull={cull} states: {ms:.3f} ms  {n/ms/1e6:.3f} G checks/s  valid={unpack_bits(out, n).mean():.3f}")
-pv.set_culling(2)
+pv.set_culling(1)
 pv.set_scene(sc.goal4_task1_pentagon())
 ne = 1 << 20
 qb = np.clip(q[:ne] + rng.normal(0, 0.3, (ne, 9)), pm.Q_LOWER, pm.Q_UPPER).astype(np.float32); qb[:, 7:] = 0.04
