@@ -296,7 +296,7 @@ def main():
         "flops_model": "algorithmic no-early-exit count of SURVEY.md 8d: F_fk + S(F_place + B F_sb + F_plane) + "
                        "H(F_place + B F_bb + 8 F_plane) + P F_ss + P2 F_sb, S=%d H=%d P=%d P2=%d B=%d" % (
                            pm.N_SPHERES, pm.N_BOXES, pm.N_SS_PAIRS, pm.N_SB_PAIRS, snap.n_obb),
-        "traffic": None,
+        "traffic": (executed or {}).get("dram_bytes_per_launch"),
         "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                 "bytes_per_check": bytes_per_check,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"},

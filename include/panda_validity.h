@@ -123,6 +123,17 @@ int pv_rrtc_batch(PvHandle *h, const float *h_starts, const float *h_goals, int 
                   const PvRrtcParams *params, float *h_path_out, int *h_path_len, int *h_iters,
                   long long *h_checks);
 
+/* robot.inverse_kinematics(link=hand, pos, quat) as the motion primitives call it before every plan_path
+ * (motion_primitives.py:131-134), batched and collision-aware.  For each of n_targets hand poses (world
+ * position, quaternion wxyz) n_seeds damped-least-squares searches run in parallel (seed 0 = h_q_init, the rest
+ * uniform in the joint limits from a counter-based RNG); converged candidates are filtered by the state-validity
+ * rule of the current scene and the valid one closest to h_q_init is returned.  Finger joints are copied from
+ * h_q_init.  h_status[i] = 1 if a solution was found; h_err[i] = {position error m, rotation error rad} (may be
+ * NULL).  pos_tol / rot_tol <= 0 select 1e-4 m / 1e-3 rad; n_seeds is rounded up to a power of two in 32..256. */
+int pv_ik_batch(PvHandle *h, const float *h_pos, const float *h_quat, int n_targets, const float *h_q_init,
+                int n_seeds, int max_iters, float pos_tol, float rot_tol, uint32_t seed, float *h_q_out,
+                int *h_status, float *h_err);
+
 /* FP32 FMA issue-rate micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP32 entry).
  * Returns achieved TFLOP/s over `iters` unrolled FFMA rounds; ms (may be NULL) gets the kernel time. */
 int pv_fp32_peak(PvHandle *h, int iters, double *tflops, float *ms);

@@ -14,7 +14,7 @@ from typing import List
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpanda_validity.so")
-SOURCES = ["pv_kernels.cu", "pv_edge.cu", "pv_rrtc.cu"]
+SOURCES = ["pv_kernels.cu", "pv_edge.cu", "pv_rrtc.cu", "pv_ik.cu"]
 HEADERS = ["pv_device.cuh", "pv_handle.h", "panda_model_gen.h", os.path.join("..", "..", "include", "panda_validity.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -26,7 +26,7 @@ EXPORTS = [
     "pv_create", "pv_destroy", "pv_last_error", "pv_version", "pv_model_info", "pv_joint_limits",
     "pv_set_scene", "pv_set_attached", "pv_set_flags", "pv_fk", "pv_check_states", "pv_state_margins",
     "pv_check_edges", "pv_edge_margins", "pv_check_states_host", "pv_check_edges_host", "pv_sweep",
-    "pv_rrtc_batch", "pv_fp32_peak", "pv_launch_count",
+    "pv_rrtc_batch", "pv_ik_batch", "pv_fp32_peak", "pv_launch_count",
 ]
 
 
@@ -112,6 +112,7 @@ def load() -> C.CDLL:
     lib.pv_check_edges_host.argtypes = [vp, fp, fp, C.c_int64, C.c_int, C.c_float, u32p]
     lib.pv_sweep.argtypes = [vp, C.c_uint64, C.c_int64, C.c_uint32, C.c_int, u32p, vp, fp, vp]
     lib.pv_rrtc_batch.argtypes = [vp, fp, fp, C.c_int, C.POINTER(PvRrtcParams), fp, i32p, i32p, vp]
+    lib.pv_ik_batch.argtypes = [vp, fp, fp, C.c_int, fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_uint32, fp, i32p, fp]
     lib.pv_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     lib.pv_launch_count.argtypes = [vp]
     lib.pv_launch_count.restype = C.c_longlong

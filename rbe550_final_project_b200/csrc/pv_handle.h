@@ -25,6 +25,8 @@ struct PvHandle {
     size_t rrtc_bytes;
     void* rrtc_host;  // pinned mirror of the RRT result block
     size_t rrtc_host_bytes;
+    void* ik_buf;
+    size_t ik_bytes;
     char err[512];
 };
 

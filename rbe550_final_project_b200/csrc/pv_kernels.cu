@@ -255,6 +255,7 @@ void pv_destroy(PvHandle* h) {
     }
     if (h->rrtc_buf) cudaFree(h->rrtc_buf);
     if (h->rrtc_host) cudaFreeHost(h->rrtc_host);
+    if (h->ik_buf) cudaFree(h->ik_buf);
     h->magic = 0;
     delete h;
 }

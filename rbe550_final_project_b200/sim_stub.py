@@ -52,6 +52,33 @@ class StubPanda(StubEntity):
     def get_qpos(self):
         return self._q.copy()
 
+    # --- kinematics through the CUDA library (only when a PandaValidity handle has been attached) ----------
+    def attach_validity(self, validity):
+        self._validity = validity
+
+    def get_link(self, name: str):
+        idx = pm.LINK_NAMES.index(name)
+        robot = self
+
+        class _Link:
+            def __init__(self):
+                self.name = name
+                self.idx = idx
+
+            def get_pos(self):
+                import torch
+                pose = robot._validity.fk(torch.as_tensor(robot._q[None], dtype=torch.float32, device=robot._validity.device))
+                return pose[0, idx, 0:3].cpu().numpy().astype(np.float64)
+
+        return _Link()
+
+    def inverse_kinematics(self, link=None, pos=None, quat=None, **kw):
+        """robot.inverse_kinematics(link=hand, pos=, quat=) (motion_primitives.py:131-134) on the GPU: returns a
+        collision-free qpos (9,) near the current one, or None."""
+        if getattr(link, "name", "hand") != "hand":
+            raise NotImplementedError("only the hand link is supported")
+        return self._validity.ik(np.asarray(pos, dtype=np.float64), np.asarray(quat, dtype=np.float64), self._q, **kw)
+
     def set_qpos(self, q):
         self.set_qpos_calls += 1
         self._q = np.asarray(q.detach().cpu().numpy() if hasattr(q, "detach") else q, dtype=np.float64).copy()

@@ -217,6 +217,28 @@ class PandaValidity:
                  "pv_rrtc_batch")
         return paths, plen, iters, checks
 
+    def ik_batch(self, pos: np.ndarray, quat: np.ndarray, q_init: Sequence[float], n_seeds: int = 128,
+                 max_iters: int = 64, pos_tol: float = 1e-4, rot_tol: float = 1e-3, seed: int = 1):
+        """Collision-aware IK for the hand: pos (n, 3), quat (n, 4) wxyz -> (q (n, 9), ok (n,), err (n, 2))."""
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        quat = np.ascontiguousarray(quat, dtype=np.float32).reshape(-1, 4)
+        n = pos.shape[0]
+        if quat.shape[0] != n:
+            raise PandaValidityError("pos and quat must have the same length")
+        qi = np.ascontiguousarray(q_init, dtype=np.float32).reshape(9)
+        q = np.zeros((n, 9), dtype=np.float32)
+        ok = np.zeros(n, dtype=np.int32)
+        err = np.zeros((n, 2), dtype=np.float32)
+        self._ck(self.lib.pv_ik_batch(self._h, pos.ctypes.data, quat.ctypes.data, n, qi.ctypes.data, int(n_seeds),
+                                      int(max_iters), float(pos_tol), float(rot_tol), int(seed) & 0xFFFFFFFF,
+                                      q.ctypes.data, ok.ctypes.data, err.ctypes.data), "pv_ik_batch")
+        return q, ok.astype(bool), err
+
+    def ik(self, pos, quat, q_init, **kw) -> Optional[np.ndarray]:
+        """One pose, the shape of `robot.inverse_kinematics(link=hand, pos=, quat=)`: qpos (9,) or None."""
+        q, ok, _ = self.ik_batch(np.asarray(pos)[None], np.asarray(quat)[None], q_init, **kw)
+        return q[0].astype(np.float64) if ok[0] else None
+
     def fp32_peak(self, iters: int = 4096) -> Tuple[float, float]:
         tf, ms = C.c_double(0), C.c_float(0)
         self._ck(self.lib.pv_fp32_peak(self._h, int(iters), C.byref(tf), C.byref(ms)), "pv_fp32_peak")

@@ -25,6 +25,17 @@ out = {
     "source": os.path.basename(path),
     "note": "FMNMX/FSETP/abs/compare work is not counted as FLOPs; FFMA counts 2",
 }
+if len(sys.argv) > 3:
+    # raw page of a `--set full` capture of the same launch: DRAM traffic
+    rows = list(csv.reader(open(sys.argv[3])))
+    hdr, unit, val = rows[0], rows[1], rows[2]
+    def grab(name):
+        i = hdr.index(name)
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit[i]]
+        return float(val[i]) * scale
+    out["dram_bytes_per_launch"] = grab("dram__bytes_read.sum") + grab("dram__bytes_write.sum")
+    out["algorithmic_bytes_per_launch"] = n * (32 + 0.125)
+    out["dram_source"] = os.path.basename(sys.argv[3])
 dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "executed_flops.json")
 json.dump(out, open(dst, "w"), indent=1)
 print(json.dumps(out, indent=1))
