@@ -129,6 +129,21 @@ class PlannerInterface:
         w = self.validity.check_edges_host(np.asarray(qa, np.float32)[None], np.asarray(qb, np.float32)[None], n_steps=0)
         return bool(w[0] & 1)
 
+    def validate_trajectory(self, waypoints, attached_object=None) -> np.ndarray:
+        """Swept validation of an executed joint trajectory (next-row component 8f-4): the reference plays back the
+        150 planned waypoints and many un-planned joint-space lerps (motion_primitives.py:163-173, 294-299, 404-409)
+        with no collision check.  Returns one bool per segment (waypoint k -> k+1), each segment discretised at the
+        motion-validity resolution."""
+        if self._snapshot is None:
+            self.refresh_scene()
+        pts = np.stack([tensor_to_array(w) for w in waypoints]).astype(np.float32)
+        if len(pts) < 2:
+            return np.ones(0, dtype=bool)
+        self.validity.set_attached(self._attached_index(attached_object))
+        bits = self.validity.check_edges_host(pts[:-1], pts[1:], n_steps=0)
+        self.validity.set_attached(-1)
+        return ((bits[:, None] >> np.arange(32, dtype=np.uint32)) & 1).ravel()[: len(pts) - 1].astype(bool)
+
     # ---- plan_path (planning.py:59-207) ---------------------------------------------------------------------
     def plan_path(self, qpos_goal, qpos_start=None, timeout=5.0, smooth_path=True, num_waypoints=100,
                   attached_object=None, planner="RRTConnect") -> List[torch.Tensor]:

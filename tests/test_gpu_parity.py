@@ -220,3 +220,34 @@ def test_error_paths(pv):
         h.set_attached(17)
     assert h.check_states(_dev(np.zeros((0, 9), np.float32))).numel() == 0
     h.close()
+
+
+def test_cuda_reproduces_committed_golden_vectors(pv):
+    """tests/golden/validity_golden.npz (tools/make_golden.py): FK, state and edge verdicts, sweep stream."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "validity_golden.npz"))
+    assert str(G["model_fingerprint"]) == pm.model_fingerprint()
+    q, qb = G["q"], G["qb"]
+    n = len(q)
+    pv.set_scene(sc.goal1_scattered())
+    pose = pv.fk(_dev(q)).cpu().numpy()
+    assert np.abs(pose[:, :, :3] - G["fk_p"]).max() < 2e-6
+    assert np.abs(pose[:, :, 3:].reshape(n, 11, 3, 3) - G["fk_R"]).max() < 2e-6
+    for name in SCENES:
+        pv.set_scene(sc.FIXTURES[name]())
+        for att, flags, key in ((-1, (True, False), "margin"), (2, (True, False), "margin_attached2"),
+                                (-1, (False, False), "margin_noself")):
+            pv.set_attached(att)
+            pv.set_flags(*flags)
+            gpu = unpack_bits(pv.check_states(_dev(q)), n)
+            _assert_verdicts(gpu, G[f"{name}/{key}"], f"golden {name}/{key}")
+        pv.set_attached(-1)
+        pv.set_flags(True, False)
+        k = 256
+        for steps, key in ((64, "edge64"), (0, "edge_res")):
+            gpu = unpack_bits(pv.check_edges(_dev(q[:k]), _dev(qb[:k]), n_steps=steps), k)
+            _assert_verdicts(gpu, G[f"{name}/{key}"], f"golden {name}/{key}")
+            m = pv.edge_margins(_dev(q[:k]), _dev(qb[:k]), n_steps=steps).cpu().numpy()
+            assert np.abs(m - G[f"{name}/{key}"]).max() < 2e-5
+    _, _, qd = pv.sweep(64, 512, 20251212, fingers_open=False, want_configs=True)
+    assert np.array_equal(qd.cpu().numpy().view(np.uint32), G["sweep_q"].view(np.uint32))

@@ -166,3 +166,19 @@ def test_device_rrtc_follows_the_oracle_planner(pv, c32):
             solved_both += 1
     assert same >= int(0.97 * nq), f"only {same}/{nq} searches identical to the oracle planner"
     assert solved_both >= int(0.9 * nq)
+
+
+def test_validate_trajectory(pv):
+    scene, franka, blocks = create_scene("goal3_tower")
+    franka.set_qpos(pm.Q_SAFE_HOME)
+    planner = PlannerInterface(franka, scene, validity=pv)
+    goal = np.array(GOALS["goal3_tower"]["approach_top"]["q"])
+    path = planner.plan_path(qpos_goal=goal, num_waypoints=60, timeout=10.0)
+    ok = planner.validate_trajectory(path)
+    assert ok.shape == (59,) and ok.all()
+    # an un-planned joint-space lerp straight through the tower is caught
+    through = np.array(GOALS["goal3_tower"]["approach_top"]["q"])
+    low = through.copy()
+    low[1] += 0.6   # shoulder forward: the hand sweeps down into the tower
+    lerp = [through + t * (low - through) for t in np.linspace(0, 1, 20)]
+    assert not planner.validate_trajectory(lerp).all()
