@@ -29,7 +29,7 @@ struct RrtcArgs {
     const float* goals;   // [nq][9]
     int n_queries;
     float range, resolution;
-    int max_iters, max_nodes, max_path, replicas, shortcut_passes;
+    int max_iters, max_nodes, max_path, replicas, shortcut_passes, check_endpoints;
     unsigned seed;
     float* tree_q;      // [search][2][9][max_nodes]
     int* parent;        // [search][2][max_nodes]
@@ -108,6 +108,30 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
         par[M] = -1;
     }
     __syncwarp();
+
+    if (A.check_endpoints) {
+        // OMPL drops out-of-bounds / invalid start and goal states at intake (planning.py:163-187): lane 0 judges
+        // the start, the other lanes the goal
+        const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
+        float qe[9];
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            qe[k] = (lane == 0) ? A.starts[query * 9 + k] : A.goals[query * 9 + k];
+            bad |= (qe[k] < lo[k]) || (qe[k] > hi[k]);
+        }
+        PvAcc<PV_MODE_BITS> acc0;
+        pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE>(qe, S, acc0);
+        bad |= acc0.hit;
+        const int code = (__shfl_sync(FULL, bad ? 1 : 0, 0) ? 1 : 0) | (__shfl_sync(FULL, bad ? 1 : 0, 1) ? 2 : 0);
+        if (code) {
+            if (lane == 0 && search % A.replicas == 0) {
+                A.iters_out[query] = -code;
+                A.path_len[query] = 0;
+            }
+            return;
+        }
+    }
 
     int size0 = 1, size1 = 1;  // tree sizes (warp-uniform)
     int cur = 0;               // tree grown by EXTEND in this iteration (0 = start tree)
@@ -334,6 +358,7 @@ extern "C" int pv_rrtc_batch(PvHandle* h, const float* h_starts, const float* h_
     a.max_path = params->max_path >= 2 ? params->max_path : 128;
     a.replicas = params->replicas >= 1 ? params->replicas : 1;
     a.shortcut_passes = params->shortcut_passes >= 0 ? params->shortcut_passes : 0;
+    a.check_endpoints = params->check_endpoints ? 1 : 0;
     a.seed = params->seed;
     const size_t n_search = (size_t)n_queries * a.replicas;
 

@@ -193,28 +193,28 @@ class PlannerInterface:
             logger.warning("OMPL goal state out of bounds")
             self.diagnose_bounds_violation(qpos_goal, lower, upper)
         sg = np.stack([qpos_start, qpos_goal]).astype(np.float32)
-        w = self.validity.check_states_host(sg)
-        start_valid, goal_valid = bool(w[0] & 1), bool(w[0] & 2)
-        if not start_valid:
-            logger.warning("OMPL start state invalid")
-            self.diagnose_valid_violation(qpos_start)
-        if not goal_valid:
-            logger.warning("OMPL goal state invalid")
-            self.diagnose_valid_violation(qpos_goal)
-
         waypoints: List[torch.Tensor] = []
         stats = {"solved": False, "iters": 0, "state_checks": 0, "attempts": 0, "n_obb": snap.n_obb}
-        # OMPL drops out-of-bounds / invalid starts and goals at intake -> "no solution" 
-        if start_in and goal_in and start_valid and goal_valid:
+        # Validity of start and goal (planning.py:175-183) is judged inside the solve kernel; OMPL drops
+        # out-of-bounds / invalid starts and goals at intake -> "no solution" 
+        if start_in and goal_in:
             path = None
             attempt = 0
             while path is None:
                 paths, plen, iters, checks = self.validity.rrtc_batch(
                     sg[0:1], sg[1:2], max_iters=2000, max_nodes=2048, max_path=256,
                     seed=self.rng_seed + 7919 * attempt, replicas=self.replicas,
-                    shortcut_passes=2 if smooth_path else 0)
+                    shortcut_passes=2 if smooth_path else 0, check_endpoints=True)
                 attempt += 1
                 stats["attempts"] = attempt
+                if iters[0] < 0:
+                    if (-iters[0]) & 1:
+                        logger.warning("OMPL start state invalid")
+                        self.diagnose_valid_violation(qpos_start)
+                    if (-iters[0]) & 2:
+                        logger.warning("OMPL goal state invalid")
+                        self.diagnose_valid_violation(qpos_goal)
+                    break
                 stats["iters"] += int(iters[0])
                 stats["state_checks"] += int(checks[0])
                 if plen[0] > 0:

@@ -202,13 +202,23 @@ def snapshot_from_sim(scene: Any, robot: Any) -> SceneSnapshot:
     for k, ent in enumerate(getattr(scene, "entities", [])):
         if ent is raw or ent is robot:
             continue
-        morph = getattr(ent, "morph", None)
-        size = getattr(morph, "size", None)
+        size = getattr(getattr(ent, "morph", None), "size", None)
         if size is None:
             continue
-        pos = _to_np(ent.get_pos())[:3]
-        quat = _to_np(ent.get_quat())[:4] if hasattr(ent, "get_quat") else np.array([1.0, 0, 0, 0])
-        recs.append(make_obb(pos, _to_np(size)[:3], quat_wxyz_to_mat(quat)))
+        # plain-float arithmetic: this runs once per plan_path and numpy calls on 3-4 element arrays dominate otherwise
+        px, py, pz = (float(v) for v in _to_np(ent.get_pos())[:3])
+        if hasattr(ent, "get_quat"):
+            w, x, y, z = (float(v) for v in _to_np(ent.get_quat())[:4])
+            nq = math.sqrt(w * w + x * x + y * y + z * z)
+            w, x, y, z = w / nq, x / nq, y / nq, z / nq
+        else:
+            w, x, y, z = 1.0, 0.0, 0.0, 0.0
+        hx, hy, hz = (0.5 * float(v) for v in size[:3])
+        recs.append((px, py, pz, hx, hy, hz,
+                     1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                     2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                     2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y),
+                     math.sqrt(hx * hx + hy * hy + hz * hz)))
         names.append(str(getattr(ent, "name", f"entity{k}")))
         idxs.append(int(getattr(ent, "idx", k)))
     if len(recs) > PV_MAX_OBB:
@@ -216,7 +226,7 @@ def snapshot_from_sim(scene: Any, robot: Any) -> SceneSnapshot:
     base = pm.BASE_LIFT
     if hasattr(raw, "get_pos"):
         try:
-            base = tuple(_to_np(raw.get_pos())[:3])
+            base = tuple(float(v) for v in _to_np(raw.get_pos())[:3])
         except Exception:
             base = pm.BASE_LIFT
     obb = np.array(recs, dtype=np.float32).reshape(len(recs), 16)

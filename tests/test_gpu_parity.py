@@ -251,3 +251,65 @@ def test_cuda_reproduces_committed_golden_vectors(pv):
             assert np.abs(m - G[f"{name}/{key}"]).max() < 2e-5
     _, _, qd = pv.sweep(64, 512, 20251212, fingers_open=False, want_configs=True)
     assert np.array_equal(qd.cpu().numpy().view(np.uint32), G["sweep_q"].view(np.uint32))
+
+
+def _random_rotation(rng):
+    q = rng.normal(size=4)
+    return sc.quat_wxyz_to_mat(q / np.linalg.norm(q))
+
+
+def test_general_obbs_max_scene(pv, c64):
+    """32 boxes (PV_MAX_OBB) of assorted sizes with arbitrary 3-D rotations (toppled blocks): exercises the general
+    sphere-vs-OBB path and the 15-axis SAT that the yaw-only fixtures never reach."""
+    rng = np.random.default_rng(99)
+    recs = []
+    for k in range(32):
+        center = [rng.uniform(0.25, 0.75), rng.uniform(-0.5, 0.5), rng.uniform(0.03, 0.6)]
+        size = rng.uniform(0.03, 0.12, size=3)
+        R = _random_rotation(rng) if k % 4 else sc.yaw_mat(rng.uniform(-180, 180))
+        recs.append(sc.make_obb(center, size, R))
+    snap = sc.SceneSnapshot(obb=np.array(recs, dtype=np.float32), names=[f"x{k}" for k in range(32)],
+                            entity_idx=list(range(1, 33)))
+    pv.set_scene(snap)
+    pv.set_flags(True, False)
+    n = 150_000
+    q = random_configs(n, 2024, fingers="random")
+    for att in (-1, 5):
+        pv.set_attached(att)
+        margin = c64.state_margin(q.astype(np.float64), snap.as_oracle_scene(), attached=att)
+        for mode in (1, 0):
+            pv.set_culling(mode)
+            gpu = unpack_bits(pv.check_states(_dev(q)), n)
+            _assert_verdicts(gpu, margin, f"general obbs att={att} mode={mode}")
+        pv.set_culling(1)
+        assert 0.05 < (margin >= 0).mean() < 0.9
+    pv.set_attached(-1)
+    m = pv.state_margins(_dev(q[:20000])).cpu().numpy()
+    ref = c64.state_margin(q[:20000].astype(np.float64), snap.as_oracle_scene())
+    assert np.abs(m - ref).max() < 2e-5
+    qb = np.clip(q[:4000] + 0.15, pm.Q_LOWER, pm.Q_UPPER).astype(np.float32)
+    ge = unpack_bits(pv.check_edges(_dev(q[:4000]), _dev(qb), n_steps=0), 4000)
+    _assert_verdicts(ge, c64.edge_margin(q[:4000].astype(np.float64), qb.astype(np.float64), snap.as_oracle_scene(), n_steps=0),
+                     "general obbs edges")
+
+
+def test_order_and_batch_size_invariance(pv):
+    """A verdict depends on its configuration only: permuting the batch permutes the bits; splitting the batch at
+    arbitrary (unaligned) points changes nothing; empty scene = self / table rule only."""
+    pv.set_scene(sc.goal4_task1_pentagon())
+    n = 50_001
+    q = random_configs(n, 7, fingers="random")
+    base = unpack_bits(pv.check_states(_dev(q)), n)
+    perm = np.random.default_rng(1).permutation(n)
+    assert np.array_equal(unpack_bits(pv.check_states(_dev(q[perm])), n), base[perm])
+    cuts = [0, 1, 33, 1000, 31_999, n]
+    parts = [unpack_bits(pv.check_states(_dev(q[a:b])), b - a) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(np.concatenate(parts), base)
+    assert np.array_equal(unpack_bits(pv.check_states_host(q), n), base)
+    # single-state calls agree with the batch
+    for i in (0, 17, 4242):
+        assert pv.is_state_valid(q[i]) == bool(base[i])
+    empty = sc.SceneSnapshot(obb=np.zeros((0, 16), np.float32))
+    pv.set_scene(empty)
+    e = unpack_bits(pv.check_states(_dev(q)), n)
+    assert (e | ~base).all()  # removing obstacles can only turn invalid states valid
