@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-plan", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true", help="N>1: gather verdict words with NCCL instead of the fused peer-memory path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -181,7 +182,25 @@ def main():
     gathered = [torch.empty(words * world, dtype=torch.int32, device="cuda") for _ in range(2)] if world > 1 else None
     pending = [None, None]
 
+    # N > 1: the verdict words of every step are gathered on every rank.  Preferred: fused into the validity kernel
+    # over NVLink peer memory / NVSwitch multicast (FusedVerdictGather); fallback: NCCL all-gather, double-buffered.
+    fused = None
+    gather_mode = "none"
+    if world > 1 and not args.nccl_gather:
+        try:
+            from rbe550_final_project_b200.distributed import FusedVerdictGather
+            fused = FusedVerdictGather(pv, words)
+            gather_mode = "fused_peer_stores_multicast" if fused.multicast else "fused_peer_stores"
+        except Exception as exc:  # symmetric memory not available: keep going with NCCL
+            print(f"[bench] fused gather unavailable ({exc!r}); using NCCL all-gather", file=sys.stderr)
+            fused = None
+    if world > 1 and fused is None:
+        gather_mode = "nccl_allgather_overlapped"
+
     def step(i):
+        if fused is not None:
+            pv.check_states(planes[i % N_ROT], out=bits2[i & 1])  # the kernel also stores the words on every rank
+            return
         # double-buffered: the NCCL all-gather of step i's verdict words overlaps step i+1's kernel
         k = i & 1
         if pending[k] is not None:
@@ -192,6 +211,9 @@ def main():
             pending[k] = dist.all_gather_into_tensor(gathered[k], bits2[k], async_op=True)
 
     def drain():
+        if fused is not None:
+            fused.finish()  # symmetric-memory barrier: every rank's words of every issued step have landed
+            return
         for k in range(2):
             if pending[k] is not None:
                 pending[k].wait()
@@ -217,6 +239,11 @@ def main():
     drain()
     e1.record()
     barrier()
+    if fused is not None:
+        # the gathered mask on this rank holds this rank's own last-step words in its slot (the other slots are
+        # checked against an NCCL gather by tools/multi_gpu_sweep.py)
+        assert torch.equal(fused.buf[rank * words:(rank + 1) * words], bits2[(args.steps - 1) & 1]), \
+            "fused gather: own slot differs from the local verdict words"
     launches = pv.launch_count - launches0
     ms = e0.elapsed_time(e1)
     clocks_in_region = len(sampler.samples)
@@ -256,6 +283,8 @@ def main():
     e2e_value = world * n * e2e_steps / e2e_s
     assert np.array_equal(out_np, pv.check_states(planes[(e2e_steps - 1) % 4]).cpu().numpy().view(np.uint32))
 
+    if fused is not None:
+        fused.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -324,7 +353,7 @@ def main():
         "config": {"workload": f"{n} random Panda configs per GPU per step, state validity vs {SCENE} scene "
                                f"({snap.n_obb} OBBs + table, self-collision on)", "scene": SCENE, "configs_per_step": n * world,
                    "l2": f"inputs rotate over {N_ROT} distinct batches ({N_ROT * n * 32 >> 20} MiB > L2)",
-                   "layout": "SoA float4 x2", "parallelism": f"shard{world}" + ("+nccl_allgather_bits" if world > 1 else "")},
+                   "layout": "SoA float4 x2", "parallelism": f"shard{world}" + (f"+{gather_mode}" if world > 1 else "")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 36, "d2h_bytes_per_step": words * 4,
                 "steps": e2e_steps, "call": "pv_check_states_host (pinned AoS rows in, verdict bits out)"},

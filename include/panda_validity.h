@@ -65,6 +65,14 @@ int pv_set_scene(PvHandle *h, const float *h_obb, int n_obb, float table_z, cons
 int pv_set_attached(PvHandle *h, int obb_index);
 int pv_set_flags(PvHandle *h, unsigned flags);
 
+/* Fused verdict gather for multi-GPU runs: after this call pv_check_states and pv_sweep also store
+ * every verdict word w of this rank at word (word_offset + w) of EVERY rank's gather buffer, from inside the
+ * kernel, over peer memory: d_peer_ptrs is a device array of n_peers buffer base pointers (symmetric memory, one per
+ * rank, this rank included); d_multicast, if not NULL, is the NVSwitch multicast address of the same buffer and is
+ * used instead (one store, replicated by the switch).  The caller synchronises the ranks (e.g. the symmetric-memory
+ * barrier) before reading.  n_peers = 0 switches the gather off.  d_bits of those calls may then be NULL. */
+int pv_set_gather(PvHandle *h, const void *d_peer_ptrs, int n_peers, void *d_multicast, long long word_offset);
+
 /* robot.set_qpos(q) -> link poses (planning.py:210; Genesis FK).  d_pose_out is [n][11][12]:
  * per link position xyz then rotation row-major. */
 int pv_fk(PvHandle *h, const float *d_qA, const float *d_qB, const float *d_q9, int64_t n,

@@ -9,6 +9,15 @@
 #define PV_N_STREAMS 3
 #define PV_HOST_CHUNK (1 << 18)  // configs per pipelined chunk of the host-buffer entry points
 
+// Fused verdict gather: where each rank's verdict words also go (peer memory over NVLink / NVSwitch multicast).
+struct PvGather {
+    uint32_t* const* peers;  // device array of n_peers buffer base pointers (one per rank, symmetric memory), or null
+    uint32_t* mc;            // multicast address of the same buffer (NVLS): one store reaches every rank, or null
+    int n_peers;
+    int pad_;
+    long long word_off;      // this rank's first word inside every peer's buffer
+};
+
 struct PvHandle {
     uint32_t magic;
     int device;
@@ -17,6 +26,7 @@ struct PvHandle {
     int cull;
     long long launches;
     PvScene scene;
+    PvGather gather;
     cudaStream_t streams[PV_N_STREAMS];
     float* stage_q[PV_N_STREAMS];
     float* stage_q2[PV_N_STREAMS];

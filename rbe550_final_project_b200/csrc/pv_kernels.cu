@@ -34,6 +34,20 @@ static char g_create_error[512] = "";
 // kernels
 // =========================================================================================================
 
+// Epilogue shared by the verdict-producing kernels: one word per warp to the local buffer and, when a gather is
+// configured, straight into every rank's gather buffer -- through the NVSwitch multicast address when there is one
+// (a single store, replicated by the switch), else one peer store per rank issued by lanes 0..n_peers-1.  This fuses
+// the verdict all-gather into the kernel that produces the verdicts: no collective launch, no SMs taken from the
+// compute kernel.  Visibility on the peers is guaranteed at kernel completion + the symmetric-memory barrier.
+__device__ __forceinline__ void pv_emit_word(uint32_t* __restrict__ bits, const PvGather& G, int64_t w, unsigned word, int lane) {
+    if (lane == 0 && bits) bits[w] = word;
+    if (G.mc) {
+        if (lane == 0) asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(G.mc + G.word_off + w), "r"(word) : "memory");
+    } else if (G.peers) {
+        if (lane < G.n_peers) G.peers[lane][G.word_off + w] = word;
+    }
+}
+
 // K2: one thread per configuration, warp-ballot bit packing.  Persistent blocks; the warps of a block walk the
 // verdict words in lockstep (block barriers inside pv_check_config) so they share instruction fetches.
 #ifndef PV_SB_THREADS
@@ -49,7 +63,8 @@ template <bool AOS, bool CULL>
 __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     pv_state_bits_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA,
                          const float4* __restrict__ qB, const float* __restrict__ q9,
-                         const float* __restrict__ q_aos, int64_t n, uint32_t* __restrict__ bits) {
+                         const float* __restrict__ q_aos, int64_t n, uint32_t* __restrict__ bits,
+                         const __grid_constant__ PvGather G) {
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
@@ -67,7 +82,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         PvAcc<PV_MODE_BITS> acc;
         pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, PV_SB_SYNC>(q, S, acc);
         const unsigned word = __ballot_sync(0xffffffffu, in && !acc.hit);
-        if (lane == 0 && w < n_words) bits[w] = word;
+        if (w < n_words) pv_emit_word(bits, G, w, word, lane);
     }
 }
 
@@ -112,7 +127,7 @@ template <bool CULL>
 __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     pv_sweep_kernel(const __grid_constant__ PvScene S, uint64_t first, int64_t n, unsigned seed, int fingers_open,
                     uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid,
-                    float* __restrict__ q_out) {
+                    float* __restrict__ q_out, const __grid_constant__ PvGather G) {
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
@@ -132,9 +147,9 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         PvAcc<PV_MODE_BITS> acc;
         pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, 0>(q, S, acc);
         const unsigned word = __ballot_sync(0xffffffffu, in && !acc.hit);
-        if (lane == 0 && w < n_words) {
-            bits[w] = word;
-            count += __popc(word);
+        if (w < n_words) {
+            pv_emit_word(bits, G, w, word, lane);
+            if (lane == 0) count += __popc(word);
         }
     }
     if (n_valid && lane == 0 && count) atomicAdd(n_valid, count);
@@ -333,6 +348,22 @@ int pv_set_attached(PvHandle* h, int obb_index) {
     return PV_OK;
 }
 
+int pv_set_gather(PvHandle* h, const void* d_peer_ptrs, int n_peers, void* d_multicast, long long word_offset) {
+    if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
+    if (n_peers < 0 || n_peers > 32 || word_offset < 0 || (n_peers > 0 && !d_peer_ptrs && !d_multicast)) {
+        snprintf(h->err, sizeof(h->err), "pv_set_gather: bad arguments");
+        return PV_ERR_BAD_ARG;
+    }
+    memset(&h->gather, 0, sizeof(h->gather));
+    if (n_peers > 0) {
+        h->gather.peers = (uint32_t* const*)d_peer_ptrs;
+        h->gather.mc = (uint32_t*)d_multicast;
+        h->gather.n_peers = n_peers;
+        h->gather.word_off = word_offset;
+    }
+    return PV_OK;
+}
+
 int pv_set_flags(PvHandle* h, unsigned flags) {
     if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
     h->scene.flags = flags & (PV_FLAG_SELF | PV_FLAG_LIMITS);
@@ -381,7 +412,8 @@ static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_q
     {                                                                                                         \
         int grid = pv_grid_for(h, (const void*)pv_state_bits_kernel<AOS, CULL>, PV_SB_THREADS, words);        \
         pv_state_bits_kernel<AOS, CULL><<<grid, PV_SB_THREADS, 0, st>>>(h->scene, (const float4*)d_qA,        \
-                                                                     (const float4*)d_qB, d_q9, d_aos, n, d_bits); \
+                                                                     (const float4*)d_qB, d_q9, d_aos, n, d_bits, \
+                                                                        d_aos ? PvGather{} : h->gather); \
     }
     if (d_aos) {
         if (h->cull) PV_LAUNCH_SB(true, true) else PV_LAUNCH_SB(true, false)
@@ -490,7 +522,7 @@ int pv_sweep(PvHandle* h, uint64_t first, int64_t n, uint32_t seed, int fingers_
     const int64_t words = (n + 31) / 32;
     {
         int grid = pv_grid_for(h, (const void*)pv_sweep_kernel<true>, PV_SB_THREADS, words);
-        pv_sweep_kernel<true><<<grid, PV_SB_THREADS, 0, st>>>(h->scene, first, n, seed, fingers_open, d_bits, d_n_valid, d_q_out);
+        pv_sweep_kernel<true><<<grid, PV_SB_THREADS, 0, st>>>(h->scene, first, n, seed, fingers_open, d_bits, d_n_valid, d_q_out, h->gather);
     }
     h->launches++;
     PV_CUDA(h, cudaGetLastError());

@@ -64,6 +64,20 @@ def sweep_sharded(pv, n_total: int, seed: int, fingers_open: bool = True, group=
     return full, n_valid
 
 
+def sweep_sharded_fused(pv, gather: "FusedVerdictGather", n_total: int, seed: int, fingers_open: bool = True):
+    """Same result as sweep_sharded, but the verdict words travel inside the sweep kernel (peer / multicast stores)
+    and the only synchronisation is the symmetric-memory barrier.  `gather` must have words_per_rank =
+    words_per_shard(n_total, world)."""
+    first, count = shard_range(n_total, gather.rank, gather.world)
+    n_valid = torch.zeros(1, dtype=torch.int64, device=pv.device)
+    if count > 0:
+        _, n_valid = pv.sweep(first, count, seed, fingers_open=fingers_open)
+    full = gather.finish()[: (n_total + 31) // 32]
+    if gather.world > 1:
+        dist.all_reduce(n_valid, op=dist.ReduceOp.SUM, group=gather.group)
+    return full, n_valid
+
+
 def merge_nn_candidates(local_d2: torch.Tensor, local_idx: torch.Tensor, group=None):
     """Nearest-tree-node search over a tree sharded across ranks: each rank contributes, per query, the best
     (squared distance, local node index) of its shard; returns (best_d2, owner_rank, owner_local_idx) per query.
@@ -81,3 +95,39 @@ def merge_nn_candidates(local_d2: torch.Tensor, local_idx: torch.Tensor, group=N
     # torch.min returns the first minimal index on CPU and CUDA for exact ties along dim 0 -> lowest rank
     owner = (d_all == best.values[None]).to(torch.int64).argmax(dim=0)
     return best.values, owner, i_all.gather(0, owner[None]).squeeze(0)
+
+
+class FusedVerdictGather:
+    """Verdict all-gather fused into the validity kernels over NVLink peer memory (no collective launch).
+
+    A symmetric-memory buffer of world x words_per_rank int32 words is allocated on every rank
+    (torch.distributed._symmetric_memory, i.e. CUDA VMM handles exchanged once at rendezvous); the handle is told
+    (pv_set_gather) to store each verdict word of this rank into every rank's copy at this rank's slot -- through
+    the NVSwitch multicast mapping when the fabric offers one, else with one peer store per rank.  `finish()` is
+    the only synchronisation: a symmetric-memory barrier after which `self.buf` holds the full mask everywhere.
+    """
+
+    def __init__(self, pv, words_per_rank: int, group=None, use_multicast: bool = True):
+        import torch.distributed._symmetric_memory as symm
+        self.pv = pv
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.words_per_rank = int(words_per_rank)
+        self.buf = symm.empty(self.world * self.words_per_rank, dtype=torch.int32, device=pv.device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.buf.zero_()
+        mc = 0
+        if use_multicast and getattr(self.hdl, "has_multicast_support", False):
+            mc = int(self.hdl.multicast_ptr or 0)
+        self.multicast = bool(mc)
+        pv.set_gather(int(self.hdl.buffer_ptrs_dev), self.world, mc, self.rank * self.words_per_rank)
+        self.hdl.barrier()
+
+    def finish(self) -> torch.Tensor:
+        """All ranks' kernels issued so far have completed and their words are visible: returns the gathered mask."""
+        self.hdl.barrier()
+        return self.buf
+
+    def close(self):
+        self.pv.set_gather(0, 0, 0, 0)

@@ -32,6 +32,28 @@ torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
 if world > 1:
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+# ---- fused variant: verdict words stored into every rank's buffer from inside the sweep kernel ----------------
+fused = None
+if world > 1:
+    try:
+        from rbe550_final_project_b200.distributed import FusedVerdictGather, sweep_sharded_fused, words_per_shard
+        g = FusedVerdictGather(pv, words_per_shard(n_total, world))
+        for _ in range(2):
+            f_full, f_valid = sweep_sharded_fused(pv, g, n_total, seed)
+        dist.barrier(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            f_full, f_valid = sweep_sharded_fused(pv, g, n_total, seed)
+        e1.record(); torch.cuda.synchronize()
+        fms = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
+        dist.all_reduce(fms, op=dist.ReduceOp.MAX)
+        same_t = torch.tensor([int(torch.equal(f_full, full))], device="cuda")
+        dist.all_reduce(same_t, op=dist.ReduceOp.MIN)
+        fused = {"ms": float(fms.item()), "checks_per_s": n_total / (float(fms.item()) * 1e-3), "multicast": g.multicast,
+                 "identical_to_nccl_gather_on_all_ranks": bool(same_t.item()), "n_valid": int(f_valid.item())}
+        g.close()
+    except Exception as exc:
+        fused = {"error": repr(exc)[:300]}
 if rank == 0:
     # invariance: the gathered mask equals what one GPU computes for the same index range
     k = min(n_total, 4_194_304)
@@ -52,6 +74,6 @@ if rank == 0:
                       "n_total": n_total, "n_gpus": world, "ms": float(ms.item()),
                       "checks_per_s": n_total / (float(ms.item()) * 1e-3), "n_valid": total_valid,
                       "count_matches_mask": popc == total_valid, "matches_single_gpu": same, "matches_oracle": ok,
-                      "gather_bytes": int(full.numel() * 4)}))
+                      "gather_bytes": int(full.numel() * 4), "fused_peer_gather": fused}))
 if world > 1:
     dist.destroy_process_group()
