@@ -70,8 +70,10 @@ int pv_set_flags(PvHandle *h, unsigned flags);
  * kernel, over peer memory: d_peer_ptrs is a device array of n_peers buffer base pointers (symmetric memory, one per
  * rank, this rank included); d_multicast, if not NULL, is the NVSwitch multicast address of the same buffer and is
  * used instead (one store, replicated by the switch).  The caller synchronises the ranks (e.g. the symmetric-memory
- * barrier) before reading.  n_peers = 0 switches the gather off.  d_bits of those calls may then be NULL. */
-int pv_set_gather(PvHandle *h, const void *d_peer_ptrs, int n_peers, void *d_multicast, long long word_offset);
+ * barrier) before reading.  Words at or beyond word_capacity (this rank's slot size) are not forwarded.  n_peers = 0
+ * switches the gather off.  d_bits of those calls may then be NULL. */
+int pv_set_gather(PvHandle *h, const void *d_peer_ptrs, int n_peers, void *d_multicast, long long word_offset,
+                  long long word_capacity);
 
 /* robot.set_qpos(q) -> link poses (planning.py:210; Genesis FK).  d_pose_out is [n][11][12]:
  * per link position xyz then rotation row-major. */

@@ -104,7 +104,7 @@ def load() -> C.CDLL:
     lib.pv_set_attached.argtypes = [vp, C.c_int]
     lib.pv_set_flags.argtypes = [vp, C.c_uint]
     lib.pv_set_culling.argtypes = [vp, C.c_int]
-    lib.pv_set_gather.argtypes = [vp, vp, C.c_int, vp, C.c_longlong]
+    lib.pv_set_gather.argtypes = [vp, vp, C.c_int, vp, C.c_longlong, C.c_longlong]
     lib.pv_fk.argtypes = [vp, fp, fp, fp, C.c_int64, fp, vp]
     lib.pv_check_states.argtypes = [vp, fp, fp, fp, C.c_int64, u32p, vp]
     lib.pv_state_margins.argtypes = [vp, fp, fp, fp, C.c_int64, fp, i32p, vp]

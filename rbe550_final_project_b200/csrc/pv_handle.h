@@ -16,6 +16,7 @@ struct PvGather {
     int n_peers;
     int pad_;
     long long word_off;      // this rank's first word inside every peer's buffer
+    long long word_cap;      // words this rank may write there (stores beyond it are dropped)
 };
 
 struct PvHandle {

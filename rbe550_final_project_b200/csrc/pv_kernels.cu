@@ -41,6 +41,7 @@ static char g_create_error[512] = "";
 // compute kernel.  Visibility on the peers is guaranteed at kernel completion + the symmetric-memory barrier.
 __device__ __forceinline__ void pv_emit_word(uint32_t* __restrict__ bits, const PvGather& G, int64_t w, unsigned word, int lane) {
     if (lane == 0 && bits) bits[w] = word;
+    if (w >= G.word_cap) return;
     if (G.mc) {
         if (lane == 0) asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(G.mc + G.word_off + w), "r"(word) : "memory");
     } else if (G.peers) {
@@ -348,9 +349,10 @@ int pv_set_attached(PvHandle* h, int obb_index) {
     return PV_OK;
 }
 
-int pv_set_gather(PvHandle* h, const void* d_peer_ptrs, int n_peers, void* d_multicast, long long word_offset) {
+int pv_set_gather(PvHandle* h, const void* d_peer_ptrs, int n_peers, void* d_multicast, long long word_offset,
+                  long long word_capacity) {
     if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
-    if (n_peers < 0 || n_peers > 32 || word_offset < 0 || (n_peers > 0 && !d_peer_ptrs && !d_multicast)) {
+    if (n_peers < 0 || n_peers > 32 || word_offset < 0 || word_capacity < 0 || (n_peers > 0 && !d_peer_ptrs && !d_multicast)) {
         snprintf(h->err, sizeof(h->err), "pv_set_gather: bad arguments");
         return PV_ERR_BAD_ARG;
     }
@@ -360,6 +362,7 @@ int pv_set_gather(PvHandle* h, const void* d_peer_ptrs, int n_peers, void* d_mul
         h->gather.mc = (uint32_t*)d_multicast;
         h->gather.n_peers = n_peers;
         h->gather.word_off = word_offset;
+        h->gather.word_cap = word_capacity;
     }
     return PV_OK;
 }

@@ -121,7 +121,7 @@ class FusedVerdictGather:
         if use_multicast and getattr(self.hdl, "has_multicast_support", False):
             mc = int(self.hdl.multicast_ptr or 0)
         self.multicast = bool(mc)
-        pv.set_gather(int(self.hdl.buffer_ptrs_dev), self.world, mc, self.rank * self.words_per_rank)
+        pv.set_gather(int(self.hdl.buffer_ptrs_dev), self.world, mc, self.rank * self.words_per_rank, self.words_per_rank)
         self.hdl.barrier()
 
     def finish(self) -> torch.Tensor:
@@ -130,4 +130,4 @@ class FusedVerdictGather:
         return self.buf
 
     def close(self):
-        self.pv.set_gather(0, 0, 0, 0)
+        self.pv.set_gather(0, 0, 0, 0, 0)

@@ -87,10 +87,10 @@ class PandaValidity:
         self.flags = (FLAG_SELF if self_collision else 0) | (FLAG_LIMITS if joint_limits else 0)
         self._ck(self.lib.pv_set_flags(self._h, self.flags), "pv_set_flags")
 
-    def set_gather(self, peer_ptrs_dev: int, n_peers: int, multicast_ptr: int, word_offset: int):
+    def set_gather(self, peer_ptrs_dev: int, n_peers: int, multicast_ptr: int, word_offset: int, word_capacity: int = 0):
         """Fused verdict gather (see pv_set_gather); n_peers = 0 switches it off."""
         self._ck(self.lib.pv_set_gather(self._h, C.c_void_p(peer_ptrs_dev or None), int(n_peers),
-                                        C.c_void_p(multicast_ptr or None), int(word_offset)), "pv_set_gather")
+                                        C.c_void_p(multicast_ptr or None), int(word_offset), int(word_capacity)), "pv_set_gather")
 
     def set_culling(self, mode):
         """State-kernel variant: 0 brute force, 1 per-lane bounding-ball culling (default); bit-identical verdicts."""
