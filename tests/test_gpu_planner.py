@@ -182,3 +182,42 @@ def test_validate_trajectory(pv):
     low[1] += 0.6   # shoulder forward: the hand sweeps down into the tower
     lerp = [through + t * (low - through) for t in np.linspace(0, 1, 20)]
     assert not planner.validate_trajectory(lerp).all()
+
+
+def test_nontrivial_planning_around_a_wall(pv, c64, c32):
+    """A wall between start and goal forces real tree growth (several iterations, multi-segment paths): the device
+    planner must still return oracle-valid paths and follow the CPU planner decision for decision."""
+    wall = sc.make_obb((0.55, 0.0, 0.35), (0.5, 0.04, 0.7))
+    snap = sc.SceneSnapshot(obb=np.array([wall], dtype=np.float32), names=["wall"], entity_idx=[1])
+    pv.set_scene(snap)
+    pv.set_attached(-1)
+    pv.set_flags(True, False)
+    quat = np.array([0.0, 1.0, 0.0, 0.0])
+    q_left, ok1, _ = pv.ik_batch(np.array([[0.5, 0.3, 0.3]]), quat[None], pm.Q_SAFE_HOME, n_seeds=128)
+    q_right, ok2, _ = pv.ik_batch(np.array([[0.5, -0.3, 0.3]]), quat[None], pm.Q_SAFE_HOME, n_seeds=128)
+    assert ok1[0] and ok2[0]
+    # the straight joint-space segment crosses the wall
+    assert not unpack_bits(pv.check_edges_host(q_left, q_right, n_steps=0), 1)[0]
+    nq = 64
+    starts, goals = np.repeat(q_left, nq, axis=0), np.repeat(q_right, nq, axis=0)
+    paths, plen, iters, checks = pv.rrtc_batch(starts, goals, max_iters=2000, max_nodes=2048, max_path=128, seed=21,
+                                               replicas=1, shortcut_passes=2)
+    assert (plen > 0).mean() > 0.95
+    assert np.median(iters[plen > 0]) >= 2 and (plen[plen > 0] >= 3).all()
+    same = 0
+    for k in range(nq):
+        if plen[k] == 0:
+            continue
+        p = paths[k, : plen[k]]
+        _path_ok(pv, c64, snap, p)
+        if k < 24:
+            po_path, it, ch = c32.rrtc(starts[k], goals[k], snap.as_oracle_scene(), seed=21, search=k, max_iters=2000,
+                                       max_nodes=2048, max_path=128, shortcut_passes=2)
+            same += int(len(po_path) == plen[k] and np.array_equal(po_path, p) and it == iters[k])
+    assert same >= 21, f"only {same}/24 searches identical to the CPU planner"
+    # and through the drop-in, with OR-parallel replicas
+    scene, franka, _ = create_scene("goal1_scattered")
+    franka.set_qpos(q_left[0])
+    planner = PlannerInterface(franka, snap, validity=pv)
+    path = planner.plan_path(qpos_goal=q_right[0], num_waypoints=200, timeout=10.0)
+    assert len(path) == 200 and planner.validate_trajectory(path).all()
