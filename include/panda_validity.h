@@ -91,6 +91,12 @@ int pv_check_states(PvHandle *h, const float *d_qA, const float *d_qB, const flo
 int pv_state_margins(PvHandle *h, const float *d_qA, const float *d_qB, const float *d_q9, int64_t n,
                      float *d_margin, int32_t *d_culprit, void *stream);
 
+/* robot.detect_collision() for n states (planning.py:47, 211): every colliding pair, not only the deepest one.
+ * d_codes is [n][32] culprit codes as above, one per distinct (link, other) pair; d_count[n] the number of
+ * distinct pairs found (only the first 32 are stored). */
+int pv_state_contacts(PvHandle *h, const float *d_qA, const float *d_qB, const float *d_q9, int64_t n,
+                      int32_t *d_codes, int32_t *d_count, void *stream);
+
 /* si.checkMotion(a, b) for n edges at once (OMPL DiscreteMotionValidator installed by SimpleSetup,
  * planning.py:151-156).  States q(t) = a + t (b - a), t = k/nd, k = 1..nd (a is assumed valid).
  * n_steps > 0: nd = n_steps for every edge.  n_steps == 0: nd = ceil(|b - a|_2 / resolution). */

@@ -34,16 +34,34 @@ struct PvScene {
     unsigned short reach_mask[PV_MAX_OBB];
 };
 
-enum { PV_MODE_BITS = 0, PV_MODE_MARGIN = 1 };
+enum { PV_MODE_BITS = 0, PV_MODE_MARGIN = 1, PV_MODE_LIST = 2 };
+#define PV_MAX_CONTACTS 32
 enum { PV_EXIT_NONE = 0, PV_EXIT_ALL = 1, PV_EXIT_ANY = 2 };
 
 #define PV_CODE(kind, a, b) (((kind) << 16) | ((a) << 8) | (b))
+// link of arm sphere i (compile-time lookups: the indices at the call sites are literals)
+__device__ constexpr int pv_sphere_link[PV_N_SPHERES] = PV_SPHERE_LINK;
+#define PV_SELF_CODE(a, lb) PV_CODE(3, pv_sphere_link[a], lb)
 
 template <int MODE>
 struct PvAcc;
 template <>
 struct PvAcc<PV_MODE_BITS> {
     bool hit = false;
+};
+// contact list (diagnostics): the codes of every test in penetration, like the pair list detect_collision returns
+template <>
+struct PvAcc<PV_MODE_LIST> {
+    int n = 0;
+    int codes[PV_MAX_CONTACTS];
+    __device__ __forceinline__ void take(float g, int c) {
+        if (g < 0.f) {
+            for (int k = 0; k < n && k < PV_MAX_CONTACTS; ++k)
+                if (codes[k] == c) return;  // one entry per (link, other) pair
+            if (n < PV_MAX_CONTACTS) codes[n] = c;
+            ++n;
+        }
+    }
 };
 template <>
 struct PvAcc<PV_MODE_MARGIN> {
@@ -368,7 +386,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
 
     // ---- self collision ------------------------------------------------------------------------------
     if (S.flags & PV_FLAG_SELF) {
-#define PV_SS(a, b, rr2, rr) pv_sphere_sphere<MODE>(acc, s[a], s[b], rr2, rr, PV_CODE(3, a, b));
+#define PV_SS(a, b, rr2, rr) pv_sphere_sphere<MODE>(acc, s[a], s[b], rr2, rr, PV_SELF_CODE(a, pv_sphere_link[b]));
 #define PV_LP(la, lb, ca, cb, cull2)                         \
     {                                                        \
         float3 d_ = v_sub(s[ca], s[cb]);                     \
@@ -398,7 +416,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
         lr_ = r;                                                        \
         lr2_ = r2;                                                      \
     }
-#define PV_SBH_B(a, k) pv_sphere_box_local<MODE>(acc, loc_, lr_, lr2_, bcl[k], bhl[k], PV_CODE(3, a, 33 + k));
+#define PV_SBH_B(a, k) pv_sphere_box_local<MODE>(acc, loc_, lr_, lr2_, bcl[k], bhl[k], PV_SELF_CODE(a, 8 + k));
 #define PV_LB(la, ca, c0, c1, c2)                                                                       \
     {                                                                                                   \
         float3 d0_ = v_sub(s[ca], bc[0]), d1_ = v_sub(s[ca], bc[1]), d2_ = v_sub(s[ca], bc[2]);         \

@@ -103,6 +103,23 @@ __global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
     }
 }
 
+// diagnostics: every colliding pair of one state (the pair list robot.detect_collision() returns, planning.py:47-57)
+__global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
+    pv_state_contacts_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA,
+                             const float4* __restrict__ qB, const float* __restrict__ q9, int64_t n,
+                             int32_t* __restrict__ codes, int32_t* __restrict__ count) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float q[9];
+        pv_load_soa(qA, qB, q9, i, q);
+        PvAcc<PV_MODE_LIST> acc;
+        pv_check_config<PV_MODE_LIST, false, PV_EXIT_NONE>(q, S, acc);
+        count[i] = acc.n;
+        for (int k = 0; k < PV_MAX_CONTACTS; ++k)
+            codes[i * PV_MAX_CONTACTS + k] = (k < acc.n && k < PV_MAX_CONTACTS) ? acc.codes[k] : 0;
+    }
+}
+
 // K1: forward kinematics only; [n][11][12] = position then row-major rotation per link.
 __global__ void __launch_bounds__(128)
     pv_fk_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA, const float4* __restrict__ qB,
@@ -403,6 +420,18 @@ int pv_fk(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9, 
     if (blocks > (int64_t)h->sm_count * 16) blocks = (int64_t)h->sm_count * 16;
     pv_fk_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(h->scene, (const float4*)d_qA, (const float4*)d_qB,
                                                                     d_q9, n, d_pose_out);
+    h->launches++;
+    PV_CUDA(h, cudaGetLastError());
+    return PV_OK;
+}
+
+int pv_state_contacts(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9, int64_t n,
+                      int32_t* d_codes, int32_t* d_count, void* stream) {
+    PV_PRECHECK(h, n);
+    if (!d_qA || !d_qB || !d_codes || !d_count) return PV_ERR_BAD_ARG;
+    int grid = pv_grid_for(h, (const void*)pv_state_contacts_kernel, PV_THREADS, (n + 31) / 32);
+    pv_state_contacts_kernel<<<grid, PV_THREADS, 0, (cudaStream_t)stream>>>(h->scene, (const float4*)d_qA, (const float4*)d_qB,
+                                                                            d_q9, n, d_codes, d_count);
     h->launches++;
     PV_CUDA(h, cudaGetLastError());
     return PV_OK;

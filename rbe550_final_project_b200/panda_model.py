@@ -367,6 +367,7 @@ def header_text() -> str:
     a("// link0 is fixed and tested exactly) and of the 3 gripper boxes")
     a("#define PV_LINK_REACH {" + ", ".join(_f(v) for v in lr) + "}")
     a("#define PV_BOX_REACH {" + ", ".join(_f(v) for v in br_) + "}")
+    a("#define PV_SPHERE_LINK {" + ", ".join(str(int(v)) for v in SPHERE_LINK) + "}")
     a("// joint limits")
     a("#define PV_Q_LOWER {" + ", ".join(_f(v) for v in Q_LOWER) + "}")
     a("#define PV_Q_UPPER {" + ", ".join(_f(v) for v in Q_UPPER) + "}")

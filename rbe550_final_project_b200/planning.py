@@ -109,7 +109,11 @@ class PlannerInterface:
         q = np.array([float(state[i]) for i in range(pm.N_Q)], dtype=np.float32)
         m, cu = self.validity.state_margins(torch.as_tensor(q[None], device=self.validity.device), want_culprit=True)
         culprit = decode_culprit(int(cu[0].item()))
-        logger.warning(f"State causes collisions: {culprit} (clearance {float(m[0].item()):.4f} m)")
+        pairs = self.validity.contacts(torch.as_tensor(q[None], device=self.validity.device))[0]
+        bad_links = sorted({name for pair in pairs for name in pair})
+        # planning.py:49-57 prints the link names of every contact pair
+        logger.warning(f"State causes collisions between links: {bad_links}; deepest: {culprit} "
+                       f"(clearance {float(m[0].item()):.4f} m)")
         return culprit
 
     # ---- the validity callback (planning.py:209-219) ---------------------------------------------------------

@@ -131,6 +131,23 @@ class PandaValidity:
                                            self._stream(stream)), "pv_state_margins")
         return (m, cu) if want_culprit else m
 
+    def contacts(self, q, stream=None):
+        """detect_collision-like report: for each state the set of colliding (link, other) name pairs, where other
+        is a robot link, 'ground' or 'box<k>' (scene box index)."""
+        A, B, q9, n = self._planes(q)
+        codes = torch.empty((n, 32), dtype=torch.int32, device=self.device)
+        count = torch.empty(n, dtype=torch.int32, device=self.device)
+        self._ck(self.lib.pv_state_contacts(self._h, A.data_ptr(), B.data_ptr(), q9.data_ptr() if q9 is not None else None,
+                                            n, codes.data_ptr(), count.data_ptr(), self._stream(stream)), "pv_state_contacts")
+        codes, count = codes.cpu().numpy(), count.cpu().numpy()
+        out = []
+        for i in range(n):
+            pairs = set()
+            for c in codes[i, : min(int(count[i]), 32)]:
+                pairs.add(decode_culprit_pair(int(c)))
+            out.append(pairs)
+        return out
+
     def fk(self, q, stream=None) -> torch.Tensor:
         """(n, 11, 12): per link position xyz then row-major rotation."""
         A, B, q9, n = self._planes(q)
@@ -259,6 +276,20 @@ def unpack_bits(words, n: int) -> np.ndarray:
     return b.reshape(-1)[:n].astype(bool)
 
 
+def decode_culprit_pair(code: int):
+    """(link name, other name) of a culprit code; other is a link name, 'ground', 'box<k>' or 'joint_limit'."""
+    kind, a, b = (code >> 16) & 0xFF, (code >> 8) & 0xFF, code & 0xFF
+    if kind == 1:
+        return (pm.LINK_NAMES[a], "ground")
+    if kind == 2:
+        return (pm.LINK_NAMES[a], f"box{b}")
+    if kind == 3:
+        return (pm.LINK_NAMES[a], pm.LINK_NAMES[b])
+    if kind == 4:
+        return (f"joint{a + 1}", "joint_limit")
+    return ("none", "none")
+
+
 def decode_culprit(code: int) -> str:
     kind, a, b = (code >> 16) & 0xFF, (code >> 8) & 0xFF, code & 0xFF
     if kind == 1:
@@ -266,9 +297,7 @@ def decode_culprit(code: int) -> str:
     if kind == 2:
         return f"{pm.LINK_NAMES[a]} vs scene box {b}"
     if kind == 3:
-        la = pm.LINK_NAMES[int(pm.SPHERE_LINK[a])]
-        lb = pm.LINK_NAMES[int(pm.BOX_LINK[b - 33])] if b >= 33 else pm.LINK_NAMES[int(pm.SPHERE_LINK[b])]
-        return f"{la} vs {lb}"
+        return f"{pm.LINK_NAMES[a]} vs {pm.LINK_NAMES[b]}"
     if kind == 4:
         return f"joint {a + 1} outside its limits"
     return "none"

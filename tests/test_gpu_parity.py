@@ -313,3 +313,24 @@ def test_order_and_batch_size_invariance(pv):
     pv.set_scene(empty)
     e = unpack_bits(pv.check_states(_dev(q)), n)
     assert (e | ~base).all()  # removing obstacles can only turn invalid states valid
+
+
+def test_contact_lists(pv, c64, model):
+    """pv_state_contacts = the pair list detect_collision() gives: empty iff valid, contains the deepest culprit."""
+    scene = sc.goal3_tower()
+    pv.set_scene(scene)
+    pv.set_flags(True, False)
+    q = random_configs(4000, 404, fingers="random")
+    lists = pv.contacts(_dev(q))
+    margin = c64.state_margin(q.astype(np.float64), scene.as_oracle_scene())
+    far = np.abs(margin) > BAND
+    for i in np.nonzero(far)[0]:
+        assert (len(lists[i]) == 0) == (margin[i] >= 0), i
+    m, cu = pv.state_margins(_dev(q), want_culprit=True)
+    from rbe550_final_project_b200.validity import decode_culprit_pair
+    for i in np.nonzero(far & (margin < 0))[0][:300]:
+        assert decode_culprit_pair(int(cu[i].item())) in lists[i]
+    # a pose deep in the table lists ground contacts of several links
+    bad = np.array([[0, 1.7, 0, -0.1, 0, 0.5, 0, 0.04, 0.04]], dtype=np.float32)
+    pairs = pv.contacts(_dev(bad))[0]
+    assert any(o == "ground" for _, o in pairs) and len(pairs) >= 2
