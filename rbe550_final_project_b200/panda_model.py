@@ -419,20 +419,6 @@ def header_text() -> str:
                 rs = float(np.float32(SPHERE_RADIUS[p] + SPHERE_RADIUS[q]))
                 a(f"  X({p}, {q}, {_f(rs * rs)}, {_f(rs)}) \\")
         a("")
-    a("// sphere-vs-gripper-box self pairs grouped by (link, box).  LB(la, k, ca, cull_r2); X(a, k, r^2, r)")
-    a("#define PV_SB_LINKBOX(LB) \\")
-    lbs = sorted({(int(SPHERE_LINK[p]), int(k)) for p, k in SB_PAIRS})
-    for la, k in lbs:
-        rr = g[la][1] + BOX_BOUND_RADIUS[k] + CULL_SLACK
-        a(f"  LB({la}, {k}, {g[la][0]}, {_f(rr * rr)}) \\")
-    a("")
-    for la, k in lbs:
-        a(f"#define PV_SB_PAIRS_{la}_{k}(X) \\")
-        for p, kk in SB_PAIRS:
-            if (int(SPHERE_LINK[p]), int(kk)) == (la, k):
-                r = float(np.float32(SPHERE_RADIUS[p]))
-                a(f"  X({p}, {k}, {_f(r * r)}, {_f(r)}) \\")
-        a("")
     # ---- sphere-vs-gripper self pairs evaluated in the hand frame ---------------------------------------------
     a("// gripper boxes in the HAND frame: X(k, cx, cy0, cz, slide_sign, finger_q_index, hx, hy, hz); the centre's y is")
     a("// cy0 + slide_sign * q[finger_q_index] (hand: sign 0).  All three boxes share the hand's axes.")
