@@ -186,6 +186,8 @@ def state_margin(q, scene, model, attached=-1, self_collision=True, base=(0.0, 0
             take("self", d - (sr[a] + sr[b]))
         for a, k in model["sb_pairs"]:
             take("self", _sphere_obb_margin(wc[:, a], sr[a], bw[:, k], bh[k], bR[:, k]))
+    junk = ~(np.abs(q) <= 1.0e4).all(axis=1)  # non-finite joint values are never valid (NaN compares false)
+    margin = np.where(junk, -1e30, margin)
     if detail:
         return margin, parts
     return margin

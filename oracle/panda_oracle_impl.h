@@ -134,6 +134,8 @@ static REAL FN(state_margin_one)(const FN(po_model) * m, const REAL *obb, int n_
     REAL R[11 * 9], p[11 * 3];
     REAL wc[64 * 3], bw[8 * 3];
     REAL best = (REAL)1e30;
+    for (int j = 0; j < 9; ++j)
+        if (!(fabs((double)q[j]) <= 1.0e4)) return -(REAL)1e30; /* non-finite joint value: never valid */
     if (flags & PO_FLAG_LIMITS)
         for (int j = 0; j < 9; ++j)
             if (q[j] < m->q_lower[j] || q[j] > m->q_upper[j]) return -(REAL)1e30;

@@ -322,6 +322,18 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
         if (EXIT == PV_EXIT_ALL ? __all_sync(FULL, h_) : __any_sync(FULL, h_)) return; \
     }
 
+    {
+        // a non-finite (or absurdly large) joint value can never be a valid state: every later comparison with a
+        // NaN would come out "no contact"
+        bool junk = false;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) junk |= !(fabsf(q[j]) <= 1.0e4f);
+        if constexpr (MODE == PV_MODE_BITS) {
+            acc.hit |= junk;
+        } else {
+            if (junk) acc.take(-1e30f, PV_CODE(4, 0, 1));
+        }
+    }
     if (S.flags & PV_FLAG_LIMITS) {
         const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
 #pragma unroll

@@ -334,3 +334,26 @@ def test_contact_lists(pv, c64, model):
     bad = np.array([[0, 1.7, 0, -0.1, 0, 0.5, 0, 0.04, 0.04]], dtype=np.float32)
     pairs = pv.contacts(_dev(bad))[0]
     assert any(o == "ground" for _, o in pairs) and len(pairs) >= 2
+
+
+def test_non_finite_joint_values_are_invalid(pv, c64):
+    scene = sc.goal1_scattered()
+    pv.set_scene(scene)
+    q = np.tile(pm.Q_SAFE_HOME.astype(np.float32), (64, 1))
+    q[3, 2] = np.nan
+    q[10, 0] = np.inf
+    q[20, 8] = -np.inf
+    q[33, 5] = 1e30
+    gpu = unpack_bits(pv.check_states(_dev(q)), 64)
+    expect = np.ones(64, bool)
+    expect[[3, 10, 20, 33]] = False
+    assert np.array_equal(gpu, expect)
+    with np.errstate(all="ignore"):
+        ref = c64.state_margin(q.astype(np.float64), scene.as_oracle_scene())
+    assert np.array_equal(ref >= 0, expect)
+    m = pv.state_margins(_dev(q)).cpu().numpy()
+    assert (m[[3, 10, 20, 33]] < -1e29).all()
+    qb = q.copy()
+    qb[:, 0] += 0.1
+    ge = unpack_bits(pv.check_edges(_dev(q), _dev(qb), n_steps=8), 64)
+    assert not ge[[3, 10, 20, 33]].any()
