@@ -153,3 +153,28 @@ if 4 in which:
         bad += int((m < -1e-4).any())
     res["oracle_invalid_paths_in_200"] = bad
     print(json.dumps(res))
+
+if 6 in which:
+    # next-row component 8f-2: batched collision-aware IK (not a BASELINE config)
+    snap = sc.goal3_tower()
+    pv.set_scene(snap)
+    rng = np.random.default_rng(6)
+    n = 4096
+    pos = np.stack([rng.uniform(0.3, 0.7, n), rng.uniform(-0.4, 0.4, n), rng.uniform(0.15, 0.6, n)], axis=1)
+    quat = np.tile(np.array([0.0, 1.0, 0.0, 0.0]), (n, 1))
+    res = {"config": "ik", "scene": "goal3_tower", "n_targets": n, "runs": {}}
+    for seeds in (32, 128):
+        pv.ik_batch(pos[:64], quat[:64], pm.Q_SAFE_HOME, n_seeds=seeds)
+        t = time.perf_counter()
+        q, ok, err = pv.ik_batch(pos, quat, pm.Q_SAFE_HOME, n_seeds=seeds, seed=3)
+        dt = time.perf_counter() - t
+        res["runs"][f"seeds_{seeds}"] = {"wall_ms": dt * 1e3, "targets_per_s": n / dt, "solved": float(ok.mean()),
+                                         "pos_err_p95_m": float(np.percentile(err[ok, 0], 95)),
+                                         "rot_err_p95_rad": float(np.percentile(err[ok, 1], 95))}
+    lat = []
+    for k in range(100):
+        t = time.perf_counter()
+        pv.ik_batch(pos[k:k + 1], quat[k:k + 1], pm.Q_SAFE_HOME, n_seeds=128)
+        lat.append((time.perf_counter() - t) * 1e3)
+    res["single_target_ms"] = {"p50": float(np.median(lat)), "p95": float(np.percentile(lat, 95))}
+    print(json.dumps(res))
