@@ -16,6 +16,6 @@ q = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n, 9)).astype(np.float32); q[:, 7:
 A, B, q9 = soa_from_aos(torch.as_tensor(q, device="cuda"))
 out = torch.empty(n // 32, dtype=torch.int32, device="cuda")
 for _ in range(4):
-    pv.check_states((A, B, q9), out=out)
+    pv.check_states((A, B), out=out)  # symmetric gripper: two float4 planes, as in bench.py
 torch.cuda.synchronize()
 print("ok", int(out[0].item()))
