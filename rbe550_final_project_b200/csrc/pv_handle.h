@@ -6,8 +6,12 @@
 #include "pv_device.cuh"
 
 #define PV_HANDLE_MAGIC 0x50564831u
+#ifndef PV_N_STREAMS
 #define PV_N_STREAMS 3
+#endif
+#ifndef PV_HOST_CHUNK
 #define PV_HOST_CHUNK (1 << 18)  // configs per pipelined chunk of the host-buffer entry points
+#endif
 
 // Fused verdict gather: where each rank's verdict words also go (peer memory over NVLink / NVSwitch multicast).
 struct PvGather {
