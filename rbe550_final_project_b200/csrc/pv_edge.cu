@@ -9,12 +9,6 @@
 #include "pv_device.cuh"
 #include "pv_handle.h"
 
-#ifndef PV_THREADS
-#define PV_THREADS 128
-#endif
-#ifndef PV_MIN_BLOCKS
-#define PV_MIN_BLOCKS 3
-#endif
 
 #define PV_CUDA(h, expr)                                                                              \
     do {                                                                                              \

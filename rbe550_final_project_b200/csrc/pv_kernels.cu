@@ -54,6 +54,8 @@ __device__ __forceinline__ void pv_emit_word(uint32_t* __restrict__ bits, const 
 #ifndef PV_SB_THREADS
 #define PV_SB_THREADS 512  // 16 warps in lockstep, 127 registers, no spills (swept 128..1024: profiles/r1_notes.md)
 #endif
+// extra block barriers INSIDE the check (levels 1..3 of pv_check_config's SYNC); 0 = only the one per iteration below,
+// which measured best (profiles/r1_notes.md)
 #ifndef PV_SB_SYNC
 #define PV_SB_SYNC 0
 #endif
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         float q[9];
         if (AOS) pv_load_aos(q_aos, ii, q);
         else pv_load_soa(qA, qB, q9, ii, q);
-        if (PV_SB_SYNC >= 0) __syncthreads();
+        __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
         PvAcc<PV_MODE_BITS> acc;
         pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, PV_SB_SYNC>(q, S, acc);
         const unsigned word = __ballot_sync(0xffffffffu, in && !acc.hit);
