@@ -357,3 +357,14 @@ def test_non_finite_joint_values_are_invalid(pv, c64):
     qb[:, 0] += 0.1
     ge = unpack_bits(pv.check_edges(_dev(q), _dev(qb), n_steps=8), 64)
     assert not ge[[3, 10, 20, 33]].any()
+
+
+def test_edges_host_entry_point_multi_chunk(pv):
+    pv.set_scene(sc.goal1_scattered())
+    n = 600_013  # three pipeline chunks, ragged
+    qa = random_configs(n, 71)
+    qb = np.clip(qa + 0.1, pm.Q_LOWER, pm.Q_UPPER).astype(np.float32)
+    qb[:, 7:] = 0.04
+    d = pv.check_edges(_dev(qa), _dev(qb), n_steps=4).cpu().numpy().view(np.uint32)
+    h = pv.check_edges_host(qa, qb, n_steps=4)
+    assert np.array_equal(d, h)

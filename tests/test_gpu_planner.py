@@ -221,3 +221,47 @@ def test_nontrivial_planning_around_a_wall(pv, c64, c32):
     planner = PlannerInterface(franka, snap, validity=pv)
     path = planner.plan_path(qpos_goal=q_right[0], num_waypoints=200, timeout=10.0)
     assert len(path) == 200 and planner.validate_trajectory(path).all()
+
+
+def test_rrtc_capacity_limits_fail_cleanly(pv):
+    """Exhausted path / node / iteration budgets give 'no solution' (length 0), never garbage."""
+    wall = sc.make_obb((0.55, 0.0, 0.35), (0.5, 0.04, 0.7))
+    snap = sc.SceneSnapshot(obb=np.array([wall], dtype=np.float32), names=["wall"], entity_idx=[1])
+    pv.set_scene(snap)
+    pv.set_attached(-1)
+    quat = np.array([[0.0, 1.0, 0.0, 0.0]])
+    ql, _, _ = pv.ik_batch(np.array([[0.5, 0.3, 0.3]]), quat, pm.Q_SAFE_HOME, n_seeds=100)  # rounded up to 128
+    qr, _, _ = pv.ik_batch(np.array([[0.5, -0.3, 0.3]]), quat, pm.Q_SAFE_HOME, n_seeds=100)
+    starts, goals = np.repeat(ql, 16, axis=0), np.repeat(qr, 16, axis=0)
+    for kw in (dict(max_path=2), dict(max_nodes=8), dict(max_iters=1)):
+        args = dict(max_iters=2000, max_nodes=2048, max_path=128, seed=3, replicas=1, shortcut_passes=2)
+        args.update(kw)
+        paths, plen, iters, checks = pv.rrtc_batch(starts, goals, **args)
+        if "max_nodes" in kw:
+            # tiny trees may still connect; whatever comes back must be a valid path, and some searches must give up
+            assert (plen == 0).any()
+            for k in np.nonzero(plen > 0)[0]:
+                p = paths[k, : plen[k]]
+                assert np.array_equal(p[0], starts[k]) and np.array_equal(p[-1], goals[k])
+                assert unpack_bits(pv.check_edges_host(p[:-1], p[1:], n_steps=0), len(p) - 1).all()
+        else:
+            assert (plen == 0).all(), kw
+    # invalid end points are reported through the iteration count
+    bad = np.array([[0, 1.7, 0, -0.1, 0, 0.5, 0, 0.04, 0.04]], dtype=np.float32)
+    oob = ql.copy()
+    oob[0, 7] = 0.05
+    _, plen, iters, _ = pv.rrtc_batch(np.concatenate([bad, ql, oob]), np.concatenate([qr, bad, qr]), check_endpoints=True)
+    assert list(plen) == [0, 0, 0] and list(iters) == [-1, -2, -1]
+
+
+def test_unknown_attached_entity_forgives_nothing(pv):
+    scene, franka, blocks = create_scene("goal1_scattered")
+    planner = PlannerInterface(franka, scene, validity=pv)
+    planner.refresh_scene()
+
+    class Ghost:
+        idx = 99
+
+    assert planner._attached_index(Ghost()) == -1
+    assert planner._attached_index(None) == -1
+    assert planner._attached_index(blocks["m"]) == 4
