@@ -133,6 +133,46 @@ class PlannerInterface:
         w = self.validity.check_edges_host(np.asarray(qa, np.float32)[None], np.asarray(qb, np.float32)[None], n_steps=0)
         return bool(w[0] & 1)
 
+    def _cut_corners(self, path: np.ndarray, rounds: int = 2) -> np.ndarray:
+        """Second half of `ss.simplifySolution()` (planning.py:196): OMPL's simplifier also shortcuts between points
+        INSIDE segments (partialShortcutPath), not only between vertices as the device kernel does.  Deterministic
+        stand-in: every interior vertex v_k is replaced by the two points at fraction alpha of its adjacent segments
+        when the straight motion between them is valid (largest alpha of 1/2, 1/4 wins); all candidates of a round go
+        through ONE batched edge-validity call, and the result is re-validated as a whole before it is accepted."""
+        path = np.asarray(path, dtype=np.float64)
+        for _ in range(rounds):
+            n = len(path)
+            if n < 3:
+                break
+            alphas = (0.5, 0.25)
+            a_pts, b_pts = [], []
+            for k in range(1, n - 1):
+                for al in alphas:
+                    a_pts.append(path[k] + al * (path[k - 1] - path[k]))
+                    b_pts.append(path[k] + al * (path[k + 1] - path[k]))
+            bits = self.validity.check_edges_host(np.asarray(a_pts, np.float32), np.asarray(b_pts, np.float32), n_steps=0)
+            ok = ((bits[:, None] >> np.arange(32, dtype=np.uint32)) & 1).ravel()[: len(a_pts)].astype(bool)
+            new, changed = [path[0]], False
+            for k in range(1, n - 1):
+                base = (k - 1) * len(alphas)
+                for j in range(len(alphas)):
+                    if ok[base + j]:
+                        new.extend([a_pts[base + j], b_pts[base + j]])
+                        changed = True
+                        break
+                else:
+                    new.append(path[k])
+            new.append(path[-1])
+            if not changed:
+                break
+            cand = np.asarray(new)
+            seg = self.validity.check_edges_host(cand[:-1].astype(np.float32), cand[1:].astype(np.float32), n_steps=0)
+            seg_ok = ((seg[:, None] >> np.arange(32, dtype=np.uint32)) & 1).ravel()[: len(cand) - 1].astype(bool)
+            if not seg_ok.all():
+                break  # keep the last fully validated path
+            path = cand
+        return path
+
     def validate_trajectory(self, waypoints, attached_object=None) -> np.ndarray:
         """Swept validation of an executed joint trajectory (next-row component 8f-4): the reference plays back the
         150 planned waypoints and many un-planned joint-space lerps (motion_primitives.py:163-173, 294-299, 404-409)
@@ -229,6 +269,9 @@ class PlannerInterface:
             if path is not None:
                 logger.info("Path solution found successfully.")
                 path[0], path[-1] = qpos_start, qpos_goal  # exact end points, as OMPL keeps them in fp64
+                if smooth_path and len(path) > 2:
+                    path = self._cut_corners(path)
+                    stats["vertices_after_simplify"] = len(path)
                 if num_waypoints is not None:
                     path = interpolate(path, int(num_waypoints))
                 print("Number of waypoints in path:", len(path))  # planning.py:199

@@ -265,3 +265,33 @@ def test_unknown_attached_entity_forgives_nothing(pv):
     assert planner._attached_index(Ghost()) == -1
     assert planner._attached_index(None) == -1
     assert planner._attached_index(blocks["m"]) == 4
+
+
+def test_corner_cutting_shortens_and_stays_valid(pv, c64):
+    from rbe550_final_project_b200.pathutil import path_length
+    wall = sc.make_obb((0.55, 0.0, 0.35), (0.5, 0.04, 0.7))
+    snap = sc.SceneSnapshot(obb=np.array([wall], dtype=np.float32), names=["wall"], entity_idx=[1])
+    pv.set_scene(snap)
+    pv.set_attached(-1)
+    quat = np.array([[0.0, 1.0, 0.0, 0.0]])
+    ql, _, _ = pv.ik_batch(np.array([[0.5, 0.3, 0.3]]), quat, pm.Q_SAFE_HOME, n_seeds=128)
+    qr, _, _ = pv.ik_batch(np.array([[0.5, -0.3, 0.3]]), quat, pm.Q_SAFE_HOME, n_seeds=128)
+    scene, franka, _ = create_scene("goal1_scattered")
+    franka.set_qpos(ql[0])
+    planner = PlannerInterface(franka, snap, validity=pv)
+    planner.refresh_scene()
+    shorter = 0
+    for seed in range(12):
+        paths, plen, _, _ = pv.rrtc_batch(ql, qr, seed=40 + seed, replicas=1, shortcut_passes=2)
+        assert plen[0] >= 3
+        raw = paths[0, : plen[0]].astype(np.float64)
+        cut = planner._cut_corners(raw)
+        assert np.array_equal(cut[0], raw[0]) and np.array_equal(cut[-1], raw[-1])
+        assert path_length(cut) <= path_length(raw) + 1e-9
+        shorter += path_length(cut) < path_length(raw) - 1e-6
+        _path_ok(pv, c64, snap, cut)
+    assert shorter >= 6
+    # smooth_path=False returns the raw tree path resampled; both variants are valid trajectories
+    for smooth in (True, False):
+        path = planner.plan_path(qpos_goal=qr[0], num_waypoints=120, smooth_path=smooth, timeout=10.0)
+        assert len(path) >= 120 and planner.validate_trajectory(path).all()
