@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         else pv_load_soa(qA, qB, q9, ii, q);
         __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
         PvAcc<PV_MODE_BITS> acc;
-        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, PV_SB_SYNC>(q, S, acc);
+        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, PV_SB_SYNC, true>(q, S, acc);
         const unsigned word = __ballot_sync(0xffffffffu, in && !acc.hit);
         if (w < n_words) pv_emit_word(bits, G, w, word, lane);
     }
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         }
         __syncthreads();  // lockstep: the warps of the block share instruction fetches
         PvAcc<PV_MODE_BITS> acc;
-        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, 0>(q, S, acc);
+        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, 0, true>(q, S, acc);
         const unsigned word = __ballot_sync(0xffffffffu, in && !acc.hit);
         if (w < n_words) {
             pv_emit_word(bits, G, w, word, lane);
