@@ -133,6 +133,7 @@ typedef struct {
     int shortcut_passes; /* deterministic shortcutting passes after the solve (simplifySolution) */
     int check_endpoints; /* != 0: test start and goal first (bounds + validity, planning.py:163-183); a query whose
                             start / goal / both fail returns path length 0 and iters = -1 / -2 / -3 */
+    int planner;         /* 0 = RRTConnect (the reference's default, planning.py:67), 1 = RRT (single tree, 5 % goal bias) */
 } PvRrtcParams;
 
 /* h_starts/h_goals: [n_queries][9] host AoS.  h_path_out: [n_queries][max_path][9]; h_path_len: states

@@ -118,7 +118,7 @@ class COracle:
 
     def rrtc(self, start, goal, scene, seed=1, search=0, max_iters=2000, max_nodes=2048, max_path=128,
              shortcut_passes=2, rrt_range=2.6074318092713376, resolution=0.13037159046356686, attached=-1,
-             flags=FLAG_SELF, base=(0.0, 0.0, 0.01)):
+             flags=FLAG_SELF, base=(0.0, 0.0, 0.01), planner="RRTConnect"):
         """CPU restatement of one device RRT-Connect search (fp32 only).  Returns (path (len, 9), iters, checks)."""
         assert self.np_t is np.float32, "the planner restatement mirrors the device arithmetic: use precision 'f32'"
         s = np.ascontiguousarray(start, dtype=np.float32).reshape(9)
@@ -132,6 +132,7 @@ class COracle:
         n = fn(C.byref(self.model), self._p(obb), C.c_int(obb.shape[0]), C.c_float(scene["table_z"]), self._p(b),
                C.c_int(attached), C.c_int(flags), self._p(s), self._p(g), C.c_float(np.float32(rrt_range)),
                C.c_float(np.float32(resolution)), C.c_int(max_iters), C.c_int(max_nodes), C.c_int(max_path),
-               C.c_uint32(seed & 0xFFFFFFFF), C.c_uint32(search), C.c_int(shortcut_passes), self._p(path),
+               C.c_uint32(seed & 0xFFFFFFFF), C.c_uint32(search), C.c_int(shortcut_passes),
+               C.c_int({"RRTConnect": 0, "RRT": 1}[planner]), self._p(path),
                C.byref(iters), C.byref(checks))
         return path[:n].copy(), iters.value, checks.value

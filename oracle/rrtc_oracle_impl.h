@@ -20,7 +20,7 @@ static void po_philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
     }
 }
 
-static void po_rrtc_sample(const po_model_f32 *m, uint32_t seed, uint32_t search, uint32_t it, float *q) {
+static void po_rrtc_sample(const po_model_f32 *m, uint32_t seed, uint32_t search, uint32_t it, float *q, float *extra) {
     float u[12];
     for (uint32_t blk = 0; blk < 3; ++blk) {
         uint32_t c[4] = {it, search, blk, 1u};
@@ -28,6 +28,7 @@ static void po_rrtc_sample(const po_model_f32 *m, uint32_t seed, uint32_t search
         for (int j = 0; j < 4; ++j) u[4 * blk + j] = (float)(c[j] >> 8) * 5.9604644775390625e-08f;
     }
     for (int j = 0; j < 9; ++j) q[j] = fmaf(u[j], m->q_upper[j] - m->q_lower[j], m->q_lower[j]);
+    *extra = u[9];
 }
 
 typedef struct {
@@ -76,8 +77,8 @@ static int po_rrtc_motion_valid(po_rrtc_ctx *c, const float *a, const float *b) 
 /* returns the path length (0 = no solution); path_out is [max_path][9] */
 int po_rrtc_f32(const po_model_f32 *m, const float *obb, int n_obb, float table_z, const float *base, int attached,
                 int flags, const float *start, const float *goal, float range, float resolution, int max_iters,
-                int max_nodes, int max_path, uint32_t seed, uint32_t search, int shortcut_passes, float *path_out,
-                int *iters_out, long long *checks_out) {
+                int max_nodes, int max_path, uint32_t seed, uint32_t search, int shortcut_passes, int planner,
+                float *path_out, int *iters_out, long long *checks_out) {
     po_rrtc_ctx ctx = {m, obb, n_obb, table_z, base, attached, flags, resolution, 0};
     const int M = max_nodes;
     float *tq = (float *)malloc(sizeof(float) * 2 * 9 * (size_t)M); /* [tree][node][9] */
@@ -91,13 +92,15 @@ int po_rrtc_f32(const po_model_f32 *m, const float *obb, int n_obb, float table_
     float target[9];
     enum { EXTEND, CONNECT } phase = EXTEND;
     for (;;) {
-        float goal_q[9], ea[9], eb[9];
-        int tree;
+        float goal_q[9] = {0}, ea[9], eb[9];
+        int tree, aim_goal = 0;
         if (phase == EXTEND) {
             if (it >= max_iters || size[0] >= M - 1 || size[1] >= M - 1) break;
             tree = cur;
-            if (it == 0) memcpy(goal_q, tq + (size_t)9 * M, sizeof(goal_q));
-            else po_rrtc_sample(m, seed, search, (uint32_t)it, goal_q);
+            float u9 = 1.f;
+            if (it > 0) po_rrtc_sample(m, seed, search, (uint32_t)it, goal_q, &u9);
+            aim_goal = (it == 0) || (planner == 1 && u9 < 0.05f);
+            if (aim_goal) memcpy(goal_q, tq + (size_t)9 * M, sizeof(goal_q));
         } else {
             tree = cur ^ 1;
             memcpy(goal_q, target, sizeof(goal_q));
@@ -132,7 +135,14 @@ int po_rrtc_f32(const po_model_f32 *m, const float *obb, int n_obb, float table_
             memcpy(tq + ((size_t)tree * M + ni) * 9, eb, 9 * sizeof(float));
             par[tree * M + ni] = bi;
             size[tree] = ni + 1;
-            if (phase == EXTEND) {
+            if (phase == EXTEND && planner == 1) {
+                added_idx = ni;
+                if (reach && aim_goal) {
+                    solved = 1;
+                    break;
+                }
+                ++it;
+            } else if (phase == EXTEND) {
                 memcpy(target, eb, sizeof(target));
                 added_idx = ni;
                 phase = CONNECT;
@@ -145,7 +155,7 @@ int po_rrtc_f32(const po_model_f32 *m, const float *obb, int n_obb, float table_
             }
         } else {
             phase = EXTEND;
-            cur ^= 1;
+            if (planner == 0) cur ^= 1;
             ++it;
         }
     }
@@ -153,7 +163,8 @@ int po_rrtc_f32(const po_model_f32 *m, const float *obb, int n_obb, float table_
         const int is = cur == 0 ? added_idx : conn_idx, ig = cur == 0 ? conn_idx : added_idx;
         int ds = 0, dg = 0;
         for (int x = is; x >= 0; x = par[x]) ++ds;
-        for (int x = par[M + ig]; x >= 0; x = par[M + x]) ++dg;
+        if (planner == 0)
+            for (int x = par[M + ig]; x >= 0; x = par[M + x]) ++dg;
         path_n = ds + dg;
         if (path_n > max_path) {
             solved = 0;
@@ -164,7 +175,7 @@ int po_rrtc_f32(const po_model_f32 *m, const float *obb, int n_obb, float table_
                 memcpy(path_out + 9 * k, tq + (size_t)9 * x, 9 * sizeof(float));
                 x = par[x];
             }
-            x = par[M + ig];
+            x = planner == 0 ? par[M + ig] : -1;
             for (int k = 0; k < dg; ++k) {
                 memcpy(path_out + 9 * (ds + k), tq + ((size_t)M + x) * 9, 9 * sizeof(float));
                 x = par[M + x];

@@ -30,6 +30,7 @@ struct RrtcArgs {
     int n_queries;
     float range, resolution;
     int max_iters, max_nodes, max_path, replicas, shortcut_passes, check_endpoints;
+    int planner;  // 0 = RRTConnect (two trees), 1 = RRT (start tree only, 5 % goal bias: og.RRT defaults)
     unsigned seed;
     float* tree_q;      // [search][2][9][max_nodes]
     int* parent;        // [search][2][max_nodes]
@@ -41,7 +42,7 @@ struct RrtcArgs {
     int* winner;        // [nq], -1 until a search of that query finishes
 };
 
-__device__ __forceinline__ void rrtc_sample(unsigned seed, unsigned search, unsigned it, float* q) {
+__device__ __forceinline__ void rrtc_sample(unsigned seed, unsigned search, unsigned it, float* q, float& extra) {
     const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
     float u[12];
     const uint2 key = make_uint2(seed, 0x52525443u);
@@ -55,6 +56,7 @@ __device__ __forceinline__ void rrtc_sample(unsigned seed, unsigned search, unsi
     }
 #pragma unroll
     for (int j = 0; j < 9; ++j) q[j] = __fmaf_rn(u[j], hi[j] - lo[j], lo[j]);
+    extra = u[9];  // a tenth uniform draw of the same counter: goal bias of the single-tree planner
 }
 
 // nearest node of one tree (SoA [9][max_nodes]) to `t`: lanes stride over nodes, warp arg-min (ties -> lowest index)
@@ -154,18 +156,20 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
         }
         float ea[9], eb[9];
         int from_idx = 0, tree = 0;
-        bool reach = true;
+        bool reach = true, aim_goal = false;
         if (phase == PH_EXTEND || phase == PH_CONNECT) {
             float goal_q[9];
             if (phase == PH_EXTEND) {
                 if (it >= A.max_iters || size0 >= M - 1 || size1 >= M - 1) break;
                 tree = cur;
-                if (it == 0) {
-                    // first extension aims at the goal itself (cheap straight-line attempt)
+                float u9 = 1.f;
+                if (it > 0) rrtc_sample(A.seed, (unsigned)search, (unsigned)it, goal_q, u9);
+                // first extension aims at the goal itself (cheap straight-line attempt); the single-tree planner also
+                // does so with OMPL's default goal bias of 5 %
+                aim_goal = (it == 0) || (A.planner == 1 && u9 < 0.05f);
+                if (aim_goal) {
 #pragma unroll
                     for (int k = 0; k < 9; ++k) goal_q[k] = tq[(size_t)(9 + k) * M];
-                } else {
-                    rrtc_sample(A.seed, (unsigned)search, (unsigned)it, goal_q);
                 }
             } else {
                 tree = cur ^ 1;
@@ -192,7 +196,8 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
             int ig = cur == 0 ? conn_idx : added_idx;
             int ds = 0, dg = 0;
             for (int x = is; x >= 0; x = par[x]) ++ds;
-            for (int x = par[M + ig]; x >= 0; x = par[M + x]) ++dg;
+            if (A.planner == 0)
+                for (int x = par[M + ig]; x >= 0; x = par[M + x]) ++dg;
             path_n = ds + dg;
             if (path_n > A.max_path) {
                 solved = false;
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
                 if (lane < 9) path[k * 9 + lane] = tq[(size_t)lane * M + x];
                 x = par[x];
             }
-            x = par[M + ig];
+            x = A.planner == 0 ? par[M + ig] : -1;
             for (int k = 0; k < dg; ++k) {
                 if (lane < 9) path[(ds + k) * 9 + lane] = tq[(size_t)(9 + lane) * M + x];
                 x = par[M + x];
@@ -265,7 +270,12 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
                 if (lane == 0) par[tree * M + ni] = from_idx;
                 __syncwarp();
                 sz = ni + 1;
-                if (phase == PH_EXTEND) {
+                if (phase == PH_EXTEND && A.planner == 1) {
+                    // single tree: done when the goal itself was reached, else next sample
+                    added_idx = ni;
+                    if (reach && aim_goal) phase = PH_EXTRACT;
+                    else ++it;
+                } else if (phase == PH_EXTEND) {
 #pragma unroll
                     for (int k = 0; k < 9; ++k) target[k] = eb[k];
                     added_idx = ni;
@@ -277,9 +287,9 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
                     break;
                 }
             } else {
-                // TRAPPED: next iteration, swap trees
+                // TRAPPED: next iteration (RRTConnect swaps trees every iteration)
                 phase = PH_EXTEND;
-                cur ^= 1;
+                if (A.planner == 0) cur ^= 1;
                 ++it;
             }
         } else {  // PH_SHORTCUT
@@ -359,6 +369,7 @@ extern "C" int pv_rrtc_batch(PvHandle* h, const float* h_starts, const float* h_
     a.replicas = params->replicas >= 1 ? params->replicas : 1;
     a.shortcut_passes = params->shortcut_passes >= 0 ? params->shortcut_passes : 0;
     a.check_endpoints = params->check_endpoints ? 1 : 0;
+    a.planner = params->planner == 1 ? 1 : 0;
     a.seed = params->seed;
     const size_t n_search = (size_t)n_queries * a.replicas;
 

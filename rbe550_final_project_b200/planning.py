@@ -10,8 +10,8 @@ Differences that are deliberate and visible:
   * the simulated robot is never moved during planning (the reference poses it for every state and
     restores it at planning.py:205); `robot.set_qpos(qpos_cur)` is still issued at exit when the robot
     offers it, so callers relying on that side effect see the same final state;
-  * only RRTConnect is implemented on the device; the other seven names of planning.py:108-117 are accepted
-    by the guard and rejected with a clear error instead of being silently mapped;
+  * RRTConnect (the default every caller uses) and RRT run on the device; the other six names of
+    planning.py:108-117 pass the name guard and are then rejected with a clear error instead of being silently mapped;
   * there is no CPU fallback: without the CUDA library / a B200 the constructor raises.
 """
 from __future__ import annotations
@@ -32,7 +32,7 @@ from .validity import PandaValidity, decode_culprit
 logger = logging.getLogger("panda_validity.planning")
 
 SUPPORTED_PLANNERS = ["PRM", "RRT", "RRTConnect", "RRTstar", "EST", "FMT", "BITstar", "ABITstar"]  # planning.py:108-117
-DEVICE_PLANNERS = ["RRTConnect"]
+DEVICE_PLANNERS = ["RRTConnect", "RRT"]
 
 
 class PlanningError(Exception):
@@ -177,7 +177,9 @@ class PlannerInterface:
         """Swept validation of an executed joint trajectory (next-row component 8f-4): the reference plays back the
         150 planned waypoints and many un-planned joint-space lerps (motion_primitives.py:163-173, 294-299, 404-409)
         with no collision check.  Returns one bool per segment (waypoint k -> k+1), each segment discretised at the
-        motion-validity resolution."""
+        motion-validity resolution.  Dense waypoints make this check FINER than the planner's own validator (which
+        samples an edge every 1 % of the space extent), so it can flag grazing contacts the planner stepped over --
+        the same holds for OMPL's DiscreteMotionValidator in the reference."""
         if self._snapshot is None:
             self.refresh_scene()
         pts = np.stack([tensor_to_array(w) for w in waypoints]).astype(np.float32)
@@ -248,7 +250,7 @@ class PlannerInterface:
                 paths, plen, iters, checks = self.validity.rrtc_batch(
                     sg[0:1], sg[1:2], max_iters=2000, max_nodes=2048, max_path=256,
                     seed=self.rng_seed + 7919 * attempt, replicas=self.replicas,
-                    shortcut_passes=2 if smooth_path else 0, check_endpoints=True)
+                    shortcut_passes=2 if smooth_path else 0, check_endpoints=True, planner=planner)
                 attempt += 1
                 stats["attempts"] = attempt
                 if iters[0] < 0:

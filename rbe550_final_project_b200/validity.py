@@ -222,14 +222,16 @@ class PandaValidity:
 
     def rrtc_batch(self, starts: np.ndarray, goals: np.ndarray, max_iters: int = 2000, max_nodes: int = 2048,
                    max_path: int = 128, seed: int = 1, replicas: int = 1, shortcut_passes: int = 2,
-                   rrt_range: float = 0.0, resolution: float = 0.0, check_endpoints: bool = False):
+                   rrt_range: float = 0.0, resolution: float = 0.0, check_endpoints: bool = False,
+                   planner: str = "RRTConnect"):
         starts = np.ascontiguousarray(starts, dtype=np.float32).reshape(-1, 9)
         goals = np.ascontiguousarray(goals, dtype=np.float32).reshape(-1, 9)
         nq = starts.shape[0]
         if goals.shape[0] != nq:
             raise PandaValidityError("starts and goals must have the same length")
         prm = _cabi.PvRrtcParams(float(rrt_range), float(resolution), int(max_iters), int(max_nodes), int(max_path),
-                                 int(seed) & 0xFFFFFFFF, int(replicas), int(shortcut_passes), 1 if check_endpoints else 0)
+                                 int(seed) & 0xFFFFFFFF, int(replicas), int(shortcut_passes), 1 if check_endpoints else 0,
+                                 {"RRTConnect": 0, "RRT": 1}[planner])
         paths = np.zeros((nq, max_path, 9), dtype=np.float32)
         plen = np.zeros(nq, dtype=np.int32)
         iters = np.zeros(nq, dtype=np.int32)
