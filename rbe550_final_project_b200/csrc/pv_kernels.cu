@@ -301,7 +301,8 @@ int pv_set_scene(PvHandle* h, const float* h_obb, int n_obb, float table_z, cons
         snprintf(h->err, sizeof(h->err), "pv_set_scene: n_obb=%d outside 0..%d (or null buffer)", n_obb, PV_MAX_OBB);
         return PV_ERR_BAD_ARG;
     }
-    PvScene& S = h->scene;
+    // build into a copy and commit at the end: a rejected call leaves the previous scene intact
+    PvScene S = h->scene;
     memset(S.obb, 0, sizeof(S.obb));
     S.yaw_only_mask = 0;
     for (int b = 0; b < n_obb; ++b) {
@@ -319,6 +320,14 @@ int pv_set_scene(PvHandle* h, const float* h_obb, int n_obb, float table_z, cons
         }
         S.obb[b][15] = sqrtf(o[3] * o[3] + o[4] * o[4] + o[5] * o[5]);
         const float* R = o + 6;
+        for (int i = 0; i < 3; ++i)
+            for (int j = i; j < 3; ++j) {
+                const float dot = R[3 * i] * R[3 * j] + R[3 * i + 1] * R[3 * j + 1] + R[3 * i + 2] * R[3 * j + 2];
+                if (fabsf(dot - (i == j ? 1.f : 0.f)) > 1e-3f) {
+                    snprintf(h->err, sizeof(h->err), "pv_set_scene: box %d rotation is not orthonormal", b);
+                    return PV_ERR_BAD_ARG;
+                }
+            }
         if (R[2] == 0.f && R[5] == 0.f && R[6] == 0.f && R[7] == 0.f && R[8] == 1.f) S.yaw_only_mask |= 1u << b;
     }
     S.n_obb = n_obb;
@@ -354,6 +363,7 @@ int pv_set_scene(PvHandle* h, const float* h_obb, int n_obb, float table_z, cons
             S.reach_mask[b] = (unsigned short)m;
         }
     }
+    h->scene = S;
     h->has_scene = 1;
     return PV_OK;
 }

@@ -368,3 +368,22 @@ def test_edges_host_entry_point_multi_chunk(pv):
     d = pv.check_edges(_dev(qa), _dev(qb), n_steps=4).cpu().numpy().view(np.uint32)
     h = pv.check_edges_host(qa, qb, n_steps=4)
     assert np.array_equal(d, h)
+
+
+def test_rejected_scene_keeps_the_previous_one(pv):
+    from rbe550_final_project_b200.validity import PandaValidityError
+    good = sc.goal1_scattered()
+    pv.set_scene(good)
+    q = random_configs(20_000, 5)
+    before = pv.check_states(_dev(q)).cpu().numpy()
+    bad = sc.goal3_tower()
+    bad.obb = bad.obb.copy()
+    bad.obb[4, 6:15] *= 1.3  # not a rotation
+    with pytest.raises(PandaValidityError):
+        pv.set_scene(bad)
+    bad2 = sc.goal3_tower()
+    bad2.obb = bad2.obb.copy()
+    bad2.obb[2, 3] = -0.02
+    with pytest.raises(PandaValidityError):
+        pv.set_scene(bad2)
+    assert np.array_equal(pv.check_states(_dev(q)).cpu().numpy(), before)
