@@ -433,8 +433,8 @@ def header_text() -> str:
             a(f"  X({k}, {_f(sign * c[0] + off[0])}, {_f(sign * c[1] + off[1])}, {_f(c[2] + off[2])}, {_f(sign)}, {6 + k}, "
               f"{_f(h[0])}, {_f(h[1])}, {_f(h[2])}) \\")
     a("")
-    a("// LB(la, ca, cull0, cull1, cull2): link la's block runs when its bounding ball (centre s[ca]) reaches the")
-    a("// bounding ball of gripper box k for any k (cull_k = squared reach, 0 when the link has no pair with box k)")
+    a("// LB(la, ca, cull0, cull1, cull2, r_la): link la's block runs when its bounding ball (centre s[ca], radius r_la)")
+    a("// reaches the bounding ball of gripper box k for any k (cull_k = squared reach, 0 when the link has no pair with box k)")
     a("#define PV_SBH_LINKS(LB) \\")
     sb_links = sorted({int(SPHERE_LINK[p]) for p, _ in SB_PAIRS})
     for la in sb_links:
@@ -445,7 +445,7 @@ def header_text() -> str:
                 culls.append(_f(rr * rr))
             else:
                 culls.append("0.0f")
-        a(f"  LB({la}, {g[la][0]}, {', '.join(culls)}) \\")
+        a(f"  LB({la}, {g[la][0]}, {', '.join(culls)}, {_f(g[la][1] + CULL_SLACK)}) \\")
     a("")
     a("// per link: S(a, r, r2) brings sphere a into the hand frame, B(a, k) tests it against gripper box k")
     for la in sb_links:
