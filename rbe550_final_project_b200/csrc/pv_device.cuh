@@ -517,29 +517,29 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
         float3 ok = oc;
         if constexpr (FMAK) ok = make_float3(v_dot(oc, BX), v_dot(oc, BY), yaw_only ? oc.z : v_dot(oc, BZ));
         const unsigned rmask = S.reach_mask[b];
-#define PV_ENV_SPHERE(i, link, cx, cy, cz, r)                                                            \
-    if constexpr (FMAK) {                                                                                \
-        if (yaw_only)                                                                                    \
-            pv_sphere_box_yaw_k<MODE>(acc, s[i], r, (r) * (r), ok, oh, BX.x, BX.y, PV_CODE(2, link, b)); \
-        else                                                                                             \
-            pv_sphere_box_k<MODE>(acc, s[i], r, (r) * (r), ok, oh, BX, BY, BZ, PV_CODE(2, link, b));     \
-    } else {                                                                                             \
-        if (yaw_only)                                                                                    \
-            pv_sphere_box_yaw<MODE>(acc, s[i], r, (r) * (r), oc, oh, BX.x, BX.y, PV_CODE(2, link, b));   \
-        else                                                                                             \
-            pv_sphere_box<MODE>(acc, s[i], r, (r) * (r), oc, oh, BX, BY, BZ, PV_CODE(2, link, b));       \
-    }
+        // one uniform yaw / general decision per GROUP keeps the hot (yaw-only) sphere tests contiguous in the code
+#define PV_ENV_SPHERE_YAW(i, link, cx, cy, cz, r)                                                         \
+    if constexpr (FMAK) pv_sphere_box_yaw_k<MODE>(acc, s[i], r, (r) * (r), ok, oh, BX.x, BX.y, PV_CODE(2, link, b)); \
+    else pv_sphere_box_yaw<MODE>(acc, s[i], r, (r) * (r), oc, oh, BX.x, BX.y, PV_CODE(2, link, b));
+#define PV_ENV_SPHERE_GEN(i, link, cx, cy, cz, r)                                                         \
+    if constexpr (FMAK) pv_sphere_box_k<MODE>(acc, s[i], r, (r) * (r), ok, oh, BX, BY, BZ, PV_CODE(2, link, b)); \
+    else pv_sphere_box<MODE>(acc, s[i], r, (r) * (r), oc, oh, BX, BY, BZ, PV_CODE(2, link, b));
 #define PV_ENV_GROUP(l, cs, br)                                 \
     if (MODE == PV_MODE_MARGIN || (rmask & (1u << l))) {        \
         float3 d_ = v_sub(s[cs], oc);                           \
         float rr_ = (br + PV_CULL_SLACK) + obr;                 \
         if (!CULL || v_dot(d_, d_) < rr_ * rr_) {               \
-            PV_SPHERES_LINK##l(PV_ENV_SPHERE)                   \
+            if (yaw_only) {                                     \
+                PV_SPHERES_LINK##l(PV_ENV_SPHERE_YAW)           \
+            } else {                                            \
+                PV_SPHERES_LINK##l(PV_ENV_SPHERE_GEN)           \
+            }                                                   \
         }                                                       \
     }
         PV_LINK_GROUPS(PV_ENV_GROUP)
 #undef PV_ENV_GROUP
-#undef PV_ENV_SPHERE
+#undef PV_ENV_SPHERE_YAW
+#undef PV_ENV_SPHERE_GEN
         // one bounding ball around the whole gripper (hand + both fingers, radius from this configuration's finger
         // openings) goes first: the three per-box culls and SATs behind it are reached by ~1 % of the lanes
         bool near_gripper = true;
