@@ -63,6 +63,17 @@ int pv_set_scene(PvHandle *h, const float *h_obb, int n_obb, float table_z, cons
 /* self.attached_object = attached_object (planning.py:153): scene-box index whose contacts with hand /
  * left_finger / right_finger are forgiven (planning.py:221-230); -1 = none. */
 int pv_set_attached(PvHandle *h, int obb_index);
+
+/* Physically-correct alternative to pv_set_attached (NOT what planning.py does: there the
+ * grasped block stays a static obstacle where it was, planning.py:216-230, although the simulation moves it with the
+ * gripper, motion_primitives.py:367-376).  Scene box obb_index is held rigidly by the hand: hand_from_box is its pose
+ * in the hand frame, 9 floats of row-major rotation then 3 of translation.  The box is no longer an obstacle at its
+ * snapshot pose; instead it rides on the hand and is checked against the plane, every other scene box and the arm
+ * links link0..link6 (culprit / contact link id 11).  In those tests its half extents are shrunk by
+ * contact_allowance (metres, >= 0): a block that rests on the table or on another block touches it, which is not a
+ * collision.  -1 (pose may be NULL) or pv_set_attached() leave the mode.  A new pv_set_scene keeps the mode while
+ * obb_index still exists (the pose in the hand frame does not depend on the snapshot). */
+int pv_set_carried(PvHandle *h, int obb_index, const float *hand_from_box, float contact_allowance);
 int pv_set_flags(PvHandle *h, unsigned flags);
 
 /* Fused verdict gather for multi-GPU runs: after this call pv_check_states and pv_sweep also store

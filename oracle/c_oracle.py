@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "_build", "libpanda_oracle.so")
 
 FLAG_SELF = 1
 FLAG_LIMITS = 2
+FLAG_CARRY = 4
 
 
 def build(force: bool = False) -> str:
@@ -79,6 +80,22 @@ class COracle:
     def _p(self, a):
         return a.ctypes.data_as(C.POINTER(self.c_t))
 
+    def _scene(self, scene, attached, flags):
+        """(obb array, n_obb, attached, flags); a scene["carried"] entry (see panda_oracle.state_margin) becomes the
+        extra record obb[n_obb] plus FLAG_CARRY, with `attached` = the carried box."""
+        obb = np.ascontiguousarray(scene["obb"], dtype=self.np_t).reshape(-1, 16)
+        n = obb.shape[0]
+        carried = scene.get("carried")
+        if carried is not None:
+            k = int(carried["index"])
+            rec = np.zeros((1, 16), dtype=self.np_t)
+            rec[0, 0:3] = np.asarray(carried["t"], dtype=np.float64)
+            rec[0, 3:6] = obb[k, 3:6] - self.np_t(carried.get("shrink", 0.0))
+            rec[0, 6:15] = np.asarray(carried["R"], dtype=np.float64).reshape(9)
+            obb = np.ascontiguousarray(np.concatenate([obb, rec], axis=0))
+            attached, flags = k, flags | FLAG_CARRY
+        return obb, n, attached, flags
+
     def fk(self, q, base=(0.0, 0.0, 0.01)):
         q = np.ascontiguousarray(np.atleast_2d(q), dtype=self.np_t)
         n = q.shape[0]
@@ -91,11 +108,11 @@ class COracle:
     def state_margin(self, q, scene, attached=-1, flags=FLAG_SELF, base=(0.0, 0.0, 0.01), nthreads=0):
         q = np.ascontiguousarray(np.atleast_2d(q), dtype=self.np_t)
         n = q.shape[0]
-        obb = np.ascontiguousarray(scene["obb"], dtype=self.np_t).reshape(-1, 16)
+        obb, n_obb, attached, flags = self._scene(scene, attached, flags)
         out = np.empty(n, dtype=self.np_t)
         b = np.asarray(base, dtype=self.np_t)
         getattr(self.lib, "po_state_margin" + self.sfx)(
-            C.byref(self.model), self._p(obb), C.c_int(obb.shape[0]), self.c_t(scene["table_z"]), self._p(b),
+            C.byref(self.model), self._p(obb), C.c_int(n_obb), self.c_t(scene["table_z"]), self._p(b),
             C.c_int(attached), C.c_int(flags), self._p(q), C.c_long(n), self._p(out),
             C.c_int(nthreads or os.cpu_count() or 1))
         return out
@@ -105,12 +122,12 @@ class COracle:
         qa = np.ascontiguousarray(np.atleast_2d(qa), dtype=self.np_t)
         qb = np.ascontiguousarray(np.atleast_2d(qb), dtype=self.np_t)
         n = qa.shape[0]
-        obb = np.ascontiguousarray(scene["obb"], dtype=self.np_t).reshape(-1, 16)
+        obb, n_obb, attached, flags = self._scene(scene, attached, flags)
         out = np.empty(n, dtype=self.np_t)
         b = np.asarray(base, dtype=self.np_t)
         cnt = C.c_long(0)
         getattr(self.lib, "po_edge_margin" + self.sfx)(
-            C.byref(self.model), self._p(obb), C.c_int(obb.shape[0]), self.c_t(scene["table_z"]), self._p(b),
+            C.byref(self.model), self._p(obb), C.c_int(n_obb), self.c_t(scene["table_z"]), self._p(b),
             C.c_int(attached), C.c_int(flags), self._p(qa), self._p(qb), C.c_long(n), C.c_int(n_steps),
             self.c_t(resolution), C.c_int(1 if early_exit else 0), self._p(out), C.byref(cnt),
             C.c_int(nthreads or os.cpu_count() or 1))
@@ -123,13 +140,13 @@ class COracle:
         assert self.np_t is np.float32, "the planner restatement mirrors the device arithmetic: use precision 'f32'"
         s = np.ascontiguousarray(start, dtype=np.float32).reshape(9)
         g = np.ascontiguousarray(goal, dtype=np.float32).reshape(9)
-        obb = np.ascontiguousarray(scene["obb"], dtype=np.float32).reshape(-1, 16)
+        obb, n_obb, attached, flags = self._scene(scene, attached, flags)
         b = np.asarray(base, dtype=np.float32)
         path = np.zeros((max_path, 9), dtype=np.float32)
         iters, checks = C.c_int(0), C.c_longlong(0)
         fn = self.lib.po_rrtc_f32
         fn.restype = C.c_int
-        n = fn(C.byref(self.model), self._p(obb), C.c_int(obb.shape[0]), C.c_float(scene["table_z"]), self._p(b),
+        n = fn(C.byref(self.model), self._p(obb), C.c_int(n_obb), C.c_float(scene["table_z"]), self._p(b),
                C.c_int(attached), C.c_int(flags), self._p(s), self._p(g), C.c_float(np.float32(rrt_range)),
                C.c_float(np.float32(resolution)), C.c_int(max_iters), C.c_int(max_nodes), C.c_int(max_path),
                C.c_uint32(seed & 0xFFFFFFFF), C.c_uint32(search), C.c_int(shortcut_passes),

@@ -91,6 +91,10 @@ def fk(q, base=(0.0, 0.0, 0.01)):
 
 
 # --- primitive distances (signed margins; < 0 means penetration) ---------------------------------------
+HAND_LINK = 8
+CARRY_LAST_ARM_LINK = 6  # the carried box is tested against the spheres of link0..link6
+
+
 def _sphere_obb_margin(c, r, bc, bh, bR):
     """c (n,3) sphere centres, r scalar or (n,), box centre bc (.., 3), half bh (..,3), rot bR (..,3,3)
     (world-from-box).  Returns margin (n,)."""
@@ -139,6 +143,12 @@ def state_margin(q, scene, model, attached=-1, self_collision=True, base=(0.0, 0
     scene: dict(obb=(B,16) rows [c.xyz, half.xyz, R row-major 9, pad], table_z=float)
     attached: scene-box index whose contacts with hand / fingers are forgiven (planning.py:221-230);
               -1 for none.  The attached box stays a static obstacle for every other link (App. E-3).
+    scene["carried"] (optional, NOT reference behaviour: SURVEY.md 8f-3 / App. E-3 "physically-correct mode"):
+              dict(index=k, R=(3,3), t=(3,), shrink=float) -- scene box k is rigidly held by the hand with pose
+              hand-from-box (R, t); in its own tests its half extents are reduced by `shrink` (contact allowance:
+              a block resting on the table or on another block is not in collision with it).  It then stops being a static obstacle and instead moves with the hand: it is tested
+              against the plane, every other scene box and the arm spheres of link0..link6 (link7, hand and
+              fingers are rigid or in grasp contact with it).
     Follows planning.py:209-219: any robot contact invalidates the state unless forgiven.
     """
     q = np.atleast_2d(np.asarray(q, dtype=np.float64))
@@ -170,9 +180,25 @@ def state_margin(q, scene, model, attached=-1, self_collision=True, base=(0.0, 0
         ext = (np.abs(bR[:, k, 2, :]) * bh[k]).sum(-1)
         take("table", bw[:, k, 2] - ext - tz)
 
+    carried = scene.get("carried") if isinstance(scene, dict) else None
+    ck = -1
+    if carried is not None:
+        ck = int(carried["index"])
+        ch = obb[ck, 3:6] - float(carried.get("shrink", 0.0))
+        cR = R[:, HAND_LINK] @ np.asarray(carried["R"], dtype=np.float64).reshape(3, 3)  # (n,3,3) world-from-box
+        cc = p[:, HAND_LINK] + R[:, HAND_LINK] @ np.asarray(carried["t"], dtype=np.float64)
+        take("carried", cc[:, 2] - (np.abs(cR[:, 2, :]) * ch).sum(-1) - tz)
+        for i in range(S):
+            if sl[i] <= CARRY_LAST_ARM_LINK:
+                take("carried", _sphere_obb_margin(wc[:, i], sr[i], cc, ch, cR))
+
     # robot vs scene boxes
     for b in range(obb.shape[0]):
+        if b == ck:
+            continue  # carried: it is where the hand is, not where the snapshot saw it
         cb, hb, Rb = obb[b, 0:3], obb[b, 3:6], obb[b, 6:15].reshape(3, 3)
+        if ck >= 0:
+            take("carried", _obb_obb_margin(cc, ch, cR, cb, hb, Rb))
         for i in range(S):
             take("env", _sphere_obb_margin(wc[:, i], sr[i], cb, hb, Rb))
         if b == attached:

@@ -126,6 +126,11 @@ static REAL FN(obb_obb)(const REAL *ca, const REAL *ha, const REAL *Ra, const RE
 
 #define PO_FLAG_SELF 1
 #define PO_FLAG_LIMITS 2
+/* carry mode (not reference behaviour): scene box `attached` is held rigidly by the hand.  Its pose
+ * in the hand frame is the extra record obb[n_obb] = [t.xyz, half.xyz, R row-major (hand-from-box), pad]. */
+#define PO_FLAG_CARRY 4
+#define PO_HAND_LINK 8
+#define PO_CARRY_LAST_ARM_LINK 6
 
 /* Minimum signed clearance of one configuration (valid iff >= 0).  With PO_FLAG_LIMITS an
  * out-of-bounds configuration returns -1e30. */
@@ -156,8 +161,30 @@ static REAL FN(state_margin_one)(const FN(po_model) * m, const REAL *obb, int n_
         REAL s = bw[3 * k + 2] - ext - table_z;
         if (s < best) best = s;
     }
+    const int carry = (flags & PO_FLAG_CARRY) && attached >= 0 && attached < n_obb;
+    REAL cc[3], cR[9];
+    const REAL *chalf = obb + 16 * n_obb + 3;
+    if (carry) {
+        const REAL *rec = obb + 16 * n_obb, *Rh = R + 9 * PO_HAND_LINK, *ph = p + 3 * PO_HAND_LINK;
+        FN(mat_mul)(Rh, rec + 6, cR);
+        for (int a = 0; a < 3; ++a) cc[a] = ph[a] + Rh[3 * a] * rec[0] + Rh[3 * a + 1] * rec[1] + Rh[3 * a + 2] * rec[2];
+        REAL ext = (REAL)fabs((double)cR[6]) * chalf[0] + (REAL)fabs((double)cR[7]) * chalf[1] +
+                   (REAL)fabs((double)cR[8]) * chalf[2];
+        REAL s = cc[2] - ext - table_z;
+        if (s < best) best = s;
+        for (int i = 0; i < m->n_spheres; ++i) {
+            if (m->sphere_link[i] > PO_CARRY_LAST_ARM_LINK) continue;
+            s = FN(sphere_obb)(wc + 3 * i, m->sphere_radius[i], cc, chalf, cR);
+            if (s < best) best = s;
+        }
+    }
     for (int b = 0; b < n_obb; ++b) {
         const REAL *o = obb + 16 * b;
+        if (carry && b == attached) continue; /* it moves with the hand */
+        if (carry) {
+            REAL s = FN(obb_obb)(cc, chalf, cR, o, o + 3, o + 6);
+            if (s < best) best = s;
+        }
         for (int i = 0; i < m->n_spheres; ++i) {
             REAL s = FN(sphere_obb)(wc + 3 * i, m->sphere_radius[i], o, o + 3, o + 6);
             if (s < best) best = s;

@@ -32,7 +32,17 @@ struct PvScene {
     unsigned yaw_only_mask;  // bit b: box b is rotated about world z only
     // bit l (0..7): link group l can reach box b at all; bit 8+k: gripper box k can (static, joint-independent)
     unsigned short reach_mask[PV_MAX_OBB];
+    // carry mode (not reference behaviour): box `attached` is held rigidly by the hand and moves with
+    // it instead of staying a static obstacle.  Pose of the box in the hand frame: centre carry_t, axes = COLUMNS of
+    // carry_R (row-major hand-from-box); carry_h = half extents of the scene record shrunk by the contact allowance
+    // (a block resting on the table or on another block touches it: that is not a collision), carry_br = |carry_h|.
+    int carry;
+    float carry_t[3];
+    float carry_R[9];
+    float carry_h[3];
+    float carry_br;
 };
+#define PV_LINK_CARRIED 11  // link id reported for the carried box in culprit / contact codes
 
 enum { PV_MODE_BITS = 0, PV_MODE_MARGIN = 1, PV_MODE_LIST = 2 };
 #define PV_MAX_CONTACTS 32
@@ -346,7 +356,7 @@ __device__ __forceinline__ void pv_fk_visit(const float* q, float bx, float by, 
 // SYNC: every warp of the block calls this together and block-level barriers keep the warps within one
 // code region of each other, so the (large, straight-line) instruction stream is fetched once per SM instead
 // of once per warp (ncu showed stall_no_instruction as the top stall of the free-running version).
-template <int MODE, bool CULL, int EXIT, int SYNC = 0, bool FMAK = false>
+template <int MODE, bool CULL, int EXIT, int SYNC = 0, bool FMAK = false, bool CARRY = false>
 __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S, PvAcc<MODE>& acc) {
     static_assert(!SYNC || EXIT == PV_EXIT_NONE, "block barriers and warp-level early exit do not mix");
     const unsigned FULL = 0xffffffffu;
@@ -429,6 +439,26 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
         float ext = fmaf(fabsf(hZ.z), bh[k][2], fmaf(fabsf(hY.z), bh[k][1], fabsf(hX.z) * bh[k][0]));
         pv_plane<MODE>(acc, bc[k].z - ext, tz, PV_CODE(1, blink[k], 0));
     }
+    // ---- carried box: placed by the hand, checked against the plane and the arm spheres of link0..link6 --------
+    float3 cC = hP, cH = make_float3(0.f, 0.f, 0.f), cX = hX, cY = hY, cZ = hZ;
+    float cbr = 0.f;
+    if constexpr (CARRY) {
+        cH = make_float3(S.carry_h[0], S.carry_h[1], S.carry_h[2]);
+        cbr = S.carry_br;
+        cC = v_fma(hZ, S.carry_t[2], v_fma(hY, S.carry_t[1], v_fma(hX, S.carry_t[0], hP)));
+#define PV_CARRY_AXIS(j) \
+    v_fma(hZ, S.carry_R[6 + j], v_fma(hY, S.carry_R[3 + j], make_float3(hX.x * S.carry_R[j], hX.y * S.carry_R[j], hX.z * S.carry_R[j])))
+        cX = PV_CARRY_AXIS(0);
+        cY = PV_CARRY_AXIS(1);
+        cZ = PV_CARRY_AXIS(2);
+#undef PV_CARRY_AXIS
+        float ext = fmaf(fabsf(cZ.z), cH.z, fmaf(fabsf(cY.z), cH.y, fabsf(cX.z) * cH.x));
+        pv_plane<MODE>(acc, cC.z - ext, tz, PV_CODE(1, PV_LINK_CARRIED, 0));
+#define PV_CARRY_SPHERE(i, link, cx, cy, cz, r) \
+    if (link <= 6) pv_sphere_box<MODE>(acc, s[i], r, (r) * (r), cC, cH, cX, cY, cZ, PV_CODE(3, link, PV_LINK_CARRIED));
+        PV_SPHERES(PV_CARRY_SPHERE)
+#undef PV_CARRY_SPHERE
+    }
     PV_EARLY_EXIT()
     PV_LOCKSTEP(2)
 
@@ -507,6 +537,9 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
     const int nb = S.n_obb;
     for (int b = 0; b < nb; ++b) {
         PV_LOCKSTEP(3)
+        if constexpr (CARRY) {
+            if (b == S.attached) continue;  // it is where the hand is, not where the snapshot saw it
+        }
         const float3 oc = make_float3(S.obb[b][0], S.obb[b][1], S.obb[b][2]);
         const float3 oh = make_float3(S.obb[b][3], S.obb[b][4], S.obb[b][5]);
         const float obr = S.obb[b][15];
@@ -517,6 +550,12 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
         float3 ok = oc;
         if constexpr (FMAK) ok = make_float3(v_dot(oc, BX), v_dot(oc, BY), yaw_only ? oc.z : v_dot(oc, BZ));
         const unsigned rmask = S.reach_mask[b];
+        if constexpr (CARRY) {
+            float3 d_ = v_sub(cC, oc);
+            float rr_ = (cbr + PV_CULL_SLACK) + obr;
+            if (MODE == PV_MODE_MARGIN || v_dot(d_, d_) < rr_ * rr_)
+                pv_box_box<MODE>(acc, cC, cH, cX, cY, cZ, oc, oh, BX, BY, BZ, PV_CODE(2, PV_LINK_CARRIED, b));
+        }
         // one uniform yaw / general decision per GROUP keeps the hot (yaw-only) sphere tests contiguous in the code
 #define PV_ENV_SPHERE_YAW(i, link, cx, cy, cz, r)                                                         \
     if constexpr (FMAK) pv_sphere_box_yaw_k<MODE>(acc, s[i], r, (r) * (r), ok, oh, BX.x, BX.y, PV_CODE(2, link, b)); \

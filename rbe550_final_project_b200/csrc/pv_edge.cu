@@ -45,7 +45,7 @@
 #define PV_E_LOCKSTEP 1
 #endif
 
-template <bool CULL, int MODE>
+template <bool CULL, int MODE, bool CARRY>
 __global__ void __launch_bounds__(PV_E_THREADS, 1)
     pv_edge_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ aA, const float4* __restrict__ aB,
                    const float* __restrict__ a9, const float4* __restrict__ bA, const float4* __restrict__ bB,
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
 #pragma unroll
         for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, eb[c] - ea[c], ea[c]);
         PvAcc<MODE> acc;
-        pv_check_config<MODE, CULL, (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE)>(q, S, acc);
+        pv_check_config<MODE, CULL, (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE), 0, false, CARRY>(q, S, acc);
         bool edge_done;
         bool edge_hit = false;
         if constexpr (MODE == PV_MODE_BITS) {
@@ -155,17 +155,17 @@ int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* 
         return PV_ERR_BAD_ARG;
     }
     const int64_t words = (n + 31) / 32;
-#define PV_LAUNCH_E(CULL, MODE)                                                                                \
+#define PV_LAUNCH_E(CULL, MODE, CARRY)                                                                         \
     {                                                                                                          \
-        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE>, PV_E_THREADS, words);                 \
-        pv_edge_kernel<CULL, MODE><<<grid, PV_E_THREADS, 0, st>>>(h->scene, (const float4*)aA, (const float4*)aB, a9, \
-                                                                (const float4*)bA, (const float4*)bB, b9, a_aos, b_aos, \
-                                                                n, n_steps, resolution, d_bits, d_margin);     \
+        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE, CARRY>, PV_E_THREADS, words);        \
+        pv_edge_kernel<CULL, MODE, CARRY><<<grid, PV_E_THREADS, 0, st>>>(                                      \
+            h->scene, (const float4*)aA, (const float4*)aB, a9, (const float4*)bA, (const float4*)bB, b9, a_aos, \
+            b_aos, n, n_steps, resolution, d_bits, d_margin);                                                  \
     }
     if (d_bits) {
-        PV_LAUNCH_E(true, PV_MODE_BITS)
-    } else {
-        PV_LAUNCH_E(false, PV_MODE_MARGIN)  // margins: always brute force
+        if (h->scene.carry) PV_LAUNCH_E(true, PV_MODE_BITS, true) else PV_LAUNCH_E(true, PV_MODE_BITS, false)
+    } else {  // margins: always brute force
+        if (h->scene.carry) PV_LAUNCH_E(false, PV_MODE_MARGIN, true) else PV_LAUNCH_E(false, PV_MODE_MARGIN, false)
     }
 #undef PV_LAUNCH_E
     h->launches++;

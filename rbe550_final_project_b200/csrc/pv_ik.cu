@@ -32,6 +32,7 @@ __device__ __forceinline__ float3 v_cross(float3 a, float3 b) {
     return make_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 
+template <bool CARRY>
 __global__ void __launch_bounds__(IK_MAX_SEEDS, 1) pv_ik_kernel(const __grid_constant__ PvScene S,
                                                                 const __grid_constant__ IkArgs A) {
     const int target = blockIdx.x;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(IK_MAX_SEEDS, 1) pv_ik_kernel(const __grid_con
 
     // validity of the candidate (all lanes call together; non-converged lanes are masked afterwards)
     PvAcc<PV_MODE_BITS> acc;
-    pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE>(q, S, acc);
+    pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, 0, false, CARRY>(q, S, acc);
     const bool good = converged && !acc.hit;
 
     // the valid candidate closest to q_init (L2 over the arm joints); ties -> lowest thread index
@@ -252,7 +253,8 @@ extern "C" int pv_ik_batch(PvHandle* h, const float* h_pos, const float* h_quat,
     IK_CUDA(cudaMemcpyAsync(d_quat, h_quat, (size_t)n_targets * 16, cudaMemcpyHostToDevice, st));
     IK_CUDA(cudaMemcpyAsync(d_qi, h_q_init, 36, cudaMemcpyHostToDevice, st));
     IK_CUDA(cudaMemsetAsync(a.q_out, 0, b_q + b_st + b_err, st));
-    pv_ik_kernel<<<n_targets, n_seeds, 0, st>>>(h->scene, a);
+    if (h->scene.carry) pv_ik_kernel<true><<<n_targets, n_seeds, 0, st>>>(h->scene, a);
+    else pv_ik_kernel<false><<<n_targets, n_seeds, 0, st>>>(h->scene, a);
     h->launches++;
     IK_CUDA(cudaGetLastError());
     IK_CUDA(cudaMemcpyAsync(h_q_out, a.q_out, (size_t)n_targets * 36, cudaMemcpyDeviceToHost, st));

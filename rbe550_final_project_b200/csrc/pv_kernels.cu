@@ -62,7 +62,7 @@ __device__ __forceinline__ void pv_emit_word(uint32_t* __restrict__ bits, const 
 #ifndef PV_SB_MINB
 #define PV_SB_MINB 1
 #endif
-template <bool AOS, bool CULL>
+template <bool AOS, bool CULL, bool CARRY>
 __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     pv_state_bits_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA,
                          const float4* __restrict__ qB, const float* __restrict__ q9,
@@ -83,13 +83,13 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         else pv_load_soa(qA, qB, q9, ii, q);
         __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
         PvAcc<PV_MODE_BITS> acc;
-        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, PV_SB_SYNC, true>(q, S, acc);
+        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, PV_SB_SYNC, true, CARRY>(q, S, acc);
         const unsigned word = __ballot_sync(0xffffffffu, in && !acc.hit);
         if (w < n_words) pv_emit_word(bits, G, w, word, lane);
     }
 }
 
-template <bool CULL>
+template <bool CULL, bool CARRY>
 __global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
     pv_state_margin_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA,
                            const float4* __restrict__ qB, const float* __restrict__ q9, int64_t n,
@@ -99,13 +99,14 @@ __global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
         float q[9];
         pv_load_soa(qA, qB, q9, i, q);
         PvAcc<PV_MODE_MARGIN> acc;
-        pv_check_config<PV_MODE_MARGIN, CULL, PV_EXIT_NONE>(q, S, acc);
+        pv_check_config<PV_MODE_MARGIN, CULL, PV_EXIT_NONE, 0, false, CARRY>(q, S, acc);
         margin[i] = acc.m;
         if (culprit) culprit[i] = acc.m < 0.f ? acc.code : 0;
     }
 }
 
 // diagnostics: every colliding pair of one state (the pair list robot.detect_collision() returns, planning.py:47-57)
+template <bool CARRY>
 __global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
     pv_state_contacts_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA,
                              const float4* __restrict__ qB, const float* __restrict__ q9, int64_t n,
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
         float q[9];
         pv_load_soa(qA, qB, q9, i, q);
         PvAcc<PV_MODE_LIST> acc;
-        pv_check_config<PV_MODE_LIST, false, PV_EXIT_NONE>(q, S, acc);
+        pv_check_config<PV_MODE_LIST, false, PV_EXIT_NONE, 0, false, CARRY>(q, S, acc);
         count[i] = acc.n;
         for (int k = 0; k < PV_MAX_CONTACTS; ++k)
             codes[i * PV_MAX_CONTACTS + k] = (k < acc.n && k < PV_MAX_CONTACTS) ? acc.codes[k] : 0;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(128)
 }
 
 // Config-5 sweep: configurations generated on device from a counter-based RNG, checked, bit-packed, counted.
-template <bool CULL>
+template <bool CULL, bool CARRY>
 __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     pv_sweep_kernel(const __grid_constant__ PvScene S, uint64_t first, int64_t n, unsigned seed, int fingers_open,
                     uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid,
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         }
         __syncthreads();  // lockstep: the warps of the block share instruction fetches
         PvAcc<PV_MODE_BITS> acc;
-        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, 0, true>(q, S, acc);
+        pv_check_config<PV_MODE_BITS, CULL, PV_EXIT_NONE, 0, true, CARRY>(q, S, acc);
         const unsigned word = __ballot_sync(0xffffffffu, in && !acc.hit);
         if (w < n_words) {
             pv_emit_word(bits, G, w, word, lane);
@@ -337,7 +338,10 @@ int pv_set_scene(PvHandle* h, const float* h_obb, int n_obb, float table_z, cons
         S.base[1] = base_xyz[1];
         S.base[2] = base_xyz[2];
     }
-    if (S.attached >= n_obb) S.attached = -1;
+    if (S.attached >= n_obb) {
+        S.attached = -1;
+        S.carry = 0;
+    }
     // static reach masks: which link groups / gripper boxes can touch which scene box at all
     {
         const float link_reach[8] = PV_LINK_REACH, box_reach[3] = PV_BOX_REACH;
@@ -375,6 +379,49 @@ int pv_set_attached(PvHandle* h, int obb_index) {
         return PV_ERR_BAD_ARG;
     }
     h->scene.attached = obb_index;
+    h->scene.carry = 0;
+    return PV_OK;
+}
+
+int pv_set_carried(PvHandle* h, int obb_index, const float* hand_from_box, float contact_allowance) {
+    if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
+    if (obb_index == -1) {
+        h->scene.attached = -1;
+        h->scene.carry = 0;
+        return PV_OK;
+    }
+    if (obb_index < 0 || obb_index >= h->scene.n_obb || !hand_from_box) {
+        snprintf(h->err, sizeof(h->err), "pv_set_carried: index %d outside -1..%d (or null pose)", obb_index,
+                 h->scene.n_obb - 1);
+        return PV_ERR_BAD_ARG;
+    }
+    const float* R = hand_from_box;
+    for (int k = 0; k < 12; ++k)
+        if (!isfinite(hand_from_box[k])) {
+            snprintf(h->err, sizeof(h->err), "pv_set_carried: non-finite pose entry");
+            return PV_ERR_BAD_ARG;
+        }
+    for (int i = 0; i < 3; ++i)
+        for (int j = i; j < 3; ++j) {
+            const float dot = R[3 * i] * R[3 * j] + R[3 * i + 1] * R[3 * j + 1] + R[3 * i + 2] * R[3 * j + 2];
+            if (fabsf(dot - (i == j ? 1.f : 0.f)) > 1e-3f) {
+                snprintf(h->err, sizeof(h->err), "pv_set_carried: rotation is not orthonormal");
+                return PV_ERR_BAD_ARG;
+            }
+        }
+    const float* o = h->scene.obb[obb_index];
+    if (!(contact_allowance >= 0.f) || !(contact_allowance < fminf(o[3], fminf(o[4], o[5])))) {
+        snprintf(h->err, sizeof(h->err), "pv_set_carried: contact allowance %g outside [0, smallest half extent)",
+                 (double)contact_allowance);
+        return PV_ERR_BAD_ARG;
+    }
+    for (int k = 0; k < 3; ++k) h->scene.carry_h[k] = o[3 + k] - contact_allowance;
+    h->scene.carry_br = sqrtf(h->scene.carry_h[0] * h->scene.carry_h[0] + h->scene.carry_h[1] * h->scene.carry_h[1] +
+                              h->scene.carry_h[2] * h->scene.carry_h[2]);
+    for (int k = 0; k < 9; ++k) h->scene.carry_R[k] = R[k];
+    for (int k = 0; k < 3; ++k) h->scene.carry_t[k] = hand_from_box[9 + k];
+    h->scene.attached = obb_index;
+    h->scene.carry = 1;
     return PV_OK;
 }
 
@@ -441,9 +488,15 @@ int pv_state_contacts(PvHandle* h, const float* d_qA, const float* d_qB, const f
                       int32_t* d_codes, int32_t* d_count, void* stream) {
     PV_PRECHECK(h, n);
     if (!d_qA || !d_qB || !d_codes || !d_count) return PV_ERR_BAD_ARG;
-    int grid = pv_grid_for(h, (const void*)pv_state_contacts_kernel, PV_THREADS, (n + 31) / 32);
-    pv_state_contacts_kernel<<<grid, PV_THREADS, 0, (cudaStream_t)stream>>>(h->scene, (const float4*)d_qA, (const float4*)d_qB,
-                                                                            d_q9, n, d_codes, d_count);
+    if (h->scene.carry) {
+        int grid = pv_grid_for(h, (const void*)pv_state_contacts_kernel<true>, PV_THREADS, (n + 31) / 32);
+        pv_state_contacts_kernel<true><<<grid, PV_THREADS, 0, (cudaStream_t)stream>>>(
+            h->scene, (const float4*)d_qA, (const float4*)d_qB, d_q9, n, d_codes, d_count);
+    } else {
+        int grid = pv_grid_for(h, (const void*)pv_state_contacts_kernel<false>, PV_THREADS, (n + 31) / 32);
+        pv_state_contacts_kernel<false><<<grid, PV_THREADS, 0, (cudaStream_t)stream>>>(
+            h->scene, (const float4*)d_qA, (const float4*)d_qB, d_q9, n, d_codes, d_count);
+    }
     h->launches++;
     PV_CUDA(h, cudaGetLastError());
     return PV_OK;
@@ -452,17 +505,19 @@ int pv_state_contacts(PvHandle* h, const float* d_qA, const float* d_qB, const f
 static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9,
                                 const float* d_aos, int64_t n, uint32_t* d_bits, cudaStream_t st) {
     const int64_t words = (n + 31) / 32;
-#define PV_LAUNCH_SB(AOS, CULL)                                                                               \
+#define PV_LAUNCH_SB(AOS, CULL, CARRY)                                                                        \
     {                                                                                                         \
-        int grid = pv_grid_for(h, (const void*)pv_state_bits_kernel<AOS, CULL>, PV_SB_THREADS, words);        \
-        pv_state_bits_kernel<AOS, CULL><<<grid, PV_SB_THREADS, 0, st>>>(h->scene, (const float4*)d_qA,        \
-                                                                     (const float4*)d_qB, d_q9, d_aos, n, d_bits, \
-                                                                        d_aos ? PvGather{} : h->gather); \
+        int grid = pv_grid_for(h, (const void*)pv_state_bits_kernel<AOS, CULL, CARRY>, PV_SB_THREADS, words); \
+        pv_state_bits_kernel<AOS, CULL, CARRY><<<grid, PV_SB_THREADS, 0, st>>>(                               \
+            h->scene, (const float4*)d_qA, (const float4*)d_qB, d_q9, d_aos, n, d_bits,                       \
+            d_aos ? PvGather{} : h->gather);                                                                  \
     }
-    if (d_aos) {
-        if (h->cull) PV_LAUNCH_SB(true, true) else PV_LAUNCH_SB(true, false)
+    if (h->scene.carry) {  // carry mode always culls (the brute-force variant exists for the A/B identity test)
+        if (d_aos) PV_LAUNCH_SB(true, true, true) else PV_LAUNCH_SB(false, true, true)
+    } else if (d_aos) {
+        if (h->cull) PV_LAUNCH_SB(true, true, false) else PV_LAUNCH_SB(true, false, false)
     } else {
-        if (h->cull) PV_LAUNCH_SB(false, true) else PV_LAUNCH_SB(false, false)
+        if (h->cull) PV_LAUNCH_SB(false, true, false) else PV_LAUNCH_SB(false, false, false)
     }
 #undef PV_LAUNCH_SB
     h->launches++;
@@ -485,9 +540,15 @@ int pv_state_margins(PvHandle* h, const float* d_qA, const float* d_qB, const fl
     {
         // margins are a diagnostic: always brute force (culling only guarantees that contacts are never
         // missed, it may skip the far-away primitive that defines a positive clearance)
-        int grid = pv_grid_for(h, (const void*)pv_state_margin_kernel<false>, PV_THREADS, (n + 31) / 32);
-        pv_state_margin_kernel<false><<<grid, PV_THREADS, 0, st>>>(h->scene, (const float4*)d_qA, (const float4*)d_qB,
-                                                                   d_q9, n, d_margin, d_culprit);
+        if (h->scene.carry) {
+            int grid = pv_grid_for(h, (const void*)pv_state_margin_kernel<false, true>, PV_THREADS, (n + 31) / 32);
+            pv_state_margin_kernel<false, true><<<grid, PV_THREADS, 0, st>>>(
+                h->scene, (const float4*)d_qA, (const float4*)d_qB, d_q9, n, d_margin, d_culprit);
+        } else {
+            int grid = pv_grid_for(h, (const void*)pv_state_margin_kernel<false, false>, PV_THREADS, (n + 31) / 32);
+            pv_state_margin_kernel<false, false><<<grid, PV_THREADS, 0, st>>>(
+                h->scene, (const float4*)d_qA, (const float4*)d_qB, d_q9, n, d_margin, d_culprit);
+        }
     }
     h->launches++;
     PV_CUDA(h, cudaGetLastError());
@@ -565,8 +626,15 @@ int pv_sweep(PvHandle* h, uint64_t first, int64_t n, uint32_t seed, int fingers_
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t words = (n + 31) / 32;
     {
-        int grid = pv_grid_for(h, (const void*)pv_sweep_kernel<true>, PV_SB_THREADS, words);
-        pv_sweep_kernel<true><<<grid, PV_SB_THREADS, 0, st>>>(h->scene, first, n, seed, fingers_open, d_bits, d_n_valid, d_q_out, h->gather);
+        if (h->scene.carry) {
+            int grid = pv_grid_for(h, (const void*)pv_sweep_kernel<true, true>, PV_SB_THREADS, words);
+            pv_sweep_kernel<true, true><<<grid, PV_SB_THREADS, 0, st>>>(h->scene, first, n, seed, fingers_open, d_bits,
+                                                                        d_n_valid, d_q_out, h->gather);
+        } else {
+            int grid = pv_grid_for(h, (const void*)pv_sweep_kernel<true, false>, PV_SB_THREADS, words);
+            pv_sweep_kernel<true, false><<<grid, PV_SB_THREADS, 0, st>>>(h->scene, first, n, seed, fingers_open, d_bits,
+                                                                         d_n_valid, d_q_out, h->gather);
+        }
     }
     h->launches++;
     PV_CUDA(h, cudaGetLastError());

@@ -89,6 +89,7 @@ __device__ __forceinline__ int rrtc_nearest(const float* __restrict__ tq, int si
     return bi;
 }
 
+template <bool CARRY>
 __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_constant__ PvScene S,
                                                                    const __grid_constant__ RrtcArgs A) {
     const unsigned FULL = 0xffffffffu;
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
             bad |= (qe[k] < lo[k]) || (qe[k] > hi[k]);
         }
         PvAcc<PV_MODE_BITS> acc0;
-        pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE>(qe, S, acc0);
+        pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, 0, false, CARRY>(qe, S, acc0);
         bad |= acc0.hit;
         const int code = (__shfl_sync(FULL, bad ? 1 : 0, 0) ? 1 : 0) | (__shfl_sync(FULL, bad ? 1 : 0, 1) ? 2 : 0);
         if (code) {
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
 #pragma unroll
             for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, de[c], ea[c]);
             PvAcc<PV_MODE_BITS> acc;
-            pv_check_config<PV_MODE_BITS, true, PV_EXIT_ANY>(q, S, acc);
+            pv_check_config<PV_MODE_BITS, true, PV_EXIT_ANY, 0, false, CARRY>(q, S, acc);
             n_checks += min(nd - r * 32, 32);
             if (__any_sync(FULL, acc.hit)) {
                 hit = true;
@@ -434,7 +435,8 @@ extern "C" int pv_rrtc_batch(PvHandle* h, const float* h_starts, const float* h_
     RR_CUDA(cudaMemsetAsync(a.winner, 0xFF, b_i, st));
     const int warps_per_block = RRTC_THREADS / 32;
     const int grid = (int)((n_search + warps_per_block - 1) / warps_per_block);
-    pv_rrtc_kernel<<<grid, RRTC_THREADS, 0, st>>>(h->scene, a);
+    if (h->scene.carry) pv_rrtc_kernel<true><<<grid, RRTC_THREADS, 0, st>>>(h->scene, a);
+    else pv_rrtc_kernel<false><<<grid, RRTC_THREADS, 0, st>>>(h->scene, a);
     h->launches++;
     RR_CUDA(cudaGetLastError());
     // small batches: one packed copy; large batches: skip the unused tail of each path? (paths are max_path long)

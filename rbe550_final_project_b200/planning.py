@@ -68,10 +68,15 @@ class StateValidityChecker:
 
 
 class PlannerInterface:
-    def __init__(self, robot: Any, scene: Any, device: int = 0, validity: Optional[PandaValidity] = None):
+    def __init__(self, robot: Any, scene: Any, device: int = 0, validity: Optional[PandaValidity] = None,
+                 carry_attached: bool = False):
         self.robot = _ensure_adapter(robot, scene)
         self.scene = scene
         self.attached_object = None
+        # False = the reference's rule (planning.py:216-230): the grasped block stays an obstacle where it is and only
+        # hand / finger contacts with it are forgiven.  True = the block rides on the hand:
+        # its grasp pose is taken from the robot configuration and block pose at the moment plan_path is called.
+        self.carry_attached = bool(carry_attached)
         self.validity = validity if validity is not None else PandaValidity(device)
         self._snapshot: Optional[SceneSnapshot] = None
         self.rng_seed = 1
@@ -95,6 +100,13 @@ class PlannerInterface:
         if idx is None:
             raise PlanningError("attached_object has no .idx (planning.py:226)")
         return self._snapshot.index_of_entity(int(idx))
+
+    def _apply_attached(self, attached_object, q_grasp=None):
+        k = self._attached_index(attached_object)
+        if self.carry_attached and k >= 0 and q_grasp is not None:
+            self.validity.set_carried(k, q_grasp=np.asarray(tensor_to_array(q_grasp), dtype=np.float32))
+        else:
+            self.validity.set_attached(k)
 
     # ---- diagnostics (planning.py:32-57) ----------------------------------------------------------------
     def diagnose_bounds_violation(self, state, lower=None, upper=None):
@@ -173,7 +185,7 @@ class PlannerInterface:
             path = cand
         return path
 
-    def validate_trajectory(self, waypoints, attached_object=None) -> np.ndarray:
+    def validate_trajectory(self, waypoints, attached_object=None, q_grasp=None) -> np.ndarray:
         """Swept validation of an executed joint trajectory (next-row component 8f-4): the reference plays back the
         150 planned waypoints and many un-planned joint-space lerps (motion_primitives.py:163-173, 294-299, 404-409)
         with no collision check.  Returns one bool per segment (waypoint k -> k+1), each segment discretised at the
@@ -185,7 +197,8 @@ class PlannerInterface:
         pts = np.stack([tensor_to_array(w) for w in waypoints]).astype(np.float32)
         if len(pts) < 2:
             return np.ones(0, dtype=bool)
-        self.validity.set_attached(self._attached_index(attached_object))
+        # carry mode: the block is where the snapshot saw it when the robot is at q_grasp (default: the first waypoint)
+        self._apply_attached(attached_object, pts[0] if q_grasp is None else q_grasp)
         bits = self.validity.check_edges_host(pts[:-1], pts[1:], n_steps=0)
         self.validity.set_attached(-1)
         return ((bits[:, None] >> np.arange(32, dtype=np.uint32)) & 1).ravel()[: len(pts) - 1].astype(bool)
@@ -225,7 +238,7 @@ class PlannerInterface:
         t0 = time.perf_counter()
         snap = self.refresh_scene()
         self.attached_object = attached_object  # planning.py:153
-        self.validity.set_attached(self._attached_index(attached_object))
+        self._apply_attached(attached_object, tensor_to_array(qpos_cur))
         self.validity.set_flags(True, False)
 
         # diagnostics on start / goal (planning.py:163-183): log, keep going

@@ -42,6 +42,7 @@ class PandaValidity:
         self.device = torch.device("cuda", int(device))
         self.scene: Optional[SceneSnapshot] = None
         self.attached = -1
+        self.carried = None
         self.flags = FLAG_SELF
 
     # -- plumbing -------------------------------------------------------------------------------------
@@ -76,12 +77,42 @@ class PandaValidity:
         base = (C.c_float * 3)(*[float(v) for v in scene.base])
         self._ck(self.lib.pv_set_scene(self._h, obb.ctypes.data_as(C.POINTER(C.c_float)), obb.shape[0],
                                        float(scene.table_z), base), "pv_set_scene")
+        self._ck(self.lib.pv_set_attached(self._h, -1), "pv_set_attached")  # a new snapshot starts with nothing held
         self.scene = scene
         self.attached = -1
+        self.carried = None
 
     def set_attached(self, obb_index: int):
         self._ck(self.lib.pv_set_attached(self._h, int(obb_index)), "pv_set_attached")
         self.attached = int(obb_index)
+        self.carried = None
+
+    def set_carried(self, obb_index: int, hand_from_box=None, q_grasp=None, contact_allowance: float = 1e-3):
+        """Physically-correct alternative to `set_attached` (not what planning.py:216-230
+        does): scene box `obb_index` rides rigidly on the hand.  Give its pose in the hand frame as `hand_from_box` =
+        (R (3,3), t (3,)), or the configuration `q_grasp` the robot has while the box sits at its snapshot pose (the
+        moment of the grasp, motion_primitives.py:367-376).  The box is shrunk by `contact_allowance` in its own tests
+        so that resting contacts (block on the table, block on a block) do not read as collisions.  -1 leaves the
+        mode.  Returns (R, t)."""
+        k = int(obb_index)
+        if k < 0:
+            self._ck(self.lib.pv_set_carried(self._h, -1, None, 0.0), "pv_set_carried")
+            self.attached, self.carried = -1, None
+            return None
+        if hand_from_box is None:
+            if q_grasp is None or self.scene is None or not (0 <= k < self.scene.n_obb):
+                raise PandaValidityError("set_carried needs hand_from_box or q_grasp (and a valid scene-box index)")
+            pose = self.fk(torch.as_tensor(np.asarray(q_grasp, dtype=np.float32).reshape(1, 9)))[0, 8].double().cpu().numpy()
+            ph, Rh = pose[:3], pose[3:].reshape(3, 3)
+            rec = np.asarray(self.scene.obb, dtype=np.float64).reshape(-1, 16)[k]
+            R, t = Rh.T @ rec[6:15].reshape(3, 3), Rh.T @ (rec[0:3] - ph)
+        else:
+            R, t = (np.asarray(v, dtype=np.float64) for v in hand_from_box)
+        buf = np.ascontiguousarray(np.concatenate([R.reshape(9), t.reshape(3)]), dtype=np.float32)
+        self._ck(self.lib.pv_set_carried(self._h, k, buf.ctypes.data_as(C.POINTER(C.c_float)), float(contact_allowance)),
+                 "pv_set_carried")
+        self.attached, self.carried = k, (R.reshape(3, 3).copy(), t.reshape(3).copy(), float(contact_allowance))
+        return self.carried
 
     def set_flags(self, self_collision: bool = True, joint_limits: bool = False):
         self.flags = (FLAG_SELF if self_collision else 0) | (FLAG_LIMITS if joint_limits else 0)
@@ -278,15 +309,20 @@ def unpack_bits(words, n: int) -> np.ndarray:
     return b.reshape(-1)[:n].astype(bool)
 
 
+def _link_name(i: int) -> str:
+    """Link ids 0..10 are the Panda bodies; 11 is the box carried by the hand (pv_set_carried)."""
+    return pm.LINK_NAMES[i] if i < len(pm.LINK_NAMES) else "carried_object"
+
+
 def decode_culprit_pair(code: int):
     """(link name, other name) of a culprit code; other is a link name, 'ground', 'box<k>' or 'joint_limit'."""
     kind, a, b = (code >> 16) & 0xFF, (code >> 8) & 0xFF, code & 0xFF
     if kind == 1:
-        return (pm.LINK_NAMES[a], "ground")
+        return (_link_name(a), "ground")
     if kind == 2:
-        return (pm.LINK_NAMES[a], f"box{b}")
+        return (_link_name(a), f"box{b}")
     if kind == 3:
-        return (pm.LINK_NAMES[a], pm.LINK_NAMES[b])
+        return (_link_name(a), _link_name(b))
     if kind == 4:
         return (f"joint{a + 1}", "joint_limit")
     return ("none", "none")
@@ -295,11 +331,11 @@ def decode_culprit_pair(code: int):
 def decode_culprit(code: int) -> str:
     kind, a, b = (code >> 16) & 0xFF, (code >> 8) & 0xFF, code & 0xFF
     if kind == 1:
-        return f"{pm.LINK_NAMES[a]} vs ground plane"
+        return f"{_link_name(a)} vs ground plane"
     if kind == 2:
-        return f"{pm.LINK_NAMES[a]} vs scene box {b}"
+        return f"{_link_name(a)} vs scene box {b}"
     if kind == 3:
-        return f"{pm.LINK_NAMES[a]} vs {pm.LINK_NAMES[b]}"
+        return f"{_link_name(a)} vs {_link_name(b)}"
     if kind == 4:
         return f"joint {a + 1} outside its limits"
     return "none"

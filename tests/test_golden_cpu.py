@@ -42,3 +42,23 @@ def test_numpy_oracle_reproduces_golden(model):
     assert np.array_equal(m, G["goal4_task1_pentagon/margin"][:300])
     assert np.array_equal(po.sweep_configs(64, 512, 20251212, model, fingers_open=False).view(np.uint32),
                           G["sweep_q"].view(np.uint32))
+
+
+def test_oracle_vs_genesis_goldens(c64):
+    """Pins the oracle to the real reference stack -- IF tools/export_genesis_goldens.py has ever been run where
+    Genesis is installed.  It cannot be run in the build container, so this is skipped there and the
+    parity of the robot model vs Genesis stays "unpinned"."""
+    import glob
+    import pytest
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "genesis_*.npz")))
+    if not files:
+        pytest.skip("no Genesis golden vectors committed (Genesis/OMPL are not installable here): parity unpinned")
+    for f in files:
+        g = np.load(f)
+        s = sc.FIXTURES[str(g["scene"])]().as_oracle_scene()
+        R, p = c64.fk(g["q"])
+        assert np.abs(p - g["link_pos"]).max() < 1e-5  # the FK chain is exact; only the collision hulls are approximated
+        m = c64.state_margin(g["q"], s)
+        far = np.abs(m) > 5e-3  # primitives vs convexified meshes: agreement is only claimed away from contact
+        agree = ((m >= 0) == g["valid"])[far].mean()
+        assert agree > 0.99, (f, agree)

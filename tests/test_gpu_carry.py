@@ -1,0 +1,168 @@
+"""GPU tests of carry mode (pv_set_carried): the grasped block rides on the hand
+instead of staying a static obstacle where the snapshot saw it.  Same bars as test_gpu_parity.py: verdicts equal
+to the fp64 oracle outside the 1e-4 m band, margins within 1e-5 m."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import random_configs
+from rbe550_final_project_b200 import panda_model as pm
+from rbe550_final_project_b200 import scenes as sc
+from rbe550_final_project_b200.planning import PlannerInterface
+from rbe550_final_project_b200.sim_stub import create_scene
+from rbe550_final_project_b200.validity import PandaValidityError, decode_culprit_pair, unpack_bits
+
+pytestmark = pytest.mark.gpu
+
+BAND = 1e-4
+GOALS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "goal_configs.json")))
+
+
+def _dev(q):
+    return torch.as_tensor(q, device="cuda")
+
+
+def _rot(rz, rx):
+    cz, sz, cx, sx = np.cos(rz), np.sin(rz), np.cos(rx), np.sin(rx)
+    return np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1.0]]) @ np.array([[1.0, 0, 0], [0, cx, -sx], [0, sx, cx]])
+
+
+def _mismatch(gpu_valid, margin):
+    far = np.abs(margin) > BAND
+    return np.nonzero((gpu_valid != (margin >= 0)) & far)[0]
+
+
+@pytest.mark.parametrize("scene_name,k", [("goal3_tower", 8), ("goal4_task1_pentagon", 3)])
+def test_carry_states_edges_margins_match_oracle(pv, c64, scene_name, k):
+    scene = sc.FIXTURES[scene_name]()
+    pv.set_scene(scene)
+    pv.set_flags(True, False)
+    R, t = _rot(0.3, 0.1), np.array([0.004, -0.006, 0.1034])
+    pv.set_carried(k, hand_from_box=(R, t), contact_allowance=1e-3)
+    osc = scene.as_oracle_scene()
+    osc["carried"] = dict(index=k, R=R, t=t, shrink=1e-3)
+
+    n = 100_003
+    q = random_configs(n, 61 + k, fingers="random")
+    gpu = unpack_bits(pv.check_states(_dev(q)), n)
+    ref = c64.state_margin(q.astype(np.float64), osc)
+    bad = _mismatch(gpu, ref)
+    assert bad.size == 0, (bad[:5], ref[bad[:5]])
+    # the carried box really matters: verdicts differ from the reference rule (block left behind, contacts forgiven)
+    ref_attached = c64.state_margin(q.astype(np.float64), scene.as_oracle_scene(), attached=k)
+    assert ((ref >= 0) != (ref_attached >= 0)).mean() > 0.001
+
+    m, cu = pv.state_margins(_dev(q), want_culprit=True)
+    m, cu = m.cpu().numpy(), cu.cpu().numpy()
+    assert np.abs(m - ref).max() < 1e-5
+    names = {decode_culprit_pair(int(c)) for c in cu[m < 0][:20000]}
+    assert any("carried_object" in pair for pair in names)
+    # host entry point (AoS rows) == device entry point
+    assert (unpack_bits(pv.check_states_host(q[:70_001]), 70_001) == gpu[:70_001]).all()
+
+    # edges, fixed-step and resolution mode
+    ne = 10_001
+    qa = q[:ne]
+    rng = np.random.default_rng(7)
+    qb = np.clip(qa + rng.normal(0, 0.3, qa.shape), pm.Q_LOWER, pm.Q_UPPER).astype(np.float32)
+    for n_steps in (64, 0):
+        ge = unpack_bits(pv.check_edges(_dev(qa), _dev(qb), n_steps=n_steps), ne)
+        re_ = c64.edge_margin(qa.astype(np.float64), qb.astype(np.float64), osc, n_steps=n_steps)
+        bad = _mismatch(ge, re_)
+        assert bad.size == 0, (n_steps, bad[:5], re_[bad[:5]])
+        me = pv.edge_margins(_dev(qa), _dev(qb), n_steps=n_steps).cpu().numpy()
+        assert np.abs(me - re_).max() < 2e-5
+
+    # contact lists name the carried box
+    hit = np.nonzero((m < 0) & ((((cu >> 8) & 0xFF) == 11) | ((cu & 0xFF) == 11)))[0][:50]
+    if hit.size:
+        lists = pv.contacts(_dev(q[hit]))
+        assert all(any("carried_object" in pair for pair in lst) for lst in lists)
+
+    # leaving the mode restores the reference rule exactly
+    pv.set_attached(k)
+    gpu2 = unpack_bits(pv.check_states(_dev(q)), n)
+    assert _mismatch(gpu2, ref_attached).size == 0
+    pv.set_carried(k, hand_from_box=(R, t))
+    pv.set_carried(-1)
+    assert pv.attached == -1
+    gpu3 = unpack_bits(pv.check_states(_dev(q)), n)
+    assert _mismatch(gpu3, c64.state_margin(q.astype(np.float64), scene.as_oracle_scene())).size == 0
+
+
+def test_carry_semantics_on_the_goal1_pick_and_place(pv, c64):
+    """block r grasped at grasp_r: resting contacts are fine, pushing it into the table or into block g is not"""
+    scene = sc.goal1_scattered()
+    pv.set_scene(scene)
+    pv.set_flags(True, False)
+    g = GOALS["goal1_scattered"]
+    q_grasp = np.array(g["grasp_r"]["q"])
+    R, t, _ = pv.set_carried(0, q_grasp=q_grasp)
+    assert np.allclose(t, [0, 0, 0.12], atol=1e-5) and np.allclose(np.abs(np.diag(R)), 1, atol=1e-5)
+    osc = scene.as_oracle_scene()
+    osc["carried"] = dict(index=0, R=R, t=t, shrink=1e-3)
+    expect = {"grasp_r": True, "place_050_000": True, "carry_on_g": True, "carry_low_r": False, "carry_into_g": False}
+    for name, ok in expect.items():
+        q = np.array(g[name]["q"])
+        assert pv.is_state_valid(q) == ok, name
+        assert (c64.state_margin(q[None], osc)[0] >= 0) == ok, name
+    # culprits: the table, then block g (scene box 1)
+    m, cu = pv.state_margins(_dev(np.stack([g["carry_low_r"]["q"], g["carry_into_g"]["q"]]).astype(np.float32)),
+                             want_culprit=True)
+    assert decode_culprit_pair(int(cu[0])) == ("carried_object", "ground")
+    assert decode_culprit_pair(int(cu[1])) == ("carried_object", "box1")
+    assert abs(float(m[0]) + 0.014) < 1e-4 and abs(float(m[1]) + 0.019) < 1e-4
+    # under the reference rule all five poses pass: the block is "left behind" and forgiven
+    pv.set_attached(0)
+    assert all(pv.is_state_valid(np.array(g[name]["q"])) for name in expect)
+    pv.set_attached(-1)
+
+
+def test_carry_rejects_bad_arguments(pv):
+    pv.set_scene(sc.goal1_scattered())
+    with pytest.raises(PandaValidityError):
+        pv.set_carried(6, hand_from_box=(np.eye(3), np.zeros(3)))
+    with pytest.raises(PandaValidityError):
+        pv.set_carried(0, hand_from_box=(2.0 * np.eye(3), np.zeros(3)))
+    with pytest.raises(PandaValidityError):
+        pv.set_carried(0, hand_from_box=(np.eye(3), np.zeros(3)), contact_allowance=0.02)  # >= half extent
+    with pytest.raises(PandaValidityError):
+        pv.set_carried(0)
+    assert pv.carried is None
+
+
+def test_plan_path_carrying_the_block(pv, c64):
+    """plan_path(attached_object=blk) with carry_attached=True: the whole path keeps the CARRIED block clear of the
+    table and of the other blocks; the reference rule does not promise that."""
+    scene, franka, blocks = create_scene("goal1_scattered")
+    g = GOALS["goal1_scattered"]
+    q_grasp = np.array(g["grasp_r"]["q"])
+    q_grasp[7:] = 0.02                   # fingers closed onto the 4 cm block
+    franka.set_qpos(q_grasp)
+    goal = np.array(g["carry_on_g"]["q"])  # put r down on top of g
+    goal[7:] = 0.02
+    planner = PlannerInterface(franka, scene, validity=pv, carry_attached=True)
+    path = planner.plan_path(qpos_goal=goal, num_waypoints=150, attached_object=blocks["r"], timeout=10.0)
+    assert len(path) == 150 and planner.last_stats["solved"]
+    arr = np.stack([w.numpy() for w in path]).astype(np.float64)
+    assert np.allclose(arr[0], q_grasp, atol=1e-6) and np.allclose(arr[-1], goal, atol=1e-6)
+    R, t, shrink = pv.carried
+    osc = sc.goal1_scattered().as_oracle_scene()
+    osc["carried"] = dict(index=0, R=R, t=t, shrink=shrink)
+    # waypoints are resampled BETWEEN the states the planner validated, and both end points rest in contact (1 mm
+    # allowance), so allow a few grazing waypoints but nothing deeper than the allowance
+    wm = c64.state_margin(arr, osc)
+    assert (wm > -1e-4).mean() > 0.97 and wm.min() > -2e-3
+    seg = planner.validate_trajectory(path, attached_object=blocks["r"])
+    assert seg.mean() > 0.95
+    # a goal that sinks the carried block into g is refused (soft failure: [] as for any invalid goal) ...
+    bad_goal = np.array(g["carry_into_g"]["q"])
+    bad_goal[7:] = 0.02
+    assert planner.plan_path(qpos_goal=bad_goal, attached_object=blocks["r"], timeout=1.0) == []
+    # ... while the reference rule happily plans to it
+    ref_planner = PlannerInterface(franka, scene, validity=pv)
+    assert len(ref_planner.plan_path(qpos_goal=bad_goal, num_waypoints=50, attached_object=blocks["r"], timeout=10.0)) == 50
+    pv.set_attached(-1)

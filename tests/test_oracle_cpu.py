@@ -86,6 +86,33 @@ def test_acceptance_constraints(model):
             assert np.allclose(R[0, 8][:, 2], [0, 0, -1], atol=1e-5)  # quat [0,1,0,0]: hand z down
 
 
+def test_carry_mode_semantics(model, c64, c32):
+    """SURVEY.md 8f-3 / App. E-3 (not reference behaviour): block r rides on the hand; resting contacts pass
+    (1 mm allowance), pushing the block into the table or into block g does not; numpy == C oracle."""
+    scene = sc.goal1_scattered()
+    s = scene.as_oracle_scene()
+    goals = json.load(open(os.path.join(GOLD, "goal_configs.json")))["goal1_scattered"]
+    qg = np.array(goals["grasp_r"]["q"])
+    R, p = po.fk(qg[None])
+    Rh, ph = R[0, 8], p[0, 8]
+    rec = np.asarray(s["obb"], dtype=np.float64).reshape(-1, 16)[0]
+    s["carried"] = dict(index=0, R=Rh.T @ rec[6:15].reshape(3, 3), t=Rh.T @ (rec[0:3] - ph), shrink=1e-3)
+    expect = {"grasp_r": 0.001, "place_050_000": 0.103, "carry_on_g": 0.001, "carry_low_r": -0.014, "carry_into_g": -0.019}
+    for name, m in expect.items():
+        got = po.state_margin(np.array(goals[name]["q"])[None], s, model)[0]
+        assert abs(got - m) < 1e-6, (name, got)
+    q = random_configs(4000, 77, fingers="random").astype(np.float64)
+    a = po.state_margin(q, s, model)
+    assert np.abs(a - c64.state_margin(q, s)).max() < 1e-12
+    assert np.abs(a - c32.state_margin(q, s)).max() < 1e-5
+    base = dict(s)
+    del base["carried"]
+    assert ((a >= 0) != (po.state_margin(q, base, model, attached=0) >= 0)).mean() > 0.002
+    qb = np.clip(q + np.random.default_rng(3).normal(0, 0.3, q.shape), pm.Q_LOWER, pm.Q_UPPER)
+    e = po.edge_margin(q[:300], qb[:300], s, model, n_steps=0)
+    assert np.abs(e - c64.edge_margin(q[:300], qb[:300], s, n_steps=0)).max() < 1e-12
+
+
 def test_attached_and_self_semantics(model):
     s = sc.goal1_scattered().as_oracle_scene()
     goals = json.load(open(os.path.join(GOLD, "goal_configs.json")))
