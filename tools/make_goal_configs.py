@@ -54,9 +54,10 @@ def main():
         "goal1_scattered": [("approach_r", (0.65, 0.0, 0.02 + 0.02 + 0.18)), ("grasp_r", (0.65, 0.0, 0.02 + 0.12)),
                             ("approach_c", (0.45, 0.4, 0.22)), ("place_050_000", (0.50, 0.0, 0.02 + 0.12 + 0.15)),
                             # carry-mode cases (block r in the hand, grasped at grasp_r): pushed 15 mm into the table,
-                            # resting exactly on block g, and sunk half-way into block g
+                            # resting exactly on block g, hovering 3 cm above it, and sunk half-way into block g
                             ("carry_low_r", (0.65, 0.0, 0.02 + 0.12 - 0.015)),
                             ("carry_on_g", (0.65, 0.2, 0.02 + 0.04 + 0.12)),
+                            ("carry_above_g", (0.65, 0.2, 0.02 + 0.04 + 0.12 + 0.03)),
                             ("carry_into_g", (0.65, 0.2, 0.02 + 0.02 + 0.12))],
         # goal3 tower: approach above the 8-high tower top (z = 0.30 centre) and the loose blocks
         "goal3_tower": [("approach_top", (0.45, 0.0, 0.30 + 0.02 + 0.18)), ("approach_r2", (0.65, -0.4, 0.22)),
