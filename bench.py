@@ -9,7 +9,7 @@ total size exceeds L2, so no step re-reads a cached batch.
   value     device-resident throughput: inputs already in HBM as SoA float4 planes, CUDA-event timed
   e2e       the same metric through the reference-facing C-ABI call pv_check_states_host: AoS host rows
             in pinned memory -> H2D -> kernel -> D2H verdict bits, every step, wall-clock around the call
-  roofline  FP32 CUDA-core roofline of the dominant kernel (pv_state_bits_kernel), plus the HBM fraction
+  roofline  FP32 CUDA-core roofline of the dominant kernel (pv_state_bits_sorted_kernel), plus the HBM fraction
   cpu_baseline  the CPU oracle port (fp32, OpenMP) on a bounded sample, timed on this box's host cores
 
 N > 1 (torchrun): every rank checks its own batches (weak scaling; config 5 flavour) and the verdict
@@ -320,7 +320,7 @@ def main():
         # same kernel on the same workload, committed under profiles/) x the rate measured live in this run
         achieved_tflops = float(executed["fp32_flops_per_check"]) * per_gpu_rate / 1e12
     roofline = {
-        "bound": "fp32", "kernel": "pv_state_bits_kernel", "achieved": achieved_tflops, "peak": fp32_peak_tflops,
+        "bound": "fp32", "kernel": "pv_state_bits_sorted_kernel", "achieved": achieved_tflops, "peak": fp32_peak_tflops,
         "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
         "achieved_definition": ("executed FP32 FLOPs/check from profiles/executed_flops.json x live checks/s"
                                 if executed and executed.get("fp32_flops_per_check") else

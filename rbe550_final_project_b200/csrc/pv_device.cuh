@@ -55,10 +55,68 @@ __device__ constexpr int pv_sphere_link[PV_N_SPHERES] = PV_SPHERE_LINK;
 
 template <int MODE>
 struct PvAcc;
+// PV_PACK (opt-in experiment, off): two sphere-sphere tests per instruction with the packed FP32 forms of sm_100a
+// (FADD2 / FFMA2, PTX *.f32x2).  A packed instruction takes one issue slot for two results (tools/probes/
+// f32x2_probe.cu: FFMA2 sustains the FLOP/s of FFMA at half the issue rate) and the self-collision block shrinks from 88
+// scalar to 51 packed tests, yet the kernel came out 1 % SLOWER on the same box (9.04 vs 9.14 G checks/s, verdicts
+// bit-identical): with 4 warps per scheduler the check is bound by dependent-instruction latency as much as by issue
+// slots (profiles/r1_notes.md), and the packed forms do not shorten the chains.
+#ifndef PV_PACK
+#define PV_PACK 0
+#endif
+#ifndef PV_PACK_ACC
+#define PV_PACK_ACC 1
+#endif
 template <>
 struct PvAcc<PV_MODE_BITS> {
     bool hit = false;
+    // packed tests accumulate min(d^2 - r^2) here (one FMNMX3 per two tests); hit |= min(m) < 0 at the end.  PV_PACK_ACC
+    // independent accumulators keep the FMNMX3 chain from serialising the tests.
+    float m[4] = {1e30f, 1e30f, 1e30f, 1e30f};
+    __device__ __forceinline__ bool packed_hit() const { return fminf(fminf(m[0], m[1]), fminf(m[2], m[3])) < 0.f; }
 };
+
+typedef unsigned long long pv_f2;  // two floats in an aligned register pair
+__device__ __forceinline__ pv_f2 pv_pk(float lo, float hi) {
+    pv_f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void pv_upk(pv_f2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ pv_f2 pv_fma2(pv_f2 a, pv_f2 b, pv_f2 c) {
+    pv_f2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ pv_f2 pv_sub2(pv_f2 a, pv_f2 b) {
+    pv_f2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ pv_f2 pv_add2(pv_f2 a, pv_f2 b) {
+    pv_f2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ pv_f2 pv_mul2(pv_f2 a, pv_f2 b) {
+    pv_f2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// sphere a against spheres b0 and b1 at once: n0, n1 = -(ra + rb)^2 (0 masks a half)
+template <int K>
+__device__ __forceinline__ void pv_sphere_sphere2(PvAcc<PV_MODE_BITS>& acc, float3 a, float3 b0, float3 b1, float n0,
+                                                  float n1) {
+    pv_f2 dx = pv_sub2(pv_pk(a.x, a.x), pv_pk(b0.x, b1.x));
+    pv_f2 dy = pv_sub2(pv_pk(a.y, a.y), pv_pk(b0.y, b1.y));
+    pv_f2 dz = pv_sub2(pv_pk(a.z, a.z), pv_pk(b0.z, b1.z));
+    pv_f2 d2 = pv_fma2(dz, dz, pv_fma2(dy, dy, pv_fma2(dx, dx, pv_pk(n0, n1))));
+    float lo, hi;
+    pv_upk(d2, lo, hi);
+    acc.m[K % PV_PACK_ACC] = fminf(acc.m[K % PV_PACK_ACC], fminf(lo, hi));
+}
 // contact list (diagnostics): the codes of every test in penetration, like the pair list detect_collision returns
 template <>
 struct PvAcc<PV_MODE_LIST> {
@@ -364,6 +422,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
     if constexpr (SYNC >= level) __syncthreads();
 #define PV_EARLY_EXIT()                                                              \
     if constexpr (MODE == PV_MODE_BITS && EXIT != PV_EXIT_NONE) {                    \
+        if constexpr (PV_PACK) acc.hit |= acc.packed_hit();                             \
         bool h_ = acc.hit;                                                           \
         if (EXIT == PV_EXIT_ALL ? __all_sync(FULL, h_) : __any_sync(FULL, h_)) return; \
     }
@@ -471,16 +530,22 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
     }
     if (S.flags & PV_FLAG_SELF) {
 #define PV_SS(a, b, rr2, rr) pv_sphere_sphere<MODE>(acc, s[a], s[b], rr2, rr, PV_SELF_CODE(a, pv_sphere_link[b]));
+#define PV_SS2(a, b0, b1, n0, n1, k) pv_sphere_sphere2<k>(acc, s[a], s[b0], s[b1], n0, n1);
 #define PV_LP(la, lb, ca, cb, cull2)                         \
     {                                                        \
         float3 d_ = v_sub(s[ca], s[cb]);                     \
         if (!CULL || v_dot(d_, d_) < cull2) {                \
-            PV_SS_PAIRS_##la##_##lb(PV_SS)                   \
+            if constexpr (MODE == PV_MODE_BITS && PV_PACK) { \
+                PV_SS2_PAIRS_##la##_##lb(PV_SS2)             \
+            } else {                                         \
+                PV_SS_PAIRS_##la##_##lb(PV_SS)               \
+            }                                                \
         }                                                    \
     }
         PV_SS_LINKPAIRS(PV_LP)
 #undef PV_LP
 #undef PV_SS
+#undef PV_SS2
         PV_EARLY_EXIT()
         PV_LOCKSTEP(1)
         // sphere-vs-gripper pairs: the three gripper boxes share the hand's axes, so each proximal sphere is moved
@@ -602,6 +667,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
         }
         PV_EARLY_EXIT()
     }
+    if constexpr (MODE == PV_MODE_BITS && PV_PACK) acc.hit |= acc.packed_hit();
 #undef PV_EARLY_EXIT
 #undef PV_LOCKSTEP
 }

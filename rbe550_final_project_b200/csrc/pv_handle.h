@@ -29,6 +29,7 @@ struct PvHandle {
     int sm_count;
     int has_scene;
     int cull;
+    unsigned smem_attr_mask;  // which sorted-kernel instantiations already have their dynamic shared memory opt-in
     long long launches;
     PvScene scene;
     PvGather gather;

@@ -89,6 +89,191 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     }
 }
 
+// ---- sorted variant ------------------------------------------------------------------------------------------
+// The per-lane culls only pay when a whole warp can skip a block of tests, and with unordered inputs some lane of the
+// 32 nearly always needs it (self-collision blocks ran with ~8 of 32 lanes live: profiles/r1_notes.md).  Which blocks
+// a configuration needs is decided mostly by the elbow angle q[3] (it alone fixes the shoulder-wrist distance), so a
+// block first counting-sorts ITS share of the batch (the same 512-configuration chunks the unsorted kernel gives it,
+// up to PV_ST configurations at a time) by q[3] in shared memory -- keys and 16-bit indices only; the configurations
+// stay in global memory / L2 and are gathered -- and then walks that share in sorted order: the 32 lanes of a warp,
+// and the 16 warps that meet at the lockstep barrier, hold near-equal elbow angles and skip or take the same blocks.
+// Verdict bits return to their ORIGINAL positions through a shared-memory bit array, so the output (and the fused
+// gather) is unchanged.
+#ifndef PV_ST
+#define PV_ST 16384  // super-tile: at most this many configurations are sorted together (32 chunks)
+#endif
+#define PV_SORT_BUCKETS 256
+static_assert(PV_ST % PV_SB_THREADS == 0 && PV_ST <= 65536, "super-tile = whole chunks, indices fit 16 bits");
+
+__device__ __forceinline__ void pv_emit_word_thread(uint32_t* __restrict__ bits, const PvGather& G, int64_t w, unsigned word) {
+    if (bits) bits[w] = word;
+    if (w >= G.word_cap) return;
+    if (G.mc) {
+        asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(G.mc + G.word_off + w), "r"(word) : "memory");
+    } else if (G.peers) {
+        for (int p = 0; p < G.n_peers; ++p) G.peers[p][G.word_off + w] = word;
+    }
+}
+
+__device__ __forceinline__ int pv_sort_key(float q3) {
+    const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
+    const float scale = (float)PV_SORT_BUCKETS / (hi[3] - lo[3]);
+    return (int)fminf(fmaxf((q3 - lo[3]) * scale, 0.f), (float)(PV_SORT_BUCKETS - 1));  // NaN -> bucket 0
+}
+
+__device__ __forceinline__ void pv_cp_async4(void* smem, const void* g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g));
+}
+__device__ __forceinline__ void pv_cp_async16(void* smem, const void* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g));
+}
+
+// shared memory of the sorted kernel (dynamic: above the 48 KB static limit)
+struct PvSortSmem {
+    static constexpr int ST = PV_ST;
+    float4 stA[2][PV_SB_THREADS], stB[2][PV_SB_THREADS];  // double-buffered staging of the NEXT iteration's configuration
+    float st9[2][PV_SB_THREADS];                         // (SoA inputs; AoS inputs use stq)
+    float stq[2][9][PV_SB_THREADS];
+    unsigned short order[PV_ST];
+    unsigned char key8[PV_ST];
+    unsigned hist[PV_SORT_BUCKETS];
+    unsigned vbits[PV_ST / 32];
+    int cnt;
+};
+// where the configurations come from: two float4 planes (+ optional ninth plane) or (n, 9) rows.  (The device-generated
+// sweep keeps the unsorted kernel: it has no loads to hide, and parking the generated configurations in shared memory
+// for the sort cost as much as the sort saved -- 8.87 vs 8.91 G checks/s, profiles/r1_notes.md.)
+enum { PV_SRC_SOA = 0, PV_SRC_AOS = 1 };
+
+template <int SRC, bool CARRY>
+__global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
+    pv_state_bits_sorted_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA,
+                                const float4* __restrict__ qB, const float* __restrict__ q9,
+                                const float* __restrict__ q_aos, int64_t n, uint32_t* __restrict__ bits,
+                                const __grid_constant__ PvGather G) {
+    constexpr bool AOS = SRC == PV_SRC_AOS;
+    typedef PvSortSmem Smem;
+    constexpr int ST_CHUNKS = Smem::ST / PV_SB_THREADS;
+    extern __shared__ __align__(16) unsigned char pv_sort_smem_raw[];
+    Smem& M = *reinterpret_cast<Smem*>(pv_sort_smem_raw);
+    unsigned short* order = M.order;
+    unsigned* hist = M.hist;
+    unsigned* vbits = M.vbits;
+    int& s_cnt = M.cnt;
+    const int tid = threadIdx.x;
+    const int64_t n_words = (n + 31) >> 5;
+    const int64_t n_chunks = (n + PV_SB_THREADS - 1) / PV_SB_THREADS;
+    if ((int64_t)blockIdx.x >= n_chunks) return;
+    const int64_t my_chunks = (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    // local index L = jj * 512 + t of super-tile j0  <->  configuration (blockIdx.x + (j0 + jj) * gridDim.x) * 512 + t
+#define PV_GI(jj, t) ((((int64_t)blockIdx.x + (j0 + (jj)) * (int64_t)gridDim.x) * PV_SB_THREADS) + (t))
+#define PV_Q3_OF(i) (AOS ? __ldg(q_aos + 9 * (i) + 3) : __ldg(reinterpret_cast<const float*>(qA) + 4 * (i) + 3))
+    for (int64_t j0 = 0; j0 < my_chunks; j0 += ST_CHUNKS) {
+        const int nc = (int)((my_chunks - j0 < (int64_t)ST_CHUNKS) ? (my_chunks - j0) : (int64_t)ST_CHUNKS);
+        if (tid < PV_SORT_BUCKETS) hist[tid] = 0;
+        for (int w = tid; w < nc * (PV_SB_THREADS / 32); w += PV_SB_THREADS) vbits[w] = 0;
+        __syncthreads();
+        // pass 1: keys (kept as bytes for pass 2) and their histogram; the key loads of 8 chunks are in flight together
+        for (int j8 = 0; j8 < nc; j8 += 8) {
+            float kq[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t i = PV_GI(j8 + u, tid);
+                kq[u] = 0.f;
+                if (j8 + u < nc && i < n) kq[u] = PV_Q3_OF(i);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t i = PV_GI(j8 + u, tid);
+                if (j8 + u < nc && i < n) {
+                    const int key = pv_sort_key(kq[u]);
+                    M.key8[(j8 + u) * PV_SB_THREADS + tid] = (unsigned char)key;
+                    atomicAdd(&hist[key], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {  // exclusive prefix sum: 8 buckets per lane + a warp scan
+            constexpr int PER = PV_SORT_BUCKETS / 32;
+            unsigned v[PER], sum = 0;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                v[j] = hist[tid * PER + j];
+                sum += v[j];
+            }
+            unsigned incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (tid >= d) incl += o;
+            }
+            unsigned run = incl - sum;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                hist[tid * PER + j] = run;
+                run += v[j];
+            }
+            if (tid == 31) s_cnt = (int)incl;
+        }
+        __syncthreads();
+        for (int jj = 0; jj < nc; ++jj) {  // pass 2: scatter the local indices (order inside a bucket does not matter)
+            const int64_t i = PV_GI(jj, tid);
+            if (i < n) order[atomicAdd(&hist[M.key8[jj * PV_SB_THREADS + tid]], 1u)] = (unsigned short)(jj * PV_SB_THREADS + tid);
+        }
+        __syncthreads();
+        const int cnt = s_cnt;
+        // the gathers of iteration r + 1 are issued (cp.async into shared memory, no registers held) before the check of
+        // iteration r starts, so their L2 latency hides behind ~2000 instructions of work
+        int L_next = 0;
+#define PV_PREFETCH(r_)                                                                         \
+    {                                                                                           \
+        const int slot_ = (r_) * PV_SB_THREADS + tid;                                           \
+        L_next = order[slot_ < cnt ? slot_ : cnt - 1];                                          \
+        const int64_t i_ = PV_GI(L_next / PV_SB_THREADS, L_next % PV_SB_THREADS);               \
+        const int b_ = (r_) & 1;                                                                \
+        if constexpr (AOS) {                                                                    \
+            _Pragma("unroll") for (int j = 0; j < 9; ++j) pv_cp_async4(&M.stq[b_][j][tid], q_aos + 9 * i_ + j); \
+        } else {                                                                                \
+            pv_cp_async16(&M.stA[b_][tid], qA + i_);                                            \
+            pv_cp_async16(&M.stB[b_][tid], qB + i_);                                            \
+            if (q9) pv_cp_async4(&M.st9[b_][tid], q9 + i_);                                     \
+        }                                                                                       \
+        asm volatile("cp.async.commit_group;" ::: "memory");                                    \
+    }
+        PV_PREFETCH(0)
+        for (int r = 0; r < nc; ++r) {
+            const int slot = r * PV_SB_THREADS + tid;
+            const bool in = slot < cnt;
+            const int L = L_next;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            float q[9];
+            if constexpr (AOS) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) q[j] = M.stq[r & 1][j][tid];
+            } else {
+                const float4 a = M.stA[r & 1][tid], b = M.stB[r & 1][tid];
+                q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w;
+                q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
+                q[8] = q9 ? M.st9[r & 1][tid] : b.w;
+            }
+            if (r + 1 < nc) PV_PREFETCH(r + 1)
+            __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
+            PvAcc<PV_MODE_BITS> acc;
+            pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, PV_SB_SYNC, true, CARRY>(q, S, acc);
+            if (in && !acc.hit) atomicOr(&vbits[L >> 5], 1u << (L & 31));
+        }
+        __syncthreads();
+        for (int wl = tid; wl < nc * (PV_SB_THREADS / 32); wl += PV_SB_THREADS) {
+            const int64_t w = (PV_GI(wl / (PV_SB_THREADS / 32), 0) >> 5) + (wl % (PV_SB_THREADS / 32));
+            if (w < n_words) pv_emit_word_thread(bits, G, w, vbits[wl]);
+        }
+        __syncthreads();  // the next super-tile clears hist / vbits
+    }
+#undef PV_PREFETCH
+#undef PV_GI
+#undef PV_Q3_OF
+}
+
 template <bool CULL, bool CARRY>
 __global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
     pv_state_margin_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA,
@@ -263,7 +448,7 @@ int pv_create(int device, PvHandle** out) {
     h->scene.attached = -1;
     h->scene.flags = PV_FLAG_SELF;
     h->scene.base[2] = 0.01f;
-    h->cull = 1;
+    h->cull = 2;
     if ((e = cudaSetDevice(device)) != cudaSuccess) {
         snprintf(g_create_error, sizeof(g_create_error), "cudaSetDevice: %s", cudaGetErrorString(e));
         delete h;
@@ -453,7 +638,7 @@ int pv_set_flags(PvHandle* h, unsigned flags) {
 // bounding-ball culling in front of each block of tests (default).  Verdicts are bit-identical.
 int pv_set_culling(PvHandle* h, int on) {
     if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
-    h->cull = on ? 1 : 0;
+    h->cull = on < 0 ? 0 : (on > 2 ? 2 : on);  // 0 brute force, 1 per-lane culling, 2 tile-sorted + culling
     return PV_OK;
 }
 
@@ -512,7 +697,28 @@ static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_q
             h->scene, (const float4*)d_qA, (const float4*)d_qB, d_q9, d_aos, n, d_bits,                       \
             d_aos ? PvGather{} : h->gather);                                                                  \
     }
-    if (h->scene.carry) {  // carry mode always culls (the brute-force variant exists for the A/B identity test)
+#define PV_LAUNCH_SORTED(AOS_, CARRY)                                                                         \
+    {                                                                                                         \
+        int64_t chunks = (n + PV_SB_THREADS - 1) / PV_SB_THREADS;                                             \
+        int grid = (int)(chunks < (int64_t)h->sm_count ? chunks : (int64_t)h->sm_count);                      \
+        constexpr int SRC_ = (AOS_) ? PV_SRC_AOS : PV_SRC_SOA;                                                \
+        const unsigned bit_ = 1u << (2 * SRC_ + (CARRY ? 1 : 0));                                             \
+        if (!(h->smem_attr_mask & bit_)) {                                                                    \
+            PV_CUDA(h, cudaFuncSetAttribute(pv_state_bits_sorted_kernel<SRC_, CARRY>,                         \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PvSortSmem))); \
+            h->smem_attr_mask |= bit_;                                                                        \
+        }                                                                                                     \
+        pv_state_bits_sorted_kernel<SRC_, CARRY><<<grid, PV_SB_THREADS, sizeof(PvSortSmem), st>>>(            \
+            h->scene, (const float4*)d_qA, (const float4*)d_qB, d_q9, d_aos, n, d_bits,                       \
+            d_aos ? PvGather{} : h->gather);                                                                  \
+    }
+    if (h->cull == 2) {  // tile-sorted + per-lane culling (the default)
+        if (h->scene.carry) {
+            if (d_aos) PV_LAUNCH_SORTED(true, true) else PV_LAUNCH_SORTED(false, true)
+        } else {
+            if (d_aos) PV_LAUNCH_SORTED(true, false) else PV_LAUNCH_SORTED(false, false)
+        }
+    } else if (h->scene.carry) {  // carry mode always culls (the brute-force variant exists for the A/B identity test)
         if (d_aos) PV_LAUNCH_SB(true, true, true) else PV_LAUNCH_SB(false, true, true)
     } else if (d_aos) {
         if (h->cull) PV_LAUNCH_SB(true, true, false) else PV_LAUNCH_SB(true, false, false)
@@ -520,6 +726,7 @@ static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_q
         if (h->cull) PV_LAUNCH_SB(false, true, false) else PV_LAUNCH_SB(false, false, false)
     }
 #undef PV_LAUNCH_SB
+#undef PV_LAUNCH_SORTED
     h->launches++;
     PV_CUDA(h, cudaGetLastError());
     return PV_OK;

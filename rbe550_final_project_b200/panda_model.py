@@ -419,6 +419,38 @@ def header_text() -> str:
                 rs = float(np.float32(SPHERE_RADIUS[p] + SPHERE_RADIUS[q]))
                 a(f"  X({p}, {q}, {_f(rs * rs)}, {_f(rs)}) \\")
         a("")
+    # ---- the same pairs, two per instruction (sm_100a packed FP32: FADD2 / FFMA2) -----------------------------
+    a("// Packed form of the pair lists above: X2(a, b0, b1, n0, n1, k) tests sphere a against spheres b0 and b1 in one go")
+    a("// (k = running index mod 4, for callers that spread the results over independent accumulators);")
+    a("// n = -(ra+rb)^2, or 0 for a half that is not on the list (then d^2 + 0 < 0 never fires).  b0, b1 are neighbours")
+    a("// inside one link (b1 == b0 for the odd one out), so each sphere has ONE register partner.")
+    for la, lb in lps:
+        pairs = {(int(p), int(q)) for p, q in SS_PAIRS if (int(SPHERE_LINK[p]), int(SPHERE_LINK[q])) == (la, lb)}
+        best = None
+        for swap in (False, True):  # broadcast side = la (pack lb) or lb (pack la)
+            pl = lb if not swap else la
+            idx = [i for i in range(N_SPHERES) if int(SPHERE_LINK[i]) == pl]
+            slots = [(idx[k], idx[k + 1] if k + 1 < len(idx) else idx[k]) for k in range(0, len(idx), 2)]
+            bl = la if not swap else lb
+            rows = []
+            for s_ in [i for i in range(N_SPHERES) if int(SPHERE_LINK[i]) == bl]:
+                for b0, b1 in slots:
+                    def rr2(x):
+                        key = (s_, x) if not swap else (x, s_)
+                        if key not in pairs:
+                            return None
+                        rs = float(np.float32(SPHERE_RADIUS[key[0]] + SPHERE_RADIUS[key[1]]))
+                        return rs * rs
+                    n0, n1 = rr2(b0), (rr2(b1) if b1 != b0 else None)
+                    if n0 is None and n1 is None:
+                        continue
+                    rows.append((s_, b0, b1, -n0 if n0 is not None else 0.0, -n1 if n1 is not None else 0.0))
+            if best is None or len(rows) < len(best):
+                best = rows
+        a(f"#define PV_SS2_PAIRS_{la}_{lb}(X2) \\")
+        for k_, (s_, b0, b1, n0, n1) in enumerate(best):
+            a(f"  X2({s_}, {b0}, {b1}, {_f(n0)}, {_f(n1)}, {k_ % 4}) \\")
+        a("")
     # ---- sphere-vs-gripper self pairs evaluated in the hand frame ---------------------------------------------
     a("// gripper boxes in the HAND frame: X(k, cx, cy0, cz, slide_sign, finger_q_index, hx, hy, hz); the centre's y is")
     a("// cy0 + slide_sign * q[finger_q_index] (hand: sign 0).  All three boxes share the hand's axes.")

@@ -124,7 +124,9 @@ class PandaValidity:
                                         C.c_void_p(multicast_ptr or None), int(word_offset), int(word_capacity)), "pv_set_gather")
 
     def set_culling(self, mode):
-        """State-kernel variant: 0 brute force, 1 per-lane bounding-ball culling (default); bit-identical verdicts."""
+        """State-kernel variant: 0 brute force, 1 per-lane bounding-ball culling, 2 (default) = 1 with each block's
+        share of the batch visited in order of elbow angle so that warps agree on which tests to skip; bit-identical
+        verdicts."""
         self._ck(self.lib.pv_set_culling(self._h, int(mode)), "pv_set_culling")
 
     # -- device-buffer calls --------------------------------------------------------------------------

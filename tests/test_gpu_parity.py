@@ -116,11 +116,17 @@ def test_state_kernel_variants_are_bit_identical(pv):
             pv.set_attached(att)
             q = _dev(random_configs(300_007, 77 + att, fingers=fingers))
             res = []
-            for mode in (0, 1):
+            for mode in (0, 1, 2):  # brute force, per-lane culling, sorted by elbow angle + culling (the default)
                 pv.set_culling(mode)
                 res.append(pv.check_states(q).cpu().numpy())
-            pv.set_culling(1)
-            assert (res[0] == res[1]).all(), (name, att)
+            pv.set_culling(2)
+            assert (res[0] == res[1]).all() and (res[0] == res[2]).all(), (name, att)
+            # the sorted kernel with far fewer configurations than one block's share, and a ragged tail
+            for m_ in (1, 33, 511, 513, 70_001):
+                pv.set_culling(1)
+                a_ = pv.check_states(q[:m_]).cpu().numpy()
+                pv.set_culling(2)
+                assert (pv.check_states(q[:m_]).cpu().numpy() == a_).all(), (name, att, m_)
     pv.set_attached(-1)
 
 
@@ -277,11 +283,11 @@ def test_general_obbs_max_scene(pv, c64):
     for att in (-1, 5):
         pv.set_attached(att)
         margin = c64.state_margin(q.astype(np.float64), snap.as_oracle_scene(), attached=att)
-        for mode in (1, 0):
+        for mode in (2, 1, 0):
             pv.set_culling(mode)
             gpu = unpack_bits(pv.check_states(_dev(q)), n)
             _assert_verdicts(gpu, margin, f"general obbs att={att} mode={mode}")
-        pv.set_culling(1)
+        pv.set_culling(2)
         assert 0.05 < (margin >= 0).mean() < 0.9
     pv.set_attached(-1)
     m = pv.state_margins(_dev(q[:20000])).cpu().numpy()

@@ -6,7 +6,7 @@ from rbe550_final_project_b200 import panda_model as pm, scenes as sc
 from rbe550_final_project_b200.validity import PandaValidity, soa_from_aos
 
 scene = sys.argv[1] if len(sys.argv) > 1 else "goal1_scattered"
-cull = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+cull = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 pv = PandaValidity(0)
 pv.set_scene(sc.FIXTURES[scene]())
 pv.set_culling(cull)
