@@ -69,7 +69,7 @@ class StateValidityChecker:
 
 class PlannerInterface:
     def __init__(self, robot: Any, scene: Any, device: int = 0, validity: Optional[PandaValidity] = None,
-                 carry_attached: bool = False):
+                 carry_attached: bool = False, strict_planners: bool = False):
         self.robot = _ensure_adapter(robot, scene)
         self.scene = scene
         self.attached_object = None
@@ -77,6 +77,10 @@ class PlannerInterface:
         # hand / finger contacts with it are forgiven.  True = the block rides on the hand:
         # its grasp pose is taken from the robot configuration and block pose at the moment plan_path is called.
         self.carry_attached = bool(carry_attached)
+        # The six planner names of planning.py:108-117 without a device kernel (PRM, RRTstar, EST, FMT, BITstar, ABITstar)
+        # are answered by the device RRT-Connect + shortcutting with a warning, so that a caller passing them keeps
+        # working; strict_planners=True raises instead.  (Every caller in the reference uses the default.)
+        self.strict_planners = bool(strict_planners)
         self.validity = validity if validity is not None else PandaValidity(device)
         self._snapshot: Optional[SceneSnapshot] = None
         self.rng_seed = 1
@@ -209,7 +213,10 @@ class PlannerInterface:
         if planner not in SUPPORTED_PLANNERS:
             raise PlanningError(f"Planner {planner} is not supported. Supported planners: {SUPPORTED_PLANNERS}.")
         if planner not in DEVICE_PLANNERS:
-            raise PlanningError(f"Planner {planner} has no device implementation; available: {DEVICE_PLANNERS}.")
+            if self.strict_planners:
+                raise PlanningError(f"Planner {planner} has no device implementation; available: {DEVICE_PLANNERS}.")
+            logger.warning(f"Planner {planner} has no device implementation: using the device RRTConnect + shortcutting.")
+            planner = "RRTConnect"
         solver = getattr(self.robot, "_solver", None)
         if solver is not None and getattr(solver, "n_envs", 0) > 0:
             raise PlanningError("Motion planning is not supported for batched envs (yet).")

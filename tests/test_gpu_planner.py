@@ -68,7 +68,12 @@ def test_plan_path_hard_errors(pv):
     scene, franka, _ = create_scene("goal1_scattered")
     planner = PlannerInterface(franka, scene, validity=pv)
     with pytest.raises(PlanningError):
-        planner.plan_path(qpos_goal=pm.Q_SAFE_HOME, planner="LazyPRM")
+        planner.plan_path(qpos_goal=pm.Q_SAFE_HOME, planner="LazyPRM")  # not one of planning.py:108-117
+    # names the reference accepts but the device has no kernel for: answered by RRTConnect unless strict
+    franka.set_qpos(pm.Q_SCENE_INIT)
+    assert len(planner.plan_path(qpos_goal=pm.Q_SAFE_HOME, planner="BITstar", num_waypoints=20)) == 20
+    with pytest.raises(PlanningError):
+        PlannerInterface(franka, scene, validity=pv, strict_planners=True).plan_path(qpos_goal=pm.Q_SAFE_HOME, planner="BITstar")
     with pytest.raises(PlanningError):
         planner.plan_path(qpos_goal=pm.Q_SAFE_HOME[:7])
     franka.raw._solver.n_envs = 4
