@@ -393,3 +393,60 @@ def test_rejected_scene_keeps_the_previous_one(pv):
     with pytest.raises(PandaValidityError):
         pv.set_scene(bad2)
     assert np.array_equal(pv.check_states(_dev(q)).cpu().numpy(), before)
+
+
+@pytest.mark.parametrize("fingers", ["open", "random"])
+def test_config2_full_size_against_the_oracle(pv, c64, fingers):
+    """BASELINE config 2 at its full size: 1 048 576 configurations, joints uniform in the limits from
+    numpy default_rng(20251212), fingers open / uniform in [0, 0.04], goal-1 scene: every verdict equals the fp64
+    oracle's outside the 1e-4 m band, through the device AND the host entry point."""
+    scene = sc.goal1_scattered()
+    pv.set_scene(scene)
+    pv.set_flags(True, False)
+    n = 1 << 20
+    rng = np.random.default_rng(20251212)
+    q = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n, 9))
+    if fingers == "open":
+        q[:, 7:] = 0.04
+    q = q.astype(np.float32)
+    margin = c64.state_margin(q.astype(np.float64), scene.as_oracle_scene())
+    gpu = unpack_bits(pv.check_states(_dev(q)), n)
+    in_band, flips = _assert_verdicts(gpu, margin, f"config 2 fingers={fingers}")
+    assert in_band < n * 1e-3
+    host = unpack_bits(pv.check_states_host(q), n)
+    assert (host == gpu).all()
+    assert 0.80 < gpu.mean() < 0.90
+
+
+def test_config3_full_size_properties(pv, c64):
+    """BASELINE config 3 at its full size (10 485 760 edges x 64 states, finished-pentagon scene): too large for the
+    oracle, so size-independent properties -- run-to-run identity, agreement with the oracle on a random sample of the
+    same batch, and monotonicity (removing scene boxes can only turn invalid edges valid)."""
+    scene = sc.goal4_task1_pentagon()
+    pv.set_scene(scene)
+    pv.set_flags(True, False)
+    n = 10 * (1 << 20)
+    rng = np.random.default_rng(20251213)
+    qa = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n, 9)).astype(np.float32)
+    qa[:, 7:] = 0.04
+    qb = qa + rng.normal(0.0, 0.3, size=(n, 9)).astype(np.float32)
+    np.clip(qb, pm.Q_LOWER.astype(np.float32), pm.Q_UPPER.astype(np.float32), out=qb)
+    qb[:, 7:] = 0.04
+    da, db = _dev(qa), _dev(qb)
+    w1 = pv.check_edges(da, db, n_steps=64).cpu().numpy()
+    w2 = pv.check_edges(da, db, n_steps=64).cpu().numpy()
+    assert (w1 == w2).all()
+    valid = unpack_bits(w1, n)
+    assert 0.70 < valid.mean() < 0.85
+    pick = rng.choice(n, size=4096, replace=False)
+    ref = c64.edge_margin(qa[pick].astype(np.float64), qb[pick].astype(np.float64), scene.as_oracle_scene(), n_steps=64)
+    _assert_verdicts(valid[pick], ref, "config 3 sample")
+    # fewer obstacles: no valid edge may turn invalid
+    fewer = sc.SceneSnapshot(obb=scene.obb[:5].copy(), names=list(scene.names[:5]), table_z=scene.table_z, base=scene.base,
+                             entity_idx=list(scene.entity_idx[:5]))
+    pv.set_scene(fewer)
+    valid_fewer = unpack_bits(pv.check_edges(da, db, n_steps=64), n)
+    ref_fewer = c64.edge_margin(qa[pick].astype(np.float64), qb[pick].astype(np.float64), fewer.as_oracle_scene(), n_steps=64)
+    _assert_verdicts(valid_fewer[pick], ref_fewer, "config 3 sample, fewer boxes")
+    # exact, not just outside the band: the tests against the remaining boxes are the same arithmetic in both runs
+    assert not (valid & ~valid_fewer).any()
