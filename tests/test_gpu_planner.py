@@ -342,5 +342,6 @@ def test_single_tree_rrt_planner(pv, c64, c32):
     # the resampled waypoints fall between the states the planner's validator sampled (1 % resolution, App. D), so a
     # path that grazes the wall edge can show a few waypoint-level contacts: the finer check must agree almost everywhere
     assert len(path) >= 100 and planner.validate_trajectory(path).mean() > 0.9
+    planner.strict_planners = True
     with pytest.raises(PlanningError):
         planner.plan_path(qpos_goal=qr[0], planner="PRM")
