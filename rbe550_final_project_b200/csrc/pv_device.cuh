@@ -41,6 +41,12 @@ struct PvScene {
     float carry_R[9];
     float carry_h[3];
     float carry_br;
+    // scene-level cull (exact, see pv_check_config): axis-aligned bounds of all scene boxes (their true extents
+    // |R| h); the same bounds padded by each link group's bounding radius (+ slack): lo - r in [0..2], hi + r in
+    // [3..5]; bit l of group_any: link group l can reach some box at all, bit 8: the gripper can
+    float aabb_lo[3], aabb_hi[3];
+    float gpad[8][6];
+    unsigned group_any;
 };
 #define PV_LINK_CARRIED 11  // link id reported for the carried box in culprit / contact codes
 
@@ -599,7 +605,35 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
     }
 
     // ---- robot vs scene boxes ------------------------------------------------------------------------
+    // Scene-level cull in front of the whole box loop: a link group whose bounding ball stays outside the axis-aligned
+    // bounds of ALL boxes (tested as the ball's centre against the bounds padded by its radius, which is conservative)
+    // cannot touch any of them, and neither can the gripper ball or the carried box's ball.  Only ~2 % of random
+    // configurations come near the goal-1 blocks at all, so a warp whose 32 lanes all pass skips the box loads and every
+    // per-box cull (profiles/r1_notes.md: a third of the instructions of the check); the sorted kernel orders its
+    // configurations so that whole warps agree (pv_sort_key).
+    bool near_scene = true;
+    if constexpr (CULL && MODE == PV_MODE_BITS) {
+        near_scene = false;
+#define PV_SCENE_GROUP(l, cs, br)                                                                                  \
+    if (S.group_any & (1u << l))                                                                                   \
+        near_scene |= s[cs].x > S.gpad[l][0] && s[cs].x < S.gpad[l][3] && s[cs].y > S.gpad[l][1] &&                \
+                      s[cs].y < S.gpad[l][4] && s[cs].z > S.gpad[l][2] && s[cs].z < S.gpad[l][5];
+        PV_LINK_GROUPS(PV_SCENE_GROUP)
+#undef PV_SCENE_GROUP
+        if (S.group_any & 0x100u)
+            near_scene |= bc[0].x + grip_r > S.aabb_lo[0] && bc[0].x - grip_r < S.aabb_hi[0] &&
+                          bc[0].y + grip_r > S.aabb_lo[1] && bc[0].y - grip_r < S.aabb_hi[1] &&
+                          bc[0].z + grip_r > S.aabb_lo[2] && bc[0].z - grip_r < S.aabb_hi[2];
+        if constexpr (CARRY) {
+            const float rc_ = cbr + PV_CULL_SLACK;
+            near_scene |= cC.x + rc_ > S.aabb_lo[0] && cC.x - rc_ < S.aabb_hi[0] && cC.y + rc_ > S.aabb_lo[1] &&
+                          cC.y - rc_ < S.aabb_hi[1] && cC.z + rc_ > S.aabb_lo[2] && cC.z - rc_ < S.aabb_hi[2];
+        }
+        // kernels with warp votes inside the loop (EXIT) must take the branch as a whole warp
+        if constexpr (EXIT != PV_EXIT_NONE) near_scene = __any_sync(FULL, near_scene);
+    }
     const int nb = S.n_obb;
+    if (near_scene)
     for (int b = 0; b < nb; ++b) {
         PV_LOCKSTEP(3)
         if constexpr (CARRY) {

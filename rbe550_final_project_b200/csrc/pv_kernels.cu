@@ -115,10 +115,54 @@ __device__ __forceinline__ void pv_emit_word_thread(uint32_t* __restrict__ bits,
     }
 }
 
-__device__ __forceinline__ int pv_sort_key(float q3) {
+// Sort key = (distance class of the wrist point from the scene's bounds, elbow-angle bin).  The elbow angle decides
+// most self-collision culls; how far the wrist (origin of link5/link6, a function of q[0..3] only) is from the bounds of
+// the scene boxes decides whether the scene-level cull of pv_check_config lets the whole warp skip the box loop.  The key
+// only orders the work (verdicts return to their original positions), so it is computed with the fast intrinsics.
+#ifndef PV_SORT_E0
+#define PV_SORT_E0 0.20f
+#define PV_SORT_E1 0.35f
+#define PV_SORT_E2 0.50f
+#endif
+// the wrist-flex angle q[5] decides the forearm-vs-finger block, the most frequent self-collision block left
+#ifndef PV_SORT_Q5_BINS
+#define PV_SORT_Q5_BINS 4
+#endif
+#define PV_SORT_Q3_BINS (PV_SORT_BUCKETS / 4 / PV_SORT_Q5_BINS)
+__device__ __forceinline__ int pv_sort_key(float q0, float q1, float q2, float q3, float q5, const PvScene& S) {
     const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
-    const float scale = (float)PV_SORT_BUCKETS / (hi[3] - lo[3]);
-    return (int)fminf(fmaxf((q3 - lo[3]) * scale, 0.f), (float)(PV_SORT_BUCKETS - 1));  // NaN -> bucket 0
+    const float scale = (float)PV_SORT_Q3_BINS / (hi[3] - lo[3]);
+    int bin = (int)fminf(fmaxf((q3 - lo[3]) * scale, 0.f), (float)(PV_SORT_Q3_BINS - 1));  // NaN -> bin 0
+    if (PV_SORT_Q5_BINS > 1) {
+        const float scale5 = (float)PV_SORT_Q5_BINS / (hi[5] - lo[5]);
+        bin = bin * PV_SORT_Q5_BINS + (int)fminf(fmaxf((q5 - lo[5]) * scale5, 0.f), (float)(PV_SORT_Q5_BINS - 1));
+    }
+    float s, c;
+    __sincosf(q0, &s, &c);
+    float3 p = make_float3(S.base[0], S.base[1], S.base[2] + 0.333f);
+    float3 X = make_float3(c, s, 0.f), Y = make_float3(-s, c, 0.f), Z, Xp, Yp, Zp;
+    __sincosf(q1, &s, &c);  // link2: Rx(-90)
+    {
+        const float3 X1 = X;
+        X = make_float3(c * X1.x, c * X1.y, -s);
+        Z = Y;
+        Y = make_float3(-s * X1.x, -s * X1.y, -c);
+    }
+    __sincosf(q2, &s, &c);  // link3: pos (0,-0.316,0), Rx(+90)
+    p = v_fma(Y, -0.316f, p);
+    Xp = X; Yp = Z; Zp = v_neg(Y);
+    v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
+    __sincosf(q3, &s, &c);  // link4: pos (0.0825,0,0), Rx(+90)
+    p = v_fma(X, 0.0825f, p);
+    Xp = X; Yp = Z;
+    v_rotz(Xp, Yp, c, s, X, Y);
+    p = v_fma(Y, 0.384f, v_fma(X, -0.0825f, p));  // link5 origin: pos (-0.0825,0.384,0) in link4
+    const float dx = fmaxf(fmaxf(S.aabb_lo[0] - p.x, p.x - S.aabb_hi[0]), 0.f);
+    const float dy = fmaxf(fmaxf(S.aabb_lo[1] - p.y, p.y - S.aabb_hi[1]), 0.f);
+    const float dz = fmaxf(fmaxf(S.aabb_lo[2] - p.z, p.z - S.aabb_hi[2]), 0.f);
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    const int cls = (d2 >= PV_SORT_E0 * PV_SORT_E0) + (d2 >= PV_SORT_E1 * PV_SORT_E1) + (d2 >= PV_SORT_E2 * PV_SORT_E2);
+    return cls * (PV_SORT_Q3_BINS * PV_SORT_Q5_BINS) + bin;
 }
 
 __device__ __forceinline__ void pv_cp_async4(void* smem, const void* g) {
@@ -167,7 +211,9 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     const int64_t my_chunks = (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x;
     // local index L = jj * 512 + t of super-tile j0  <->  configuration (blockIdx.x + (j0 + jj) * gridDim.x) * 512 + t
 #define PV_GI(jj, t) ((((int64_t)blockIdx.x + (j0 + (jj)) * (int64_t)gridDim.x) * PV_SB_THREADS) + (t))
-#define PV_Q3_OF(i) (AOS ? __ldg(q_aos + 9 * (i) + 3) : __ldg(reinterpret_cast<const float*>(qA) + 4 * (i) + 3))
+#define PV_Q03_OF(i)                                                                                               \
+    (AOS ? make_float4(__ldg(q_aos + 9 * (i)), __ldg(q_aos + 9 * (i) + 1), __ldg(q_aos + 9 * (i) + 2), __ldg(q_aos + 9 * (i) + 3)) \
+         : __ldg(qA + (i)))
     for (int64_t j0 = 0; j0 < my_chunks; j0 += ST_CHUNKS) {
         const int nc = (int)((my_chunks - j0 < (int64_t)ST_CHUNKS) ? (my_chunks - j0) : (int64_t)ST_CHUNKS);
         if (tid < PV_SORT_BUCKETS) hist[tid] = 0;
@@ -175,18 +221,23 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         __syncthreads();
         // pass 1: keys (kept as bytes for pass 2) and their histogram; the key loads of 8 chunks are in flight together
         for (int j8 = 0; j8 < nc; j8 += 8) {
-            float kq[8];
+            float4 kq[8];
+            float kq5[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int64_t i = PV_GI(j8 + u, tid);
-                kq[u] = 0.f;
-                if (j8 + u < nc && i < n) kq[u] = PV_Q3_OF(i);
+                kq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                kq5[u] = 0.f;
+                if (j8 + u < nc && i < n) {
+                    kq[u] = PV_Q03_OF(i);
+                    if (PV_SORT_Q5_BINS > 1) kq5[u] = AOS ? __ldg(q_aos + 9 * i + 5) : __ldg(reinterpret_cast<const float*>(qB) + 4 * i + 1);
+                }
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int64_t i = PV_GI(j8 + u, tid);
                 if (j8 + u < nc && i < n) {
-                    const int key = pv_sort_key(kq[u]);
+                    const int key = pv_sort_key(kq[u].x, kq[u].y, kq[u].z, kq[u].w, kq5[u], S);
                     M.key8[(j8 + u) * PV_SB_THREADS + tid] = (unsigned char)key;
                     atomicAdd(&hist[key], 1u);
                 }
@@ -271,7 +322,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     }
 #undef PV_PREFETCH
 #undef PV_GI
-#undef PV_Q3_OF
+#undef PV_Q03_OF
 }
 
 template <bool CULL, bool CARRY>
@@ -551,6 +602,33 @@ int pv_set_scene(PvHandle* h, const float* h_obb, int n_obb, float table_z, cons
 #undef PV_L0_REACH
             S.reach_mask[b] = (unsigned short)m;
         }
+    }
+    // scene-level cull: bounds of all boxes, padded per link group (pv_check_config skips the box loop for a
+    // configuration none of whose group balls enters them)
+    {
+        unsigned any = 0;
+        for (int k = 0; k < 3; ++k) {
+            S.aabb_lo[k] = 1e30f;
+            S.aabb_hi[k] = -1e30f;
+        }
+        for (int b = 0; b < n_obb; ++b) {
+            const float* o = S.obb[b];
+            any |= S.reach_mask[b];
+            for (int k = 0; k < 3; ++k) {  // world axis k: extent = sum_j |R[k][j]| h[j]
+                const float e = fabsf(o[6 + 3 * k]) * o[3] + fabsf(o[7 + 3 * k]) * o[4] + fabsf(o[8 + 3 * k]) * o[5];
+                S.aabb_lo[k] = fminf(S.aabb_lo[k], o[k] - e - 1e-6f);
+                S.aabb_hi[k] = fmaxf(S.aabb_hi[k], o[k] + e + 1e-6f);
+            }
+        }
+        S.group_any = (any & 0xffu) | ((any & 0x700u) ? 0x100u : 0u);
+        memset(S.gpad, 0, sizeof(S.gpad));
+#define PV_GPAD(l, cs, br)                                              \
+    for (int k = 0; k < 3; ++k) {                                       \
+        S.gpad[l][k] = S.aabb_lo[k] - ((br) + 2.0f * PV_CULL_SLACK);    \
+        S.gpad[l][3 + k] = S.aabb_hi[k] + ((br) + 2.0f * PV_CULL_SLACK); \
+    }
+        PV_LINK_GROUPS(PV_GPAD)
+#undef PV_GPAD
     }
     h->scene = S;
     h->has_scene = 1;

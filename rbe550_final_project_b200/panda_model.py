@@ -292,6 +292,17 @@ def _f(x: float) -> str:
 CULL_SLACK = 1e-4  # metres added to every culling radius so fp32 rounding can never cull a true contact
 
 
+def bounding_ball(idx):
+    """(centre sphere, radius) of the smallest ball centred on one of the spheres `idx` (all on one link) that contains
+    all of them.  Distances inside a link do not depend on the configuration."""
+    best = None
+    for c in idx:
+        rad = max(float(np.linalg.norm(SPHERE_CENTER[i] - SPHERE_CENTER[c]) + SPHERE_RADIUS[i]) for i in idx)
+        if best is None or rad < best[1]:
+            best = (c, rad)
+    return best
+
+
 def link_groups():
     """Per arm link: (link, centre sphere index, bounding radius) of a ball, centred on one of the
     link's own sphere centres, that contains all spheres of that link.  Used for conservative culling."""
@@ -409,8 +420,12 @@ def header_text() -> str:
     a("#define PV_SS_LINKPAIRS(LP) \\")
     lps = sorted({(int(SPHERE_LINK[p]), int(SPHERE_LINK[q])) for p, q in SS_PAIRS})
     for la, lb in lps:
-        rr = g[la][1] + g[lb][1] + CULL_SLACK
-        a(f"  LP({la}, {lb}, {g[la][0]}, {g[lb][0]}, {_f(rr * rr)}) \\")
+        # balls around the spheres that actually take part in this block (often a few at one end of the link), not
+        # around the whole links: link2-vs-link5 passes for 1.7 % of random configurations instead of 33 %
+        ca, ra = bounding_ball(sorted({int(p) for p, q in SS_PAIRS if (int(SPHERE_LINK[p]), int(SPHERE_LINK[q])) == (la, lb)}))
+        cb, rb = bounding_ball(sorted({int(q) for p, q in SS_PAIRS if (int(SPHERE_LINK[p]), int(SPHERE_LINK[q])) == (la, lb)}))
+        rr = ra + rb + CULL_SLACK
+        a(f"  LP({la}, {lb}, {ca}, {cb}, {_f(rr * rr)}) \\")
     a("")
     for la, lb in lps:
         a(f"#define PV_SS_PAIRS_{la}_{lb}(X) \\")
@@ -471,13 +486,14 @@ def header_text() -> str:
     sb_links = sorted({int(SPHERE_LINK[p]) for p, _ in SB_PAIRS})
     for la in sb_links:
         culls = []
+        ca, ra = bounding_ball(sorted({int(p) for p, _ in SB_PAIRS if int(SPHERE_LINK[p]) == la}))
         for k in range(N_BOXES):
             if any(int(SPHERE_LINK[p]) == la and int(kk) == k for p, kk in SB_PAIRS):
-                rr = g[la][1] + BOX_BOUND_RADIUS[k] + CULL_SLACK
+                rr = ra + BOX_BOUND_RADIUS[k] + CULL_SLACK
                 culls.append(_f(rr * rr))
             else:
                 culls.append("0.0f")
-        a(f"  LB({la}, {g[la][0]}, {', '.join(culls)}, {_f(g[la][1] + CULL_SLACK)}) \\")
+        a(f"  LB({la}, {ca}, {', '.join(culls)}, {_f(ra + CULL_SLACK)}) \\")
     a("")
     a("// per link: S(a, r, r2) brings sphere a into the hand frame, B(a, k) tests it against gripper box k")
     for la in sb_links:

@@ -13,7 +13,7 @@ for lib in libs:
     pv = PandaValidity(0)
     A, B, q9 = soa_from_aos(torch.as_tensor(q, device="cuda"))
     out = torch.empty(n // 32, dtype=torch.int32, device="cuda")
-    for scene in ("goal1_scattered", "goal3_tower"):
+    for scene in ("goal1_scattered", "goal3_tower", "goal4_task1_pentagon"):
         pv.set_scene(sc.FIXTURES[scene]())
         for mode in (1, 2):
             pv.set_culling(mode)
