@@ -59,6 +59,9 @@ __device__ __forceinline__ void pv_emit_word(uint32_t* __restrict__ bits, const 
 #ifndef PV_SB_SYNC
 #define PV_SB_SYNC 0
 #endif
+#ifndef PV_SB_BAR_EVERY
+#define PV_SB_BAR_EVERY 1
+#endif
 #ifndef PV_SB_MINB
 #define PV_SB_MINB 1
 #endif
@@ -308,7 +311,12 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
                 q[8] = q9 ? M.st9[r & 1][tid] : b.w;
             }
             if (r + 1 < nc) PV_PREFETCH(r + 1)
-            __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
+#if PV_SB_BAR_EVERY > 0
+            if (PV_SB_BAR_EVERY == 1 || r % PV_SB_BAR_EVERY == 0)
+#else
+            if (false)
+#endif
+                __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
             PvAcc<PV_MODE_BITS> acc;
             pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, PV_SB_SYNC, true, CARRY>(q, S, acc);
             if (in && !acc.hit) atomicOr(&vbits[L >> 5], 1u << (L & 31));
@@ -410,6 +418,123 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         }
     }
     if (n_valid && lane == 0 && count) atomicAdd(n_valid, count);
+}
+
+// Sorted variant of the sweep (the default): the same super-tile sort as pv_state_bits_sorted_kernel, with the generated
+// configurations parked in shared memory between the key pass and the check (generating them twice would cost ~210
+// instructions per configuration, parking ~20).  A super-tile is PV_SWEEP_ST configurations (9 floats each: 144 KB).
+#ifndef PV_SWEEP_ST
+#define PV_SWEEP_ST 4096
+#endif
+static_assert(PV_SWEEP_ST % PV_SB_THREADS == 0 && PV_SWEEP_ST <= 65536, "super-tile = whole chunks, indices fit 16 bits");
+struct PvSweepSmem {
+    static constexpr int ST = PV_SWEEP_ST;
+    float park[9][PV_SWEEP_ST];
+    unsigned short order[PV_SWEEP_ST];
+    unsigned char key8[PV_SWEEP_ST];
+    unsigned hist[PV_SORT_BUCKETS];
+    unsigned vbits[PV_SWEEP_ST / 32];
+    int cnt;
+};
+
+template <bool CARRY>
+__global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
+    pv_sweep_sorted_kernel(const __grid_constant__ PvScene S, uint64_t first, int64_t n, unsigned seed, int fingers_open,
+                           uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid,
+                           float* __restrict__ q_out, const __grid_constant__ PvGather G) {
+    typedef PvSweepSmem Smem;
+    constexpr int ST_CHUNKS = Smem::ST / PV_SB_THREADS;
+    extern __shared__ __align__(16) unsigned char pv_sort_smem_raw[];
+    Smem& M = *reinterpret_cast<Smem*>(pv_sort_smem_raw);
+    const int tid = threadIdx.x;
+    const int64_t n_words = (n + 31) >> 5;
+    const int64_t n_chunks = (n + PV_SB_THREADS - 1) / PV_SB_THREADS;
+    if ((int64_t)blockIdx.x >= n_chunks) return;
+    const int64_t my_chunks = (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    unsigned long long count = 0;
+#define PV_GI(jj, t) ((((int64_t)blockIdx.x + (j0 + (jj)) * (int64_t)gridDim.x) * PV_SB_THREADS) + (t))
+    for (int64_t j0 = 0; j0 < my_chunks; j0 += ST_CHUNKS) {
+        const int nc = (int)((my_chunks - j0 < (int64_t)ST_CHUNKS) ? (my_chunks - j0) : (int64_t)ST_CHUNKS);
+        if (tid < PV_SORT_BUCKETS) M.hist[tid] = 0;
+        for (int w = tid; w < nc * (PV_SB_THREADS / 32); w += PV_SB_THREADS) M.vbits[w] = 0;
+        __syncthreads();
+        for (int jj = 0; jj < nc; ++jj) {  // pass 1: generate, park, key, histogram
+            const int64_t i = PV_GI(jj, tid);
+            if (i < n) {
+                float q[9];
+                pv_sweep_config(first + (uint64_t)i, seed, fingers_open != 0, q);
+                const int L = jj * PV_SB_THREADS + tid;
+#pragma unroll
+                for (int j = 0; j < 9; ++j) M.park[j][L] = q[j];
+                if (q_out) {
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) q_out[9 * i + j] = q[j];
+                }
+                const int key = pv_sort_key(q[0], q[1], q[2], q[3], q[5], S);
+                M.key8[L] = (unsigned char)key;
+                atomicAdd(&M.hist[key], 1u);
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {  // exclusive prefix sum: 8 buckets per lane + a warp scan
+            constexpr int PER = PV_SORT_BUCKETS / 32;
+            unsigned v[PER], sum = 0;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                v[j] = M.hist[tid * PER + j];
+                sum += v[j];
+            }
+            unsigned incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (tid >= d) incl += o;
+            }
+            unsigned run = incl - sum;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                M.hist[tid * PER + j] = run;
+                run += v[j];
+            }
+            if (tid == 31) M.cnt = (int)incl;
+        }
+        __syncthreads();
+        for (int jj = 0; jj < nc; ++jj) {  // pass 2: scatter the local indices
+            const int64_t i = PV_GI(jj, tid);
+            const int L = jj * PV_SB_THREADS + tid;
+            if (i < n) M.order[atomicAdd(&M.hist[M.key8[L]], 1u)] = (unsigned short)L;
+        }
+        __syncthreads();
+        const int cnt = M.cnt;
+        for (int r = 0; r < nc; ++r) {
+            const int slot = r * PV_SB_THREADS + tid;
+            const bool in = slot < cnt;
+            const int L = M.order[in ? slot : cnt - 1];
+            float q[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) q[j] = M.park[j][L];
+            __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
+            PvAcc<PV_MODE_BITS> acc;
+            pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY>(q, S, acc);
+            if (in && !acc.hit) atomicOr(&M.vbits[L >> 5], 1u << (L & 31));
+        }
+        __syncthreads();
+        for (int wl = tid; wl < nc * (PV_SB_THREADS / 32); wl += PV_SB_THREADS) {
+            const int64_t w = (PV_GI(wl / (PV_SB_THREADS / 32), 0) >> 5) + (wl % (PV_SB_THREADS / 32));
+            if (w < n_words) {
+                const unsigned word = M.vbits[wl];
+                pv_emit_word_thread(bits, G, w, word);
+                count += __popc(word);
+            }
+        }
+        __syncthreads();  // the next super-tile clears hist / vbits
+    }
+#undef PV_GI
+    if (n_valid) {  // one atomic per warp
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) count += __shfl_down_sync(0xffffffffu, count, d);
+        if ((tid & 31) == 0 && count) atomicAdd(n_valid, count);
+    }
 }
 
 // FP32 issue-rate probe: 8 independent FFMA chains per thread.
@@ -910,7 +1035,23 @@ int pv_sweep(PvHandle* h, uint64_t first, int64_t n, uint32_t seed, int fingers_
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t words = (n + 31) / 32;
-    {
+    if (h->cull == 2) {  // tile-sorted (the default)
+        const int64_t chunks = (n + PV_SB_THREADS - 1) / PV_SB_THREADS;
+        const int grid = (int)(chunks < (int64_t)h->sm_count ? chunks : (int64_t)h->sm_count);
+#define PV_LAUNCH_SWEEP_SORTED(CARRY)                                                                            \
+    {                                                                                                            \
+        const unsigned bit_ = 1u << (8 + (CARRY ? 1 : 0));                                                       \
+        if (!(h->smem_attr_mask & bit_)) {                                                                       \
+            PV_CUDA(h, cudaFuncSetAttribute(pv_sweep_sorted_kernel<CARRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                            (int)sizeof(PvSweepSmem)));                                          \
+            h->smem_attr_mask |= bit_;                                                                           \
+        }                                                                                                        \
+        pv_sweep_sorted_kernel<CARRY><<<grid, PV_SB_THREADS, sizeof(PvSweepSmem), st>>>(                         \
+            h->scene, first, n, seed, fingers_open, d_bits, d_n_valid, d_q_out, h->gather);                      \
+    }
+        if (h->scene.carry) PV_LAUNCH_SWEEP_SORTED(true) else PV_LAUNCH_SWEEP_SORTED(false)
+#undef PV_LAUNCH_SWEEP_SORTED
+    } else {
         if (h->scene.carry) {
             int grid = pv_grid_for(h, (const void*)pv_sweep_kernel<true, true>, PV_SB_THREADS, words);
             pv_sweep_kernel<true, true><<<grid, PV_SB_THREADS, 0, st>>>(h->scene, first, n, seed, fingers_open, d_bits,

@@ -201,6 +201,24 @@ def test_sweep_matches_oracle_stream(pv, c64, model):
         _assert_verdicts(gpu, margin, "sweep")
 
 
+def test_sweep_sorted_identical_to_unsorted(pv):
+    """The tile-sorted sweep (culling mode 2: configurations parked in shared memory, visited in key order) returns
+    the same verdict words and count as the unsorted kernels, across super-tile and chunk boundaries, in every scene."""
+    for name in ("goal1_scattered", "goal3_tower", "goal4_task1_pentagon"):
+        pv.set_scene(sc.FIXTURES[name]())
+        for n in (31, 4097, 148 * 4096 * 2 + 777):
+            ref = None
+            for mode in (0, 1, 2):
+                pv.set_culling(mode)
+                bits, count = pv.sweep(32 * 5, n, 7, fingers_open=(n % 2 == 1))
+                got = (bits.cpu().numpy().view(np.uint32).copy(), int(count.item()))
+                if ref is None:
+                    ref = got
+                assert np.array_equal(got[0], ref[0]) and got[1] == ref[1], (name, n, mode)
+            pv.set_culling(2)
+            assert ref[1] == int(unpack_bits(ref[0], n).sum())
+
+
 def test_acceptance_poses(pv):
     """App. F: the poses the reference plans from are valid in every scene; a deep table hit is not."""
     for name, f in sc.FIXTURES.items():
