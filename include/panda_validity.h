@@ -90,6 +90,10 @@ int pv_set_gather(PvHandle *h, const void *d_peer_ptrs, int n_peers, void *d_mul
  * per link position xyz then rotation row-major. */
 int pv_fk(PvHandle *h, const float *d_qA, const float *d_qB, const float *d_q9, int64_t n,
           float *d_pose_out, void *stream);
+/* The same link poses as pv_check_states / pv_sweep evaluate them internally (joint sines and cosines from the
+ * hardware approximations): for measuring how far the verdict kernels' kinematics are from pv_fk.  Same layout. */
+int pv_fk_verdict_path(PvHandle *h, const float *d_qA, const float *d_qB, const float *d_q9, int64_t n,
+                       float *d_pose_out, void *stream);
 
 /* _is_ompl_state_valid(state) for n states at once (planning.py:209-219). */
 int pv_check_states(PvHandle *h, const float *d_qA, const float *d_qB, const float *d_q9, int64_t n,

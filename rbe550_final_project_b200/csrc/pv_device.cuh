@@ -181,6 +181,21 @@ __device__ __forceinline__ void pv_sincos(float x, float& s, float& c) {
     c = ((k + 1) & 2) ? -b : b;
 }
 
+// FAST: the hardware approximations (MUFU.SIN / MUFU.COS, abs. error ~4e-7), see PV_FAST_TRIG
+template <bool FAST>
+__device__ __forceinline__ void pv_sincos_sel(float x, float& s, float& c) {
+    if constexpr (FAST) {
+        // bring x into [-pi, pi] first (exact for |x| <= pi, where k = 0): the hardware's own reduction loses accuracy
+        // in proportion to |x|, and joint values outside the limits are legal input when the limit check is off
+        const float k = rintf(x * 0.15915494309189535f);
+        float r = fmaf(k, -6.2831854820251465f, x);
+        r = fmaf(k, 1.7484555e-7f, r);
+        __sincosf(r, &s, &c);
+    } else {
+        pv_sincos(x, s, c);
+    }
+}
+
 // ---- primitive tests ---------------------------------------------------------------------------------
 // sphere (centre c, radius r) vs box (centre oc, half oh, box axes in world = columns of R)
 template <int MODE>
@@ -353,21 +368,32 @@ struct PvFrames {
 
 // Visitor-driven FK: `on_link(l, p, X, Y, Z)` is called as soon as link l's frame exists, so callers
 // that only need sphere centres never keep more than one frame live.
-template <class F>
+#ifndef PV_TABLE_MIN
+#define PV_TABLE_MIN 1
+#endif
+// The verdict-bit kernels (FMAK: state, sweep) evaluate the joint sines / cosines with the hardware approximations
+// (MUFU.SIN / MUFU.COS through __sincosf: ~120 fewer instructions per check, +10 % throughput).  Their absolute error
+// (~4e-7) moves a link by at most a few micrometres (measured: tests/test_gpu_parity.py::test_fk_verdict_path), far
+// inside the 1e-4 m band within which verdicts may differ from the fp64 oracle.  The pose kernel pv_fk, the margin /
+// contact kernels and the planners keep the accurate pv_sincos.
+#ifndef PV_FAST_TRIG
+#define PV_FAST_TRIG 1
+#endif
+template <bool FAST = false, class F>
 __device__ __forceinline__ void pv_fk_visit(const float* q, float bx, float by, float bz, F&& on_link) {
     float s, c;
     float3 p = make_float3(bx, by, bz);
     float3 X = make_float3(1.f, 0.f, 0.f), Y = make_float3(0.f, 1.f, 0.f), Z = make_float3(0.f, 0.f, 1.f);
     on_link(std::integral_constant<int, 0>{}, p, X, Y, Z);
     // link1: pos (0,0,0.333), no pre-rotation
-    pv_sincos(q[0], s, c);
+    pv_sincos_sel<FAST>(q[0], s, c);
     p.z += 0.333f;
     X = make_float3(c, s, 0.f);
     Y = make_float3(-s, c, 0.f);
     on_link(std::integral_constant<int, 1>{}, p, X, Y, Z);
     float3 Xp, Yp, Zp;
     // link2: pos 0, Rx(-90): X' = X, Y' = -Z, Z' = Y
-    pv_sincos(q[1], s, c);
+    pv_sincos_sel<FAST>(q[1], s, c);
     {
         float3 X1 = X, Y1 = Y;
         X = make_float3(c * X1.x, c * X1.y, -s);
@@ -376,30 +402,30 @@ __device__ __forceinline__ void pv_fk_visit(const float* q, float bx, float by, 
     }
     on_link(std::integral_constant<int, 2>{}, p, X, Y, Z);
     // link3: pos (0,-0.316,0), Rx(+90): X' = X, Y' = Z, Z' = -Y
-    pv_sincos(q[2], s, c);
+    pv_sincos_sel<FAST>(q[2], s, c);
     p = v_fma(Y, -0.316f, p);
     Xp = X; Yp = Z; Zp = v_neg(Y);
     v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
     on_link(std::integral_constant<int, 3>{}, p, X, Y, Z);
     // link4: pos (0.0825,0,0), Rx(+90)
-    pv_sincos(q[3], s, c);
+    pv_sincos_sel<FAST>(q[3], s, c);
     p = v_fma(X, 0.0825f, p);
     Xp = X; Yp = Z; Zp = v_neg(Y);
     v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
     on_link(std::integral_constant<int, 4>{}, p, X, Y, Z);
     // link5: pos (-0.0825,0.384,0), Rx(-90): X' = X, Y' = -Z, Z' = Y
-    pv_sincos(q[4], s, c);
+    pv_sincos_sel<FAST>(q[4], s, c);
     p = v_fma(Y, 0.384f, v_fma(X, -0.0825f, p));
     Xp = X; Yp = v_neg(Z); Zp = Y;
     v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
     on_link(std::integral_constant<int, 5>{}, p, X, Y, Z);
     // link6: pos 0, Rx(+90)
-    pv_sincos(q[5], s, c);
+    pv_sincos_sel<FAST>(q[5], s, c);
     Xp = X; Yp = Z; Zp = v_neg(Y);
     v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
     on_link(std::integral_constant<int, 6>{}, p, X, Y, Z);
     // link7: pos (0.088,0,0), Rx(+90)
-    pv_sincos(q[6], s, c);
+    pv_sincos_sel<FAST>(q[6], s, c);
     p = v_fma(X, 0.088f, p);
     Xp = X; Yp = Z; Zp = v_neg(Y);
     v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
@@ -461,7 +487,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
     // FK -> sphere centres (registers) + gripper boxes
     float3 s[PV_N_SPHERES];
     float3 hX, hY, hZ, hP, bc[3];
-    pv_fk_visit(q, S.base[0], S.base[1], S.base[2], [&](auto lc, float3 p, float3 X, float3 Y, float3 Z) {
+    pv_fk_visit<(PV_FAST_TRIG && FMAK)>(q, S.base[0], S.base[1], S.base[2], [&](auto lc, float3 p, float3 X, float3 Y, float3 Z) {
         constexpr int l = decltype(lc)::value;
         if constexpr (l == 0) { PV_PLACE_LINK0(s, p, X, Y, Z) }
         if constexpr (l == 1) { PV_PLACE_LINK1(s, p, X, Y, Z) }
@@ -495,10 +521,14 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
 
     // ---- robot vs ground plane (link0 is fixed to the world: pair filtered) -------------
     const float tz = S.table_z;
+    if constexpr (MODE == PV_MODE_BITS && PV_TABLE_MIN) {
+        pv_plane<MODE>(acc, PV_TABLE_LOWEST(s), tz, 0);
+    } else {
 #define PV_TABLE_SPHERE(i, link, cx, cy, cz, r) \
     if (link != 0) pv_plane<MODE>(acc, s[i].z - r, tz, PV_CODE(1, link, 0));
-    PV_SPHERES(PV_TABLE_SPHERE)
+        PV_SPHERES(PV_TABLE_SPHERE)
 #undef PV_TABLE_SPHERE
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float ext = fmaf(fabsf(hZ.z), bh[k][2], fmaf(fabsf(hY.z), bh[k][1], fabsf(hX.z) * bh[k][0]));

@@ -368,6 +368,7 @@ __global__ void __launch_bounds__(PV_THREADS, PV_MIN_BLOCKS)
 }
 
 // K1: forward kinematics only; [n][11][12] = position then row-major rotation per link.
+template <bool FAST>
 __global__ void __launch_bounds__(128)
     pv_fk_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA, const float4* __restrict__ qB,
                  const float* __restrict__ q9, int64_t n, float* __restrict__ out) {
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(128)
         float q[9];
         pv_load_soa(qA, qB, q9, i, q);
         float* o = out + i * 132;
-        pv_fk_visit(q, S.base[0], S.base[1], S.base[2], [&](auto lc, float3 p, float3 X, float3 Y, float3 Z) {
+        pv_fk_visit<FAST>(q, S.base[0], S.base[1], S.base[2], [&](auto lc, float3 p, float3 X, float3 Y, float3 Z) {
             constexpr int l = decltype(lc)::value;
             float* r = o + 12 * l;
             r[0] = p.x; r[1] = p.y; r[2] = p.z;
@@ -858,18 +859,32 @@ int pv_set_culling(PvHandle* h, int on) {
     if ((n) == 0) return PV_OK;                                             \
     PV_CUDA(h, cudaSetDevice((h)->device));
 
-int pv_fk(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9, int64_t n, float* d_pose_out,
-          void* stream) {
+static int pv_fk_impl(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9, int64_t n, float* d_pose_out,
+                      void* stream, bool verdict_path) {
     PV_PRECHECK(h, n);
     if (!d_qA || !d_qB || !d_pose_out) return PV_ERR_BAD_ARG;
     const int threads = 128;
     int64_t blocks = (n + threads - 1) / threads;
     if (blocks > (int64_t)h->sm_count * 16) blocks = (int64_t)h->sm_count * 16;
-    pv_fk_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(h->scene, (const float4*)d_qA, (const float4*)d_qB,
-                                                                    d_q9, n, d_pose_out);
+    if (verdict_path && PV_FAST_TRIG)
+        pv_fk_kernel<true><<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(h->scene, (const float4*)d_qA,
+                                                                              (const float4*)d_qB, d_q9, n, d_pose_out);
+    else
+        pv_fk_kernel<false><<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(h->scene, (const float4*)d_qA,
+                                                                               (const float4*)d_qB, d_q9, n, d_pose_out);
     h->launches++;
     PV_CUDA(h, cudaGetLastError());
     return PV_OK;
+}
+
+int pv_fk(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9, int64_t n, float* d_pose_out,
+          void* stream) {
+    return pv_fk_impl(h, d_qA, d_qB, d_q9, n, d_pose_out, stream, false);
+}
+
+int pv_fk_verdict_path(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9, int64_t n,
+                       float* d_pose_out, void* stream) {
+    return pv_fk_impl(h, d_qA, d_qB, d_q9, n, d_pose_out, stream, true);
 }
 
 int pv_state_contacts(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9, int64_t n,

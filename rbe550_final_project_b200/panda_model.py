@@ -402,6 +402,20 @@ def header_text() -> str:
                 c = SPHERE_CENTER[i]
                 a(f"  s[{i}] = make_float3({_place_expr(c, 'x')}, {_place_expr(c, 'y')}, {_place_expr(c, 'z')}); \\")
         a("")
+    a("// lowest point of the moving arm spheres (link1..link7) for the ground-plane test: min over spheres of z - r,")
+    a("// evaluated as one min-chain per distinct radius (rounding is monotonic, so the verdict is bit-identical to")
+    a("// testing every sphere on its own)")
+    by_r = {}
+    for i in range(N_SPHERES):
+        if int(SPHERE_LINK[i]) != 0:
+            by_r.setdefault(_f(SPHERE_RADIUS[i]), []).append(i)
+    def min_tree(items):  # balanced, so the chain of dependent FMNMX stays short
+        if len(items) == 1:
+            return items[0]
+        h = (len(items) + 1) // 2
+        return f"fminf({min_tree(items[:h])}, {min_tree(items[h:])})"
+    terms = [f"({min_tree([f's[{i}].z' for i in idx])} - {r})" for r, idx in by_r.items()]
+    a(f"#define PV_TABLE_LOWEST(s) ({min_tree(terms)})")
     a("// X(link, centre_sphere, bound_radius): conservative bounding ball of each link's spheres")
     a("#define PV_LINK_GROUPS(X) \\")
     groups = link_groups()

@@ -181,12 +181,14 @@ class PandaValidity:
             out.append(pairs)
         return out
 
-    def fk(self, q, stream=None) -> torch.Tensor:
-        """(n, 11, 12): per link position xyz then row-major rotation."""
+    def fk(self, q, stream=None, verdict_path: bool = False) -> torch.Tensor:
+        """(n, 11, 12): per link position xyz then row-major rotation.  verdict_path=True evaluates the kinematics the
+        way the verdict-bit kernels do internally (hardware sin/cos), to measure their distance from the pose kernel."""
         A, B, q9, n = self._planes(q)
         out = torch.empty((n, 11, 12), dtype=torch.float32, device=self.device)
-        self._ck(self.lib.pv_fk(self._h, A.data_ptr(), B.data_ptr(), q9.data_ptr() if q9 is not None else None, n,
-                                out.data_ptr(), self._stream(stream)), "pv_fk")
+        fn = self.lib.pv_fk_verdict_path if verdict_path else self.lib.pv_fk
+        self._ck(fn(self._h, A.data_ptr(), B.data_ptr(), q9.data_ptr() if q9 is not None else None, n,
+                    out.data_ptr(), self._stream(stream)), "pv_fk")
         return out
 
     def check_edges(self, qa, qb, n_steps: int = 0, resolution: float = pm.VALIDITY_RESOLUTION,

@@ -54,6 +54,25 @@ def test_fk_parity(pv, c64):
     assert np.allclose(out[1, 8, 0:3], [0.30702, 0, 0.60027], atol=1e-5)
 
 
+def test_fk_verdict_path(pv, c64):
+    """The verdict-bit kernels take their joint sines / cosines from the hardware approximations; the poses they work
+    with must still meet the 1e-5 m / 1e-5 rad bar (and stay far inside the 1e-4 m verdict band)."""
+    pv.set_scene(sc.goal1_scattered())
+    q = random_configs(50000, 12, fingers="random")
+    q[0] = pm.Q_UPPER
+    q[1] = pm.Q_LOWER
+    q[2] = [50.0, -40.0, 30.0, -20.0, 10.0, 25.0, -35.0, 0.02, 0.02]  # far outside the limits: still reduced exactly
+    out = pv.fk(_dev(q), verdict_path=True).cpu().numpy()
+    R, p = c64.fk(q.astype(np.float64))
+    err_p = np.abs(out[:, :, 0:3] - p).max()
+    Rg = out[:, :, 3:12].reshape(-1, 11, 3, 3)
+    rel = np.einsum("nlij,nlik->nljk", R, Rg.astype(np.float64))
+    skew = 0.5 * (rel - np.swapaxes(rel, 2, 3))
+    ang = np.arcsin(np.clip(np.sqrt((skew ** 2).sum((2, 3)) / 2), 0, 1)).max()
+    print(f"verdict-path FK: max position error {err_p:.2e} m, max angle error {ang:.2e} rad")
+    assert err_p < 2e-6 and ang < 3e-6  # measured 5.5e-7 m, 9.3e-7 rad; bars: 1e-5 m, 1e-5 rad
+
+
 @pytest.mark.parametrize("scene_name", SCENES)
 @pytest.mark.parametrize("attached", [-1, 3])
 def test_state_verdicts(pv, c64, scene_name, attached):

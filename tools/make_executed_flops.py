@@ -15,7 +15,7 @@ ffma = vals["smsp__sass_thread_inst_executed_op_ffma_pred_on.sum"]
 fadd = vals["smsp__sass_thread_inst_executed_op_fadd_pred_on.sum"]
 fmul = vals["smsp__sass_thread_inst_executed_op_fmul_pred_on.sum"]
 out = {
-    "kernel": "pv_state_bits_sorted_kernel<SoA>: per-lane culling, each block visits its share in order of elbow angle, 512-thread lockstep blocks",
+    "kernel": "pv_state_bits_sorted_kernel<SoA>: per-lane culling + scene-level cull, each block visits its share in order of (wrist distance class, elbow bin, wrist-flex bin), 512-thread lockstep blocks",
     "workload": f"{n} random Panda configs vs goal1_scattered (bench.py workload)",
     "ffma_per_check": ffma / n, "fadd_per_check": fadd / n, "fmul_per_check": fmul / n,
     "fp32_flops_per_check": (2 * ffma + fadd + fmul) / n,
