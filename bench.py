@@ -135,7 +135,10 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+_JSON_OUT = sys.stdout
 
 
 def main():
@@ -149,6 +152,12 @@ def main():
     ap.add_argument("--nccl-gather", action="store_true", help="N>1: gather verdict words with NCCL instead of the fused peer-memory path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly ONE line, the JSON: libraries that write to file descriptor 1 behind Python's back (NCCL
+    # prints its version banner there) are sent to stderr; the JSON goes to the saved descriptor.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -377,7 +386,7 @@ def main():
             line["plan"] = plan_time_probe(pv)
         except Exception as exc:  # the headline metric must still print
             line["plan"] = {"error": repr(exc)}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -59,8 +59,8 @@ __device__ __forceinline__ void pv_emit_word(uint32_t* __restrict__ bits, const 
 #ifndef PV_SB_SYNC
 #define PV_SB_SYNC 0
 #endif
-#ifndef PV_SB_BAR_EVERY
-#define PV_SB_BAR_EVERY 1
+#ifndef PV_SB_BAR_GROUPS
+#define PV_SB_BAR_GROUPS 1
 #endif
 #ifndef PV_SB_MINB
 #define PV_SB_MINB 1
@@ -95,11 +95,12 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
 // ---- sorted variant ------------------------------------------------------------------------------------------
 // The per-lane culls only pay when a whole warp can skip a block of tests, and with unordered inputs some lane of the
 // 32 nearly always needs it (self-collision blocks ran with ~8 of 32 lanes live: profiles/r1_notes.md).  Which blocks
-// a configuration needs is decided mostly by the elbow angle q[3] (it alone fixes the shoulder-wrist distance), so a
-// block first counting-sorts ITS share of the batch (the same 512-configuration chunks the unsorted kernel gives it,
-// up to PV_ST configurations at a time) by q[3] in shared memory -- keys and 16-bit indices only; the configurations
-// stay in global memory / L2 and are gathered -- and then walks that share in sorted order: the 32 lanes of a warp,
-// and the 16 warps that meet at the lockstep barrier, hold near-equal elbow angles and skip or take the same blocks.
+// a configuration needs is decided mostly by the elbow angle q[3] (it alone fixes the shoulder-wrist distance), the wrist
+// flex q[5] and how far the wrist is from the scene boxes (pv_sort_key), so a block first counting-sorts ITS share of
+// the batch (the same 512-configuration chunks the unsorted kernel gives it, up to PV_ST configurations at a time) by
+// that key in shared memory -- keys and 16-bit indices only; the configurations stay in global memory / L2 and are
+// gathered -- and then walks that share in sorted order: the 32 lanes of a warp, and the 16 warps that meet at the
+// lockstep barrier, hold near-equal keys and skip or take the same blocks.
 // Verdict bits return to their ORIGINAL positions through a shared-memory bit array, so the output (and the fused
 // gather) is unchanged.
 #ifndef PV_ST
@@ -311,12 +312,11 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
                 q[8] = q9 ? M.st9[r & 1][tid] : b.w;
             }
             if (r + 1 < nc) PV_PREFETCH(r + 1)
-#if PV_SB_BAR_EVERY > 0
-            if (PV_SB_BAR_EVERY == 1 || r % PV_SB_BAR_EVERY == 0)
+#if PV_SB_BAR_GROUPS > 1  // experiment: lockstep inside groups of warps only (named barriers)
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / (PV_SB_THREADS / PV_SB_BAR_GROUPS)), "n"(PV_SB_THREADS / PV_SB_BAR_GROUPS) : "memory");
 #else
-            if (false)
+            __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
 #endif
-                __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
             PvAcc<PV_MODE_BITS> acc;
             pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, PV_SB_SYNC, true, CARRY>(q, S, acc);
             if (in && !acc.hit) atomicOr(&vbits[L >> 5], 1u << (L & 31));

@@ -125,8 +125,8 @@ class PandaValidity:
 
     def set_culling(self, mode):
         """State-kernel variant: 0 brute force, 1 per-lane bounding-ball culling, 2 (default) = 1 with each block's
-        share of the batch visited in order of elbow angle so that warps agree on which tests to skip; bit-identical
-        verdicts."""
+        share of the batch visited in order of (wrist distance from the scene, elbow angle, wrist flex) so that warps
+        agree on which tests to skip; bit-identical verdicts."""
         self._ck(self.lib.pv_set_culling(self._h, int(mode)), "pv_set_culling")
 
     # -- device-buffer calls --------------------------------------------------------------------------

@@ -336,6 +336,45 @@ def test_general_obbs_max_scene(pv, c64):
                      "general obbs edges")
 
 
+def test_scene_level_cull_random_scenes(pv):
+    """The scene-level cull (link-group balls against the padded bounds of all boxes) and the sorted visiting order
+    never change a verdict: brute force, per-lane culling and the sorted kernel agree bit for bit on random scenes of
+    1..8 boxes -- tiny and isolated, tall, floating above the table, half sunk into it, rotated in 3-D, hugging the
+    base -- for states, edges and the device-generated sweep, also with joint values beyond the limits."""
+    rng = np.random.default_rng(4711)
+    q = random_configs(120_011, 5, fingers="random")
+    q[::13, :7] *= 1.5  # some joints outside their limits (legal input when the limit flag is off)
+    qd = _dev(q)
+    qb = _dev(np.clip(q[:6000] + rng.normal(0, 0.2, (6000, 9)), pm.Q_LOWER, pm.Q_UPPER).astype(np.float32))
+    for trial in range(12):
+        nb = int(rng.integers(1, 9))
+        recs = []
+        for k in range(nb):
+            rad = rng.uniform(0.12, 0.9)
+            ang = rng.uniform(-np.pi, np.pi)
+            size = rng.uniform(0.02, 0.05 if trial % 3 == 0 else 0.3, size=3)
+            center = [rad * np.cos(ang), rad * np.sin(ang), rng.uniform(-0.05, 1.1)]
+            R = _random_rotation(rng) if (k + trial) % 2 else sc.yaw_mat(rng.uniform(-180, 180))
+            recs.append(sc.make_obb(center, size, R))
+        snap = sc.SceneSnapshot(obb=np.array(recs, dtype=np.float32), names=[f"x{k}" for k in range(nb)],
+                                entity_idx=list(range(1, nb + 1)))
+        pv.set_scene(snap)
+        pv.set_attached(0 if trial % 4 == 1 else -1)
+        res, sres = [], []
+        for mode in (0, 1, 2):
+            pv.set_culling(mode)
+            res.append(pv.check_states(qd).cpu().numpy())
+            sres.append(pv.sweep(0, 50_000, 99 + trial)[0].cpu().numpy())
+        pv.set_culling(2)
+        assert (res[0] == res[1]).all() and (res[0] == res[2]).all(), ("states", trial)
+        # the edge kernel always culls: its bits against its own brute-force margins, outside the contact band
+        eb = unpack_bits(pv.check_edges(qd[:6000], qb, n_steps=0), 6000)
+        em = pv.edge_margins(qd[:6000], qb, n_steps=0).cpu().numpy()
+        _assert_verdicts(eb, em.astype(np.float64), f"edges trial {trial}")
+        assert (sres[0] == sres[1]).all() and (sres[0] == sres[2]).all(), ("sweep", trial)
+    pv.set_attached(-1)
+
+
 def test_order_and_batch_size_invariance(pv):
     """A verdict depends on its configuration only: permuting the batch permutes the bits; splitting the batch at
     arbitrary (unaligned) points changes nothing; empty scene = self / table rule only."""

@@ -48,7 +48,7 @@ marks=[('junk/limits',find('bool junk = false')),('fk+place',find('float3 s[PV_N
        ('carry-place',find('carried box: placed by the hand')),('self:grip_r',find('radius of a ball centred on the hand box')),('self:ss',find('if (S.flags & PV_FLAG_SELF)')),
        ('self:sbh',find('sphere-vs-gripper pairs: the three')),('env:obb-load',find('const int nb = S.n_obb;')),('env:group-macros',find('one uniform yaw / general decision per GROUP')),
        ('env:groups',find('PV_LINK_GROUPS(PV_ENV_GROUP)')),('env:gripper',find('one bounding ball around the whole gripper')),('end',find('#undef PV_EARLY_EXIT'))]
-fk_lo,fk_hi=find('template <class F>'),find('// ---- the state check')
+fk_lo,fk_hi=find('template <bool FAST = false, class F>'),find('// ---- the state check')
 prim_lo,prim_hi=find('// ---- primitive tests'),find('// ---- forward kinematics')
 def cat(fr):
     # fr: innermost first
