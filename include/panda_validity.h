@@ -75,6 +75,10 @@ int pv_set_attached(PvHandle *h, int obb_index);
  * obb_index still exists (the pose in the hand frame does not depend on the snapshot). */
 int pv_set_carried(PvHandle *h, int obb_index, const float *hand_from_box, float contact_allowance);
 int pv_set_flags(PvHandle *h, unsigned flags);
+/* Which state / sweep kernel variant answers (all return bit-identical verdict words; a test and tuning knob, no
+ * reference counterpart): 0 brute force over every kept pair, 1 per-lane bounding-volume culling, 2 (default) = 1 with
+ * each block's share of the batch visited in sorted order. */
+int pv_set_culling(PvHandle *h, int mode);
 
 /* Fused verdict gather for multi-GPU runs: after this call pv_check_states and pv_sweep also store
  * every verdict word w of this rank at word (word_offset + w) of EVERY rank's gather buffer, from inside the

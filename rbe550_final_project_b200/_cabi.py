@@ -24,7 +24,7 @@ NVCC_FLAGS = [
 # every symbol include/panda_validity.h declares
 EXPORTS = [
     "pv_create", "pv_destroy", "pv_last_error", "pv_version", "pv_model_info", "pv_joint_limits",
-    "pv_set_scene", "pv_set_attached", "pv_set_carried", "pv_set_flags", "pv_set_gather", "pv_fk", "pv_fk_verdict_path", "pv_check_states", "pv_state_margins", "pv_state_contacts",
+    "pv_set_scene", "pv_set_attached", "pv_set_carried", "pv_set_flags", "pv_set_culling", "pv_set_gather", "pv_fk", "pv_fk_verdict_path", "pv_check_states", "pv_state_margins", "pv_state_contacts",
     "pv_check_edges", "pv_edge_margins", "pv_check_states_host", "pv_check_edges_host", "pv_sweep",
     "pv_rrtc_batch", "pv_ik_batch", "pv_fp32_peak", "pv_launch_count",
 ]
