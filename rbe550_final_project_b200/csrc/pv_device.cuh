@@ -559,8 +559,10 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
 
     // ---- self collision ------------------------------------------------------------------------------
     // radius of a ball centred on the hand box that contains all three gripper boxes for THIS configuration
-    float grip_r;
-    {
+    // (with both fingers inside their travel the hand box's own bounding ball contains them -- asserted by the model
+    // generator -- so the general form only runs for out-of-limit finger values)
+    float grip_r = bbr[0] + 2.0f * PV_CULL_SLACK;
+    if (!(fabsf(q[7]) <= PV_GRIP_CONST_MAXQ && fabsf(q[8]) <= PV_GRIP_CONST_MAXQ)) {
         float3 d1 = v_sub(bc[1], bc[0]), d2 = v_sub(bc[2], bc[0]);
         grip_r = fmaxf(bbr[0], fmaxf(sqrtf(v_dot(d1, d1)) + bbr[1], sqrtf(v_dot(d2, d2)) + bbr[2])) + 2.0f * PV_CULL_SLACK;
     }

@@ -215,11 +215,21 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     const int64_t my_chunks = (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x;
     // local index L = jj * 512 + t of super-tile j0  <->  configuration (blockIdx.x + (j0 + jj) * gridDim.x) * 512 + t
 #define PV_GI(jj, t) ((((int64_t)blockIdx.x + (j0 + (jj)) * (int64_t)gridDim.x) * PV_SB_THREADS) + (t))
-#define PV_Q03_OF(i)                                                                                               \
-    (AOS ? make_float4(__ldg(q_aos + 9 * (i)), __ldg(q_aos + 9 * (i) + 1), __ldg(q_aos + 9 * (i) + 2), __ldg(q_aos + 9 * (i) + 3)) \
-         : __ldg(qA + (i)))
+    // 64-bit arithmetic once per super-tile (tile base pointers); inside a tile configurations are addressed by the
+    // 32-bit offset PV_OFF from the tile's first configuration (at most 32 chunks x grid x 512 < 2^32)
+#define PV_OFF(jj, t) ((unsigned)(jj) * stride + (unsigned)(t))
+#define PV_Q03_OF(o)                                                                                               \
+    (AOS ? make_float4(__ldg(t_aos + 9 * (o)), __ldg(t_aos + 9 * (o) + 1), __ldg(t_aos + 9 * (o) + 2), __ldg(t_aos + 9 * (o) + 3)) \
+         : __ldg(tA + (o)))
+    const unsigned stride = gridDim.x * PV_SB_THREADS;
     for (int64_t j0 = 0; j0 < my_chunks; j0 += ST_CHUNKS) {
         const int nc = (int)((my_chunks - j0 < (int64_t)ST_CHUNKS) ? (my_chunks - j0) : (int64_t)ST_CHUNKS);
+        const int64_t base0 = PV_GI(0, 0);
+        const unsigned n_rem = (unsigned)((n - base0 < (int64_t)0xffffffffll) ? (n - base0) : (int64_t)0xffffffffll);
+        const float4* __restrict__ tA = AOS ? nullptr : qA + base0;
+        const float4* __restrict__ tB = AOS ? nullptr : qB + base0;
+        const float* __restrict__ t9 = (AOS || !q9) ? nullptr : q9 + base0;
+        const float* __restrict__ t_aos = AOS ? q_aos + 9 * base0 : nullptr;
         if (tid < PV_SORT_BUCKETS) hist[tid] = 0;
         for (int w = tid; w < nc * (PV_SB_THREADS / 32); w += PV_SB_THREADS) vbits[w] = 0;
         __syncthreads();
@@ -229,18 +239,17 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
             float kq5[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int64_t i = PV_GI(j8 + u, tid);
+                const unsigned o = PV_OFF(j8 + u, tid);
                 kq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 kq5[u] = 0.f;
-                if (j8 + u < nc && i < n) {
-                    kq[u] = PV_Q03_OF(i);
-                    if (PV_SORT_Q5_BINS > 1) kq5[u] = AOS ? __ldg(q_aos + 9 * i + 5) : __ldg(reinterpret_cast<const float*>(qB) + 4 * i + 1);
+                if (j8 + u < nc && o < n_rem) {
+                    kq[u] = PV_Q03_OF(o);
+                    if (PV_SORT_Q5_BINS > 1) kq5[u] = AOS ? __ldg(t_aos + 9 * o + 5) : __ldg(reinterpret_cast<const float*>(tB) + 4 * o + 1);
                 }
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int64_t i = PV_GI(j8 + u, tid);
-                if (j8 + u < nc && i < n) {
+                if (j8 + u < nc && PV_OFF(j8 + u, tid) < n_rem) {
                     const int key = pv_sort_key(kq[u].x, kq[u].y, kq[u].z, kq[u].w, kq5[u], S);
                     M.key8[(j8 + u) * PV_SB_THREADS + tid] = (unsigned char)key;
                     atomicAdd(&hist[key], 1u);
@@ -272,8 +281,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         }
         __syncthreads();
         for (int jj = 0; jj < nc; ++jj) {  // pass 2: scatter the local indices (order inside a bucket does not matter)
-            const int64_t i = PV_GI(jj, tid);
-            if (i < n) order[atomicAdd(&hist[M.key8[jj * PV_SB_THREADS + tid]], 1u)] = (unsigned short)(jj * PV_SB_THREADS + tid);
+            if (PV_OFF(jj, tid) < n_rem) order[atomicAdd(&hist[M.key8[jj * PV_SB_THREADS + tid]], 1u)] = (unsigned short)(jj * PV_SB_THREADS + tid);
         }
         __syncthreads();
         const int cnt = s_cnt;
@@ -284,14 +292,14 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     {                                                                                           \
         const int slot_ = (r_) * PV_SB_THREADS + tid;                                           \
         L_next = order[slot_ < cnt ? slot_ : cnt - 1];                                          \
-        const int64_t i_ = PV_GI(L_next / PV_SB_THREADS, L_next % PV_SB_THREADS);               \
+        const unsigned i_ = PV_OFF(L_next / PV_SB_THREADS, L_next % PV_SB_THREADS);             \
         const int b_ = (r_) & 1;                                                                \
         if constexpr (AOS) {                                                                    \
-            _Pragma("unroll") for (int j = 0; j < 9; ++j) pv_cp_async4(&M.stq[b_][j][tid], q_aos + 9 * i_ + j); \
+            _Pragma("unroll") for (int j = 0; j < 9; ++j) pv_cp_async4(&M.stq[b_][j][tid], t_aos + 9 * i_ + j); \
         } else {                                                                                \
-            pv_cp_async16(&M.stA[b_][tid], qA + i_);                                            \
-            pv_cp_async16(&M.stB[b_][tid], qB + i_);                                            \
-            if (q9) pv_cp_async4(&M.st9[b_][tid], q9 + i_);                                     \
+            pv_cp_async16(&M.stA[b_][tid], tA + i_);                                            \
+            pv_cp_async16(&M.stB[b_][tid], tB + i_);                                            \
+            if (q9) pv_cp_async4(&M.st9[b_][tid], t9 + i_);                                     \
         }                                                                                       \
         asm volatile("cp.async.commit_group;" ::: "memory");                                    \
     }
@@ -331,6 +339,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
 #undef PV_PREFETCH
 #undef PV_GI
 #undef PV_Q03_OF
+#undef PV_OFF
 }
 
 template <bool CULL, bool CARRY>

@@ -494,6 +494,15 @@ def header_text() -> str:
             a(f"  X({k}, {_f(sign * c[0] + off[0])}, {_f(sign * c[1] + off[1])}, {_f(c[2] + off[2])}, {_f(sign)}, {6 + k}, "
               f"{_f(h[0])}, {_f(h[1])}, {_f(h[2])}) \\")
     a("")
+    # while both fingers are within +-FINGER_SLIDE_MAX of the hand's mid-plane the hand box's own bounding ball already
+    # contains both finger boxes, so the per-configuration gripper ball of pv_check_config is a constant there
+    for k in (1, 2):
+        off = np.array(BODY_POS[int(BOX_LINK[k])])
+        for qf in (-FINGER_SLIDE_MAX, FINGER_SLIDE_MAX):
+            c = np.array([BOX_CENTER[k][0] + off[0], BOX_CENTER[k][1] + qf + off[1], BOX_CENTER[k][2] + off[2]])
+            assert np.linalg.norm(c - BOX_CENTER[0]) + BOX_BOUND_RADIUS[k] < BOX_BOUND_RADIUS[0] - 1e-4
+    a("// |q7|, |q8| <= this: the gripper ball (centre = hand box centre) is the hand box's own bounding ball")
+    a(f"#define PV_GRIP_CONST_MAXQ {_f(FINGER_SLIDE_MAX)}")
     a("// LB(la, ca, cull0, cull1, cull2, r_la): link la's block runs when its bounding ball (centre s[ca], radius r_la)")
     a("// reaches the bounding ball of gripper box k for any k (cull_k = squared reach, 0 when the link has no pair with box k)")
     a("#define PV_SBH_LINKS(LB) \\")
