@@ -446,7 +446,7 @@ __device__ __forceinline__ void pv_fk_visit(const float* q, float bx, float by, 
 // SYNC: every warp of the block calls this together and block-level barriers keep the warps within one
 // code region of each other, so the (large, straight-line) instruction stream is fetched once per SM instead
 // of once per warp (ncu showed stall_no_instruction as the top stall of the free-running version).
-template <int MODE, bool CULL, int EXIT, int SYNC = 0, bool FMAK = false, bool CARRY = false>
+template <int MODE, bool CULL, int EXIT, int SYNC = 0, bool FMAK = false, bool CARRY = false, bool FTRIG = FMAK>
 __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S, PvAcc<MODE>& acc) {
     static_assert(!SYNC || EXIT == PV_EXIT_NONE, "block barriers and warp-level early exit do not mix");
     const unsigned FULL = 0xffffffffu;
@@ -487,7 +487,7 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
     // FK -> sphere centres (registers) + gripper boxes
     float3 s[PV_N_SPHERES];
     float3 hX, hY, hZ, hP, bc[3];
-    pv_fk_visit<(PV_FAST_TRIG && FMAK)>(q, S.base[0], S.base[1], S.base[2], [&](auto lc, float3 p, float3 X, float3 Y, float3 Z) {
+    pv_fk_visit<(PV_FAST_TRIG && FTRIG)>(q, S.base[0], S.base[1], S.base[2], [&](auto lc, float3 p, float3 X, float3 Y, float3 Z) {
         constexpr int l = decltype(lc)::value;
         if constexpr (l == 0) { PV_PLACE_LINK0(s, p, X, Y, Z) }
         if constexpr (l == 1) { PV_PLACE_LINK1(s, p, X, Y, Z) }

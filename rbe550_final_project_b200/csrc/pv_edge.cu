@@ -9,6 +9,12 @@
 #include "pv_device.cuh"
 #include "pv_handle.h"
 
+// verdict bits of edges from the hardware sin/cos, like the state kernels (pv_device.cuh, PV_FAST_TRIG); margins keep
+// the accurate form
+#ifndef PV_EDGE_FAST_TRIG
+#define PV_EDGE_FAST_TRIG 1
+#endif
+
 
 #define PV_CUDA(h, expr)                                                                              \
     do {                                                                                              \
@@ -113,7 +119,8 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
 #pragma unroll
         for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, eb[c] - ea[c], ea[c]);
         PvAcc<MODE> acc;
-        pv_check_config<MODE, CULL, (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE), 0, false, CARRY>(q, S, acc);
+        pv_check_config<MODE, CULL, (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE), 0, false, CARRY,
+                        (PV_EDGE_FAST_TRIG && MODE == PV_MODE_BITS)>(q, S, acc);
         bool edge_done;
         bool edge_hit = false;
         if constexpr (MODE == PV_MODE_BITS) {
