@@ -153,6 +153,9 @@ typedef struct {
     int check_endpoints; /* != 0: test start and goal first (bounds + validity, planning.py:163-183); a query whose
                             start / goal / both fail returns path length 0 and iters = -1 / -2 / -3 */
     int planner;         /* 0 = RRTConnect (the reference's default, planning.py:67), 1 = RRT (single tree, 5 % goal bias) */
+    int query_offset;    /* id of h_starts[0] inside the caller's whole batch.  The random stream of a search is keyed by
+                            (seed, global query id, replica), so a batch split over several calls or GPUs returns exactly
+                            what the unsplit call returns */
 } PvRrtcParams;
 
 /* h_starts/h_goals: [n_queries][9] host AoS.  h_path_out: [n_queries][max_path][9]; h_path_len: states

@@ -34,7 +34,7 @@ class PvRrtcParams(C.Structure):
     _fields_ = [
         ("range", C.c_float), ("resolution", C.c_float), ("max_iters", C.c_int), ("max_nodes", C.c_int),
         ("max_path", C.c_int), ("seed", C.c_uint32), ("replicas", C.c_int), ("shortcut_passes", C.c_int),
-        ("check_endpoints", C.c_int), ("planner", C.c_int),
+        ("check_endpoints", C.c_int), ("planner", C.c_int), ("query_offset", C.c_int),
     ]
 
 

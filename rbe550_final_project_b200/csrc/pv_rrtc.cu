@@ -32,6 +32,7 @@ struct RrtcArgs {
     int max_iters, max_nodes, max_path, replicas, shortcut_passes, check_endpoints;
     int planner;  // 0 = RRTConnect (two trees), 1 = RRT (start tree only, 5 % goal bias: og.RRT defaults)
     unsigned seed;
+    unsigned search_offset;  // query_offset * replicas: the RNG is keyed by the GLOBAL search id
     float* tree_q;      // [search][2][9][max_nodes]
     int* parent;        // [search][2][max_nodes]
     float* path_tmp;    // [search][max_path][9]
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
                 if (it >= A.max_iters || size0 >= M - 1 || size1 >= M - 1) break;
                 tree = cur;
                 float u9 = 1.f;
-                if (it > 0) rrtc_sample(A.seed, (unsigned)search, (unsigned)it, goal_q, u9);
+                if (it > 0) rrtc_sample(A.seed, (unsigned)search + A.search_offset, (unsigned)it, goal_q, u9);
                 // first extension aims at the goal itself (cheap straight-line attempt); the single-tree planner also
                 // does so with OMPL's default goal bias of 5 %
                 aim_goal = (it == 0) || (A.planner == 1 && u9 < 0.05f);
@@ -372,6 +373,7 @@ extern "C" int pv_rrtc_batch(PvHandle* h, const float* h_starts, const float* h_
     a.check_endpoints = params->check_endpoints ? 1 : 0;
     a.planner = params->planner == 1 ? 1 : 0;
     a.seed = params->seed;
+    a.search_offset = (unsigned)(params->query_offset > 0 ? params->query_offset : 0) * (unsigned)a.replicas;
     const size_t n_search = (size_t)n_queries * a.replicas;
 
 #define RR_CUDA(expr)                                                                                        \

@@ -78,6 +78,59 @@ def sweep_sharded_fused(pv, gather: "FusedVerdictGather", n_total: int, seed: in
     return full, n_valid
 
 
+def rrtc_batch_sharded(pv, starts, goals, group=None, packed=False, **kw):
+    """BASELINE config 4 on N GPUs: the (start, goal) queries are independent, so rank r plans the contiguous shard
+    shard_range(n, r, world, align=1) on its own GPU -- with `query_offset` = the shard's first id, which keys the
+    random streams by GLOBAL query id -- and the results (path lengths, iteration / check counts, paths) are
+    all-gathered.  Every rank returns what one GPU returns for the whole batch: (paths, lengths, iters, checks) as
+    numpy arrays.  `pv` needs rrtc_batch(starts, goals, query_offset=..., **kw) -> the same four arrays.
+    packed=True returns (states, lengths, iters, checks) with states = the used rows of all paths back to back
+    ((sum(lengths), 9); path k starts at lengths[:k].sum()) instead of the dense (n, max_path, 9) block, whose
+    allocation dominates the wall time of large batches (4.6 KB per query for typically 2..4 states)."""
+    import numpy as np
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    starts = np.ascontiguousarray(starts, dtype=np.float32).reshape(-1, 9)
+    goals = np.ascontiguousarray(goals, dtype=np.float32).reshape(-1, 9)
+    n = starts.shape[0]
+    first, count = shard_range(n, rank, world, align=1)
+    paths, plen, iters, checks = pv.rrtc_batch(starts[first:first + count], goals[first:first + count],
+                                               query_offset=first, **kw)
+    if world == 1:
+        if packed:
+            return paths[np.arange(paths.shape[1])[None, :] < plen.reshape(-1, 1)], plen, iters, checks
+        return paths, plen, iters, checks
+    per = (n + world - 1) // world  # shard_range with align=1: every shard but the last holds `per` queries
+    max_path = paths.shape[1]
+    dev = getattr(pv, "device", None)
+    dev = dev if (dev is not None and dist.get_backend(group) == "nccl") else torch.device("cpu")
+    # 1. per-query scalars (length, iterations, checks), shards padded to `per` rows
+    meta = torch.zeros((per, 3), dtype=torch.int64)
+    if count:
+        meta[:count] = torch.from_numpy(np.stack([plen, iters, checks], axis=1).astype(np.int64))
+    meta_all = torch.empty((world * per, 3), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(meta_all, meta.to(dev), group=group)
+    meta_all = meta_all.cpu().numpy()[:n]
+    plen_all = meta_all[:, 0]
+    # 2. the path states, packed: only the plen[k] used rows of each path travel (a path buffer is max_path x 9 floats,
+    # a typical path 2..4 states), every rank padded to the longest rank's total, which the lengths of step 1 give
+    totals = [int(plen_all[min(r * per, n):min((r + 1) * per, n)].sum()) for r in range(world)]
+    cap = max(max(totals), 1)
+    used = np.arange(max_path)[None, :] < plen.reshape(-1, 1)
+    send = torch.zeros((cap, 9), dtype=torch.float32)
+    if totals[rank]:
+        send[: totals[rank]] = torch.from_numpy(np.ascontiguousarray(paths[used]))
+    recv = torch.empty((world * cap, 9), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(recv, send.to(dev), group=group)
+    recv = recv.cpu().numpy().reshape(world, cap, 9)
+    states = np.concatenate([recv[r, : totals[r]] for r in range(world)])
+    if packed:
+        return states, plen_all.astype(np.int32), meta_all[:, 1].astype(np.int32), meta_all[:, 2].copy()
+    allp = np.zeros((n, max_path, 9), dtype=np.float32)
+    allp[np.arange(max_path)[None, :] < plen_all[:, None]] = states
+    return allp, plen_all.astype(np.int32), meta_all[:, 1].astype(np.int32), meta_all[:, 2].copy()
+
+
 def merge_nn_candidates(local_d2: torch.Tensor, local_idx: torch.Tensor, group=None):
     """Nearest-tree-node search over a tree sharded across ranks: each rank contributes, per query, the best
     (squared distance, local node index) of its shard; returns (best_d2, owner_rank, owner_local_idx) per query.

@@ -258,7 +258,10 @@ class PandaValidity:
     def rrtc_batch(self, starts: np.ndarray, goals: np.ndarray, max_iters: int = 2000, max_nodes: int = 2048,
                    max_path: int = 128, seed: int = 1, replicas: int = 1, shortcut_passes: int = 2,
                    rrt_range: float = 0.0, resolution: float = 0.0, check_endpoints: bool = False,
-                   planner: str = "RRTConnect"):
+                   planner: str = "RRTConnect", query_offset: int = 0):
+        """Batched multi-query planning, one launch.  `query_offset` = id of starts[0] in the caller's whole batch: the
+        random streams are keyed by global query id, so shards of a batch (other calls, other GPUs) return exactly the
+        rows the unsplit call returns."""
         starts = np.ascontiguousarray(starts, dtype=np.float32).reshape(-1, 9)
         goals = np.ascontiguousarray(goals, dtype=np.float32).reshape(-1, 9)
         nq = starts.shape[0]
@@ -266,7 +269,7 @@ class PandaValidity:
             raise PandaValidityError("starts and goals must have the same length")
         prm = _cabi.PvRrtcParams(float(rrt_range), float(resolution), int(max_iters), int(max_nodes), int(max_path),
                                  int(seed) & 0xFFFFFFFF, int(replicas), int(shortcut_passes), 1 if check_endpoints else 0,
-                                 {"RRTConnect": 0, "RRT": 1}[planner])
+                                 {"RRTConnect": 0, "RRT": 1}[planner], int(query_offset))
         paths = np.zeros((nq, max_path, 9), dtype=np.float32)
         plen = np.zeros(nq, dtype=np.int32)
         iters = np.zeros(nq, dtype=np.int32)

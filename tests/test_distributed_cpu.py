@@ -71,3 +71,64 @@ def test_shard_range_properties():
                 assert first % 32 == 0 or count == 0
                 pos = first + count
             assert words_per_shard(n, world) * world * 32 >= n
+
+
+class _OraclePlanner:
+    """Stands in for PandaValidity in the CPU test: the C restatement of the device planner, one search per query,
+    random streams keyed by global query id like pv_rrtc_batch(query_offset=...)."""
+    device = None
+
+    def __init__(self):
+        from oracle.c_oracle import COracle
+        from rbe550_final_project_b200 import panda_model as pm, scenes as sc
+        self.ora = COracle(pm.model_arrays(), "f32")
+        wall = sc.make_obb((0.55, 0.0, 0.35), (0.5, 0.04, 0.7))
+        self.scene = sc.SceneSnapshot(obb=np.array([wall], dtype=np.float32), names=["wall"], entity_idx=[1]).as_oracle_scene()
+
+    def rrtc_batch(self, starts, goals, query_offset=0, max_path=64, seed=1, **kw):
+        n = len(starts)
+        paths = np.zeros((n, max_path, 9), np.float32)
+        plen, iters, checks = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int64)
+        for k in range(n):
+            p, it, ch = self.ora.rrtc(starts[k], goals[k], self.scene, seed=seed, search=query_offset + k, max_path=max_path,
+                                      max_iters=300, max_nodes=512)
+            paths[k, : len(p)] = p
+            plen[k], iters[k], checks[k] = len(p), it, ch
+        return paths, plen, iters, checks
+
+
+def _rrtc_queries(n):
+    from rbe550_final_project_b200 import panda_model as pm
+    rng = np.random.default_rng(8)
+    a = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n, 9)).astype(np.float32)
+    b = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n, 9)).astype(np.float32)
+    return a, b
+
+
+def _rrtc_worker(rank, world, port, n, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rbe550_final_project_b200.distributed import rrtc_batch_sharded
+    a, b = _rrtc_queries(n)
+    out = rrtc_batch_sharded(_OraclePlanner(), a, b, max_path=64, seed=5)
+    ret[rank] = [np.asarray(x).copy() for x in out]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [13, 16])
+def test_sharded_rrtc_matches_single_rank(n):
+    """world_size 2 over gloo: every rank ends up with the rows one rank computes for the whole batch (ragged last shard
+    included), because the random streams follow the global query id."""
+    a, b = _rrtc_queries(n)
+    ref = _OraclePlanner().rrtc_batch(a, b, max_path=64, seed=5)
+    assert (ref[2] > 1).any() and (ref[1] > 0).any()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_rrtc_worker, args=(2, port, n, ret), nprocs=2, join=True)
+    for rank in (0, 1):
+        for j in range(4):
+            assert np.array_equal(ret[rank][j], ref[j]), (rank, j)

@@ -173,6 +173,42 @@ def test_device_rrtc_follows_the_oracle_planner(pv, c32):
     assert solved_both >= int(0.9 * nq)
 
 
+def test_rrtc_batch_is_split_invariant(pv):
+    """The random stream of a search is keyed by its GLOBAL query id (query_offset + row): a batch planned in shards --
+    other calls, other GPUs (distributed.rrtc_batch_sharded) -- gives exactly the rows of the unsplit call."""
+    from rbe550_final_project_b200.distributed import rrtc_batch_sharded
+    wall = sc.make_obb((0.55, 0.0, 0.35), (0.5, 0.04, 0.7))
+    snap = sc.SceneSnapshot(obb=np.array([wall], dtype=np.float32), names=["wall"], entity_idx=[1])
+    pv.set_scene(snap)
+    pv.set_attached(-1)
+    pv.set_flags(True, False)
+    quat = np.array([0.0, 1.0, 0.0, 0.0])
+    q_left, ok1, _ = pv.ik_batch(np.array([[0.5, 0.3, 0.3]]), quat[None], pm.Q_SAFE_HOME, n_seeds=128)
+    q_right, ok2, _ = pv.ik_batch(np.array([[0.5, -0.3, 0.3]]), quat[None], pm.Q_SAFE_HOME, n_seeds=128)
+    assert ok1[0] and ok2[0]
+    # the same hard query 101 times: the rows differ only through their random streams
+    nq = 101
+    starts, goals = np.repeat(q_left, nq, axis=0), np.repeat(q_right, nq, axis=0)
+    kw = dict(max_iters=2000, max_nodes=2048, max_path=96, seed=13, replicas=1, shortcut_passes=2)
+    full = pv.rrtc_batch(starts, goals, **kw)
+    assert (full[1] > 0).mean() > 0.9 and len(set(full[2].tolist())) > 3, "the searches must really sample"
+    used = np.arange(full[0].shape[1])[None, :] < full[1][:, None]
+    for cuts in ([0, 50, nq], [0, 1, 33, 34, 100, nq]):
+        parts = [pv.rrtc_batch(starts[a:b], goals[a:b], query_offset=a, **kw) for a, b in zip(cuts[:-1], cuts[1:])]
+        for j in (1, 2, 3):
+            assert np.array_equal(np.concatenate([p[j] for p in parts]), full[j]), (cuts, j)
+        got = np.concatenate([p[0] for p in parts])
+        assert np.array_equal(got[used], full[0][used]), cuts  # rows beyond a path's length are scratch
+    # without the offset a shard draws the streams of rows 0.. instead of 50..
+    other = pv.rrtc_batch(starts[50:], goals[50:], **kw)
+    assert np.array_equal(other[2], full[2][: nq - 50]) and not np.array_equal(other[2], full[2][50:])
+    # world size 1: the sharded front end is the plain call
+    one = rrtc_batch_sharded(pv, starts, goals, packed=True, **kw)
+    assert np.array_equal(one[0], full[0][used])
+    for j in (1, 2, 3):
+        assert np.array_equal(one[j], full[j])
+
+
 def test_validate_trajectory(pv):
     scene, franka, blocks = create_scene("goal3_tower")
     franka.set_qpos(pm.Q_SAFE_HOME)
