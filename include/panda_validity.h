@@ -158,8 +158,9 @@ typedef struct {
                             what the unsplit call returns */
 } PvRrtcParams;
 
-/* h_starts/h_goals: [n_queries][9] host AoS.  h_path_out: [n_queries][max_path][9]; h_path_len: states
- * per path (0 = no solution); h_iters: iterations used; h_checks: state checks issued (may be NULL). */
+/* h_starts/h_goals: [n_queries][9] host AoS.  h_path_out: [n_queries][max_path][9], of which only the first
+ * h_path_len[k] rows of path k are written; h_path_len: states per path (0 = no solution); h_iters: iterations
+ * used; h_checks: state checks issued (may be NULL). */
 int pv_rrtc_batch(PvHandle *h, const float *h_starts, const float *h_goals, int n_queries,
                   const PvRrtcParams *params, float *h_path_out, int *h_path_len, int *h_iters,
                   long long *h_checks);

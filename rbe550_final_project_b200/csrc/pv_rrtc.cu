@@ -448,7 +448,14 @@ extern "C" int pv_rrtc_batch(PvHandle* h, const float* h_starts, const float* h_
     memcpy(h_path_len, hp, (size_t)n_queries * sizeof(int));
     if (h_iters) memcpy(h_iters, hp + b_i, (size_t)n_queries * sizeof(int));
     if (h_checks) memcpy(h_checks, hp + 2 * b_i, (size_t)n_queries * sizeof(long long));
-    memcpy(h_path_out, hp + 2 * b_i + b_ll, (size_t)n_queries * a.max_path * 9 * sizeof(float));
+    // only the used rows of each path: rows beyond h_path_len[k] of the caller's buffer are left as they were (the
+    // device rows there are scratch of the search), and a large, freshly allocated buffer is not paged in for nothing
+    const float* hpaths = (const float*)(hp + 2 * b_i + b_ll);
+    const size_t row = (size_t)a.max_path * 9;
+    for (int k = 0; k < n_queries; ++k) {
+        const int len = h_path_len[k] < a.max_path ? h_path_len[k] : a.max_path;
+        if (len > 0) memcpy(h_path_out + k * row, hpaths + k * row, (size_t)len * 9 * sizeof(float));
+    }
     return PV_OK;
 #undef RR_CUDA
 }

@@ -58,3 +58,41 @@ def test_recertify_a_few_pairs():
     # and a pair that does collide is refuted
     a, b = pm.SS_PAIRS[0]
     assert cert.certify(("ss", int(a), int(b)))[3] in (False,)
+
+
+def test_generated_cull_constants_are_conservative():
+    """The culling constants in csrc/panda_model_gen.h: every moving sphere appears exactly once in the ground-plane
+    min-tree; the cull ball of each self-collision block contains every sphere that takes part in the block."""
+    import re
+    from rbe550_final_project_b200 import panda_model as pm
+    hdr = pm.header_text()
+    lowest = re.search(r"#define PV_TABLE_LOWEST\(s\) (.*)", hdr).group(1)
+    idx = sorted(int(i) for i in re.findall(r"s\[(\d+)\]\.z", lowest))
+    assert idx == [i for i in range(pm.N_SPHERES) if int(pm.SPHERE_LINK[i]) != 0]
+    # each radius group subtracts the radius of its own spheres
+    for grp, r in re.findall(r"\(((?:fminf\(|s\[\d+\]\.z|, |\))+) - ([0-9.e+-]+)f\)", lowest):
+        for i in re.findall(r"s\[(\d+)\]", grp):
+            assert abs(float(pm.SPHERE_RADIUS[int(i)]) - float(r)) < 1e-7
+    block = re.search(r"#define PV_SS_LINKPAIRS\(LP\) \\\n((?:.*\\\n)+)", hdr).group(1)
+    n_blocks = 0
+    for la, lb, ca, cb, c2 in re.findall(r"LP\((\d+), (\d+), (\d+), (\d+), ([0-9.e+-]+)f\)", block):
+        la, lb, ca, cb, c2 = int(la), int(lb), int(ca), int(cb), float(c2)
+        pairs = [(int(p), int(q)) for p, q in pm.SS_PAIRS if (int(pm.SPHERE_LINK[p]), int(pm.SPHERE_LINK[q])) == (la, lb)]
+        assert pairs and int(pm.SPHERE_LINK[ca]) == la and int(pm.SPHERE_LINK[cb]) == lb
+        ra = max(np.linalg.norm(pm.SPHERE_CENTER[p] - pm.SPHERE_CENTER[ca]) + pm.SPHERE_RADIUS[p] for p, _ in pairs)
+        rb = max(np.linalg.norm(pm.SPHERE_CENTER[q] - pm.SPHERE_CENTER[cb]) + pm.SPHERE_RADIUS[q] for _, q in pairs)
+        # |s[ca] - s[cb]| >= ra + rb  =>  no pair of the block can touch
+        assert np.sqrt(c2) >= ra + rb + 0.5 * pm.CULL_SLACK
+        n_blocks += 1
+    assert n_blocks == len({(int(pm.SPHERE_LINK[p]), int(pm.SPHERE_LINK[q])) for p, q in pm.SS_PAIRS})
+    block = re.search(r"#define PV_SBH_LINKS\(LB\) \\\n((?:.*\\\n)+)", hdr).group(1)
+    for la, ca, c0, c1, c2, rla in re.findall(r"LB\((\d+), (\d+), ([0-9.e+-]+)f, ([0-9.e+-]+)f, ([0-9.e+-]+)f, ([0-9.e+-]+)f\)", block):
+        la, ca, rla = int(la), int(ca), float(rla)
+        sph = sorted({int(p) for p, _ in pm.SB_PAIRS if int(pm.SPHERE_LINK[p]) == la})
+        need = max(np.linalg.norm(pm.SPHERE_CENTER[p] - pm.SPHERE_CENTER[ca]) + pm.SPHERE_RADIUS[p] for p in sph)
+        assert rla >= need + 0.5 * pm.CULL_SLACK
+        for k, c in enumerate((float(c0), float(c1), float(c2))):
+            has = any(int(pm.SPHERE_LINK[p]) == la and int(kk) == k for p, kk in pm.SB_PAIRS)
+            assert (c > 0) == has
+            if has:
+                assert np.sqrt(c) >= need + pm.BOX_BOUND_RADIUS[k] + 0.5 * pm.CULL_SLACK
