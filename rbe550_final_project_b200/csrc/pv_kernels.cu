@@ -433,26 +433,33 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
 // Sorted variant of the sweep (the default): the same super-tile sort as pv_state_bits_sorted_kernel, with the generated
 // configurations parked in shared memory between the key pass and the check (generating them twice would cost ~210
 // instructions per configuration, parking ~20).  A super-tile is PV_SWEEP_ST configurations (9 floats each: 144 KB).
-#ifndef PV_SWEEP_ST
-#define PV_SWEEP_ST 4096
+// Super-tile sizes: as many configurations as fit the 227 KB of shared memory.  With the fingers fixed open (the
+// BASELINE config-5 stream) q[7], q[8] are constants and only 7 floats per configuration are parked.
+#ifndef PV_SWEEP_ST9
+#define PV_SWEEP_ST9 5632  // 11 chunks, 9 floats each: 216 KB
 #endif
-static_assert(PV_SWEEP_ST % PV_SB_THREADS == 0 && PV_SWEEP_ST <= 65536, "super-tile = whole chunks, indices fit 16 bits");
+#ifndef PV_SWEEP_ST7
+#define PV_SWEEP_ST7 7168  // 14 chunks, 7 floats each: 219 KB
+#endif
+template <int NP, int ST_>
 struct PvSweepSmem {
-    static constexpr int ST = PV_SWEEP_ST;
-    float park[9][PV_SWEEP_ST];
-    unsigned short order[PV_SWEEP_ST];
-    unsigned char key8[PV_SWEEP_ST];
+    static constexpr int ST = ST_;
+    static_assert(ST_ % PV_SB_THREADS == 0 && ST_ <= 65536, "super-tile = whole chunks, indices fit 16 bits");
+    float park[NP][ST_];
+    unsigned short order[ST_];
+    unsigned char key8[ST_];
     unsigned hist[PV_SORT_BUCKETS];
-    unsigned vbits[PV_SWEEP_ST / 32];
+    unsigned vbits[ST_ / 32];
     int cnt;
 };
 
-template <bool CARRY>
+template <bool CARRY, bool OPEN>
 __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
-    pv_sweep_sorted_kernel(const __grid_constant__ PvScene S, uint64_t first, int64_t n, unsigned seed, int fingers_open,
+    pv_sweep_sorted_kernel(const __grid_constant__ PvScene S, uint64_t first, int64_t n, unsigned seed,
                            uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid,
                            float* __restrict__ q_out, const __grid_constant__ PvGather G) {
-    typedef PvSweepSmem Smem;
+    constexpr int NP = OPEN ? 7 : 9;
+    typedef PvSweepSmem<NP, (OPEN ? PV_SWEEP_ST7 : PV_SWEEP_ST9)> Smem;
     constexpr int ST_CHUNKS = Smem::ST / PV_SB_THREADS;
     extern __shared__ __align__(16) unsigned char pv_sort_smem_raw[];
     Smem& M = *reinterpret_cast<Smem*>(pv_sort_smem_raw);
@@ -472,10 +479,10 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
             const int64_t i = PV_GI(jj, tid);
             if (i < n) {
                 float q[9];
-                pv_sweep_config(first + (uint64_t)i, seed, fingers_open != 0, q);
+                pv_sweep_config(first + (uint64_t)i, seed, OPEN, q);
                 const int L = jj * PV_SB_THREADS + tid;
 #pragma unroll
-                for (int j = 0; j < 9; ++j) M.park[j][L] = q[j];
+                for (int j = 0; j < NP; ++j) M.park[j][L] = q[j];
                 if (q_out) {
 #pragma unroll
                     for (int j = 0; j < 9; ++j) q_out[9 * i + j] = q[j];
@@ -522,7 +529,8 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
             const int L = M.order[in ? slot : cnt - 1];
             float q[9];
 #pragma unroll
-            for (int j = 0; j < 9; ++j) q[j] = M.park[j][L];
+            for (int j = 0; j < NP; ++j) q[j] = M.park[j][L];
+            if (OPEN) q[7] = q[8] = 0.04f;  // what pv_sweep_config sets
             __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
             PvAcc<PV_MODE_BITS> acc;
             pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY>(q, S, acc);
@@ -1062,18 +1070,23 @@ int pv_sweep(PvHandle* h, uint64_t first, int64_t n, uint32_t seed, int fingers_
     if (h->cull == 2) {  // tile-sorted (the default)
         const int64_t chunks = (n + PV_SB_THREADS - 1) / PV_SB_THREADS;
         const int grid = (int)(chunks < (int64_t)h->sm_count ? chunks : (int64_t)h->sm_count);
-#define PV_LAUNCH_SWEEP_SORTED(CARRY)                                                                            \
+#define PV_LAUNCH_SWEEP_SORTED(CARRY, OPEN)                                                                      \
     {                                                                                                            \
-        const unsigned bit_ = 1u << (8 + (CARRY ? 1 : 0));                                                       \
+        typedef PvSweepSmem<(OPEN ? 7 : 9), (OPEN ? PV_SWEEP_ST7 : PV_SWEEP_ST9)> Smem_;                         \
+        const unsigned bit_ = 1u << (8 + (CARRY ? 1 : 0) + (OPEN ? 2 : 0));                                      \
         if (!(h->smem_attr_mask & bit_)) {                                                                       \
-            PV_CUDA(h, cudaFuncSetAttribute(pv_sweep_sorted_kernel<CARRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            (int)sizeof(PvSweepSmem)));                                          \
+            PV_CUDA(h, cudaFuncSetAttribute(pv_sweep_sorted_kernel<CARRY, OPEN>,                                 \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem_)));   \
             h->smem_attr_mask |= bit_;                                                                           \
         }                                                                                                        \
-        pv_sweep_sorted_kernel<CARRY><<<grid, PV_SB_THREADS, sizeof(PvSweepSmem), st>>>(                         \
-            h->scene, first, n, seed, fingers_open, d_bits, d_n_valid, d_q_out, h->gather);                      \
+        pv_sweep_sorted_kernel<CARRY, OPEN><<<grid, PV_SB_THREADS, sizeof(Smem_), st>>>(                         \
+            h->scene, first, n, seed, d_bits, d_n_valid, d_q_out, h->gather);                                    \
     }
-        if (h->scene.carry) PV_LAUNCH_SWEEP_SORTED(true) else PV_LAUNCH_SWEEP_SORTED(false)
+        if (h->scene.carry) {
+            if (fingers_open) PV_LAUNCH_SWEEP_SORTED(true, true) else PV_LAUNCH_SWEEP_SORTED(true, false)
+        } else {
+            if (fingers_open) PV_LAUNCH_SWEEP_SORTED(false, true) else PV_LAUNCH_SWEEP_SORTED(false, false)
+        }
 #undef PV_LAUNCH_SWEEP_SORTED
     } else {
         if (h->scene.carry) {

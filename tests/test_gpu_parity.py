@@ -526,3 +526,30 @@ def test_config3_full_size_properties(pv, c64):
     _assert_verdicts(valid_fewer[pick], ref_fewer, "config 3 sample, fewer boxes")
     # exact, not just outside the band: the tests against the remaining boxes are the same arithmetic in both runs
     assert not (valid & ~valid_fewer).any()
+
+
+def test_config5_full_size_properties(pv, c64, model):
+    """BASELINE config 5 at its full size on one GPU (104 857 600 device-generated configurations, goal-1 scene):
+    count = popcount of the mask; the mask is the concatenation of the masks of arbitrary 32-aligned shards (what the
+    ranks of a multi-GPU run compute); a slice re-checked through the state kernel from the exported configurations gives
+    the same words; a sample agrees with the fp64 oracle outside the contact band."""
+    scene = sc.goal1_scattered()
+    pv.set_scene(scene)
+    pv.set_flags(True, False)
+    n, seed = 104_857_600, 20251212
+    bits, count = pv.sweep(0, n, seed)
+    words = bits.cpu().numpy().view(np.uint32)
+    assert int(count.item()) == int(np.unpackbits(words.view(np.uint8)).sum())
+    assert 0.80 < int(count.item()) / n < 0.90
+    cuts = [0, 32 * 1_000_003, 32 * 2_222_222, n]
+    parts = [pv.sweep(a, b - a, seed)[0].cpu().numpy().view(np.uint32) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(np.concatenate(parts), words)
+    first, m = 32 * 1_500_000, 300_000
+    sl_bits, _, q_dev = pv.sweep(first, m, seed, want_configs=True)
+    again = pv.check_states(q_dev).cpu().numpy().view(np.uint32)
+    assert np.array_equal(again, sl_bits.cpu().numpy().view(np.uint32))
+    assert np.array_equal(again, words[first // 32: first // 32 + (m + 31) // 32])
+    k = 60_000
+    q = q_dev[:k].cpu().numpy()
+    assert np.array_equal(q.view(np.uint32), po.sweep_configs(first, k, seed, model).view(np.uint32))
+    _assert_verdicts(unpack_bits(again, k), c64.state_margin(q.astype(np.float64), scene.as_oracle_scene()), "config 5 slice")

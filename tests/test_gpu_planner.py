@@ -381,3 +381,30 @@ def test_single_tree_rrt_planner(pv, c64, c32):
     planner.strict_planners = True
     with pytest.raises(PlanningError):
         planner.plan_path(qpos_goal=qr[0], planner="PRM")
+
+
+def test_config4_full_size(pv, c64):
+    """BASELINE config 4 at its full size: 4096 start/goal pairs (valid, hand above 0.15 m) in the tall-tower scene, one
+    launch.  Every query is solved, every path starts and ends where asked, and a sample of the paths is valid in the fp64
+    oracle at the planner's own resolution."""
+    snap = sc.goal3_tower()
+    pv.set_scene(snap)
+    pv.set_attached(-1)
+    pv.set_flags(True, False)
+    cand = random_configs(60000, 4096)
+    ok = unpack_bits(pv.check_states_host(cand), len(cand))
+    ok &= pv.fk(torch.as_tensor(cand, device="cuda")).cpu().numpy()[:, 8, 2] > 0.15
+    valid = cand[ok]
+    nq = 4096
+    assert len(valid) >= 2 * nq
+    starts, goals = valid[:nq], valid[nq:2 * nq]
+    paths, plen, iters, checks = pv.rrtc_batch(starts, goals, max_iters=2000, max_nodes=2048, max_path=128, seed=7,
+                                               replicas=1, shortcut_passes=2)
+    assert (plen >= 2).all(), f"{(plen < 2).sum()} of {nq} queries unsolved"
+    idx = np.arange(nq)
+    assert np.array_equal(paths[idx, 0], starts) and np.array_equal(paths[idx, plen - 1], goals)
+    assert (iters >= 1).all() and (checks > 0).all()
+    rng = np.random.default_rng(1)
+    hard = np.argsort(-iters)[:40]  # the searches that had to grow trees, plus a random sample
+    for k in np.concatenate([hard, rng.choice(nq, 60, replace=False)]):
+        _path_ok(pv, c64, snap, paths[k, : plen[k]])
