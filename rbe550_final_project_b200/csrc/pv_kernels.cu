@@ -107,6 +107,10 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
 #define PV_ST 16384  // super-tile: at most this many configurations are sorted together (32 chunks)
 #endif
 #define PV_SORT_BUCKETS 256
+// key loads a thread keeps in flight in the key pass (where the batch is first read from HBM)
+#ifndef PV_KEY_LOADS
+#define PV_KEY_LOADS 4  // swept 1 / 2 / 4 / 8 / 14 under bench.py: 14.83 / 15.50 / 15.57 / 15.38 / 15.2 G checks/s
+#endif
 static_assert(PV_ST % PV_SB_THREADS == 0 && PV_ST <= 65536, "super-tile = whole chunks, indices fit 16 bits");
 
 __device__ __forceinline__ void pv_emit_word_thread(uint32_t* __restrict__ bits, const PvGather& G, int64_t w, unsigned word) {
@@ -234,11 +238,11 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         for (int w = tid; w < nc * (PV_SB_THREADS / 32); w += PV_SB_THREADS) vbits[w] = 0;
         __syncthreads();
         // pass 1: keys (kept as bytes for pass 2) and their histogram; the key loads of 8 chunks are in flight together
-        for (int j8 = 0; j8 < nc; j8 += 8) {
-            float4 kq[8];
-            float kq5[8];
+        for (int j8 = 0; j8 < nc; j8 += PV_KEY_LOADS) {
+            float4 kq[PV_KEY_LOADS];
+            float kq5[PV_KEY_LOADS];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < PV_KEY_LOADS; ++u) {
                 const unsigned o = PV_OFF(j8 + u, tid);
                 kq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                 kq5[u] = 0.f;
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < PV_KEY_LOADS; ++u) {
                 if (j8 + u < nc && PV_OFF(j8 + u, tid) < n_rem) {
                     const int key = pv_sort_key(kq[u].x, kq[u].y, kq[u].z, kq[u].w, kq5[u], S);
                     M.key8[(j8 + u) * PV_SB_THREADS + tid] = (unsigned char)key;

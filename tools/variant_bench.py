@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from rbe550_final_project_b200 import _cabi, panda_model as pm, scenes as sc
 libs = sorted(glob.glob(os.path.join(_cabi.CSRC, "libpv_*.so")))
-n = 1 << 21
+n = int(os.environ.get("PV_VB_N", 1 << 21))
 rng = np.random.default_rng(0)
 q = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n, 9)).astype(np.float32); q[:, 7:] = 0.04
 for lib in libs:
