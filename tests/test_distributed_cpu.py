@@ -113,6 +113,9 @@ def _rrtc_worker(rank, world, port, n, ret):
     from rbe550_final_project_b200.distributed import rrtc_batch_sharded
     a, b = _rrtc_queries(n)
     out = rrtc_batch_sharded(_OraclePlanner(), a, b, max_path=64, seed=5)
+    packed = rrtc_batch_sharded(_OraclePlanner(), a, b, packed=True, max_path=64, seed=5)
+    used = np.arange(out[0].shape[1])[None, :] < out[1][:, None]
+    assert np.array_equal(packed[0], out[0][used]) and all(np.array_equal(x, y) for x, y in zip(packed[1:], out[1:]))
     ret[rank] = [np.asarray(x).copy() for x in out]
     dist.barrier()
     dist.destroy_process_group()
