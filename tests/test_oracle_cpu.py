@@ -36,6 +36,43 @@ def test_fk_known_answers():
     assert np.allclose(R[0, 8][:, 2], [0.479, 0, -0.878], atol=1e-3)
 
 
+def test_fk_matches_the_published_dh_table():
+    """An independent pin of the oracle's kinematics: the modified (Craig) Denavit-Hartenberg table Franka publishes for
+    the Panda (a, d, alpha per joint, flange at d = 0.107), composed as Rx(alpha) Tx(a) Rz(theta) Tz(d), must give the
+    frames the oracle derives from the MJCF body chain -- every link frame, over random configurations."""
+    dh = [  # a, d, alpha
+        (0.0, 0.333, 0.0), (0.0, 0.0, -np.pi / 2), (0.0, 0.316, np.pi / 2), (0.0825, 0.0, np.pi / 2),
+        (-0.0825, 0.384, -np.pi / 2), (0.0, 0.0, np.pi / 2), (0.088, 0.0, np.pi / 2),
+    ]
+
+    def rx(a):
+        c, s = np.cos(a), np.sin(a)
+        return np.array([[1, 0, 0, 0], [0, c, -s, 0], [0, s, c, 0], [0, 0, 0, 1.0]])
+
+    def rz(a):
+        c, s = np.cos(a), np.sin(a)
+        return np.array([[c, -s, 0, 0], [s, c, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]])
+
+    def tr(x, y, z):
+        t = np.eye(4)
+        t[:3, 3] = (x, y, z)
+        return t
+
+    q = random_configs(300, 5, fingers="random").astype(np.float64)
+    q[0] = 0.0
+    q[1] = pm.Q_SAFE_HOME
+    base = (0.1, -0.2, 0.01)
+    R, p = po.fk(q, base=base)
+    for n in range(len(q)):
+        T = tr(*base)
+        for j, (a, d, al) in enumerate(dh):
+            T = T @ rx(al) @ tr(a, 0, 0) @ rz(q[n, j]) @ tr(0, 0, d)
+            assert np.allclose(T[:3, :3], R[n, j + 1], atol=1e-12) and np.allclose(T[:3, 3], p[n, j + 1], atol=1e-12), (n, j)
+        flange = T @ tr(0, 0, 0.107)
+        assert np.allclose(flange[:3, 3], p[n, 8], atol=1e-12)  # the hand body sits on the flange ...
+        assert np.allclose(flange[:3, :3] @ rz(-np.pi / 4)[:3, :3], R[n, 8], atol=1e-7)  # ... turned by -45 deg about z
+
+
 def test_derived_ompl_constants():
     assert abs(pm.SPACE_EXTENT - 13.03716) < 1e-5
     assert abs(pm.VALIDITY_RESOLUTION - 0.130372) < 1e-6
