@@ -77,8 +77,7 @@ int pv_set_carried(PvHandle *h, int obb_index, const float *hand_from_box, float
 int pv_set_flags(PvHandle *h, unsigned flags);
 /* Which state / sweep kernel variant answers (all return bit-identical verdict words; a test and tuning knob, no
  * reference counterpart): 0 brute force over every kept pair, 1 per-lane bounding-volume culling, 2 (default) = 1 with
- * the batch visited in sorted order (device batches: two blocks of a cluster sort their shares together; host rows and
- * the sweep: each block its own share), 3 = 2 with the block-level sort everywhere. */
+ * each block's share of the batch visited in sorted order. */
 int pv_set_culling(PvHandle *h, int mode);
 
 /* Fused verdict gather for multi-GPU runs: after this call pv_check_states and pv_sweep also store

@@ -2,7 +2,6 @@
 // device-generated sweeps, FP32 peak probe).  The batched RRT-Connect lives in pv_rrtc.cu.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -344,183 +343,6 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
 #undef PV_PREFETCH
 #undef PV_GI
 #undef PV_Q03_OF
-#undef PV_OFF
-}
-
-// ---- cluster-sorted variant (the default for device batches) -----------------------------------------------------
-// The size of the sort domain matters (the sweep kernel: 15.4 -> 17.4 G checks/s from 4 096- to 7 168-configuration
-// tiles), and one block's share of a 1 Mi batch is only 7 085 configurations.  Two blocks of a thread-block cluster
-// (cluster size 2 packs the 148 SMs exactly) therefore sort their shares TOGETHER over distributed shared memory: each
-// block histograms the keys of its own chunks, reads the partner's histogram, derives where its configurations go in
-// the joint order, scatters 16-bit entries (owner rank, local index) into the order array of whichever block will
-// visit them -- iteration `it` of the joint order belongs to block it & 1 -- and returns verdict bits to the owner's
-// bit array (a remote shared-memory atomic for the partner's configurations).  Three cluster barriers per super-tile.
-#ifndef PV_CS_ST
-#define PV_CS_ST 8192  // configurations per block and super-tile (the joint domain is twice that)
-#endif
-static_assert(PV_CS_ST % PV_SB_THREADS == 0 && PV_CS_ST <= 32768, "whole chunks; entry = rank << 15 | local index");
-struct PvCsortSmem {
-    float4 stA[2][PV_SB_THREADS], stB[2][PV_SB_THREADS];
-    float st9[2][PV_SB_THREADS];
-    unsigned short order[PV_CS_ST];  // entries this block visits, in joint sorted order
-    unsigned char key8[PV_CS_ST];
-    unsigned hist[PV_SORT_BUCKETS];  // keys of this block's own chunks (read by the partner)
-    unsigned off[PV_SORT_BUCKETS];   // where this block's configurations of each bucket go in the joint order
-    unsigned wsum[PV_SORT_BUCKETS / 32];
-    unsigned vbits[PV_CS_ST / 32];   // verdicts of this block's own chunks (written by both blocks)
-    unsigned cnt;                    // configurations in the joint order
-};
-
-template <bool CARRY>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PV_SB_THREADS, 1)
-    pv_state_bits_csort_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA,
-                               const float4* __restrict__ qB, const float* __restrict__ q9, int64_t n,
-                               uint32_t* __restrict__ bits, const __grid_constant__ PvGather G) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    typedef PvCsortSmem Smem;
-    constexpr int ST_CHUNKS = PV_CS_ST / PV_SB_THREADS;
-    extern __shared__ __align__(16) unsigned char pv_sort_smem_raw[];
-    Smem& M = *reinterpret_cast<Smem*>(pv_sort_smem_raw);
-    const unsigned rank = cluster.block_rank();
-    Smem& P = *cluster.map_shared_rank(&M, rank ^ 1u);  // the partner's copy
-    const int tid = threadIdx.x;
-    const int64_t n_words = (n + 31) >> 5;
-    const int64_t n_chunks = (n + PV_SB_THREADS - 1) / PV_SB_THREADS;
-    const int64_t blk0 = (int64_t)blockIdx.x - rank;  // the cluster's even block
-    // chunks of block b: b, b + grid, ...; no early exit: a block without chunks still meets the cluster barriers
-    const int64_t chunks_of0 = blk0 < n_chunks ? (n_chunks - blk0 + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t my_chunks = (int64_t)blockIdx.x < n_chunks ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const unsigned stride = gridDim.x * PV_SB_THREADS;
-#define PV_OFF(jj, t) ((unsigned)(jj) * stride + (unsigned)(t))
-    for (int64_t j0 = 0; j0 < chunks_of0; j0 += ST_CHUNKS) {  // the even block never has fewer chunks than its partner
-        const int nc = (int)(my_chunks - j0 < 0 ? 0 : (my_chunks - j0 < (int64_t)ST_CHUNKS ? my_chunks - j0 : (int64_t)ST_CHUNKS));
-        // tile base of the cluster's even block; this block's configurations start `rank` chunks later
-        const int64_t base_even = (blk0 + j0 * (int64_t)gridDim.x) * PV_SB_THREADS;
-        const int64_t base_mine = base_even + (int64_t)rank * PV_SB_THREADS;
-        const unsigned n_rem = (unsigned)(n - base_mine <= 0 ? 0 : (n - base_mine < (int64_t)0xffffffffll ? n - base_mine : (int64_t)0xffffffffll));
-        const float4* __restrict__ tA = qA + base_mine;
-        const float4* __restrict__ tB = qB + base_mine;
-        if (tid < PV_SORT_BUCKETS) M.hist[tid] = 0;
-        for (int w = tid; w < nc * (PV_SB_THREADS / 32); w += PV_SB_THREADS) M.vbits[w] = 0;
-        __syncthreads();
-        // ---- keys of the own chunks + their histogram ----------------------------------------------------------------
-        for (int j8 = 0; j8 < nc; j8 += PV_KEY_LOADS) {
-            float4 kq[PV_KEY_LOADS];
-            float kq5[PV_KEY_LOADS];
-#pragma unroll
-            for (int u = 0; u < PV_KEY_LOADS; ++u) {
-                const unsigned o = PV_OFF(j8 + u, tid);
-                kq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                kq5[u] = 0.f;
-                if (j8 + u < nc && o < n_rem) {
-                    kq[u] = __ldg(tA + o);
-                    if (PV_SORT_Q5_BINS > 1) kq5[u] = __ldg(reinterpret_cast<const float*>(tB) + 4 * o + 1);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < PV_KEY_LOADS; ++u) {
-                if (j8 + u < nc && PV_OFF(j8 + u, tid) < n_rem) {
-                    const int key = pv_sort_key(kq[u].x, kq[u].y, kq[u].z, kq[u].w, kq5[u], S);
-                    M.key8[(j8 + u) * PV_SB_THREADS + tid] = (unsigned char)key;
-                    atomicAdd(&M.hist[key], 1u);
-                }
-            }
-        }
-        cluster.sync();  // both histograms complete
-        // ---- joint offsets: all lower buckets of both blocks, + the even block's share of this bucket for the odd one ----
-        if (tid < PV_SORT_BUCKETS) {
-            const unsigned mine = M.hist[tid], theirs = P.hist[tid];
-            const unsigned tot = mine + theirs;
-            unsigned incl = tot;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
-                if ((tid & 31) >= d) incl += o;
-            }
-            if ((tid & 31) == 31) M.wsum[tid >> 5] = incl;
-            M.off[tid] = incl - tot + (rank ? theirs : 0u);  // + the lower warps' totals, below
-        }
-        __syncthreads();
-        if (tid < PV_SORT_BUCKETS) {
-            unsigned add = 0;
-            for (int w = 0; w < (tid >> 5); ++w) add += M.wsum[w];
-            M.off[tid] += add;
-            if (tid == PV_SORT_BUCKETS - 1) {
-                unsigned all = 0;
-                for (int w = 0; w < PV_SORT_BUCKETS / 32; ++w) all += M.wsum[w];
-                M.cnt = all;
-            }
-        }
-        __syncthreads();
-        // ---- scatter: position p of the joint order is visited by block (p / 512) & 1 in its slot (p / 1024) * 512 + p % 512
-        for (int jj = 0; jj < nc; ++jj) {
-            if (PV_OFF(jj, tid) < n_rem) {
-                const int L = jj * PV_SB_THREADS + tid;
-                const unsigned p = atomicAdd(&M.off[M.key8[L]], 1u);
-                const unsigned it = p / PV_SB_THREADS;
-                const unsigned slot = (it >> 1) * PV_SB_THREADS + (p % PV_SB_THREADS);
-                const unsigned short e = (unsigned short)((rank << 15) | (unsigned)L);
-                if ((it & 1u) == rank) M.order[slot] = e;
-                else P.order[slot] = e;
-            }
-        }
-        cluster.sync();  // both order arrays complete
-        const unsigned cnt = M.cnt;
-        const unsigned n_it = (cnt + PV_SB_THREADS - 1) / PV_SB_THREADS;
-        // ---- main loop over this block's iterations of the joint order ---------------------------------------------------
-        unsigned e_next = 0;
-#define PV_ENTRY(it_)                                                                          \
-    {                                                                                          \
-        const unsigned p_ = (it_) * PV_SB_THREADS + tid;                                       \
-        e_next = M.order[((it_) >> 1) * PV_SB_THREADS + (p_ < cnt ? tid : 0)];                 \
-    }
-#define PV_PREFETCH(b_)                                                                        \
-    {                                                                                          \
-        const unsigned L_ = e_next & 0x7fffu;                                                  \
-        const int64_t i_ = base_even + (int64_t)(e_next >> 15) * PV_SB_THREADS +               \
-                           (int64_t)PV_OFF(L_ / PV_SB_THREADS, L_ % PV_SB_THREADS);            \
-        pv_cp_async16(&M.stA[b_][tid], qA + i_);                                               \
-        pv_cp_async16(&M.stB[b_][tid], qB + i_);                                               \
-        if (q9) pv_cp_async4(&M.st9[b_][tid], q9 + i_);                                        \
-        asm volatile("cp.async.commit_group;" ::: "memory");                                   \
-    }
-        if (rank < n_it) {
-            PV_ENTRY(rank)
-            PV_PREFETCH(0)
-        }
-        int par = 0;
-        for (unsigned it = rank; it < n_it; it += 2, par ^= 1) {
-            const bool in = it * PV_SB_THREADS + tid < cnt;
-            const unsigned e = e_next;
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            const float4 a = M.stA[par][tid], b = M.stB[par][tid];
-            float q[9];
-            q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w;
-            q[4] = b.x; q[5] = b.y; q[6] = b.z; q[7] = b.w;
-            q[8] = q9 ? M.st9[par][tid] : b.w;
-            if (it + 2 < n_it) {
-                PV_ENTRY(it + 2)
-                PV_PREFETCH(par ^ 1)
-            }
-            __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
-            PvAcc<PV_MODE_BITS> acc;
-            pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, PV_SB_SYNC, true, CARRY>(q, S, acc);
-            if (in && !acc.hit) {
-                const unsigned L = e & 0x7fffu;
-                unsigned* vb = ((e >> 15) == rank) ? M.vbits : P.vbits;
-                atomicOr(vb + (L >> 5), 1u << (L & 31));
-            }
-        }
-#undef PV_PREFETCH
-#undef PV_ENTRY
-        cluster.sync();  // every verdict bit of both blocks is in place
-        for (int wl = tid; wl < nc * (PV_SB_THREADS / 32); wl += PV_SB_THREADS) {
-            const int64_t w = ((base_mine + (int64_t)(wl / (PV_SB_THREADS / 32)) * stride) >> 5) + (wl % (PV_SB_THREADS / 32));
-            if (w < n_words) pv_emit_word_thread(bits, G, w, M.vbits[wl]);
-        }
-        __syncthreads();  // the next super-tile clears hist / vbits (the partner touches them only after its next cluster barrier)
-    }
 #undef PV_OFF
 }
 
@@ -1041,7 +863,7 @@ int pv_set_flags(PvHandle* h, unsigned flags) {
 // bounding-ball culling in front of each block of tests (default).  Verdicts are bit-identical.
 int pv_set_culling(PvHandle* h, int on) {
     if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
-    h->cull = on < 0 ? 0 : (on > 3 ? 3 : on);  // 0 brute force, 1 per-lane culling, 2 sorted (pairs of blocks together for device batches), 3 block-sorted always
+    h->cull = on < 0 ? 0 : (on > 2 ? 2 : on);  // 0 brute force, 1 per-lane culling, 2 tile-sorted + culling
     return PV_OK;
 }
 
@@ -1129,26 +951,7 @@ static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_q
             h->scene, (const float4*)d_qA, (const float4*)d_qB, d_q9, d_aos, n, d_bits,                       \
             d_aos ? PvGather{} : h->gather);                                                                  \
     }
-    if (h->cull == 2 && !d_aos) {  // cluster-sorted (pairs of blocks sort together) + per-lane culling: the default
-        int64_t chunks = (n + PV_SB_THREADS - 1) / PV_SB_THREADS;
-        int grid = (int)(chunks < (int64_t)h->sm_count ? chunks : (int64_t)h->sm_count);
-        grid = (grid + 1) & ~1;  // whole clusters; a block without chunks only meets the barriers
-        if (grid > h->sm_count) grid -= 2;
-        if (grid < 2) grid = 2;
-#define PV_LAUNCH_CS(CARRY)                                                                                     \
-    {                                                                                                           \
-        const unsigned bit_ = 1u << (12 + (CARRY ? 1 : 0));                                                     \
-        if (!(h->smem_attr_mask & bit_)) {                                                                      \
-            PV_CUDA(h, cudaFuncSetAttribute(pv_state_bits_csort_kernel<CARRY>,                                  \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PvCsortSmem))); \
-            h->smem_attr_mask |= bit_;                                                                          \
-        }                                                                                                       \
-        pv_state_bits_csort_kernel<CARRY><<<grid, PV_SB_THREADS, sizeof(PvCsortSmem), st>>>(                    \
-            h->scene, (const float4*)d_qA, (const float4*)d_qB, d_q9, n, d_bits, h->gather);                    \
-    }
-        if (h->scene.carry) PV_LAUNCH_CS(true) else PV_LAUNCH_CS(false)
-#undef PV_LAUNCH_CS
-    } else if (h->cull >= 2) {  // block-sorted (host rows; mode 3: always)
+    if (h->cull == 2) {  // tile-sorted + per-lane culling (the default)
         if (h->scene.carry) {
             if (d_aos) PV_LAUNCH_SORTED(true, true) else PV_LAUNCH_SORTED(false, true)
         } else {
@@ -1268,7 +1071,7 @@ int pv_sweep(PvHandle* h, uint64_t first, int64_t n, uint32_t seed, int fingers_
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t words = (n + 31) / 32;
-    if (h->cull >= 2) {  // tile-sorted (the default)
+    if (h->cull == 2) {  // tile-sorted (the default)
         const int64_t chunks = (n + PV_SB_THREADS - 1) / PV_SB_THREADS;
         const int grid = (int)(chunks < (int64_t)h->sm_count ? chunks : (int64_t)h->sm_count);
 #define PV_LAUNCH_SWEEP_SORTED(CARRY, OPEN)                                                                      \

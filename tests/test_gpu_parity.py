@@ -135,14 +135,13 @@ def test_state_kernel_variants_are_bit_identical(pv):
             pv.set_attached(att)
             q = _dev(random_configs(300_007, 77 + att, fingers=fingers))
             res = []
-            # brute force, per-lane culling, sorted (the default: pairs of blocks sort together), block-sorted
-            for mode in (0, 1, 2, 3):
+            for mode in (0, 1, 2):  # brute force, per-lane culling, sorted by elbow angle + culling (the default)
                 pv.set_culling(mode)
                 res.append(pv.check_states(q).cpu().numpy())
             pv.set_culling(2)
-            assert (res[0] == res[1]).all() and (res[0] == res[2]).all() and (res[0] == res[3]).all(), (name, att)
+            assert (res[0] == res[1]).all() and (res[0] == res[2]).all(), (name, att)
             # the sorted kernel with far fewer configurations than one block's share, and a ragged tail
-            for m_ in (1, 33, 511, 512, 513, 1025, 70_001, 148 * 512 + 1, 149 * 512, 296 * 512 - 31):
+            for m_ in (1, 33, 511, 513, 70_001):
                 pv.set_culling(1)
                 a_ = pv.check_states(q[:m_]).cpu().numpy()
                 pv.set_culling(2)

@@ -15,7 +15,7 @@ for lib in libs:
     out = torch.empty(n // 32, dtype=torch.int32, device="cuda")
     for scene in ("goal1_scattered", "goal3_tower", "goal4_task1_pentagon"):
         pv.set_scene(sc.FIXTURES[scene]())
-        for mode in (1, 2, 3):
+        for mode in (1, 2):
             pv.set_culling(mode)
             for _ in range(3): pv.check_states((A, B, q9), out=out)
             torch.cuda.synchronize()
