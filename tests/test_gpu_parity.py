@@ -141,7 +141,7 @@ def test_state_kernel_variants_are_bit_identical(pv):
             pv.set_culling(2)
             assert (res[0] == res[1]).all() and (res[0] == res[2]).all(), (name, att)
             # the sorted kernel with far fewer configurations than one block's share, and a ragged tail
-            for m_ in (1, 33, 511, 513, 70_001):
+            for m_ in (1, 33, 511, 512, 513, 1025, 70_001, 148 * 512 + 1, 149 * 512, 296 * 512 - 31):
                 pv.set_culling(1)
                 a_ = pv.check_states(q[:m_]).cpu().numpy()
                 pv.set_culling(2)
