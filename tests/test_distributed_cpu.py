@@ -135,3 +135,51 @@ def test_sharded_rrtc_matches_single_rank(n):
     for rank in (0, 1):
         for j in range(4):
             assert np.array_equal(ret[rank][j], ref[j]), (rank, j)
+
+
+class _FakePlanner:
+    """Deterministic stand-in: path k has (global id * 7) % 6 states (0 = unsolved) whose entries encode (id, row)."""
+    device = None
+
+    def rrtc_batch(self, starts, goals, query_offset=0, max_path=8, **kw):
+        n = len(starts)
+        ids = query_offset + np.arange(n)
+        plen = ((ids * 7) % 6).astype(np.int32)
+        paths = np.full((n, max_path, 9), -1.0, np.float32)  # rows beyond a path's length: scratch, must not travel
+        for k in range(n):
+            for r in range(plen[k]):
+                paths[k, r] = ids[k] * 100 + r + starts[k, 0]
+        return paths, plen, (ids % 5).astype(np.int32), (ids * 3).astype(np.int64)
+
+
+def _fake_worker(rank, world, port, n, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rbe550_final_project_b200.distributed import rrtc_batch_sharded
+    a = np.arange(n * 9, dtype=np.float32).reshape(n, 9) / 1000.0
+    dense = rrtc_batch_sharded(_FakePlanner(), a, a, max_path=8)
+    packed = rrtc_batch_sharded(_FakePlanner(), a, a, packed=True, max_path=8)
+    ret[rank] = ([np.asarray(x).copy() for x in dense], [np.asarray(x).copy() for x in packed])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 1), (3, 10), (3, 12), (4, 3)])
+def test_sharded_rrtc_packing(world, n):
+    """Ragged shards (also empty ones: more ranks than queries), unsolved queries and scratch rows: the gathered result
+    equals the one-rank result in its used rows, is zero elsewhere, and the packed form is the used rows back to back."""
+    a = np.arange(n * 9, dtype=np.float32).reshape(n, 9) / 1000.0
+    ref = _FakePlanner().rrtc_batch(a, a, max_path=8)
+    used = np.arange(8)[None, :] < ref[1][:, None]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 33500 + (os.getpid() % 2000) + world
+    mp.spawn(_fake_worker, args=(world, port, n, ret), nprocs=world, join=True)
+    for rank in range(world):
+        dense, packed = ret[rank]
+        assert np.array_equal(dense[0][used], ref[0][used]) and (dense[0][~used] == 0).all()
+        assert np.array_equal(packed[0], ref[0][used])
+        for j in (1, 2, 3):
+            assert np.array_equal(dense[j], ref[j]) and np.array_equal(packed[j], ref[j]), (rank, j)
