@@ -40,15 +40,17 @@
     PV_CUDA(h, cudaSetDevice((h)->device));
 
 // K3: one warp per edge, lanes = interpolation states, coarse-to-fine rounds, any-hit early exit.
-// Each warp owns 32 consecutive edges at a time and emits one verdict word.  The warps of a block advance
-// ROUND by round behind a block barrier (one pv_check_config per warp per round), so the 16 warps share
-// instruction fetches exactly like the state kernel; the loop ends when __syncthreads_or says no warp has
-// work left.
+// Each warp owns 32 consecutive edges at a time and emits one verdict word.
+// PV_E_LOCKSTEP = 1 makes the warps of a block advance ROUND by round behind a block barrier (one pv_check_config per
+// warp per round, the loop ends when __syncthreads_or says no warp has work left) so that they share instruction
+// fetches like the state kernel.  That was neutral while a round cost ~3 700 instructions; since the scene-level cull
+// (a round: ~1 400) the barrier is the top stall (2.7 warp-cycles per issue, issue-active 39 %) and free-running warps
+// are 20-25 % faster (config 3: 305 -> 367 M edges/s), so it is off.
 #ifndef PV_E_THREADS
 #define PV_E_THREADS 384
 #endif
 #ifndef PV_E_LOCKSTEP
-#define PV_E_LOCKSTEP 1
+#define PV_E_LOCKSTEP 0
 #endif
 
 template <bool CULL, int MODE, bool CARRY>
