@@ -36,10 +36,15 @@ extern "C" {
 #define PV_ERR_CUDA (-3)
 #define PV_ERR_NO_DEVICE (-4)
 #define PV_ERR_NO_SCENE (-5)
+#define PV_ERR_CAPACITY (-6) /* a caller-supplied output buffer is too small (the needed size is reported) */
 
 /* validity rule switches */
 #define PV_FLAG_SELF 1u   /* robot-vs-robot pairs on (Genesis enable_self_collision) */
-#define PV_FLAG_LIMITS 2u /* also require lower <= q <= upper (planning.py:139-150, 165-173) */
+#define PV_FLAG_LIMITS 2u /* accepted, changes nothing: lower <= q <= upper (planning.py:139-150, 165-173) is ALWAYS
+                             required.  The joint limits are part of the model's validity domain -- the self-collision
+                             pair lists are pruned by a certificate that holds inside them only -- and OMPL never hands
+                             the reference's callback a state outside its RealVectorBounds.  A state outside the limits
+                             (or with a non-finite joint value) is invalid, culprit kind 4. */
 
 typedef struct PvHandle PvHandle;
 
@@ -160,10 +165,91 @@ typedef struct {
 
 /* h_starts/h_goals: [n_queries][9] host AoS.  h_path_out: [n_queries][max_path][9], of which only the first
  * h_path_len[k] rows of path k are written; h_path_len: states per path (0 = no solution); h_iters: iterations
- * used; h_checks: state checks issued (may be NULL). */
+ * used; h_checks: state checks issued (may be NULL).
+ * Parameters: 0 selects the default of max_iters (2000), max_nodes (2048), max_path (128) and replicas (1); values
+ * outside max_iters 1..2^23-1, max_nodes 8..2^22, max_path 2..2^20, replicas 1..256 are PV_ERR_BAD_ARG (never silently
+ * replaced: the caller sized h_path_out from ITS max_path).  With replicas > 1 the winner is the search with the
+ * smallest (iterations, replica id), so the result is the same on every run.  Memory on the device is bounded
+ * whatever n_queries is (the batch is planned in chunks; searches start with small trees and only those that outgrow
+ * them are re-planned with max_nodes), results are identical to one full-size run. */
 int pv_rrtc_batch(PvHandle *h, const float *h_starts, const float *h_goals, int n_queries,
                   const PvRrtcParams *params, float *h_path_out, int *h_path_len, int *h_iters,
                   long long *h_checks);
+
+/* The same planner with PACKED paths: the states of all paths back to back in h_states ([state_capacity][9]); path k is
+ * rows h_path_off[k] .. h_path_off[k] + h_path_len[k] - 1.  *n_states (may be NULL) receives the total number of rows.
+ * The dense form above needs max_path x 36 B per query on the caller's side (4.6 KB for typically 2..4 states); this
+ * one scales to 10^6 queries.  If the rows do not fit, lengths / offsets / *n_states are still complete and
+ * PV_ERR_CAPACITY is returned. */
+int pv_rrtc_batch_packed(PvHandle *h, const float *h_starts, const float *h_goals, int n_queries,
+                         const PvRrtcParams *params, float *h_states, long long state_capacity,
+                         long long *h_path_off, int *h_path_len, int *h_iters, long long *h_checks,
+                         long long *n_states);
+
+/* PlannerInterface.plan_path in one call (planning.py:59-207): intake check of start and goal (planning.py:163-183),
+ * ss.solve (planning.py:190), ss.simplifySolution() when `smooth` (planning.py:195-196: OMPL simplifyMax = partial
+ * shortcuts, B-spline smoothing, vertex reduction -- each pass validated as one batch by the edge kernel),
+ * path.interpolate(num_waypoints) (planning.py:198), and a validation of everything handed back: the first waypoint and
+ * every motion between consecutive waypoints, which is denser than the planner's own 1 % resolution.  A path that fails
+ * it is replaced by the unsimplified solution; if that fails too the query is planned again with a new seed at half the
+ * motion-validation resolution, up to max_attempts times / until timeout_s.
+ * start, goal: 9 doubles (the reference plans in fp64 and keeps the end points exact; the waypoints come back as fp32
+ * rows like the tensors of planning.py:232-242).  num_waypoints <= 0: the path vertices are returned as they are.
+ * h_waypoints: [capacity][9]; *n_waypoints = rows written (0 = no solution; planning.py:201-202 returns []).  A path
+ * with more vertices than num_waypoints is returned unchanged (PathGeometric::interpolate), so capacity should be
+ * >= max(num_waypoints, 256); PV_ERR_CAPACITY (with the needed count in *n_waypoints) otherwise. */
+typedef struct {
+    float range;       /* <= 0 -> OMPL default (0.2 x extent) */
+    float resolution;  /* <= 0 -> OMPL default (0.01 x extent) */
+    int max_iters;     /* per attempt; 0 -> 2000 */
+    int max_nodes;     /* per tree; 0 -> 2048 */
+    uint32_t seed;
+    int replicas;      /* OR-parallel searches per attempt; 0 -> 1.  Deterministic winner (see pv_rrtc_batch) */
+    int smooth;        /* smooth_path (planning.py:62, 195) */
+    int planner;       /* 0 RRTConnect, 1 RRT */
+    int validate;      /* != 0: dense validation of the returned waypoints, with fallback and re-planning */
+    int max_attempts;  /* 0 -> 4 */
+    double timeout_s;  /* ss.solve(timeout) (planning.py:190); checked between attempts */
+} PvPlanParams;
+
+typedef struct {
+    int solved;
+    int endpoint_status;      /* bit 0: start invalid / out of bounds, bit 1: goal (planning.py:165-183) */
+    int attempts;             /* solves issued */
+    int refinements;          /* attempts that halved the resolution after a failed dense validation */
+    int iters;                /* planner iterations over all attempts */
+    long long checks;         /* state checks of the planner over all attempts */
+    int vertices_raw;         /* vertices of the solution as the trees found it (after the in-kernel vertex shortcuts) */
+    int vertices;             /* vertices of the path that was resampled and returned */
+    int partial_rounds, bspline_steps, reduce_rounds; /* batches each simplifier pass ran */
+    int simplify_motions;     /* candidate motions the simplifier had validated */
+    int fallback_unsimplified; /* 1: the simplified path failed the dense validation, the raw solution was returned */
+    int validated;            /* 1: the returned waypoints passed the dense validation */
+    int speculative_hit;      /* 1: the straight-line answer had been validated in the shadow of the solve */
+    int launches;             /* kernel launches of this call */
+    float ms_solve, ms_simplify, ms_post, ms_total; /* host wall clock inside the call */
+} PvPlanStats;
+
+int pv_plan_path(PvHandle *h, const double *start, const double *goal, int num_waypoints, const PvPlanParams *params,
+                 float *h_waypoints, int capacity, int *n_waypoints, PvPlanStats *stats);
+
+/* path.interpolate(count) (planning.py:198; OMPL PathGeometric::interpolate for a RealVectorStateSpace) on its own:
+ * host arithmetic only (no device, no handle).  states [n_states][9] fp64 -> out [capacity][9]; *n_out = rows. */
+int pv_interpolate_path(const double *states, int n_states, int count, double *out, int capacity, int *n_out);
+
+/* ss.simplifySolution() (planning.py:196) on a caller-supplied vertex list: the simplifier of pv_plan_path on its own,
+ * every candidate motion validated by the edge kernel against the current scene.  states [n_states][9] fp64 ->
+ * out [capacity][9]; resolution <= 0 -> OMPL default.  counters as for pv_simplify_path_cb. */
+int pv_simplify_path(PvHandle *h, const double *states, int n_states, uint32_t seed, float resolution, double *out,
+                     int capacity, int *n_out, int *counters);
+
+/* The simplifier of pv_plan_path with the motion validator supplied by the caller -- a hook for testing the pass
+ * logic against another validator (tests/ hands it the CPU oracle); the product path never uses it.
+ * cb(user, a, b, n, ok): validate n motions a[k] -> b[k] (fp32 rows of 9), ok[k] = 1 when valid; returns 0.
+ * counters (may be NULL): {partial rounds, B-spline steps, reduce rounds, motions validated}. */
+typedef int (*pv_edge_callback)(void *user, const float *a, const float *b, int n, unsigned char *ok);
+int pv_simplify_path_cb(const double *states, int n_states, uint32_t seed, pv_edge_callback cb, void *user,
+                        double *out, int capacity, int *n_out, int *counters);
 
 /* robot.inverse_kinematics(link=hand, pos, quat) as the motion primitives call it before every plan_path
  * (motion_primitives.py:131-134), batched and collision-aware.  For each of n_targets hand poses (world

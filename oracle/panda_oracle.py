@@ -212,8 +212,15 @@ def state_margin(q, scene, model, attached=-1, self_collision=True, base=(0.0, 0
             take("self", d - (sr[a] + sr[b]))
         for a, k in model["sb_pairs"]:
             take("self", _sphere_obb_margin(wc[:, a], sr[a], bw[:, k], bh[k], bR[:, k]))
-    junk = ~(np.abs(q) <= 1.0e4).all(axis=1)  # non-finite joint values are never valid (NaN compares false)
-    margin = np.where(junk, -1e30, margin)
+    # joint limits (planning.py:139-150) are part of the validity domain: OMPL never hands the callback a state outside
+    # them, and the pruned self-pair lists are certified inside them only.  Compared in fp32 (the value the kernels,
+    # whose inputs are fp32, see), so a state AT a limit is inside in either precision; the negated comparison also
+    # rejects non-finite joint values
+    lo32, hi32 = model["q_lower"].astype(np.float32), model["q_upper"].astype(np.float32)
+    with np.errstate(invalid="ignore", over="ignore"):
+        q32 = q.astype(np.float32)
+        outside = ~((q32 >= lo32) & (q32 <= hi32)).all(axis=1)
+    margin = np.where(outside, -1e30, margin)
     if detail:
         return margin, parts
     return margin

@@ -132,18 +132,22 @@ static REAL FN(obb_obb)(const REAL *ca, const REAL *ha, const REAL *Ra, const RE
 #define PO_HAND_LINK 8
 #define PO_CARRY_LAST_ARM_LINK 6
 
-/* Minimum signed clearance of one configuration (valid iff >= 0).  With PO_FLAG_LIMITS an
- * out-of-bounds configuration returns -1e30. */
+/* Minimum signed clearance of one configuration (valid iff >= 0).  An out-of-bounds configuration
+ * returns -1e30. */
 static REAL FN(state_margin_one)(const FN(po_model) * m, const REAL *obb, int n_obb, REAL table_z,
                                  const REAL *base, int attached, int flags, const REAL *q) {
     REAL R[11 * 9], p[11 * 3];
     REAL wc[64 * 3], bw[8 * 3];
     REAL best = (REAL)1e30;
-    for (int j = 0; j < 9; ++j)
-        if (!(fabs((double)q[j]) <= 1.0e4)) return -(REAL)1e30; /* non-finite joint value: never valid */
-    if (flags & PO_FLAG_LIMITS)
-        for (int j = 0; j < 9; ++j)
-            if (q[j] < m->q_lower[j] || q[j] > m->q_upper[j]) return -(REAL)1e30;
+    /* Joint limits are part of the validity domain and always enforced (PO_FLAG_LIMITS is accepted and ignored):
+     * OMPL only ever hands the callback states inside the RealVectorBounds of planning.py:139-150, and the pruned
+     * self-collision pair lists of the model are certified inside the limits only.  The comparison is made on the
+     * fp32 value of the joint against the fp32 limits -- what the kernels, whose inputs are fp32, see -- so a state
+     * AT a limit is inside whichever precision it is handed over in; the negated form also rejects non-finite values. */
+    for (int j = 0; j < 9; ++j) {
+        const float qf = (float)q[j];
+        if (!(qf >= (float)m->q_lower[j] && qf <= (float)m->q_upper[j])) return -(REAL)1e30;
+    }
     FN(fk_one)(q, base, R, p);
     for (int i = 0; i < m->n_spheres; ++i) {
         const REAL *Rl = R + 9 * m->sphere_link[i], *pl = p + 3 * m->sphere_link[i], *c = m->sphere_center + 3 * i;

@@ -14,7 +14,7 @@ from typing import List
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpanda_validity.so")
-SOURCES = ["pv_kernels.cu", "pv_edge.cu", "pv_rrtc.cu", "pv_ik.cu"]
+SOURCES = ["pv_kernels.cu", "pv_edge.cu", "pv_rrtc.cu", "pv_ik.cu", "pv_plan.cu"]
 HEADERS = ["pv_device.cuh", "pv_handle.h", "panda_model_gen.h", os.path.join("..", "..", "include", "panda_validity.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -26,8 +26,13 @@ EXPORTS = [
     "pv_create", "pv_destroy", "pv_last_error", "pv_version", "pv_model_info", "pv_joint_limits",
     "pv_set_scene", "pv_set_attached", "pv_set_carried", "pv_set_flags", "pv_set_culling", "pv_set_gather", "pv_fk", "pv_fk_verdict_path", "pv_check_states", "pv_state_margins", "pv_state_contacts",
     "pv_check_edges", "pv_edge_margins", "pv_check_states_host", "pv_check_edges_host", "pv_sweep",
-    "pv_rrtc_batch", "pv_ik_batch", "pv_fp32_peak", "pv_launch_count",
+    "pv_rrtc_batch", "pv_rrtc_batch_packed", "pv_plan_path", "pv_interpolate_path", "pv_simplify_path",
+    "pv_simplify_path_cb",
+    "pv_ik_batch", "pv_fp32_peak", "pv_launch_count",
 ]
+
+
+PV_ERR_CAPACITY = -6
 
 
 class PvRrtcParams(C.Structure):
@@ -36,6 +41,32 @@ class PvRrtcParams(C.Structure):
         ("max_path", C.c_int), ("seed", C.c_uint32), ("replicas", C.c_int), ("shortcut_passes", C.c_int),
         ("check_endpoints", C.c_int), ("planner", C.c_int), ("query_offset", C.c_int),
     ]
+
+
+class PvPlanParams(C.Structure):
+    _fields_ = [
+        ("range", C.c_float), ("resolution", C.c_float), ("max_iters", C.c_int), ("max_nodes", C.c_int),
+        ("seed", C.c_uint32), ("replicas", C.c_int), ("smooth", C.c_int), ("planner", C.c_int), ("validate", C.c_int),
+        ("max_attempts", C.c_int), ("timeout_s", C.c_double),
+    ]
+
+
+class PvPlanStats(C.Structure):
+    _fields_ = [
+        ("solved", C.c_int), ("endpoint_status", C.c_int), ("attempts", C.c_int), ("refinements", C.c_int),
+        ("iters", C.c_int), ("checks", C.c_longlong), ("vertices_raw", C.c_int), ("vertices", C.c_int),
+        ("partial_rounds", C.c_int), ("bspline_steps", C.c_int), ("reduce_rounds", C.c_int),
+        ("simplify_motions", C.c_int), ("fallback_unsimplified", C.c_int), ("validated", C.c_int),
+        ("speculative_hit", C.c_int), ("launches", C.c_int), ("ms_solve", C.c_float), ("ms_simplify", C.c_float),
+        ("ms_post", C.c_float), ("ms_total", C.c_float),
+    ]
+
+    def as_dict(self) -> dict:
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+EDGE_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,
+                            C.POINTER(C.c_ubyte))
 
 
 def _nvcc() -> str:
@@ -117,6 +148,12 @@ def load() -> C.CDLL:
     lib.pv_check_edges_host.argtypes = [vp, fp, fp, C.c_int64, C.c_int, C.c_float, u32p]
     lib.pv_sweep.argtypes = [vp, C.c_uint64, C.c_int64, C.c_uint32, C.c_int, u32p, vp, fp, vp]
     lib.pv_rrtc_batch.argtypes = [vp, fp, fp, C.c_int, C.POINTER(PvRrtcParams), fp, i32p, i32p, vp]
+    lib.pv_rrtc_batch_packed.argtypes = [vp, fp, fp, C.c_int, C.POINTER(PvRrtcParams), fp, C.c_longlong, vp, i32p, i32p, vp, vp]
+    lib.pv_plan_path.argtypes = [vp, vp, vp, C.c_int, C.POINTER(PvPlanParams), fp, C.c_int, C.POINTER(C.c_int),
+                                 C.POINTER(PvPlanStats)]
+    lib.pv_interpolate_path.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
+    lib.pv_simplify_path.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_float, vp, C.c_int, C.POINTER(C.c_int), vp]
+    lib.pv_simplify_path_cb.argtypes = [vp, C.c_int, C.c_uint32, EDGE_CALLBACK, vp, vp, C.c_int, C.POINTER(C.c_int), vp]
     lib.pv_ik_batch.argtypes = [vp, fp, fp, C.c_int, fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_uint32, fp, i32p, fp]
     lib.pv_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     lib.pv_launch_count.argtypes = [vp]

@@ -37,7 +37,7 @@
         return PV_ERR_BAD_ARG;                                              \
     }                                                                       \
     if ((n) == 0) return PV_OK;                                             \
-    PV_CUDA(h, cudaSetDevice((h)->device));
+    PvDeviceGuard pv_guard_((h)->device);
 
 // K3: one warp per edge, lanes = interpolation states, coarse-to-fine rounds, any-hit early exit.
 // Each warp owns 32 consecutive edges at a time and emits one verdict word.

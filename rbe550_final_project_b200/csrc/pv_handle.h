@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
+
+#include "../../include/panda_validity.h"
 #include "pv_device.cuh"
 
 #define PV_HANDLE_MAGIC 0x50564831u
@@ -37,14 +40,41 @@ struct PvHandle {
     float* stage_q[PV_N_STREAMS];
     float* stage_q2[PV_N_STREAMS];
     uint32_t* stage_bits[PV_N_STREAMS];
-    void* rrtc_buf;
+    void* rrtc_buf;   // device arena of the batched planner (grow-only; bounded by its chunking, see pv_rrtc.cu)
     size_t rrtc_bytes;
-    void* rrtc_host;  // pinned mirror of the RRT result block
+    void* rrtc_host;  // host-mapped pinned block: queries in, per-query results out (and packed paths of small calls)
     size_t rrtc_host_bytes;
+    void* rrtc_rows_host;  // pinned mirror of the packed path rows of a large chunk
+    size_t rrtc_rows_host_bytes;
+    int rrtc_parity;       // which of the two row cursors the next launch uses
+    void* plan_host;       // host-mapped pinned staging of pv_plan_path's edge batches (end points in, verdict words out)
+    size_t plan_host_bytes;
     void* ik_buf;
     size_t ik_bytes;
     char err[512];
 };
+
+// The entry points select the handle's device for their own duration and put the caller's current device back
+// (a pv_* call used to leave the process on the handle's device).
+struct PvDeviceGuard {
+    int prev = -1;
+    explicit PvDeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) cudaSetDevice(device);
+        else prev = -1;
+    }
+    ~PvDeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    PvDeviceGuard(const PvDeviceGuard&) = delete;
+    PvDeviceGuard& operator=(const PvDeviceGuard&) = delete;
+};
+
+// results of one chunk of the batched planner: (first query, count, length[], first row[], iterations[], checks[],
+// packed path rows of the chunk)
+typedef std::function<void(int, int, const int*, const int*, const int*, const long long*, const float*)> PvRrtcSink;
+int pv_rrtc_run(PvHandle* h, const float* h_starts, const float* h_goals, int n, const PvRrtcParams* params,
+                const PvRrtcSink& sink, const std::function<void(cudaStream_t)>* after_first_launch);
 
 int pv_grid_for(PvHandle* h, const void* kernel, int threads, int64_t warps_needed);
 int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* a9, const float* bA,

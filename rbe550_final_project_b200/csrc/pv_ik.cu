@@ -220,7 +220,7 @@ extern "C" int pv_ik_batch(PvHandle* h, const float* h_pos, const float* h_quat,
             return PV_ERR_CUDA;                                                                              \
         }                                                                                                    \
     } while (0)
-    IK_CUDA(cudaSetDevice(h->device));
+    PvDeviceGuard guard(h->device);
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t b_pos = al((size_t)n_targets * 3 * 4), b_quat = al((size_t)n_targets * 4 * 4), b_qi = al(9 * 4);
     const size_t b_q = al((size_t)n_targets * 9 * 4), b_st = al((size_t)n_targets * 4), b_err = al((size_t)n_targets * 8);

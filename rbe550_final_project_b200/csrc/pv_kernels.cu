@@ -647,7 +647,8 @@ int pv_create(int device, PvHandle** out) {
     h->scene.flags = PV_FLAG_SELF;
     h->scene.base[2] = 0.01f;
     h->cull = 2;
-    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+    PvDeviceGuard guard(device);  // the streams are created on `device`; the caller's current device is put back
+    if ((e = cudaGetLastError()) != cudaSuccess) {
         snprintf(g_create_error, sizeof(g_create_error), "cudaSetDevice: %s", cudaGetErrorString(e));
         delete h;
         return PV_ERR_CUDA;
@@ -665,7 +666,7 @@ int pv_create(int device, PvHandle** out) {
 
 void pv_destroy(PvHandle* h) {
     if (pv_check_handle(h)) return;
-    cudaSetDevice(h->device);
+    PvDeviceGuard guard(h->device);
     for (int i = 0; i < PV_N_STREAMS; ++i) {
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
         if (h->stage_q[i]) cudaFree(h->stage_q[i]);
@@ -674,6 +675,8 @@ void pv_destroy(PvHandle* h) {
     }
     if (h->rrtc_buf) cudaFree(h->rrtc_buf);
     if (h->rrtc_host) cudaFreeHost(h->rrtc_host);
+    if (h->rrtc_rows_host) cudaFreeHost(h->rrtc_rows_host);
+    if (h->plan_host) cudaFreeHost(h->plan_host);
     if (h->ik_buf) cudaFree(h->ik_buf);
     h->magic = 0;
     delete h;
@@ -878,7 +881,7 @@ int pv_set_culling(PvHandle* h, int on) {
         return PV_ERR_BAD_ARG;                                              \
     }                                                                       \
     if ((n) == 0) return PV_OK;                                             \
-    PV_CUDA(h, cudaSetDevice((h)->device));
+    PvDeviceGuard pv_guard_((h)->device);
 
 static int pv_fk_impl(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9, int64_t n, float* d_pose_out,
                       void* stream, bool verdict_path) {
@@ -1111,7 +1114,7 @@ int pv_sweep(PvHandle* h, uint64_t first, int64_t n, uint32_t seed, int fingers_
 int pv_fp32_peak(PvHandle* h, int iters, double* tflops, float* ms_out) {
     if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
     if (iters < 1 || !tflops) return PV_ERR_BAD_ARG;
-    PV_CUDA(h, cudaSetDevice(h->device));
+    PvDeviceGuard guard(h->device);
     float* d_out = nullptr;
     PV_CUDA(h, cudaMalloc(&d_out, sizeof(float)));
     cudaEvent_t e0, e1;

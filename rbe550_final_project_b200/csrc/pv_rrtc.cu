@@ -11,6 +11,19 @@
 // nodes, SoA so the loads coalesce) and over the interpolated states of the edge being validated (one
 // pv_check_config per lane, __any_sync early exit).  The solve is a small state machine so the ~10k-instruction
 // state check is instantiated exactly once.
+//
+// Memory: a search's arena is 2 trees x 9 x M floats + parents + a path buffer.  Sized for the
+// caller's max_nodes (2 048) that is 168 KB per search while the median search uses 2 nodes, so a batch is planned in
+// two tiers: tier 1 gives every search small trees (RRTC_T1_NODES per tree); a query one of whose searches hit that
+// cap BEFORE any search of the query had connected is planned again in tier 2 with the full max_nodes.  A search is a
+// deterministic function of (seed, global search id) and of nothing else, and the tree capacity only decides where
+// it gives up, so both tiers return exactly what a single full-size run returns.  Batches are cut into chunks of at most
+// RRTC_CHUNK_SEARCHES searches (tier 1) / RRTC_T2_ARENA_BYTES of trees (tier 2), so the arena is bounded whatever
+// the batch size, and only the USED rows of each path are gathered (packed) and copied to the host.
+//
+// Replicas (several searches per query) are OR-parallel but DETERMINISTIC: the winner is the search with the smallest
+// key (iterations, replica id).  A running search gives up as soon as a published key is smaller than any key it can
+// still reach, which never removes the eventual minimum, so the answer does not depend on warp scheduling.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -21,26 +34,56 @@
 
 #define RRTC_THREADS 128
 #define RRTC_MAX_SHORTCUT_CHECKS 96
+#ifndef RRTC_T1_NODES
+#define RRTC_T1_NODES 64
+#endif
+#ifndef RRTC_CHUNK_SEARCHES
+#define RRTC_CHUNK_SEARCHES 32768
+#endif
+#ifndef RRTC_T2_ARENA_BYTES
+#define RRTC_T2_ARENA_BYTES ((size_t)2 << 30)
+#endif
+#define RRTC_SMALL_QUERIES 64  // calls up to this size use host-mapped inputs / results: no copy operations at all
+#define RRTC_MAX_REPLICAS 256
+#define RRTC_NO_KEY 0xffffffffu
 
 enum { PH_EXTEND = 0, PH_CONNECT = 1, PH_EXTRACT = 2, PH_SHORTCUT = 3, PH_DONE = 4 };
+// how a search ended (s_status)
+enum { ST_NONE = 0, ST_SOLVED = 1, ST_ITERCAP = 2, ST_NODECAP = 3, ST_PATHCAP = 4, ST_ABORTED = 5, ST_BADEND = 16 };
+// what the collect kernel decided for a query (q_status)
+enum { QS_FINAL = 1, QS_TIER2 = 2 };
 
 struct RrtcArgs {
-    const float* starts;  // [nq][9]
-    const float* goals;   // [nq][9]
-    int n_queries;
+    const float* starts;  // [rows of the chunk][9]
+    const float* goals;
+    const int* qmap;      // tier 2: launch-local query -> row of the chunk (null = identity)
+    int n_queries;        // queries of this launch
     float range, resolution;
-    int max_iters, max_nodes, max_path, replicas, shortcut_passes, check_endpoints;
-    int planner;  // 0 = RRTConnect (two trees), 1 = RRT (start tree only, 5 % goal bias: og.RRT defaults)
+    int max_iters, max_path, replicas, shortcut_passes, check_endpoints;
+    int planner;          // 0 = RRTConnect (two trees), 1 = RRT (start tree only, 5 % goal bias: og.RRT defaults)
+    int tree_nodes;       // M: capacity of one tree in THIS launch's arena (tier 1: RRTC_T1_NODES, tier 2: max_nodes)
+    int path_rows;        // rows of one search's path buffer: min(max_path, 2 M)
+    int tier1;            // 1: a node-cap failure may be an artefact of the small arena (collect flags the query)
     unsigned seed;
-    unsigned search_offset;  // query_offset * replicas: the RNG is keyed by the GLOBAL search id
-    float* tree_q;      // [search][2][9][max_nodes]
-    int* parent;        // [search][2][max_nodes]
-    float* path_tmp;    // [search][max_path][9]
-    float* path_out;    // [nq][max_path][9]
-    int* path_len;      // [nq]
-    int* iters_out;     // [nq]
-    long long* checks;  // [nq]
-    int* winner;        // [nq], -1 until a search of that query finishes
+    unsigned query_base;  // global id of row 0 of the chunk: the RNG is keyed by the GLOBAL search id
+    float* tree_q;        // [search][2][9][M]
+    int* parent;          // [search][2][M]
+    float* path_tmp;      // [search][path_rows][9]
+    // per search (launch-local), consumed by the collect kernel
+    int* s_status;
+    int* s_iters;
+    long long* s_checks;
+    int* s_plen;
+    unsigned* best_key;   // [rows]: min over the connected searches of a query of (iteration << 8 | replica)
+    // per row of the chunk, written by the collect kernel (device or host-mapped memory)
+    int* q_status;
+    int* q_len;
+    int* q_off;           // first row of the query's path in `rows`
+    int* q_iters;
+    long long* q_checks;
+    float* rows;          // packed path states [sum of lengths][9]
+    unsigned* cursor;     // rows handed out so far (device)
+    unsigned* cursor_next;  // the other call parity's cursor: zeroed here so the next call needs no memset
 };
 
 __device__ __forceinline__ void rrtc_sample(unsigned seed, unsigned search, unsigned it, float* q, float& extra) {
@@ -97,15 +140,20 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
     const int lane = threadIdx.x & 31;
     const int search = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (search >= A.n_queries * A.replicas) return;
-    const int query = search / A.replicas;
-    const int M = A.max_nodes;
+    const int lq = search / A.replicas;
+    const unsigned rep = (unsigned)(search - lq * A.replicas);
+    const int row = A.qmap ? A.qmap[lq] : lq;
+    const unsigned gsearch = (A.query_base + (unsigned)row) * (unsigned)A.replicas + rep;
+    const int M = A.tree_nodes;
     float* tq = A.tree_q + (size_t)search * 2 * 9 * M;
     int* par = A.parent + (size_t)search * 2 * M;
-    float* path = A.path_tmp + (size_t)search * A.max_path * 9;
+    float* path = A.path_tmp + (size_t)search * A.path_rows * 9;
+    const float* q_start = A.starts + (size_t)row * 9;
+    const float* q_goal = A.goals + (size_t)row * 9;
 
     if (lane < 9) {
-        tq[(size_t)lane * M] = A.starts[query * 9 + lane];
-        tq[(size_t)(9 + lane) * M] = A.goals[query * 9 + lane];
+        tq[(size_t)lane * M] = q_start[lane];
+        tq[(size_t)(9 + lane) * M] = q_goal[lane];
     }
     if (lane == 0) {
         par[0] = -1;
@@ -113,48 +161,43 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
     }
     __syncwarp();
 
+    int status = ST_NONE;
+    int it = 0;
+    long long n_checks = 0;
+    int path_n = 0;
+
     if (A.check_endpoints) {
         // OMPL drops out-of-bounds / invalid start and goal states at intake (planning.py:163-187): lane 0 judges
-        // the start, the other lanes the goal
-        const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
+        // the start, the other lanes the goal (the state check itself enforces the bounds)
         float qe[9];
-        bool bad = false;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            qe[k] = (lane == 0) ? A.starts[query * 9 + k] : A.goals[query * 9 + k];
-            bad |= (qe[k] < lo[k]) || (qe[k] > hi[k]);
-        }
+        for (int k = 0; k < 9; ++k) qe[k] = (lane == 0) ? q_start[k] : q_goal[k];
         PvAcc<PV_MODE_BITS> acc0;
         pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, 0, false, CARRY>(qe, S, acc0);
-        bad |= acc0.hit;
+        const bool bad = acc0.hit;
         const int code = (__shfl_sync(FULL, bad ? 1 : 0, 0) ? 1 : 0) | (__shfl_sync(FULL, bad ? 1 : 0, 1) ? 2 : 0);
-        if (code) {
-            if (lane == 0 && search % A.replicas == 0) {
-                A.iters_out[query] = -code;
-                A.path_len[query] = 0;
-            }
-            return;
-        }
+        if (code) status = ST_BADEND + code;
     }
 
     int size0 = 1, size1 = 1;  // tree sizes (warp-uniform)
     int cur = 0;               // tree grown by EXTEND in this iteration (0 = start tree)
-    int it = 0;
-    int phase = PH_EXTEND;
-    long long n_checks = 0;
+    int phase = status ? PH_DONE : PH_EXTEND;
     float target[9];           // CONNECT target = state of the node just added by EXTEND
     int added_idx = 0;         // its index in tree `cur`
     int conn_idx = -1;         // node of the other tree that reached the target
-    int path_n = 0;
     int sc_pass = 0, sc_i = 0, sc_j = 0, sc_budget = RRTC_MAX_SHORTCUT_CHECKS;
-    bool solved = false;
 
     while (phase != PH_DONE) {
-        // another replica of this query already finished
-        if (A.replicas > 1 && phase <= PH_CONNECT) {
-            int w = 0;
-            if (lane == 0) w = *((volatile int*)(A.winner + query));
-            if (__shfl_sync(FULL, w, 0) != -1) return;
+        // OR-parallel replicas: give up once a published key beats every key this search can still reach (its key can
+        // only grow with `it`), which never removes the eventual minimum -> the winner is independent of scheduling
+        if (A.replicas > 1) {
+            unsigned b = RRTC_NO_KEY;
+            if (lane == 0) b = *((volatile unsigned*)(A.best_key + row));
+            b = __shfl_sync(FULL, b, 0);
+            if (b < (((unsigned)it << 8) | rep)) {
+                status = ST_ABORTED;
+                break;
+            }
         }
         float ea[9], eb[9];
         int from_idx = 0, tree = 0;
@@ -162,10 +205,17 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
         if (phase == PH_EXTEND || phase == PH_CONNECT) {
             float goal_q[9];
             if (phase == PH_EXTEND) {
-                if (it >= A.max_iters || size0 >= M - 1 || size1 >= M - 1) break;
+                if (it >= A.max_iters) {
+                    status = ST_ITERCAP;
+                    break;
+                }
+                if (size0 >= M - 1 || size1 >= M - 1) {
+                    status = ST_NODECAP;
+                    break;
+                }
                 tree = cur;
                 float u9 = 1.f;
-                if (it > 0) rrtc_sample(A.seed, (unsigned)search + A.search_offset, (unsigned)it, goal_q, u9);
+                if (it > 0) rrtc_sample(A.seed, gsearch, (unsigned)it, goal_q, u9);
                 // first extension aims at the goal itself (cheap straight-line attempt); the single-tree planner also
                 // does so with OMPL's default goal bias of 5 %
                 aim_goal = (it == 0) || (A.planner == 1 && u9 < 0.05f);
@@ -202,7 +252,8 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
                 for (int x = par[M + ig]; x >= 0; x = par[M + x]) ++dg;
             path_n = ds + dg;
             if (path_n > A.max_path) {
-                solved = false;
+                status = ST_PATHCAP;
+                path_n = 0;
                 break;
             }
             int x = is;
@@ -216,7 +267,8 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
                 x = par[M + x];
             }
             __syncwarp();
-            solved = true;
+            status = ST_SOLVED;
+            if (A.replicas > 1 && lane == 0) atomicMin(A.best_key + row, ((unsigned)it << 8) | rep);
             sc_pass = 0;
             sc_i = 0;
             sc_j = path_n - 1;
@@ -286,6 +338,7 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
                     conn_idx = ni;
                     phase = PH_EXTRACT;
                 } else if (sz >= M - 1) {
+                    status = ST_NODECAP;
                     break;
                 }
             } else {
@@ -325,57 +378,90 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
         }
     }
 
-    if (!solved) {
-        // report the effort of failed searches only if no replica succeeds (winner stays -1)
-        if (A.replicas == 1 && lane == 0) {
-            A.iters_out[query] = it;
-            A.checks[query] = n_checks;
+    if (lane == 0) {
+        A.s_status[search] = status;
+        A.s_iters[search] = status == ST_SOLVED ? it + 1 : it;
+        A.s_checks[search] = n_checks;
+        A.s_plen[search] = status == ST_SOLVED ? path_n : 0;
+    }
+}
+
+// One warp per query, after all its searches have ended: pick the winner (smallest (iterations, replica) among the
+// connected searches), decide whether the small tier-1 arena may have changed the answer, hand out rows of the packed
+// path buffer and copy the winner's path there.
+__global__ void __launch_bounds__(128) pv_rrtc_collect_kernel(const __grid_constant__ RrtcArgs A) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int lq = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (lq == 0 && lane == 0 && A.cursor_next) *A.cursor_next = 0u;
+    if (lq >= A.n_queries) return;
+    const int row = A.qmap ? A.qmap[lq] : lq;
+    unsigned best = RRTC_NO_KEY, capkey = RRTC_NO_KEY;
+    long long sum_checks = 0;
+    int max_it = 0;
+    for (int rep = lane; rep < A.replicas; rep += 32) {
+        const int s = lq * A.replicas + rep;
+        const int st = A.s_status[s], si = A.s_iters[s];
+        if (st == ST_SOLVED) best = min(best, ((unsigned)(si - 1) << 8) | (unsigned)rep);
+        if (st == ST_NODECAP) capkey = min(capkey, ((unsigned)si << 8) | (unsigned)rep);
+        sum_checks += A.s_checks[s];
+        max_it = max(max_it, si);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        best = min(best, __shfl_xor_sync(FULL, best, o));
+        capkey = min(capkey, __shfl_xor_sync(FULL, capkey, o));
+        sum_checks += __shfl_xor_sync(FULL, sum_checks, o);
+        max_it = max(max_it, __shfl_xor_sync(FULL, max_it, o));
+    }
+    const int st0 = A.s_status[lq * A.replicas];
+    if (lane == 0) A.best_key[row] = RRTC_NO_KEY;  // left clean for the next launch that uses this row
+    if (st0 >= ST_BADEND) {
+        if (lane == 0) {
+            A.q_status[row] = QS_FINAL;
+            A.q_len[row] = 0;
+            A.q_off[row] = 0;
+            A.q_iters[row] = -(st0 - ST_BADEND);
+            A.q_checks[row] = 0;
         }
         return;
     }
-    int won = 0;
-    if (lane == 0) won = (atomicCAS(A.winner + query, -1, search) == -1);
-    won = __shfl_sync(FULL, won, 0);
-    if (!won) return;
-    float* po = A.path_out + (size_t)query * A.max_path * 9;
-    for (int k = lane; k < path_n * 9; k += 32) po[k] = path[k];
+    if (A.tier1 && capkey < best) {
+        // a search ran out of its SMALL trees at a point where it could still have become the winner: plan the query
+        // again with full-size trees
+        if (lane == 0) A.q_status[row] = QS_TIER2;
+        return;
+    }
+    if (best == RRTC_NO_KEY) {
+        if (lane == 0) {
+            A.q_status[row] = QS_FINAL;
+            A.q_len[row] = 0;
+            A.q_off[row] = 0;
+            A.q_iters[row] = max_it;
+            A.q_checks[row] = sum_checks;
+        }
+        return;
+    }
+    const int s = lq * A.replicas + (int)(best & 255u);
+    const int len = A.s_plen[s];
+    unsigned off = 0;
+    if (lane == 0) off = atomicAdd(A.cursor, (unsigned)len);
+    off = __shfl_sync(FULL, off, 0);
+    const float* src = A.path_tmp + (size_t)s * A.path_rows * 9;
+    float* dst = A.rows + (size_t)off * 9;
+    for (int k = lane; k < len * 9; k += 32) dst[k] = src[k];
     if (lane == 0) {
-        A.path_len[query] = path_n;
-        A.iters_out[query] = it + 1;
-        A.checks[query] = n_checks;
+        A.q_status[row] = QS_FINAL;
+        A.q_len[row] = len;
+        A.q_off[row] = (int)off;
+        A.q_iters[row] = A.s_iters[s];
+        A.q_checks[row] = A.s_checks[s];
     }
 }
 
 // =========================================================================================================
-extern "C" int pv_rrtc_batch(PvHandle* h, const float* h_starts, const float* h_goals, int n_queries,
-                             const PvRrtcParams* params, float* h_path_out, int* h_path_len, int* h_iters,
-                             long long* h_checks) {
-    if (!h || h->magic != PV_HANDLE_MAGIC) return PV_ERR_BAD_HANDLE;
-    if (!h->has_scene) {
-        snprintf(h->err, sizeof(h->err), "no scene set (pv_set_scene)");
-        return PV_ERR_NO_SCENE;
-    }
-    if (n_queries < 0 || !params || (n_queries > 0 && (!h_starts || !h_goals || !h_path_out || !h_path_len))) {
-        snprintf(h->err, sizeof(h->err), "pv_rrtc_batch: bad arguments");
-        return PV_ERR_BAD_ARG;
-    }
-    if (n_queries == 0) return PV_OK;
-    RrtcArgs a;
-    memset(&a, 0, sizeof(a));
-    a.n_queries = n_queries;
-    a.range = params->range > 0.f ? params->range : PV_RRTC_RANGE;
-    a.resolution = params->resolution > 0.f ? params->resolution : PV_VALIDITY_RESOLUTION;
-    a.max_iters = params->max_iters > 0 ? params->max_iters : 2000;
-    a.max_nodes = params->max_nodes >= 8 ? params->max_nodes : 2048;
-    a.max_path = params->max_path >= 2 ? params->max_path : 128;
-    a.replicas = params->replicas >= 1 ? params->replicas : 1;
-    a.shortcut_passes = params->shortcut_passes >= 0 ? params->shortcut_passes : 0;
-    a.check_endpoints = params->check_endpoints ? 1 : 0;
-    a.planner = params->planner == 1 ? 1 : 0;
-    a.seed = params->seed;
-    a.search_offset = (unsigned)(params->query_offset > 0 ? params->query_offset : 0) * (unsigned)a.replicas;
-    const size_t n_search = (size_t)n_queries * a.replicas;
-
+// host side
+// =========================================================================================================
 #define RR_CUDA(expr)                                                                                        \
     do {                                                                                                     \
         cudaError_t e_ = (expr);                                                                             \
@@ -385,77 +471,336 @@ extern "C" int pv_rrtc_batch(PvHandle* h, const float* h_starts, const float* h_
             return PV_ERR_CUDA;                                                                              \
         }                                                                                                    \
     } while (0)
-    RR_CUDA(cudaSetDevice(h->device));
 
-    // one grow-only arena in the handle, carved up per call
-    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t b_sg = al((size_t)n_queries * 9 * sizeof(float));
-    const size_t b_tree = al(n_search * 2 * 9 * a.max_nodes * sizeof(float));
-    const size_t b_par = al(n_search * 2 * a.max_nodes * sizeof(int));
-    const size_t b_ptmp = al(n_search * a.max_path * 9 * sizeof(float));
-    const size_t b_pout = al((size_t)n_queries * a.max_path * 9 * sizeof(float));
-    const size_t b_i = al((size_t)n_queries * sizeof(int));
-    const size_t b_ll = al((size_t)n_queries * sizeof(long long));
-    const size_t total = 2 * b_sg + b_tree + b_par + b_ptmp + b_pout + 3 * b_i + b_ll;
-    if (total > h->rrtc_bytes) {
-        if (h->rrtc_buf) cudaFree(h->rrtc_buf);
-        h->rrtc_buf = nullptr;
-        h->rrtc_bytes = 0;
-        RR_CUDA(cudaMalloc(&h->rrtc_buf, total));
-        h->rrtc_bytes = total;
+static inline size_t rr_al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// grow-only device / pinned host buffers of the handle
+static int rr_reserve_dev(PvHandle* h, void** buf, size_t* have, size_t need) {
+    if (need <= *have) return PV_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *have = 0;
+    RR_CUDA(cudaMalloc(buf, need));
+    *have = need;
+    return PV_OK;
+}
+static int rr_reserve_host(PvHandle* h, void** buf, size_t* have, size_t need) {
+    if (need <= *have) return PV_OK;
+    if (*buf) cudaFreeHost(*buf);
+    *buf = nullptr;
+    *have = 0;
+    RR_CUDA(cudaHostAlloc(buf, need, cudaHostAllocMapped));
+    *have = need;
+    return PV_OK;
+}
+
+int pv_rrtc_validate(PvHandle* h, const PvRrtcParams* p, RrtcArgs* a) {
+    memset(a, 0, sizeof(*a));
+    a->range = p->range > 0.f ? p->range : PV_RRTC_RANGE;
+    a->resolution = p->resolution > 0.f ? p->resolution : PV_VALIDITY_RESOLUTION;
+    a->max_iters = p->max_iters == 0 ? 2000 : p->max_iters;
+    const int max_nodes = p->max_nodes == 0 ? 2048 : p->max_nodes;
+    a->max_path = p->max_path == 0 ? 128 : p->max_path;
+    a->replicas = p->replicas == 0 ? 1 : p->replicas;
+    a->shortcut_passes = p->shortcut_passes;
+    // out-of-range capacities are an error, not a silent default: a caller who sized its path buffer from
+    // its own max_path must never be written beyond it
+    if (a->max_iters < 1 || a->max_iters >= (1 << 23) || max_nodes < 8 || max_nodes > (1 << 22) || a->max_path < 2 ||
+        a->max_path > (1 << 20) || a->replicas < 1 || a->replicas > RRTC_MAX_REPLICAS || a->shortcut_passes < 0 ||
+        p->query_offset < 0 || (p->planner != 0 && p->planner != 1)) {
+        snprintf(h->err, sizeof(h->err),
+                 "pv_rrtc_batch: parameter out of range (max_iters 1..2^23-1, max_nodes 8..2^22, max_path 2..2^20, "
+                 "replicas 1..%d, shortcut_passes >= 0, query_offset >= 0, planner 0|1; 0 selects the default of the "
+                 "first four)", RRTC_MAX_REPLICAS);
+        return PV_ERR_BAD_ARG;
     }
-    char* p = (char*)h->rrtc_buf;
-    float* d_starts = (float*)p; p += b_sg;
-    float* d_goals = (float*)p; p += b_sg;
-    a.tree_q = (float*)p; p += b_tree;
-    a.parent = (int*)p; p += b_par;
-    a.path_tmp = (float*)p; p += b_ptmp;
-    // results are contiguous so that one memset clears them and one D2H fetches them
-    char* res0 = p;
-    a.path_len = (int*)p; p += b_i;
-    a.iters_out = (int*)p; p += b_i;
-    a.checks = (long long*)p; p += b_ll;
-    a.path_out = (float*)p; p += b_pout;
-    const size_t res_bytes = (size_t)(p - res0);
-    a.winner = (int*)p; p += b_i;
-    a.starts = d_starts;
-    a.goals = d_goals;
+    a->check_endpoints = p->check_endpoints ? 1 : 0;
+    a->planner = p->planner;
+    a->seed = p->seed;
+    a->tree_nodes = max_nodes;  // the caller's capacity; the launches below set the tier's own
+    return PV_OK;
+}
 
-    // pinned host mirror of the result block (grow-only)
-    if (res_bytes > h->rrtc_host_bytes) {
-        if (h->rrtc_host) cudaFreeHost(h->rrtc_host);
-        h->rrtc_host = nullptr;
-        h->rrtc_host_bytes = 0;
-        RR_CUDA(cudaMallocHost(&h->rrtc_host, res_bytes));
-        h->rrtc_host_bytes = res_bytes;
-    }
-
+// Plans queries [0, n) (host AoS rows).  `sink(first, count, len, off, iters, checks, rows)` receives each chunk's
+// results: per-query arrays indexed from the chunk's first query and the packed path rows of the chunk.
+// `after_first_launch` (optional) runs right after the first chunk's kernels are queued and before the host waits for
+// them: pv_plan_path queues its speculative straight-line validation there, so an easy plan costs ONE synchronisation.
+int pv_rrtc_run(PvHandle* h, const float* h_starts, const float* h_goals, int n, const PvRrtcParams* params,
+                const PvRrtcSink& sink, const std::function<void(cudaStream_t)>* after_first_launch) {
+    RrtcArgs base;
+    int rc = pv_rrtc_validate(h, params, &base);
+    if (rc) return rc;
+    const int max_nodes = base.tree_nodes;
+    const int R = base.replicas;
     cudaStream_t st = h->streams[0];
-    RR_CUDA(cudaMemcpyAsync(d_starts, h_starts, (size_t)n_queries * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
-    RR_CUDA(cudaMemcpyAsync(d_goals, h_goals, (size_t)n_queries * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
-    RR_CUDA(cudaMemsetAsync(a.path_len, 0, 2 * b_i + b_ll, st));  // path_len, iters, checks
-    RR_CUDA(cudaMemsetAsync(a.winner, 0xFF, b_i, st));
-    const int warps_per_block = RRTC_THREADS / 32;
-    const int grid = (int)((n_search + warps_per_block - 1) / warps_per_block);
-    if (h->scene.carry) pv_rrtc_kernel<true><<<grid, RRTC_THREADS, 0, st>>>(h->scene, a);
-    else pv_rrtc_kernel<false><<<grid, RRTC_THREADS, 0, st>>>(h->scene, a);
-    h->launches++;
-    RR_CUDA(cudaGetLastError());
-    // small batches: one packed copy; large batches: skip the unused tail of each path? (paths are max_path long)
-    RR_CUDA(cudaMemcpyAsync(h->rrtc_host, res0, res_bytes, cudaMemcpyDeviceToHost, st));
-    RR_CUDA(cudaStreamSynchronize(st));
-    const char* hp = (const char*)h->rrtc_host;
-    memcpy(h_path_len, hp, (size_t)n_queries * sizeof(int));
-    if (h_iters) memcpy(h_iters, hp + b_i, (size_t)n_queries * sizeof(int));
-    if (h_checks) memcpy(h_checks, hp + 2 * b_i, (size_t)n_queries * sizeof(long long));
-    // only the used rows of each path: rows beyond h_path_len[k] of the caller's buffer are left as they were (the
-    // device rows there are scratch of the search), and a large, freshly allocated buffer is not paged in for nothing
-    const float* hpaths = (const float*)(hp + 2 * b_i + b_ll);
-    const size_t row = (size_t)a.max_path * 9;
-    for (int k = 0; k < n_queries; ++k) {
-        const int len = h_path_len[k] < a.max_path ? h_path_len[k] : a.max_path;
-        if (len > 0) memcpy(h_path_out + k * row, hpaths + k * row, (size_t)len * 9 * sizeof(float));
+
+    const int t1_nodes = max_nodes < RRTC_T1_NODES ? max_nodes : RRTC_T1_NODES;
+    const bool two_tier = t1_nodes < max_nodes;
+    auto path_rows_for = [&](int M) { return base.max_path < 2 * M ? base.max_path : 2 * M; };
+    int chunk_q = RRTC_CHUNK_SEARCHES / R;
+    // the packed-row buffer of a chunk (worst case: every path at full length) stays below 1 GB
+    const size_t rows_budget = ((size_t)1 << 30) / ((size_t)path_rows_for(max_nodes) * 9 * sizeof(float));
+    if ((size_t)chunk_q > rows_budget) chunk_q = (int)rows_budget;
+    if (chunk_q < 1) chunk_q = 1;
+    if (chunk_q > n) chunk_q = n;
+    const bool small = n <= RRTC_SMALL_QUERIES && (size_t)n * path_rows_for(max_nodes) * 9 * sizeof(float) <= ((size_t)4 << 20);
+
+    auto arena_per_search = [&](int M) {
+        return (size_t)2 * 9 * M * sizeof(float) + (size_t)2 * M * sizeof(int) + (size_t)path_rows_for(M) * 9 * sizeof(float);
+    };
+    // tier-2 sub-chunks: as many queries as fit the arena budget (at least one)
+    size_t t2_q = two_tier ? RRTC_T2_ARENA_BYTES / (arena_per_search(max_nodes) * R) : 0;
+    if (two_tier && t2_q < 1) t2_q = 1;
+    if (t2_q > (size_t)chunk_q) t2_q = chunk_q;
+
+    // ---- carve the handle's grow-only buffers ---------------------------------------------------------------
+    const size_t n_s1 = (size_t)chunk_q * R, n_s2 = t2_q * R;
+    const size_t n_s = n_s1 > n_s2 ? n_s1 : n_s2;
+    size_t arena = n_s1 * arena_per_search(t1_nodes);
+    if (n_s2 * arena_per_search(max_nodes) > arena) arena = n_s2 * arena_per_search(max_nodes);
+    const size_t rows_cap = (size_t)chunk_q * (size_t)path_rows_for(max_nodes);
+    const size_t b_q9 = rr_al((size_t)chunk_q * 9 * sizeof(float));
+    const size_t b_qi = rr_al((size_t)chunk_q * sizeof(int));
+    const size_t b_ql = rr_al((size_t)chunk_q * sizeof(long long));
+    const size_t b_si = rr_al(n_s * sizeof(int));
+    const size_t b_sl = rr_al(n_s * sizeof(long long));
+    const size_t b_meta = 4 * b_qi + b_ql;  // q_status, q_len, q_off, q_iters | q_checks
+    const size_t b_rows = rr_al(rows_cap * 9 * sizeof(float));
+    // counters and the per-row keys sit at FIXED offsets at the front of the buffer (their "left clean" invariant must
+    // survive calls of different sizes, which carve the rest differently)
+    const size_t b_ctr = 256;
+    const size_t b_keys = rr_al((size_t)RRTC_CHUNK_SEARCHES * sizeof(unsigned));
+    const size_t dev_need = b_ctr + b_keys + rr_al(arena + 256) + 2 * b_q9 + b_qi /*qmap*/ + 3 * b_si + b_sl +
+                            (small ? 0 : b_meta + b_rows);
+    const bool fresh = dev_need > h->rrtc_bytes;
+    rc = rr_reserve_dev(h, &h->rrtc_buf, &h->rrtc_bytes, dev_need);
+    if (rc) return rc;
+    const size_t host_need = 2 * b_q9 + b_meta + (small ? b_rows : 0) + b_qi;
+    rc = rr_reserve_host(h, &h->rrtc_host, &h->rrtc_host_bytes, host_need);
+    if (rc) return rc;
+    // the packed rows of a large chunk come back in a second copy whose size is only known after the first
+    if (!small) {
+        rc = rr_reserve_host(h, &h->rrtc_rows_host, &h->rrtc_rows_host_bytes, (size_t)1 << 20);
+        if (rc) return rc;
+    }
+
+    char* p = (char*)h->rrtc_buf;
+    unsigned* ctr = (unsigned*)p; p += b_ctr;  // [0], [1]: row cursors of even / odd launches
+    base.best_key = (unsigned*)p; p += b_keys;
+    char* arena_p = p; p += rr_al(arena + 256);
+    float* d_starts = (float*)p; p += b_q9;
+    float* d_goals = (float*)p; p += b_q9;
+    int* d_qmap = (int*)p; p += b_qi;
+    base.s_status = (int*)p; p += b_si;
+    base.s_iters = (int*)p; p += b_si;
+    base.s_plen = (int*)p; p += b_si;
+    base.s_checks = (long long*)p; p += b_sl;
+    char* d_meta = p;
+    float* d_rows = nullptr;
+    if (!small) {
+        p += b_meta;
+        d_rows = (float*)p; p += b_rows;
+    }
+    char* hp = (char*)h->rrtc_host;
+    float* hm_starts = (float*)hp; hp += b_q9;
+    float* hm_goals = (float*)hp; hp += b_q9;
+    char* h_meta = hp; hp += b_meta;
+    int* h_qmap = (int*)hp; hp += b_qi;
+    float* hm_rows = small ? (float*)hp : nullptr;
+
+    if (fresh) {
+        // a new arena: counters and keys start clean; from then on the collect kernel leaves them clean
+        RR_CUDA(cudaMemsetAsync(ctr, 0, b_ctr, st));
+        RR_CUDA(cudaMemsetAsync(base.best_key, 0xFF, b_keys, st));
+        h->rrtc_parity = 0;
+    }
+    auto meta_ptrs = [&](RrtcArgs& a, char* m) {
+        a.q_status = (int*)m;
+        a.q_len = (int*)(m + b_qi);
+        a.q_off = (int*)(m + 2 * b_qi);
+        a.q_iters = (int*)(m + 3 * b_qi);
+        a.q_checks = (long long*)(m + 4 * b_qi);
+    };
+    auto carve_arena = [&](RrtcArgs& a, int M, size_t n_search) {
+        char* q = arena_p;
+        a.tree_nodes = M;
+        a.path_rows = path_rows_for(M);
+        a.tree_q = (float*)q; q += rr_al(n_search * 2 * 9 * M * sizeof(float));
+        a.parent = (int*)q; q += rr_al(n_search * 2 * M * sizeof(int));
+        a.path_tmp = (float*)q;
+    };
+    auto launch = [&](const RrtcArgs& a) {
+        const size_t n_search = (size_t)a.n_queries * R;
+        const int wpb = RRTC_THREADS / 32;
+        const int grid = (int)((n_search + wpb - 1) / wpb);
+        if (h->scene.carry) pv_rrtc_kernel<true><<<grid, RRTC_THREADS, 0, st>>>(h->scene, a);
+        else pv_rrtc_kernel<false><<<grid, RRTC_THREADS, 0, st>>>(h->scene, a);
+        pv_rrtc_collect_kernel<<<(a.n_queries + 3) / 4, 128, 0, st>>>(a);
+        h->launches += 2;
+    };
+
+    for (int first = 0; first < n; first += chunk_q) {
+        const int nq = n - first < chunk_q ? n - first : chunk_q;
+        RrtcArgs a = base;
+        a.n_queries = nq;
+        a.query_base = (unsigned)params->query_offset + (unsigned)first;
+        a.qmap = nullptr;
+        a.tier1 = two_tier ? 1 : 0;
+        const int par = h->rrtc_parity & 1;
+        h->rrtc_parity ^= 1;
+        a.cursor = ctr + par;
+        a.cursor_next = ctr + (par ^ 1);
+        carve_arena(a, t1_nodes, (size_t)nq * R);
+        memcpy(hm_starts, h_starts + (size_t)first * 9, (size_t)nq * 9 * sizeof(float));
+        memcpy(hm_goals, h_goals + (size_t)first * 9, (size_t)nq * 9 * sizeof(float));
+        if (small) {
+            // zero-copy: the kernels read the queries from, and write the results to, host-mapped pinned memory
+            a.starts = hm_starts;
+            a.goals = hm_goals;
+            meta_ptrs(a, h_meta);
+            a.rows = hm_rows;
+        } else {
+            RR_CUDA(cudaMemcpyAsync(d_starts, hm_starts, (size_t)nq * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+            RR_CUDA(cudaMemcpyAsync(d_goals, hm_goals, (size_t)nq * 9 * sizeof(float), cudaMemcpyHostToDevice, st));
+            a.starts = d_starts;
+            a.goals = d_goals;
+            meta_ptrs(a, d_meta);
+            a.rows = d_rows;
+        }
+        launch(a);
+        RR_CUDA(cudaGetLastError());
+        if (first == 0 && after_first_launch && *after_first_launch) (*after_first_launch)(st);
+        if (!small) RR_CUDA(cudaMemcpyAsync(h_meta, d_meta, b_meta, cudaMemcpyDeviceToHost, st));
+        RR_CUDA(cudaStreamSynchronize(st));
+        RrtcArgs hm;  // host view of the meta block
+        meta_ptrs(hm, h_meta);
+
+        if (two_tier) {
+            int n2 = 0;
+            for (int k = 0; k < nq; ++k)
+                if (hm.q_status[k] == QS_TIER2) h_qmap[n2++] = k;
+            if (n2 > 0) {
+                for (int f2 = 0; f2 < n2; f2 += (int)t2_q) {
+                    const int m2 = n2 - f2 < (int)t2_q ? n2 - f2 : (int)t2_q;
+                    RrtcArgs b = a;
+                    b.n_queries = m2;
+                    b.tier1 = 0;
+                    b.cursor_next = nullptr;  // the same call parity keeps handing out rows behind tier 1's
+                    RR_CUDA(cudaMemcpyAsync(d_qmap, h_qmap + f2, (size_t)m2 * sizeof(int), cudaMemcpyHostToDevice, st));
+                    b.qmap = d_qmap;
+                    carve_arena(b, max_nodes, (size_t)m2 * R);
+                    launch(b);
+                    RR_CUDA(cudaGetLastError());
+                    // d_qmap and the arena are reused by the next sub-chunk
+                    RR_CUDA(cudaStreamSynchronize(st));
+                }
+                if (!small) {
+                    RR_CUDA(cudaMemcpyAsync(h_meta, d_meta, b_meta, cudaMemcpyDeviceToHost, st));
+                    RR_CUDA(cudaStreamSynchronize(st));
+                }
+            }
+        }
+        const float* rows = hm_rows;
+        if (!small) {
+            size_t total = 0;
+            for (int k = 0; k < nq; ++k) {
+                const size_t end = (size_t)hm.q_off[k] + (size_t)hm.q_len[k];
+                if (hm.q_len[k] > 0 && end > total) total = end;
+            }
+            if (total > 0) {
+                rc = rr_reserve_host(h, &h->rrtc_rows_host, &h->rrtc_rows_host_bytes, total * 9 * sizeof(float));
+                if (rc) return rc;
+                RR_CUDA(cudaMemcpyAsync(h->rrtc_rows_host, d_rows, total * 9 * sizeof(float), cudaMemcpyDeviceToHost, st));
+                RR_CUDA(cudaStreamSynchronize(st));
+            }
+            rows = (const float*)h->rrtc_rows_host;
+        }
+        sink(first, nq, hm.q_len, hm.q_off, hm.q_iters, hm.q_checks, rows);
     }
     return PV_OK;
-#undef RR_CUDA
+}
+
+static int rr_check_call(PvHandle* h, int n_queries, const PvRrtcParams* params, bool ptrs_ok) {
+    if (!h || h->magic != PV_HANDLE_MAGIC) return PV_ERR_BAD_HANDLE;
+    if (!h->has_scene) {
+        snprintf(h->err, sizeof(h->err), "no scene set (pv_set_scene)");
+        return PV_ERR_NO_SCENE;
+    }
+    if (n_queries < 0 || !params || (n_queries > 0 && !ptrs_ok)) {
+        snprintf(h->err, sizeof(h->err), "pv_rrtc_batch: bad arguments");
+        return PV_ERR_BAD_ARG;
+    }
+    return PV_OK;
+}
+
+extern "C" int pv_rrtc_batch(PvHandle* h, const float* h_starts, const float* h_goals, int n_queries,
+                             const PvRrtcParams* params, float* h_path_out, int* h_path_len, int* h_iters,
+                             long long* h_checks) {
+    int rc = rr_check_call(h, n_queries, params, h_starts && h_goals && h_path_out && h_path_len);
+    if (rc) return rc;
+    if (n_queries == 0) {
+        RrtcArgs tmp;
+        return pv_rrtc_validate(h, params, &tmp);
+    }
+    const size_t row = (size_t)(params->max_path == 0 ? 128 : params->max_path) * 9;
+    PvDeviceGuard guard(h->device);
+    // only the used rows of each path are written: rows beyond h_path_len[k] of the caller's buffer stay as they were
+    return pv_rrtc_run(h, h_starts, h_goals, n_queries, params,
+                       [&](int first, int nq, const int* len, const int* off, const int* iters, const long long* checks,
+                           const float* rows) {
+                           for (int k = 0; k < nq; ++k) {
+                               h_path_len[first + k] = len[k];
+                               if (h_iters) h_iters[first + k] = iters[k];
+                               if (h_checks) h_checks[first + k] = checks[k];
+                               if (len[k] > 0)
+                                   memcpy(h_path_out + (size_t)(first + k) * row, rows + (size_t)off[k] * 9,
+                                          (size_t)len[k] * 9 * sizeof(float));
+                           }
+                       },
+                       nullptr);
+}
+
+extern "C" int pv_rrtc_batch_packed(PvHandle* h, const float* h_starts, const float* h_goals, int n_queries,
+                                    const PvRrtcParams* params, float* h_states, long long state_capacity,
+                                    long long* h_path_off, int* h_path_len, int* h_iters, long long* h_checks,
+                                    long long* n_states) {
+    int rc = rr_check_call(h, n_queries, params, h_starts && h_goals && h_path_off && h_path_len && (h_states || state_capacity == 0));
+    if (rc) return rc;
+    if (state_capacity < 0) return PV_ERR_BAD_ARG;
+    long long used = 0;
+    bool overflow = false;
+    if (n_queries > 0) {
+        PvDeviceGuard guard(h->device);
+        rc = pv_rrtc_run(h, h_starts, h_goals, n_queries, params,
+                         [&](int first, int nq, const int* len, const int* off, const int* iters, const long long* checks,
+                             const float* rows) {
+                             for (int k = 0; k < nq; ++k) {
+                                 h_path_len[first + k] = len[k];
+                                 h_path_off[first + k] = used;
+                                 if (h_iters) h_iters[first + k] = iters[k];
+                                 if (h_checks) h_checks[first + k] = checks[k];
+                                 if (len[k] > 0) {
+                                     if (used + len[k] <= state_capacity)
+                                         memcpy(h_states + (size_t)used * 9, rows + (size_t)off[k] * 9,
+                                                (size_t)len[k] * 9 * sizeof(float));
+                                     else
+                                         overflow = true;
+                                     used += len[k];
+                                 }
+                             }
+                         },
+                         nullptr);
+        if (rc) return rc;
+    } else {
+        RrtcArgs tmp;
+        rc = pv_rrtc_validate(h, params, &tmp);
+        if (rc) return rc;
+    }
+    if (n_states) *n_states = used;
+    if (overflow) {
+        snprintf(h->err, sizeof(h->err), "pv_rrtc_batch_packed: %lld path states do not fit the capacity of %lld "
+                 "(lengths and offsets are complete; call again with a larger buffer)", used, state_capacity);
+        return PV_ERR_CAPACITY;
+    }
+    return PV_OK;
 }

@@ -41,6 +41,7 @@ class PandaValidity:
             raise PandaValidityError(f"pv_create failed ({rc}): {self.lib.pv_last_error(None).decode()}")
         self.device = torch.device("cuda", int(device))
         self.scene: Optional[SceneSnapshot] = None
+        self._scene_key = None
         self.attached = -1
         self.carried = None
         self.flags = FLAG_SELF
@@ -61,10 +62,9 @@ class PandaValidity:
         if rc != 0:
             raise PandaValidityError(f"{what} failed ({rc}): {self.lib.pv_last_error(self._h).decode()}")
 
-    @staticmethod
-    def _stream(stream) -> C.c_void_p:
+    def _stream(self, stream) -> C.c_void_p:
         if stream is None:
-            stream = torch.cuda.current_stream()
+            stream = torch.cuda.current_stream(self.device)  # the handle's device, whatever torch's current one is
         return C.c_void_p(stream.cuda_stream)
 
     @property
@@ -74,9 +74,14 @@ class PandaValidity:
     # -- configuration --------------------------------------------------------------------------------
     def set_scene(self, scene: SceneSnapshot):
         obb = np.ascontiguousarray(scene.obb, dtype=np.float32).reshape(-1, 16)
-        base = (C.c_float * 3)(*[float(v) for v in scene.base])
-        self._ck(self.lib.pv_set_scene(self._h, obb.ctypes.data_as(C.POINTER(C.c_float)), obb.shape[0],
-                                       float(scene.table_z), base), "pv_set_scene")
+        # plan_path snapshots the scene on every call (planning.py reads the live poses each time); the handle only
+        # re-derives its tables (reach masks, scene bounds) when the bytes differ from what it already holds
+        key = (obb.tobytes(), float(scene.table_z), tuple(float(v) for v in scene.base))
+        if key != self._scene_key:
+            base = (C.c_float * 3)(*key[2])
+            self._ck(self.lib.pv_set_scene(self._h, obb.ctypes.data_as(C.POINTER(C.c_float)), obb.shape[0],
+                                           key[1], base), "pv_set_scene")
+            self._scene_key = key
         self._ck(self.lib.pv_set_attached(self._h, -1), "pv_set_attached")  # a new snapshot starts with nothing held
         self.scene = scene
         self.attached = -1
@@ -115,6 +120,8 @@ class PandaValidity:
         return self.carried
 
     def set_flags(self, self_collision: bool = True, joint_limits: bool = False):
+        """`joint_limits` is kept for compatibility and changes nothing: a state outside the joint limits is always
+        invalid (the pruned self-collision model is certified inside the limits only, see include/panda_validity.h)."""
         self.flags = (FLAG_SELF if self_collision else 0) | (FLAG_LIMITS if joint_limits else 0)
         self._ck(self.lib.pv_set_flags(self._h, self.flags), "pv_set_flags")
 
@@ -258,10 +265,13 @@ class PandaValidity:
     def rrtc_batch(self, starts: np.ndarray, goals: np.ndarray, max_iters: int = 2000, max_nodes: int = 2048,
                    max_path: int = 128, seed: int = 1, replicas: int = 1, shortcut_passes: int = 2,
                    rrt_range: float = 0.0, resolution: float = 0.0, check_endpoints: bool = False,
-                   planner: str = "RRTConnect", query_offset: int = 0):
-        """Batched multi-query planning, one launch.  `query_offset` = id of starts[0] in the caller's whole batch: the
-        random streams are keyed by global query id, so shards of a batch (other calls, other GPUs) return exactly the
-        rows the unsplit call returns."""
+                   planner: str = "RRTConnect", query_offset: int = 0, packed: bool = False):
+        """Batched multi-query planning.  `query_offset` = id of starts[0] in the caller's whole batch: the random
+        streams are keyed by global query id, so shards of a batch (other calls, other GPUs) return exactly the rows
+        the unsplit call returns -- for any `replicas` (the winner of a query is the search with the smallest
+        (iterations, replica id), not the first to finish).
+        Returns (paths (n, max_path, 9), lengths, iters, checks); packed=True returns (states (sum(lengths), 9),
+        offsets, lengths, iters, checks) instead -- the form that scales to 10^6 queries."""
         starts = np.ascontiguousarray(starts, dtype=np.float32).reshape(-1, 9)
         goals = np.ascontiguousarray(goals, dtype=np.float32).reshape(-1, 9)
         nq = starts.shape[0]
@@ -270,14 +280,63 @@ class PandaValidity:
         prm = _cabi.PvRrtcParams(float(rrt_range), float(resolution), int(max_iters), int(max_nodes), int(max_path),
                                  int(seed) & 0xFFFFFFFF, int(replicas), int(shortcut_passes), 1 if check_endpoints else 0,
                                  {"RRTConnect": 0, "RRT": 1}[planner], int(query_offset))
-        paths = np.zeros((nq, max_path, 9), dtype=np.float32)
         plen = np.zeros(nq, dtype=np.int32)
         iters = np.zeros(nq, dtype=np.int32)
         checks = np.zeros(nq, dtype=np.int64)
+        if packed:
+            off = np.zeros(nq, dtype=np.int64)
+            total = C.c_longlong(0)
+            cap = max(4 * nq, 64)  # typical paths hold 2..4 states; grow once if this batch needs more
+            while True:
+                states = np.empty((cap, 9), dtype=np.float32)
+                rc = self.lib.pv_rrtc_batch_packed(self._h, starts.ctypes.data, goals.ctypes.data, nq, C.byref(prm),
+                                                   states.ctypes.data, cap, off.ctypes.data, plen.ctypes.data,
+                                                   iters.ctypes.data, checks.ctypes.data, C.byref(total))
+                if rc == _cabi.PV_ERR_CAPACITY and total.value > cap:
+                    cap = int(total.value)
+                    continue
+                self._ck(rc, "pv_rrtc_batch_packed")
+                return states[: total.value], off, plen, iters, checks
+        if max_path < 2:
+            raise PandaValidityError("max_path must be at least 2")
+        paths = np.zeros((nq, max_path, 9), dtype=np.float32)
         self._ck(self.lib.pv_rrtc_batch(self._h, starts.ctypes.data, goals.ctypes.data, nq, C.byref(prm),
                                         paths.ctypes.data, plen.ctypes.data, iters.ctypes.data, checks.ctypes.data),
                  "pv_rrtc_batch")
         return paths, plen, iters, checks
+
+    def plan_path(self, start, goal, num_waypoints: int = 100, smooth: bool = True, planner: str = "RRTConnect",
+                  seed: int = 1, replicas: int = 32, max_iters: int = 2000, max_nodes: int = 2048, validate: bool = True,
+                  max_attempts: int = 4, timeout: float = 5.0, rrt_range: float = 0.0, resolution: float = 0.0):
+        """The whole of planning.py:59-207 in one C call (pv_plan_path): intake check, solve, simplifySolution,
+        interpolate, dense validation with fallback / re-planning.  start, goal: 9 joint values (kept in fp64).
+        Returns (waypoints (n, 9) float32 -- n = 0 when no path was found --, stats dict)."""
+        qs = np.ascontiguousarray(start, dtype=np.float64).reshape(9)
+        qg = np.ascontiguousarray(goal, dtype=np.float64).reshape(9)
+        prm = _cabi.PvPlanParams(float(rrt_range), float(resolution), int(max_iters), int(max_nodes),
+                                 int(seed) & 0xFFFFFFFF, int(replicas), 1 if smooth else 0,
+                                 {"RRTConnect": 0, "RRT": 1}[planner], 1 if validate else 0, int(max_attempts),
+                                 float(timeout))
+        cap = max(int(num_waypoints) if num_waypoints else 0, 256)
+        out = np.empty((cap, 9), dtype=np.float32)
+        n = C.c_int(0)
+        st = _cabi.PvPlanStats()
+        self._ck(self.lib.pv_plan_path(self._h, qs.ctypes.data, qg.ctypes.data, int(num_waypoints or 0), C.byref(prm),
+                                       out.ctypes.data, cap, C.byref(n), C.byref(st)), "pv_plan_path")
+        return out[: n.value], st.as_dict()
+
+    def simplify_path(self, path: np.ndarray, seed: int = 1, resolution: float = 0.0, capacity: int = 256) -> np.ndarray:
+        """ss.simplifySolution() (planning.py:196) on a vertex list (n, 9): the simplifier of pv_plan_path on its own."""
+        pts = np.ascontiguousarray(np.asarray(path, dtype=np.float64).reshape(-1, 9))
+        out = np.empty((capacity, 9), dtype=np.float64)
+        n = C.c_int(0)
+        counters = (C.c_int * 4)()
+        self._ck(self.lib.pv_simplify_path(self._h, pts.ctypes.data, pts.shape[0], int(seed) & 0xFFFFFFFF,
+                                           float(resolution), out.ctypes.data, capacity, C.byref(n), counters),
+                 "pv_simplify_path")
+        self.last_simplify_counters = dict(zip(("partial_rounds", "bspline_steps", "reduce_rounds", "motions"),
+                                               [int(c) for c in counters]))
+        return out[: n.value].copy()
 
     def ik_batch(self, pos: np.ndarray, quat: np.ndarray, q_init: Sequence[float], n_seeds: int = 128,
                  max_iters: int = 64, pos_tol: float = 1e-4, rot_tol: float = 1e-3, seed: int = 1):

@@ -112,19 +112,55 @@ def test_state_margins_and_culprits(pv, c64):
 
 
 def test_flags_self_and_limits(pv, c64):
+    """Self-collision can be switched off; joint limits cannot (they are part of the model's validity domain: the
+    pruned self-pair lists are certified inside them only), so PV_FLAG_LIMITS changes nothing."""
     from oracle.c_oracle import FLAG_LIMITS, FLAG_SELF
     scene = sc.goal1_scattered()
     pv.set_scene(scene)
     q = random_configs(60_000, 31, fingers="random")
     q[::7, 3] += 3.2  # push joint 4 out of its limits on every 7th config
     q[::11, 8] = 0.0405
-    for self_on, lim_on in [(False, False), (True, True), (False, True)]:
+    outside = ~((q >= pm.Q_LOWER.astype(np.float32)) & (q <= pm.Q_UPPER.astype(np.float32))).all(axis=1)
+    assert outside.sum() > 10_000
+    for self_on, lim_on in [(False, False), (True, True), (False, True), (True, False)]:
         pv.set_flags(self_on, lim_on)
         gpu = unpack_bits(pv.check_states(_dev(q)), len(q))
+        assert not gpu[outside].any()
         fl = (FLAG_SELF if self_on else 0) | (FLAG_LIMITS if lim_on else 0)
         margin = c64.state_margin(q.astype(np.float64), scene.as_oracle_scene(), flags=fl)
         _assert_verdicts(gpu, margin, f"flags {self_on} {lim_on}")
     pv.set_flags(True, False)
+
+
+def test_out_of_limit_states_never_pass_through_a_pruned_pair(pv, model):
+    """the never-collide certificate that prunes 293 of the 425 self pairs holds inside the joint
+    limits only.  Configurations with arm joints beyond the limits that self-collide through a PRUNED pair (found with
+    the unpruned lists of the numpy oracle, limits rule bypassed) must not be reported valid -- by any entry point."""
+    from oracle import panda_oracle as po
+    rng = np.random.default_rng(77)
+    n = 40_000
+    q = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n, 9))
+    j = rng.integers(0, 7, n)
+    over = rng.uniform(0.02, 1.2, n) * rng.choice([-1.0, 1.0], n)
+    q[np.arange(n), j] = np.where(over > 0, pm.Q_UPPER[j] + over, pm.Q_LOWER[j] + over)
+    q = q.astype(np.float32)
+    empty = sc.SceneSnapshot(obb=np.zeros((0, 16), np.float32))
+    pv.set_scene(empty)
+    pv.set_flags(True, False)
+    # geometry-only margins with the pruned and the unpruned pair lists (limits rule bypassed by widening them)
+    wide = dict(model, q_lower=np.full(9, -1e3), q_upper=np.full(9, 1e3))
+    unpruned = dict(wide, ss_pairs=pm.SS_PAIRS_UNPRUNED, sb_pairs=pm.SB_PAIRS_UNPRUNED)
+    m_pruned = po.state_margin(q.astype(np.float64), empty.as_oracle_scene(), wide)
+    m_unpruned = po.state_margin(q.astype(np.float64), empty.as_oracle_scene(), unpruned)
+    leak = (m_pruned > 1e-4) & (m_unpruned < -1e-4)  # collides ONLY through pruned pairs
+    assert leak.sum() > 20, "the sample must contain states that the pruned lists alone would wave through"
+    gpu = unpack_bits(pv.check_states(_dev(q)), n)
+    assert not gpu.any()
+    assert not unpack_bits(pv.check_states_host(q[leak]), int(leak.sum())).any()
+    m = pv.state_margins(_dev(q[leak])).cpu().numpy()
+    assert (m < 0).all()
+    qa = np.clip(q[leak], pm.Q_LOWER, pm.Q_UPPER).astype(np.float32)
+    assert not unpack_bits(pv.check_edges_host(qa, q[leak], n_steps=0), int(leak.sum())).any()
 
 
 def test_state_kernel_variants_are_bit_identical(pv):
