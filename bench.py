@@ -1,26 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- Panda state-validity throughput on B200 (BASELINE.json metric), one JSON line on stdout.
 
-Workload (BASELINE.json configs[1]): batches of 1 048 576 uniformly random Panda configurations
-(q1..q7 ~ U(limits), fingers open at 0.04) checked against the goal-1 scattered-block scene; one "step" =
-one pass of the state-validity hot path over one batch.  Inputs rotate over N_ROT distinct batches whose
-total size exceeds L2, so no step re-reads a cached batch.
+Headline workload (BASELINE.json configs[1]): batches of 1 048 576 uniformly random Panda configurations
+(q1..q7 ~ U(limits), fingers open at 0.04) checked against the goal-1 scattered-block scene.  One "step" = one pass
+of the state-validity hot path over PASSES x N_ROT such batches (48 launches, 50 331 648 configurations per GPU): the
+timed region is then tens of milliseconds whatever --steps is, so launch skew, NVML sampling and the inter-rank
+barrier are noise instead of the measurement.  The N_ROT distinct batches total 256 MiB > L2, so no launch
+re-reads a cached batch.
 
-  value     device-resident throughput: inputs already in HBM as SoA float4 planes, CUDA-event timed
-  e2e       the same metric through the reference-facing C-ABI call pv_check_states_host: AoS host rows
-            in pinned memory -> H2D -> kernel -> D2H verdict bits, every step, wall-clock around the call
-  roofline  FP32 CUDA-core roofline of the dominant kernel (pv_state_bits_sorted_kernel), plus the HBM fraction
+  value     device-resident throughput: inputs already in HBM as SoA float4 planes, CUDA-event timed, MAX over ranks.
+            N > 1: every rank checks its own batches (weak scaling) and every verdict word is stored on EVERY rank from
+            inside the kernel (NVSwitch multicast / peer stores); each step ends with the symmetric-memory barrier after
+            which the whole step's mask is consumable on every rank (`value_basis`), and the fire-and-forget figure
+            (one barrier at the very end) is reported next to it.
+  e2e       the same metric through the reference-facing C-ABI call pv_check_states_host: AoS host rows in pinned
+            memory -> H2D -> kernel -> D2H verdict bits, every step, wall-clock around the call
+  roofline  of the dominant kernel (pv_state_bits_sorted_kernel): issue-slot / executed-FP32 / HBM fractions from ncu
+            counts tied to the source hash of the kernels (`executed_counts_stale` when they no longer match)
   cpu_baseline  the CPU oracle port (fp32, OpenMP) on a bounded sample, timed on this box's host cores
-
-N > 1 (torchrun): every rank checks its own batches (weak scaling; config 5 flavour) and the verdict
-words are all-gathered over NCCL inside the timed step.
+  edges / rrtc / sweep / plan   BASELINE configs 3, 4, 5 and 1 as sub-records (full sizes, CUDA-event / wall timings)
 
 --impl reference times the reference's CPU path stand-in: Genesis/OMPL are not installable, so this is
-the oracle port (kind "port"), all host threads, bounded sample per step.
+the oracle port (kind "port"), all host threads, one 1 048 576-configuration batch per step.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -32,12 +38,27 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_CONFIGS = 1 << 20
+N_CONFIGS = 1 << 20            # one batch = BASELINE config 2
 N_ROT = 8                      # 8 batches x 32 MiB (SoA planes) = 256 MiB > 126 MB L2
+PASSES = 6                     # passes over the rotating batches per step
 SCENE = "goal1_scattered"
 SEED = 20251212
 METRIC = "panda_state_validity_checks_per_sec"
 UNIT = "checks/s"
+N_EDGES = 10_485_760           # BASELINE config 3
+N_QUERIES = 4096               # BASELINE config 4
+N_SWEEP = 104_857_600          # BASELINE config 5
+
+
+def workload_config():
+    """The `config` object both arms print: what is measured, not how."""
+    return {
+        "workload": f"batches of {N_CONFIGS} uniformly random Panda configurations (q1..q7 ~ U(joint limits), fingers open), "
+                    f"state validity vs the {SCENE} scene (6 OBBs + table, self-collision on); BASELINE.json configs[1]",
+        "scene": SCENE, "configs_per_batch": N_CONFIGS, "seed": SEED,
+        "l2": f"GPU arm: inputs rotate over {N_ROT} distinct batches ({N_ROT * N_CONFIGS * 32 >> 20} MiB of SoA planes > "
+              "126 MB L2), no flush needed; CPU arm: not applicable",
+    }
 
 
 def make_batch(seed: int, n: int) -> np.ndarray:
@@ -48,13 +69,24 @@ def make_batch(seed: int, n: int) -> np.ndarray:
     return q
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+def source_hash() -> str:
+    """Hash of everything the kernels are compiled from: ties committed ncu counts to the code they were taken on."""
+    from rbe550_final_project_b200 import _cabi, panda_model
+    h = hashlib.sha256()
+    for f in sorted(_cabi.SOURCES + ["pv_device.cuh", "pv_handle.h"]):
+        h.update(open(os.path.join(_cabi.CSRC, f), "rb").read())
+    h.update(panda_model.header_text().encode())
+    h.update(" ".join(_cabi.NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
 
-    def __init__(self, index: int, period: float = 0.01):
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML; started BEFORE the pre-timing barrier."""
+
+    def __init__(self, index: int, period: float = 0.005):
         super().__init__(daemon=True)
         self.index, self.period = index, period
-        self.samples, self.reasons = [], set()
+        self.samples, self.stamps, self.reasons = [], [], set()
         self.max_mhz = None
         self._stop_evt = threading.Event()
         try:
@@ -78,62 +110,90 @@ class ClockSampler(threading.Thread):
         }
         while not self._stop_evt.is_set():
             try:
-                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
+                self.samples.append((time.perf_counter(), mhz, r))
             except Exception:
                 pass
             time.sleep(self.period)
 
-    def stop(self):
+    def stop(self, t0: float, t1: float):
         self._stop_evt.set()
         self.join(timeout=2)
-        med = int(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        names = {}
+        if self.nv is not None:
+            nv = self.nv
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        inside = [(m, r) for (t, m, r) in self.samples if t0 <= t <= t1]
+        use = inside if inside else [(m, r) for (_, m, r) in self.samples]
+        reasons = set()
+        for _, r in use:
+            for bit, nm in names.items():
+                if r & bit:
+                    reasons.add(nm)
+        med = int(np.median([m for m, _ in use])) if use else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(self.samples),
+                "samples_in_timed_region": len(inside)}
 
 
-def cpu_port_rate(n_sample: int, threads: int, repeats: int = 1):
-    """checks/s of the CPU oracle port (fp32) on `n_sample` configs of the bench workload."""
-    from oracle.c_oracle import COracle
-    from rbe550_final_project_b200 import panda_model as pm, scenes as sc
-    ora = COracle(pm.model_arrays(), "f32")
-    scene = sc.FIXTURES[SCENE]().as_oracle_scene()
-    q = make_batch(SEED, n_sample)
-    ora.state_margin(q[: min(4096, n_sample)], scene, nthreads=threads)  # warm-up
-    best = 0.0
-    for _ in range(repeats):
+# ---- CPU oracle port (the reference arm's stand-in and the cpu_baseline leg) -----------------------------------------
+class CpuPort:
+    def __init__(self):
+        from oracle.c_oracle import COracle
+        from rbe550_final_project_b200 import panda_model as pm, scenes as sc
+        self.ora = COracle(pm.model_arrays(), "f32")
+        self.scene = sc.FIXTURES[SCENE]().as_oracle_scene()
+
+    def run(self, q, threads):
         t = time.perf_counter()
-        ora.state_margin(q, scene, nthreads=threads)
-        best = max(best, n_sample / (time.perf_counter() - t))
-    return best
+        m = self.ora.state_margin(q, self.scene, nthreads=threads)
+        return time.perf_counter() - t, m
 
 
 def run_reference(args):
+    """The reference's CPU path stand-in on the SAME workload: one step = one 1 048 576-configuration batch of the bench
+    distribution on all host threads (value = configs of the timed steps / their wall time); >= 3 warm-up steps; the
+    best of the timed steps and a single-thread figure are reported next to it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = 1 << 17
-    for _ in range(args.warmup):
-        cpu_port_rate(per_step // 8, cores)
-    t = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_port_rate(per_step, cores)
-    dt = time.perf_counter() - t
-    # cpu_port_rate includes a small warm-up call; time the pure rate once more for the reported value
-    rate = cpu_port_rate(per_step * 4, cores)
+    port = CpuPort()
+    batches = [make_batch(SEED + r, N_CONFIGS) for r in range(2)]
+    for i in range(max(args.warmup, 3)):
+        port.run(batches[i % 2][: N_CONFIGS // 4], cores)
+    # bounded: the whole run stays within a few minutes whatever --steps is (the step size is stated in the line)
+    probe, _ = port.run(batches[0][: N_CONFIGS // 8], cores)
+    est_step = probe * 8
+    per_step = N_CONFIGS
+    while args.steps * est_step * (per_step / N_CONFIGS) > 150.0 and per_step > (1 << 14):
+        per_step //= 2
+    times = []
+    valid = 0
+    for i in range(args.steps):
+        dt, m = port.run(batches[i % 2][:per_step], cores)
+        times.append(dt)
+        if i == 0:
+            valid = int((m >= 0).sum())
+    total = float(sum(times))
+    rate = per_step * args.steps / total
+    best = per_step / min(times)
+    t1, _ = port.run(batches[0][: 1 << 15], 1)
+    single = (1 << 15) / t1
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True,
+        "warmup": max(args.warmup, 3), "ms_per_step": total / max(args.steps, 1) * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{per_step} random Panda configs per step vs {SCENE} scene (CPU oracle port; "
-                               "Genesis/OMPL not installable)", "scene": SCENE},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{per_step * 4} configs, fp32 C oracle, OpenMP {cores} threads"},
+        "config": workload_config(),
+        "step_detail": {"configs_per_step": per_step, "what": "one batch (or a prefix of it, when --steps would make the run "
+                        "exceed ~150 s) through the CPU oracle port; Genesis/OMPL are not installable here"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "best_step": best, "single_thread": single,
+                         "sample": f"{per_step} configs per step x {args.steps} steps, fp32 C oracle, OpenMP {cores} threads"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "valid_fraction_first_step": valid / per_step,
     }
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
@@ -141,17 +201,32 @@ def run_reference(args):
 _JSON_OUT = sys.stdout
 
 
+def ev_ms(torch, fn, iters=1, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-plan", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config 3 / 4 / 5 sub-records")
     ap.add_argument("--nccl-gather", action="store_true", help="N>1: gather verdict words with NCCL instead of the fused peer-memory path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.steps = max(args.steps, 1)
     # stdout carries exactly ONE line, the JSON: libraries that write to file descriptor 1 behind Python's back (NCCL
     # prints its version banner there) are sent to stderr; the JSON goes to the saved descriptor.
     global _JSON_OUT
@@ -182,107 +257,114 @@ def main():
     pv.set_flags(True, False)
     n = N_CONFIGS
     words = n // 32
+    L = PASSES * N_ROT                 # launches per step
+    step_words = L * words             # verdict words one rank produces per step
 
     # device-resident inputs (SoA float4 planes), distinct per rank and per rotation slot
     host_batches = [make_batch(SEED + 1000 * rank + r, n) for r in range(N_ROT)]
     # two float4 planes per config (q1..q4 | q5..q8); the gripper is symmetric in this workload (q9 = q8), so no
     # third plane is read: 32 B in + 1 bit out per check
     planes = [soa_from_aos(torch.as_tensor(b, device="cuda"))[:2] for b in host_batches]
-    bits2 = [torch.empty(words, dtype=torch.int32, device="cuda") for _ in range(2)]
-    bits = bits2[0]
-    gathered = [torch.empty(words * world, dtype=torch.int32, device="cuda") for _ in range(2)] if world > 1 else None
-    pending = [None, None]
+    local_bits = torch.empty(step_words, dtype=torch.int32, device="cuda")   # this rank's words of the current step
 
-    # N > 1: the verdict words of every step are gathered on every rank.  Preferred: fused into the validity kernel
-    # over NVLink peer memory / NVSwitch multicast (FusedVerdictGather); fallback: NCCL all-gather, double-buffered.
+    # N > 1: the verdict words of every launch are stored on every rank from inside the kernel (FusedVerdictGather),
+    # double-buffered by step so that a consumer can read step i while step i + 1 is being written
     fused = None
     gather_mode = "none"
     if world > 1 and not args.nccl_gather:
         try:
             from rbe550_final_project_b200.distributed import FusedVerdictGather
-            fused = FusedVerdictGather(pv, words)
-            gather_mode = "fused_peer_stores_multicast" if fused.multicast else "fused_peer_stores"
+            fused = [FusedVerdictGather(pv, step_words) for _ in range(2)]
+            gather_mode = "fused_peer_stores_multicast" if fused[0].multicast else "fused_peer_stores"
         except Exception as exc:  # symmetric memory not available: keep going with NCCL
             print(f"[bench] fused gather unavailable ({exc!r}); using NCCL all-gather", file=sys.stderr)
             fused = None
+    nccl_full = None
     if world > 1 and fused is None:
-        gather_mode = "nccl_allgather_overlapped"
+        gather_mode = "nccl_allgather_per_step"
+        nccl_full = [torch.empty(step_words * world, dtype=torch.int32, device="cuda") for _ in range(2)]
 
-    def step(i):
-        if fused is not None:
-            pv.check_states(planes[i % N_ROT], out=bits2[i & 1])  # the kernel also stores the words on every rank
-            return
-        # double-buffered: the NCCL all-gather of step i's verdict words overlaps step i+1's kernel
-        k = i & 1
-        if pending[k] is not None:
-            pending[k].wait()
-            pending[k] = None
-        pv.check_states(planes[i % N_ROT], out=bits2[k])
-        if world > 1:
-            pending[k] = dist.all_gather_into_tensor(gathered[k], bits2[k], async_op=True)
-
-    def drain():
-        if fused is not None:
-            fused.finish()  # symmetric-memory barrier: every rank's words of every issued step have landed
-            return
-        for k in range(2):
-            if pending[k] is not None:
-                pending[k].wait()
-                pending[k] = None
+    def step(i, consume=True):
+        """One step: L launches; N > 1: the step's whole mask is on every rank when it returns (consume=True)."""
+        g = fused[i & 1] if fused is not None else None
+        for j in range(L):
+            if g is not None:
+                g.activate(word_offset=j * words)
+            pv.check_states(planes[j % N_ROT], out=local_bits[j * words:(j + 1) * words])
+        if g is not None:
+            if consume:
+                g.finish()      # symmetric-memory barrier (device side, on this stream): all ranks' words have landed
+        elif world > 1:
+            dist.all_gather_into_tensor(nccl_full[i & 1], local_bits)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(n_steps, consume=True):
+        """CUDA-event time of n_steps steps on this rank, started behind a device-side inter-rank barrier."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if fused is not None:
+            fused[0].hdl.barrier()  # device-side: every rank's stream passes this point together
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(n_steps):
+            step(i, consume)
+        if fused is not None and not consume:
+            fused[0].finish()
+        e1.record()
+        barrier()
+        t1 = time.perf_counter()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, t0, t1
+
     fp32_peak_tflops, _ = pv.fp32_peak(8192)
+    sampler = ClockSampler(local)
+    sampler.start()                      # NVML is up and polling before any rank reaches the pre-timing barrier
     for i in range(args.warmup):
         step(i)
-    drain()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = pv.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    drain()
-    e1.record()
-    barrier()
-    if fused is not None:
-        # the gathered mask on this rank holds this rank's own last-step words in its slot (the other slots are
-        # checked against an NCCL gather by tools/multi_gpu_sweep.py)
-        assert torch.equal(fused.buf[rank * words:(rank + 1) * words], bits2[(args.steps - 1) & 1]), \
-            "fused gather: own slot differs from the local verdict words"
+    ms, t0, t1 = timed(args.steps, consume=True)
     launches = pv.launch_count - launches0
-    ms = e0.elapsed_time(e1)
-    clocks_in_region = len(sampler.samples)
-    if clocks_in_region < 5:
-        # a short timed region (few steps) ends before NVML can be polled a few times: keep the same kernel running
-        # a little longer so the sampler still sees the loaded clock state; the number of in-region samples is reported
-        t_end = time.perf_counter() + 0.25
-        while time.perf_counter() < t_end:
-            pv.check_states(planes[0], out=bits2[0])
-        torch.cuda.synchronize()
-    clocks = sampler.stop()
-    clocks["samples_in_timed_region"] = clocks_in_region
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    clocks = sampler.stop(t0, t1)
     ms_per_step = ms / args.steps
-    value = world * n / (ms_per_step * 1e-3)
-    n_valid = int(np.unpackbits(bits[:1024].cpu().numpy().view(np.uint8)).sum())
+    value = world * L * n / (ms_per_step * 1e-3)
+
+    # ---- N > 1: the mask every rank holds after the last step == an NCCL all-gather of the ranks' own words --------
+    gather_verified = None
+    unsync = None
+    if world > 1:
+        last = (args.steps - 1) & 1
+        ref = torch.empty(step_words * world, dtype=torch.int32, device="cuda")
+        dist.all_gather_into_tensor(ref, local_bits)
+        got = fused[last].buf if fused is not None else nccl_full[last]
+        same = torch.equal(got[: step_words * world], ref)
+        flag = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_verified = bool(flag.item())
+        assert gather_verified, "the gathered verdict mask differs from an NCCL all-gather of the ranks' local words"
+        if fused is not None:
+            ms_u, _, _ = timed(args.steps, consume=False)
+            unsync = {"value": world * L * n / (ms_u / args.steps * 1e-3), "ms_per_step": ms_u / args.steps,
+                      "what": "same steps with ONE barrier at the very end (no per-step consumer)"}
+    n_valid = int(np.unpackbits(local_bits[:1024].cpu().numpy().view(np.uint8)).sum())
 
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------------------
+    for g in (fused or []):
+        g.deactivate()
     pinned = [torch.from_numpy(b).pin_memory() for b in host_batches[:4]]
     out_host = torch.empty(words, dtype=torch.int32).pin_memory()
     out_np = out_host.numpy().view(np.uint32)
     for i in range(3):
         pv.check_states_host(pinned[i % 4].numpy(), out=out_np)
     barrier()
-    e2e_steps = max(min(args.steps // 2, 400), 5)
+    e2e_steps = 40
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         pv.check_states_host(pinned[i % 4].numpy(), out=out_np)
@@ -294,144 +376,324 @@ def main():
     e2e_value = world * n * e2e_steps / e2e_s
     assert np.array_equal(out_np, pv.check_states(planes[(e2e_steps - 1) % 4]).cpu().numpy().view(np.uint32))
 
-    if fused is not None:
-        fused.close()
+    # ---- BASELINE config 5 (all N): 104 857 600-config sweep, sharded, verdict words gathered on every rank ------------
+    sub = {}
+    if not args.no_configs:
+        sub["sweep"] = bench_sweep(torch, dist, pv, rank, world, args.nccl_gather)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---- roofline ---------------------------------------------------------------------------------------------
+    per_gpu_rate = L * n / (ms_per_step * 1e-3)
     flops_per_check = pm.flops_per_state_check(snap.n_obb)
-    per_gpu_rate = n / (ms_per_step * 1e-3)
-    achieved_tflops = flops_per_check * per_gpu_rate / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    executed = None
+    counts = {}
     try:
-        executed = json.load(open(os.path.join(ROOT, "profiles", "executed_flops.json")))
+        counts = json.load(open(os.path.join(ROOT, "profiles", "executed_counts.json")))
     except Exception:
         pass
+    src = source_hash()
+    state_counts = counts.get("state", {})
+    stale = counts.get("source_hash") != src
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     bytes_per_check = 32.0 + 1.0 / 8.0
     hbm_achieved = bytes_per_check * per_gpu_rate / 1e9
-    executed = None
-    try:
-        executed = json.load(open(os.path.join(ROOT, "profiles", "executed_flops.json")))
-    except Exception:
-        pass
-    algorithmic_tflops = achieved_tflops
-    if executed and executed.get("fp32_flops_per_check"):
-        # achieved = FP32 FLOPs the kernel really executes per check (ncu thread-level FFMA*2 + FADD + FMUL counts of the
-        # same kernel on the same workload, committed under profiles/) x the rate measured live in this run
-        achieved_tflops = float(executed["fp32_flops_per_check"]) * per_gpu_rate / 1e12
+    mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
+    peak_issue = 148 * 4 * mhz * 1e6
     roofline = {
-        "bound": "fp32", "kernel": "pv_state_bits_sorted_kernel", "achieved": achieved_tflops, "peak": fp32_peak_tflops,
-        "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak_tflops,
-        "achieved_definition": ("executed FP32 FLOPs/check from profiles/executed_flops.json x live checks/s"
-                                if executed and executed.get("fp32_flops_per_check") else
-                                "algorithmic brute-force FLOPs/check x live checks/s"),
-        "algorithmic_bruteforce_equiv_tflops": algorithmic_tflops,
-        "peak_source": "measured in this run by pv_fp32_peak (unrolled independent FFMA); MEASURED_PEAKS.json has no FP32 entry",
-        "flops_per_check": flops_per_check,
-        "flops_model": "algorithmic no-early-exit count of SURVEY.md 8d: F_fk + S(F_place + B F_sb + F_plane) + "
-                       "H(F_place + B F_bb + 8 F_plane) + P F_ss + P2 F_sb, S=%d H=%d P=%d P2=%d B=%d" % (
-                           pm.N_SPHERES, pm.N_BOXES, pm.N_SS_PAIRS, pm.N_SB_PAIRS, snap.n_obb),
-        "traffic": (executed or {}).get("dram_bytes_per_launch"),
+        "bound": "warp-instruction issue (FP32 CUDA-core kernel: no dense contraction, HBM at a few % of peak)",
+        "kernel": "pv_state_bits_sorted_kernel", "unit": "warp-inst/s", "peak": peak_issue,
+        "peak_source": f"148 SMs x 4 schedulers x {mhz} MHz (SM clock sampled during the timed region)",
+        "executed_counts_stale": bool(stale), "source_hash": src, "counts_source_hash": counts.get("source_hash"),
+        "algorithmic_flops_per_check": flops_per_check,
+        "algorithmic_bruteforce_equiv_tflops": flops_per_check * per_gpu_rate / 1e12,
+        "fp32_peak_tflops_measured": fp32_peak_tflops,
+        "traffic": state_counts.get("dram_bytes_per_launch"),
         "hbm": {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                 "bytes_per_check": bytes_per_check,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"},
     }
-    if executed:
-        roofline["executed"] = executed
-        if executed.get("warp_inst_per_32_checks"):
-            # the binding limit of this kernel is instruction issue (ncu: issue-active ~62 %), not FLOPs or HBM:
-            # 4 schedulers/SM x 1 warp-instruction/cycle at the SM clock sampled during the run
-            mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965
-            peak_issue = 148 * 4 * mhz * 1e6
-            rate = executed["warp_inst_per_32_checks"] * per_gpu_rate / 32.0
-            roofline["issue"] = {"bound": "warp-instruction issue", "achieved": rate, "peak": peak_issue,
-                                 "unit": "warp-inst/s", "frac": rate / peak_issue,
-                                 "lane_utilisation": executed["thread_inst_per_check"] * 32.0 / (32.0 * executed["warp_inst_per_32_checks"])}
+    if state_counts.get("warp_inst_per_32_checks"):
+        rate = state_counts["warp_inst_per_32_checks"] * per_gpu_rate / 32.0
+        roofline.update({"achieved": rate, "frac": rate / peak_issue,
+                         "achieved_definition": "warp instructions per 32 checks (ncu smsp__inst_executed.sum of this kernel "
+                                                "on this workload, profiles/executed_counts.json) x live checks/s / 32",
+                         "lane_utilisation": state_counts["thread_inst_per_check"] / state_counts["warp_inst_per_32_checks"],
+                         "fp32": {"achieved": state_counts["fp32_flops_per_check"] * per_gpu_rate / 1e12,
+                                  "peak": fp32_peak_tflops, "unit": "TFLOP/s",
+                                  "frac": state_counts["fp32_flops_per_check"] * per_gpu_rate / 1e12 / fp32_peak_tflops,
+                                  "definition": "executed FFMA x2 + FADD + FMUL per check (ncu) x live checks/s; peak = "
+                                                "pv_fp32_peak measured in this run"},
+                         "counts": state_counts})
+    else:
+        roofline.update({"achieved": None, "frac": None})
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{n} random Panda configs per GPU per step, state validity vs {SCENE} scene "
-                               f"({snap.n_obb} OBBs + table, self-collision on)", "scene": SCENE, "configs_per_step": n * world,
-                   "l2": f"inputs rotate over {N_ROT} distinct batches ({N_ROT * n * 32 >> 20} MiB > L2)",
-                   "layout": "SoA float4 x2", "parallelism": f"shard{world}" + (f"+{gather_mode}" if world > 1 else "")},
+        "config": workload_config(),
+        "step_detail": {"launches_per_step": L, "configs_per_step": L * n * world, "configs_per_gpu_per_step": L * n,
+                        "layout": "SoA float4 x2", "parallelism": f"shard{world}" + (f"+{gather_mode}" if world > 1 else ""),
+                        "timed_region_ms": ms},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 36, "d2h_bytes_per_step": words * 4,
-                "steps": e2e_steps, "call": "pv_check_states_host (pinned AoS rows in, verdict bits out)"},
+                "steps": e2e_steps, "configs_per_step": n * world,
+                "call": "pv_check_states_host (pinned AoS rows in, verdict bits out), one batch per call"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "valid_fraction_sample": n_valid / 32768.0,
     }
+    if world > 1:
+        line["value_basis"] = ("every step ends with the inter-rank barrier after which the step's whole verdict mask "
+                               f"({step_words * world * 4 >> 20} MiB) is consumable on every rank")
+        line["gather_verified"] = gather_verified
+        if unsync:
+            line["value_unsynchronised"] = unsync
+    line.update(sub)
 
+    if world == 1 and not args.no_configs:
+        for name, fn in (("edges", bench_edges), ("rrtc", bench_rrtc)):
+            try:
+                line[name] = fn(torch, pv, counts, mhz)
+            except Exception as exc:  # the headline metric must still print
+                line[name] = {"error": repr(exc)}
+        pv.set_scene(snap)
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
+        port = CpuPort()
         sample = 1 << 23  # ~2-4 s of wall time on 16 threads, ~30-60 core-seconds
-        rate = cpu_port_rate(sample, cores)
-        rate1 = cpu_port_rate(sample // 32, 1)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+        q = np.concatenate([make_batch(SEED + r, n) for r in range(sample // n)])
+        port.run(q[: 1 << 16], cores)
+        dt, _ = port.run(q, cores)
+        dt1, _ = port.run(q[: sample // 64], 1)
+        line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{sample} configs of the same workload, fp32 C oracle, OpenMP {cores} threads",
-                                "single_thread": rate1}
+                                "single_thread": (sample // 64) / dt1}
     if world == 1 and not args.no_plan:
         try:
             line["plan"] = plan_time_probe(pv)
-        except Exception as exc:  # the headline metric must still print
+        except Exception as exc:
             line["plan"] = {"error": repr(exc)}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+# ---- BASELINE config 5: device-generated sweep, strong scaling -------------------------------------------------------
+def bench_sweep(torch, dist, pv, rank, world, nccl_gather):
+    from rbe550_final_project_b200.distributed import (FusedVerdictGather, shard_range, sweep_sharded, sweep_sharded_fused,
+                                                       words_per_shard)
+    gather = None
+    mode = "none" if world == 1 else "nccl_allgather"
+    if world > 1 and not nccl_gather:
+        try:
+            gather = FusedVerdictGather(pv, words_per_shard(N_SWEEP, world))
+            mode = "fused_multicast" if gather.multicast else "fused_peer_stores"
+        except Exception:
+            gather = None
+
+    def run():
+        if gather is not None:
+            gather.activate()
+            return sweep_sharded_fused(pv, gather, N_SWEEP, SEED)
+        return sweep_sharded(pv, N_SWEEP, SEED)
+
+    full, n_valid = run()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        full, n_valid = run()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    ms = min(times)
+    # the mask every rank ends up with, reduced to a checksum that must agree across ranks and GPU counts
+    cs = int(full[: (N_SWEEP + 31) // 32].to(torch.int64).bitwise_and(0xFFFFFFFF).sum().item())
+    if gather is not None:
+        gather.deactivate()
+    return {"workload": f"{N_SWEEP} device-generated configs (Philox stream, fingers open) vs {SCENE}, contiguous shards over "
+                        f"{world} GPU(s), verdict words gathered on every rank (BASELINE config 5)",
+            "ms": ms, "value": N_SWEEP / (ms * 1e-3), "unit": UNIT, "gather": mode, "scaling": "strong",
+            "n_valid": int(n_valid.item()), "mask_checksum": cs, "timing": "CUDA events incl. the gather, max over ranks, best of 3"}
+
+
+# ---- BASELINE config 3: 10 485 760 edges x 64 interpolation states, finished-pentagon scene -----------------------------
+def bench_edges(torch, pv, counts, mhz):
+    from rbe550_final_project_b200 import panda_model as pm, scenes as sc
+    pv.set_scene(sc.goal4_task1_pentagon())
+    g = torch.Generator(device="cuda")
+    g.manual_seed(SEED)
+    lo = torch.tensor(pm.Q_LOWER, dtype=torch.float32, device="cuda")
+    hi = torch.tensor(pm.Q_UPPER, dtype=torch.float32, device="cuda")
+    out = {"workload": f"{N_EDGES} edges x 64 interpolation states vs the finished-pentagon scene (10 yawed OBBs), "
+                       "second end point = first + N(0, 0.3^2) per arm joint clipped to the limits (BASELINE config 3)",
+           "unit": "edges/s"}
+    qa = lo + (hi - lo) * torch.rand((N_EDGES, 9), generator=g, device="cuda")
+    qa[:, 7:] = 0.04
+    qb = torch.minimum(torch.maximum(qa + 0.3 * torch.randn((N_EDGES, 9), generator=g, device="cuda"), lo), hi)
+    qb[:, 7:] = 0.04
+    A = (qa[:, 0:4].contiguous(), qa[:, 4:8].contiguous())
+    B = (qb[:, 0:4].contiguous(), qb[:, 4:8].contiguous())
+    del qa, qb
+    bits = torch.empty(N_EDGES // 32, dtype=torch.int32, device="cuda")
+    ms = ev_ms(torch, lambda: pv.check_edges(A, B, n_steps=64, out=bits), iters=3, warm=1)
+    valid = float(np.unpackbits(bits.cpu().numpy().view(np.uint8)).sum()) / N_EDGES
+    rate = N_EDGES / (ms * 1e-3)
+    out.update({"ms": ms, "value": rate, "state_checks_per_s_upper": 64 * rate, "valid_fraction": valid,
+                "bytes_per_edge": 64.125, "hbm_gbs": 64.125 * rate / 1e9})
+    ec = counts.get("edges", {})
+    if ec.get("warp_inst_per_edge"):
+        peak_issue = 148 * 4 * mhz * 1e6
+        ach = ec["warp_inst_per_edge"] * rate
+        out["roofline"] = {"bound": "warp-instruction issue", "kernel": "pv_edge_kernel", "achieved": ach, "peak": peak_issue,
+                           "unit": "warp-inst/s", "frac": ach / peak_issue, "counts": ec,
+                           "executed_counts_stale": counts.get("source_hash") != source_hash()}
+    return out
+
+
+# ---- BASELINE config 4: 4096 start / goal pairs, batched RRT-Connect, tall-tower scene ------------------------------------
+def bench_rrtc(torch, pv, counts, mhz):
+    from rbe550_final_project_b200 import panda_model as pm, scenes as sc
+    from rbe550_final_project_b200.validity import unpack_bits
+    pv.set_scene(sc.goal3_tower())
+    rng = np.random.default_rng(4096)
+    cand = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(60000, 9)).astype(np.float32)
+    cand[:, 7:] = 0.04
+    ok = unpack_bits(pv.check_states_host(cand), len(cand))
+    ok &= pv.fk(torch.as_tensor(cand, device="cuda")).cpu().numpy()[:, 8, 2] > 0.15
+    valid = cand[ok]
+    starts, goals = valid[:N_QUERIES], valid[N_QUERIES:2 * N_QUERIES]
+    kw = dict(max_iters=2000, max_nodes=2048, max_path=128, seed=7, replicas=1, shortcut_passes=2, packed=True)
+    pv.rrtc_batch(starts, goals, **kw)
+    walls = []
+    for _ in range(5):
+        t = time.perf_counter()
+        states, off, plen, iters, checks = pv.rrtc_batch(starts, goals, **kw)
+        walls.append((time.perf_counter() - t) * 1e3)
+    ms = float(np.median(walls))
+    # single-query latency through the same entry (one launch pair + one synchronisation)
+    lat = []
+    for k in range(200):
+        t = time.perf_counter()
+        pv.rrtc_batch(starts[k:k + 1], goals[k:k + 1], **kw)
+        lat.append((time.perf_counter() - t) * 1e3)
+    # a large batch: the arena is bounded, the paths come back packed
+    big = 1 << 18
+    idx = rng.integers(0, len(valid), (2, big))
+    t = time.perf_counter()
+    _, _, plen_b, _, _ = pv.rrtc_batch(valid[idx[0]], valid[idx[1]], **kw)
+    big_ms = (time.perf_counter() - t) * 1e3
+    return {"workload": f"{N_QUERIES} (start, goal) pairs of valid configurations with the hand above 0.15 m, tall-tower scene "
+                        "(goal3: 8-high tower + 2 loose blocks), RRT-Connect range 2.607, resolution 0.13037, 2000 iterations "
+                        "(BASELINE config 4)",
+            "ms": ms, "value": N_QUERIES / (ms * 1e-3), "unit": "queries/s", "success": float((plen >= 2).mean()),
+            "timing": "wall clock around pv_rrtc_batch_packed incl. H2D of the queries and D2H of the packed paths, median of 5",
+            "iters_p50": float(np.median(iters)), "iters_max": int(iters.max()), "state_checks_total": int(checks.sum()),
+            "single_query_p50_ms": float(np.median(lat)), "single_query_p95_ms": float(np.percentile(lat, 95)),
+            "batch_262144": {"ms": big_ms, "value": big / (big_ms * 1e-3), "success": float((plen_b >= 2).mean())}}
+
+
 def plan_time_probe(pv, n_plans: int = 101):
-    """RRT-Connect p50 plan time for BASELINE config 1: safe_home -> approach pose above block r, goal-1 scene."""
+    """RRT-Connect plan time through PlannerInterface.plan_path (the reference-facing call, planning.py:59-207):
+    BASELINE config 1 (safe_home -> approach pose above block r, goal-1 scene: a straight-line plan) and a query that
+    needs tree growth (the hand from one side of the goal-3 tower to the other, low enough that the tower is in the way)."""
     import logging
     import contextlib
     import io
     from rbe550_final_project_b200 import panda_model as pm
+    from rbe550_final_project_b200 import scenes as sc
     from rbe550_final_project_b200.planning import PlannerInterface
     from rbe550_final_project_b200.sim_stub import create_scene
+    from rbe550_final_project_b200.pathutil import interpolate
+    from rbe550_final_project_b200.validity import unpack_bits
+    from oracle.c_oracle import COracle
     logging.getLogger("panda_validity.planning").setLevel(logging.ERROR)
     goals = json.load(open(os.path.join(ROOT, "tests", "golden", "goal_configs.json")))
-    goal = np.array(goals["goal1_scattered"]["approach_r"]["q"])
-    scene, franka, _ = create_scene("goal1_scattered")
-    franka.set_qpos(pm.Q_SAFE_HOME)
-    planner = PlannerInterface(franka, scene, validity=pv)
-    from oracle.c_oracle import COracle
-    from rbe550_final_project_b200 import scenes as sc
-    from rbe550_final_project_b200.pathutil import interpolate
     ora = COracle(pm.model_arrays(), "f32")
-    oscene = sc.goal1_scattered().as_oracle_scene()
-    times, ok, checks, cpu_times = [], 0, [], []
-    for i in range(n_plans + 3):
-        planner.rng_seed = 100 + i
-        with contextlib.redirect_stdout(io.StringIO()):
+
+    def consume(path):
+        # what the reference's caller does with the result (motion_primitives.py:163-176)
+        for wp in path:
+            wp.cpu().numpy().copy()
+        return np.array(path[-1], dtype=float)
+
+    def run_case(scene_name, start, goal, what):
+        scene, franka, _ = create_scene(scene_name)
+        franka.set_qpos(start)
+        planner = PlannerInterface(franka, scene, validity=pv)
+        oscene = sc.FIXTURES[scene_name]().as_oracle_scene()
+        rows, cpu_ms, ok = [], [], 0
+        for i in range(n_plans + 5):
+            planner.rng_seed = 100 + i
+            with contextlib.redirect_stdout(io.StringIO()):
+                t = time.perf_counter()
+                path = planner.plan_path(qpos_goal=goal, num_waypoints=150, timeout=10.0)
+                dt = time.perf_counter() - t
+                t = time.perf_counter()
+                if len(path):
+                    consume(path)
+                dcons = time.perf_counter() - t
             t = time.perf_counter()
-            path = planner.plan_path(qpos_goal=goal, num_waypoints=150, timeout=10.0)
-            dt = time.perf_counter() - t
-        t = time.perf_counter()
-        p, _, _ = ora.rrtc(pm.Q_SAFE_HOME, goal, oscene, seed=100 + i, search=0, max_path=256)
-        if len(p):
-            interpolate(p.astype(np.float64), 150)
-        dc = time.perf_counter() - t
-        if i >= 3:
-            times.append(dt * 1e3)
-            cpu_times.append(dc * 1e3)
-            ok += 1 if len(path) == 150 else 0
-            checks.append(planner.last_stats.get("state_checks", 0))
-    return {"workload": "goal1_scattered: safe_home -> approach pose above block r, RRTConnect, smooth, 150 waypoints",
-            "p50_ms": float(np.median(times)), "p95_ms": float(np.percentile(times, 95)), "success": ok / n_plans,
-            "n": n_plans, "median_state_checks": float(np.median(checks)), "replicas": planner.replicas,
-            "cpu_port_p50_ms": float(np.median(cpu_times)),
-            "cpu_port_note": "C oracle planner (fp32, 1 core, same model); not Genesis+OMPL, which cannot be installed here"}
+            p, _, _ = ora.rrtc(start, goal, oscene, seed=100 + i, search=0, max_path=256)
+            if len(p):
+                interpolate(p.astype(np.float64), 150)
+            dc = time.perf_counter() - t
+            if i >= 5:
+                st = planner.last_stats
+                rows.append((dt * 1e3, dcons * 1e3, st.get("ms_scene_snapshot", 0), st.get("ms_c_call", 0),
+                             st.get("ms_python_rest", 0), st.get("ms_solve", 0), st.get("ms_simplify", 0),
+                             st.get("ms_post", 0), st.get("checks", 0), st.get("launches", 0), st.get("vertices", 0),
+                             st.get("attempts", 0)))
+                cpu_ms.append(dc * 1e3)
+                ok += 1 if len(path) == 150 else 0
+        r = np.array(rows)
+        med = lambda k: float(np.median(r[:, k]))  # noqa: E731
+        return {"workload": what, "p50_ms": med(0), "p95_ms": float(np.percentile(r[:, 0], 95)), "success": ok / n_plans,
+                "n": n_plans, "replicas": planner.replicas,
+                "breakdown_p50_ms": {"scene_snapshot": med(2), "c_call_pv_plan_path": med(3), "python_rest": med(4),
+                                     "inside_c": {"solve": med(5), "simplify": med(6), "resample_validate": med(7)}},
+                "consume_waypoints_p50_ms": med(1),
+                "consume_note": "the waypoints are rows of one (150, 9) tensor; creating the 150 row tensors is deferred to "
+                                "the caller's iteration (motion_primitives.py:163-167) and timed here separately",
+                "median_state_checks": med(8), "median_launches": med(9), "median_vertices": med(10),
+                "median_attempts": med(11),
+                "cpu_port_p50_ms": float(np.median(cpu_ms)), "cpu_port_p95_ms": float(np.percentile(cpu_ms, 95)),
+                "cpu_port_note": "C oracle planner + the same interpolate (fp32, 1 core, same model, no dense re-validation); "
+                                 "not Genesis+OMPL, which cannot be installed here"}
+
+    out = {"config1": run_case("goal1_scattered", pm.Q_SAFE_HOME, np.array(goals["goal1_scattered"]["approach_r"]["q"]),
+                               "goal1_scattered: safe_home -> approach pose above block r, RRTConnect, smooth, 150 waypoints "
+                               "(BASELINE config 1)")}
+    # tree growth: hand 0.10 m above the table on either side of the 0.32 m tower at (0.45, 0)
+    pv.set_scene(sc.goal3_tower())
+    quat = np.array([[0.0, 1.0, 0.0, 0.0]])
+    ql, ok1, _ = pv.ik_batch(np.array([[0.45, -0.22, 0.22]]), quat, pm.Q_SAFE_HOME, n_seeds=128)
+    qr, ok2, _ = pv.ik_batch(np.array([[0.45, 0.22, 0.22]]), quat, pm.Q_SAFE_HOME, n_seeds=128)
+    if ok1[0] and ok2[0]:
+        straight = bool(unpack_bits(pv.check_edges_host(ql, qr, n_steps=0), 1)[0])
+        case = run_case("goal3_tower", ql[0].astype(np.float64), qr[0].astype(np.float64),
+                        "goal3_tower: hand at (0.45, -0.22, 0.22) -> (0.45, 0.22, 0.22), the 8-high tower in between")
+        case["straight_line_valid"] = straight
+        out["tower"] = case
+    out["p50_ms"] = out["config1"]["p50_ms"]
+    return out
 
 
 if __name__ == "__main__":

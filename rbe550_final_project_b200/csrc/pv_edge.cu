@@ -40,7 +40,9 @@
     PvDeviceGuard pv_guard_((h)->device);
 
 // K3: one warp per edge, lanes = interpolation states, coarse-to-fine rounds, any-hit early exit.
-// Each warp owns 32 consecutive edges at a time and emits one verdict word.
+// Each warp owns `epw` consecutive edges at a time: 32 for large batches (it then emits one whole verdict word, no
+// atomics), 1 for small ones (a plan's 150 waypoint motions, a simplifier batch), where 32 edges per warp would leave
+// the GPU to a handful of warps -- the verdict then goes to ok_bytes[e] (pv_plan.cu) or is OR-ed into a zeroed bit word.
 // PV_E_LOCKSTEP = 1 makes the warps of a block advance ROUND by round behind a block barrier (one pv_check_config per
 // warp per round, the loop ends when __syncthreads_or says no warp has work left) so that they share instruction
 // fetches like the state kernel.  That was neutral while a round cost ~3 700 instructions; since the scene-level cull
@@ -59,10 +61,10 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
                    const float* __restrict__ a9, const float4* __restrict__ bA, const float4* __restrict__ bB,
                    const float* __restrict__ b9, const float* __restrict__ a_aos, const float* __restrict__ b_aos,
                    int64_t n_edges, int n_steps, float resolution, uint32_t* __restrict__ bits,
-                   float* __restrict__ margin) {
+                   float* __restrict__ margin, int epw, unsigned char* __restrict__ ok_bytes) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int64_t n_words = (n_edges + 31) >> 5;
+    const int64_t n_words = (n_edges + epw - 1) / epw;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 
@@ -84,14 +86,14 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
         if (!have) break;
 #endif
         if (need_word) {
-            n_here = (int)min((int64_t)32, n_edges - (w << 5));
+            n_here = (int)min((int64_t)epw, n_edges - w * epw);
             word = 0;
             j = 0;
             need_word = false;
             need_edge = true;
         }
         if (need_edge) {
-            const int64_t e = (w << 5) + j;
+            const int64_t e = w * epw + j;
             if (a_aos) {
                 pv_load_aos(a_aos, e, ea);
                 pv_load_aos(b_aos, e, eb);
@@ -142,13 +144,17 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
             float m = edge_m;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, o));
-            if (lane == 0) margin[(w << 5) + j] = m;
+            if (lane == 0) margin[w * epw + j] = m;
         }
         ++j;
         need_edge = true;
         if (j >= n_here) {
             if constexpr (MODE == PV_MODE_BITS) {
-                if (lane == 0) bits[w] = word;
+                if (lane == 0) {
+                    if (epw == 32) bits[w] = word;
+                    else if (ok_bytes) ok_bytes[w] = (unsigned char)(word & 1u);  // epw == 1
+                    else if (word & 1u) atomicOr(bits + (w >> 5), 1u << (w & 31));  // epw == 1, bits zeroed by the launcher
+                }
             }
             w += n_warps;
             need_word = true;
@@ -156,22 +162,30 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
     }
 }
 
+// batches up to this size are validated one edge per warp (see the kernel's header)
+#ifndef PV_E_SMALL_BATCH
+#define PV_E_SMALL_BATCH 16384
+#endif
+
 int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* a9, const float* bA,
                            const float* bB, const float* b9, const float* a_aos, const float* b_aos, int64_t n,
-                           int n_steps, float resolution, uint32_t* d_bits, float* d_margin, cudaStream_t st) {
+                           int n_steps, float resolution, uint32_t* d_bits, float* d_margin, cudaStream_t st,
+                           unsigned char* d_ok_bytes) {
     if (n_steps < 0 || (n_steps == 0 && !(resolution > 0.f))) {
         snprintf(h->err, sizeof(h->err), "edge check needs n_steps > 0 or resolution > 0");
         return PV_ERR_BAD_ARG;
     }
-    const int64_t words = (n + 31) / 32;
+    const int epw = (d_ok_bytes || (d_bits && n <= PV_E_SMALL_BATCH)) ? 1 : 32;
+    const int64_t words = (n + epw - 1) / epw;
+    if (epw == 1 && d_bits && !d_ok_bytes) PV_CUDA(h, cudaMemsetAsync(d_bits, 0, (size_t)((n + 31) / 32) * sizeof(uint32_t), st));
 #define PV_LAUNCH_E(CULL, MODE, CARRY)                                                                         \
     {                                                                                                          \
         int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE, CARRY>, PV_E_THREADS, words);        \
         pv_edge_kernel<CULL, MODE, CARRY><<<grid, PV_E_THREADS, 0, st>>>(                                      \
             h->scene, (const float4*)aA, (const float4*)aB, a9, (const float4*)bA, (const float4*)bB, b9, a_aos, \
-            b_aos, n, n_steps, resolution, d_bits, d_margin);                                                  \
+            b_aos, n, n_steps, resolution, d_bits, d_margin, epw, d_ok_bytes);                                 \
     }
-    if (d_bits) {
+    if (d_bits || d_ok_bytes) {
         if (h->scene.carry) PV_LAUNCH_E(true, PV_MODE_BITS, true) else PV_LAUNCH_E(true, PV_MODE_BITS, false)
     } else {  // margins: always brute force
         if (h->scene.carry) PV_LAUNCH_E(false, PV_MODE_MARGIN, true) else PV_LAUNCH_E(false, PV_MODE_MARGIN, false)
@@ -188,7 +202,7 @@ extern "C" int pv_check_edges(PvHandle* h, const float* d_aA, const float* d_aB,
     PV_PRECHECK(h, n_edges);
     if (!d_aA || !d_aB || !d_bA || !d_bB || !d_bits) return PV_ERR_BAD_ARG;
     return pv_launch_edges(h, d_aA, d_aB, d_a9, d_bA, d_bB, d_b9, nullptr, nullptr, n_edges, n_steps, resolution,
-                           d_bits, nullptr, (cudaStream_t)stream);
+                           d_bits, nullptr, (cudaStream_t)stream, nullptr);
 }
 
 extern "C" int pv_edge_margins(PvHandle* h, const float* d_aA, const float* d_aB, const float* d_a9, const float* d_bA,
@@ -197,6 +211,6 @@ extern "C" int pv_edge_margins(PvHandle* h, const float* d_aA, const float* d_aB
     PV_PRECHECK(h, n_edges);
     if (!d_aA || !d_aB || !d_bA || !d_bB || !d_margin) return PV_ERR_BAD_ARG;
     return pv_launch_edges(h, d_aA, d_aB, d_a9, d_bA, d_bB, d_b9, nullptr, nullptr, n_edges, n_steps, resolution,
-                           nullptr, d_margin, (cudaStream_t)stream);
+                           nullptr, d_margin, (cudaStream_t)stream, nullptr);
 }
 

@@ -1054,7 +1054,7 @@ int pv_check_edges_host(PvHandle* h, const float* h_qa, const float* h_qb, int64
         PV_CUDA(h, cudaMemcpyAsync(h->stage_q2[slot], h_qb + done * 9, (size_t)m * 9 * sizeof(float),
                                    cudaMemcpyHostToDevice, st));
         rc = pv_launch_edges(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, h->stage_q[slot],
-                             h->stage_q2[slot], m, n_steps, resolution, h->stage_bits[slot], nullptr, st);
+                             h->stage_q2[slot], m, n_steps, resolution, h->stage_bits[slot], nullptr, st, nullptr);
         if (rc) return rc;
         PV_CUDA(h, cudaMemcpyAsync(h_bits + done / 32, h->stage_bits[slot], (size_t)((m + 31) / 32) * sizeof(uint32_t),
                                    cudaMemcpyDeviceToHost, st));

@@ -355,10 +355,10 @@ struct Simplifier {
 struct PlanStage {
     float* a;
     float* b;
-    uint32_t* bits;
+    unsigned char* ok;  // one byte per motion (the edge kernel's one-edge-per-warp mode)
 };
 static int plan_stage(PvHandle* h, int slot, PlanStage* s) {
-    const size_t per = (size_t)PLAN_EDGE_CAP * 9 * sizeof(float) * 2 + (size_t)PLAN_EDGE_CAP / 32 * sizeof(uint32_t);
+    const size_t per = (size_t)PLAN_EDGE_CAP * 9 * sizeof(float) * 2 + (size_t)PLAN_EDGE_CAP;
     if (!h->plan_host) {
         PL_CUDA(cudaHostAlloc(&h->plan_host, 2 * per, cudaHostAllocMapped));
         h->plan_host_bytes = 2 * per;
@@ -366,13 +366,13 @@ static int plan_stage(PvHandle* h, int slot, PlanStage* s) {
     char* p = (char*)h->plan_host + (size_t)slot * per;
     s->a = (float*)p;
     s->b = s->a + (size_t)PLAN_EDGE_CAP * 9;
-    s->bits = (uint32_t*)(s->b + (size_t)PLAN_EDGE_CAP * 9);
+    s->ok = (unsigned char*)(s->b + (size_t)PLAN_EDGE_CAP * 9);
     return PV_OK;
 }
-// queue the validation of n <= PLAN_EDGE_CAP staged motions (results land in stage.bits at stream completion)
+// queue the validation of n <= PLAN_EDGE_CAP staged motions (results land in stage.ok at stream completion)
 static int plan_queue_edges(PvHandle* h, const PlanStage& s, int n, float resolution, cudaStream_t st) {
-    return pv_launch_edges(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, s.a, s.b, n, 0, resolution, s.bits,
-                           nullptr, st);
+    return pv_launch_edges(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, s.a, s.b, n, 0, resolution, nullptr,
+                           nullptr, st, s.ok);
 }
 static int plan_check_edges(PvHandle* h, float resolution, const float* a, const float* b, int n, unsigned char* ok) {
     PlanStage s;
@@ -386,7 +386,7 @@ static int plan_check_edges(PvHandle* h, float resolution, const float* a, const
         rc = plan_queue_edges(h, s, m, resolution, st);
         if (rc) return rc;
         PL_CUDA(cudaStreamSynchronize(st));
-        for (int k = 0; k < m; ++k) ok[done + k] = (s.bits[k >> 5] >> (k & 31)) & 1u;
+        memcpy(ok + done, s.ok, (size_t)m);
     }
     return PV_OK;
 }
@@ -600,7 +600,7 @@ int pv_plan_path(PvHandle* h, const double* start, const double* goal, int num_w
                 const bool straight = path.size() == 2 && spec_queued && n == spec_n &&
                                       memcmp(rows.data(), spec_rows.data(), rows.size() * sizeof(float)) == 0;
                 if (straight) {  // already validated in the shadow of the solve
-                    for (int k = 0; k < n; ++k) valid &= ((spec.bits[k >> 5] >> (k & 31)) & 1u) != 0;
+                    for (int k = 0; k < n; ++k) valid &= spec.ok[k] != 0;
                     S.speculative_hit = 1;
                 } else {
                     std::vector<float> a, b;

@@ -67,9 +67,19 @@ def sweep_sharded(pv, n_total: int, seed: int, fingers_open: bool = True, group=
 def sweep_sharded_fused(pv, gather: "FusedVerdictGather", n_total: int, seed: int, fingers_open: bool = True):
     """Same result as sweep_sharded, but the verdict words travel inside the sweep kernel (peer / multicast stores)
     and the only synchronisation is the symmetric-memory barrier.  `gather` must have words_per_rank =
-    words_per_shard(n_total, world)."""
+    words_per_shard(n_total, world) and be the handle's active gather (gather.activate()).
+    The returned mask is a VIEW of the symmetric buffer, valid until the next sweep is launched into it: an entry
+    barrier keeps a faster rank from overwriting words a slower rank is still reading from the previous call."""
+    if gather.words_per_rank != words_per_shard(n_total, gather.world):
+        raise ValueError(f"gather slot of {gather.words_per_rank} words, but shards of {n_total} configurations over "
+                         f"{gather.world} ranks need {words_per_shard(n_total, gather.world)}")
+    gather.hdl.barrier()  # every rank has finished reading the previous call's mask
     first, count = shard_range(n_total, gather.rank, gather.world)
     n_valid = torch.zeros(1, dtype=torch.int64, device=pv.device)
+    used = (count + 31) // 32
+    if used < gather.words_per_rank:
+        # a short (or empty) last shard: the tail of this rank's slot must not keep words of an earlier, longer call
+        gather.zero_own_slot_tail(used)
     if count > 0:
         _, n_valid = pv.sweep(first, count, seed, fingers_open=fingers_open)
     full = gather.finish()[: (n_total + 31) // 32]
@@ -173,9 +183,31 @@ class FusedVerdictGather:
         mc = 0
         if use_multicast and getattr(self.hdl, "has_multicast_support", False):
             mc = int(self.hdl.multicast_ptr or 0)
+        self._mc = mc
         self.multicast = bool(mc)
-        pv.set_gather(int(self.hdl.buffer_ptrs_dev), self.world, mc, self.rank * self.words_per_rank, self.words_per_rank)
+        self.activate()
         self.hdl.barrier()
+
+    def activate(self, word_offset: int = 0):
+        """Make this buffer the handle's gather target (a handle forwards to one buffer at a time).  `word_offset`
+        places the NEXT launch's words inside this rank's slot: a caller that gathers several launches into one slot
+        (bench.py: one step = 48 launches) moves it before each launch."""
+        if not (0 <= word_offset <= self.words_per_rank):
+            raise ValueError("word_offset outside this rank's slot")
+        self.pv.set_gather(int(self.hdl.buffer_ptrs_dev), self.world, self._mc,
+                           self.rank * self.words_per_rank + int(word_offset), self.words_per_rank - int(word_offset))
+
+    def deactivate(self):
+        self.pv.set_gather(0, 0, 0, 0, 0)
+
+    def zero_own_slot_tail(self, first_word: int):
+        """Zero words [first_word, words_per_rank) of THIS rank's slot on every rank (peer stores; NCCL is not involved)."""
+        lo = self.rank * self.words_per_rank + int(first_word)
+        hi = (self.rank + 1) * self.words_per_rank
+        if hi <= lo:
+            return
+        for r in range(self.world):
+            self.hdl.get_buffer(r, (self.world * self.words_per_rank,), torch.int32)[lo:hi].zero_()
 
     def finish(self) -> torch.Tensor:
         """All ranks' kernels issued so far have completed and their words are visible: returns the gathered mask."""
@@ -183,4 +215,4 @@ class FusedVerdictGather:
         return self.buf
 
     def close(self):
-        self.pv.set_gather(0, 0, 0, 0, 0)
+        self.deactivate()

@@ -1,0 +1,141 @@
+"""Drop-in proof: the reference's OWN caller, `code/motion_primitives.py`, UNMODIFIED, imports
+`planning.PlannerInterface` (motion_primitives.py:9), builds `MotionPrimitiveExecutor(scene, robot, blocks_state)`
+(motion_primitives.py:30-44) and runs pick_up / put_down / stack_on (motion_primitives.py:256-302, 356-420, 619-755)
+against this repo's planner.  Only two things stand in for the reference's world: a shim directory that maps the module
+names `planning` / `robot_adapter` to this package, and the headless kinematic scene of sim_stub (Genesis is not
+installable).  Every path the executor received from plan_path is then checked in the fp64 CPU oracle.
+
+The reference file is not part of this repository (and /root/reference does not exist on the GPU box): `build()` in
+__graft_entry__.py stages a byte-identical copy under oracle/_ref/ (git-ignored, travels with the snapshot), and the
+test checks its SHA-256 against the committed digest before importing it.
+"""
+import hashlib
+import importlib
+import io
+import json
+import os
+import sys
+import contextlib
+
+import numpy as np
+import pytest
+
+from rbe550_final_project_b200 import panda_model as pm
+from rbe550_final_project_b200 import scenes as sc
+from rbe550_final_project_b200.sim_stub import create_scene
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED = os.path.join(ROOT, "oracle", "_ref", "reference_caller")
+DIGESTS = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_caller_sha256.json")))
+
+
+@pytest.fixture(scope="module")
+def ref_primitives(tmp_path_factory):
+    src = os.path.join(STAGED, "motion_primitives.py")
+    if not os.path.exists(src):
+        pytest.skip("oracle/_ref/reference_caller/motion_primitives.py not staged (run __graft_entry__.build() where "
+                    "/root/reference exists)")
+    assert hashlib.sha256(open(src, "rb").read()).hexdigest() == DIGESTS["motion_primitives.py"], \
+        "the staged reference caller is not the reference's file"
+    shim = tmp_path_factory.mktemp("shim")
+    # the two module names the reference caller's world provides, mapped to this package
+    (shim / "planning.py").write_text("from rbe550_final_project_b200.planning import *  # noqa\n"
+                                      "from rbe550_final_project_b200.planning import PlannerInterface  # noqa\n")
+    (shim / "robot_adapter.py").write_text("from rbe550_final_project_b200.robot_adapter import *  # noqa\n"
+                                           "from rbe550_final_project_b200.robot_adapter import RobotAdapter  # noqa\n")
+    saved = {k: sys.modules.pop(k, None) for k in ("planning", "robot_adapter", "motion_primitives")}
+    sys.path[:0] = [str(shim), STAGED]
+    try:
+        mod = importlib.import_module("motion_primitives")
+        assert os.path.samefile(mod.__file__, src)
+        import planning
+        from rbe550_final_project_b200.planning import PlannerInterface
+        assert planning.PlannerInterface is PlannerInterface and mod.PlannerInterface is PlannerInterface
+        yield mod
+    finally:
+        sys.path.remove(str(shim))
+        sys.path.remove(STAGED)
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
+
+
+class _Recorder:
+    """Wraps executor.planner.plan_path: keeps every returned path with the world it was planned in."""
+
+    def __init__(self, planner):
+        self.planner, self.inner, self.plans = planner, planner.plan_path, []
+
+    def __call__(self, *a, **kw):
+        path = self.inner(*a, **kw)
+        snap = self.planner._snapshot
+        att = self.planner._attached_index(kw.get("attached_object"))
+        self.plans.append(dict(path=np.stack([np.asarray(w) for w in path]) if len(path) else np.zeros((0, 9)),
+                               scene=snap.as_oracle_scene(), attached=att, stats=dict(self.planner.last_stats)))
+        return path
+
+
+def _check_plans(plans, c64, n_expected):
+    assert len(plans) == n_expected, [len(p["path"]) for p in plans]
+    for k, p in enumerate(plans):
+        arr = p["path"].astype(np.float64)
+        assert arr.shape == (150, 9), (k, arr.shape)  # MotionConfig.num_waypoints (motion_primitives.py:26)
+        # the first waypoint as a state, then every motion between consecutive waypoints, in the fp64 oracle
+        m0 = c64.state_margin(arr[:1], p["scene"], attached=p["attached"])
+        m = c64.edge_margin(arr[:-1], arr[1:], p["scene"], n_steps=0, attached=p["attached"])
+        assert m0[0] > -1e-4 and (m > -1e-4).all(), (k, float(m0[0]), float(m.min()))
+        assert p["stats"]["validated"] == 1
+
+
+def test_reference_executor_runs_pick_place_stack_through_the_dropin(ref_primitives, pv, c64):
+    scene, franka, blocks = create_scene("goal1_scattered")
+    franka.raw.attach_validity(pv)
+    franka.set_qpos(pm.Q_SAFE_HOME)  # goal1_scattered.py:43-64 moves to safe_home before the TAMP loop
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        ex = ref_primitives.MotionPrimitiveExecutor(scene, franka, blocks)
+        from rbe550_final_project_b200.planning import PlannerInterface
+        assert isinstance(ex.planner, PlannerInterface) and ex.planner.validity is not pv  # its own handle
+        ex.planner.validity.close()
+        ex.planner.validity = pv  # one handle for the test session (the executor's world is otherwise untouched)
+        rec = _Recorder(ex.planner)
+        ex.planner.plan_path = rec
+
+        r0 = blocks["r"].get_pos().copy()
+        assert ex.pick_up("r") is True                       # motion_primitives.py:256-302: two plans
+        assert ex.gripper_holding and scene.held is not None and scene.held[0] is blocks["r"]
+        assert blocks["r"].get_pos()[2] > r0[2] + 0.05       # lifted with the hand
+        assert ex.put_down(x=0.50, y=-0.20) is True          # motion_primitives.py:356-420: one plan, block attached
+        assert scene.held is None and not ex.gripper_holding
+        assert np.allclose(blocks["r"].get_pos(), [0.50, -0.20, 0.02], atol=3e-3)
+        assert ex.pick_up("g") is True
+        preds = {"ONTABLE(r)", "ONTABLE(g)", "CLEAR(r)", "HOLDING(g)"}
+        assert ex.stack_on("r", preds) is True               # motion_primitives.py:619-755: one plan, block attached
+        assert np.allclose(blocks["g"].get_pos(), [0.50, -0.20, 0.06], atol=3e-3)
+    log = out.getvalue()
+    assert "motion: PICK-UP SUCCESS" in log and "motion: PUT-DOWN SUCCESS" in log and "motion:STACK COMPLETE" in log
+    assert log.count("Number of waypoints in path: 150") == 6  # planning.py:199
+    _check_plans(rec.plans, c64, 6)
+    assert [p["attached"] >= 0 for p in rec.plans] == [False, False, True, False, False, True]
+    assert scene.steps > 1000  # the choreography really ran (gripper ramps, holds, descents)
+
+
+def test_reference_executor_reports_unreachable_goals_like_the_reference(ref_primitives, pv):
+    """A block outside the workspace: IK finds nothing, pick_up returns False (motion_primitives.py:273-275) -- and a
+    goal in collision makes plan_path return [] twice, so _plan_and_execute gives up (motion_primitives.py:143-158)."""
+    snap = sc.goal1_scattered()
+    snap.obb[0, 0:3] = (1.4, 0.0, 0.02)  # block r out of reach
+    from rbe550_final_project_b200.sim_stub import scene_from_snapshot
+    scene, franka, blocks = scene_from_snapshot(snap)
+    franka.raw.attach_validity(pv)
+    franka.set_qpos(pm.Q_SAFE_HOME)
+    with contextlib.redirect_stdout(io.StringIO()) as out:
+        ex = ref_primitives.MotionPrimitiveExecutor(scene, franka, blocks)
+        ex.planner.validity.close()
+        ex.planner.validity = pv
+        assert ex.pick_up("r") is False
+        bad_goal = np.array([0, 1.7, 0, -0.1, 0, 0.5, 0, 0.04, 0.04])  # arm folded into the table
+        assert ex._plan_and_execute(bad_goal) is False
+    assert "Planning failed after retries" in out.getvalue()

@@ -1,5 +1,6 @@
 """GPU tests of the drop-in planner: PlannerInterface.plan_path contract and the batched
 RRT-Connect front end.  Paths are re-validated with the edge kernel AND the CPU oracle."""
+import collections.abc
 import json
 import os
 
@@ -10,7 +11,8 @@ import torch
 from conftest import random_configs
 from rbe550_final_project_b200 import panda_model as pm
 from rbe550_final_project_b200 import scenes as sc
-from rbe550_final_project_b200.planning import PlannerInterface, PlanningError, SUPPORTED_PLANNERS
+from rbe550_final_project_b200.planning import PlannerInterface, PlanningError, SUPPORTED_PLANNERS, Waypoints
+from rbe550_final_project_b200.validity import PandaValidityError
 from rbe550_final_project_b200.sim_stub import create_scene
 from rbe550_final_project_b200.validity import unpack_bits
 
@@ -39,7 +41,9 @@ def test_plan_path_contract(pv, c64):
     for name in ("approach_r", "grasp_r", "approach_c"):
         goal = np.array(GOALS["goal1_scattered"][name]["q"])
         path = planner.plan_path(qpos_goal=goal, num_waypoints=150, attached_object=None, timeout=10.0)
-        assert isinstance(path, list) and len(path) == 150
+        # a sequence of 150 CPU fp32 tensors of shape (9,), rows of one (150, 9) block (planning.py:200, 232-242)
+        assert isinstance(path, collections.abc.Sequence) and isinstance(path, Waypoints) and len(path) == 150 and path
+        assert path.tensor.shape == (150, 9) and path[3].data_ptr() == path.tensor[3].data_ptr()
         assert all(isinstance(w, torch.Tensor) and w.device.type == "cpu" and w.dtype == torch.float32
                    and w.shape == (9,) for w in path)
         arr = np.stack([w.numpy() for w in path])
@@ -47,9 +51,20 @@ def test_plan_path_contract(pv, c64):
         # caller-side conversions of motion_primitives.py:164-176 work
         assert np.array(path[-1], dtype=float).shape == (9,)
         _path_ok(pv, c64, sc.goal1_scattered(), arr)
-        assert planner.last_stats["solved"]
+        st = planner.last_stats
+        assert st["solved"] and st["validated"] == 1 and st["attempts"] == 1
+        # these three goals are straight-line motions: solved, validated and resampled behind ONE synchronisation
+        assert st["vertices"] == 2 and st["speculative_hit"] == 1 and st["launches"] == 3
+        assert planner.validate_trajectory(path).all()
+        assert path[-1].tolist() == arr[-1].tolist() and [w.tolist() for w in path[:2]] == arr[:2].tolist()
+    # the same seed gives the same plan, whatever the 32 racing searches do
+    planner.rng_seed = 77
+    a = planner.plan_path(qpos_goal=goal, num_waypoints=150)
+    planner.rng_seed = 77
+    b = planner.plan_path(qpos_goal=goal, num_waypoints=150)
+    assert a == b and np.array_equal(a.array, b.array)
     # the robot is put back where it was (planning.py:205) and never moved in between
-    assert franka.raw.set_qpos_calls == calls_before + 3
+    assert franka.raw.set_qpos_calls == calls_before + 5
     assert np.allclose(franka.get_qpos(), pm.Q_SAFE_HOME)
 
 
@@ -260,10 +275,19 @@ def test_nontrivial_planning_around_a_wall(pv, c64, c32):
     scene, franka, _ = create_scene("goal1_scattered")
     franka.set_qpos(q_left[0])
     planner = PlannerInterface(franka, snap, validity=pv)
+    planner.rng_seed = 5
     path = planner.plan_path(qpos_goal=q_right[0], num_waypoints=200, timeout=10.0)
-    # which of the 32 racing searches wins is timing dependent, and the 200 resampled waypoints are checked more finely
-    # than the planner's 1 % resolution: allow the odd grazing waypoint
-    assert len(path) == 200 and planner.validate_trajectory(path).mean() > 0.95
+    st = planner.last_stats
+    # the 200 resampled waypoints are checked more finely than the planner's 1 % resolution inside pv_plan_path, and a
+    # path that grazes the wall between the planner's samples is replaced / re-planned: EVERY segment is valid
+    assert len(path) == 200 and planner.validate_trajectory(path).all() and st["validated"] == 1
+    arr = path.array.astype(np.float64)
+    assert (c64.edge_margin(arr[:-1], arr[1:], snap.as_oracle_scene(), n_steps=0) > -1e-4).all()
+    assert st["vertices_raw"] >= 3 and st["partial_rounds"] + st["bspline_steps"] + st["reduce_rounds"] >= 1
+    # deterministic: the winner among the 32 searches is the one with the smallest (iterations, replica id)
+    planner.rng_seed = 5
+    again = planner.plan_path(qpos_goal=q_right[0], num_waypoints=200, timeout=10.0)
+    assert np.array_equal(again.array, path.array)
 
 
 def test_rrtc_capacity_limits_fail_cleanly(pv):
@@ -276,6 +300,11 @@ def test_rrtc_capacity_limits_fail_cleanly(pv):
     ql, _, _ = pv.ik_batch(np.array([[0.5, 0.3, 0.3]]), quat, pm.Q_SAFE_HOME, n_seeds=100)  # rounded up to 128
     qr, _, _ = pv.ik_batch(np.array([[0.5, -0.3, 0.3]]), quat, pm.Q_SAFE_HOME, n_seeds=100)
     starts, goals = np.repeat(ql, 16, axis=0), np.repeat(qr, 16, axis=0)
+    for bad in (dict(max_path=1), dict(max_nodes=7), dict(max_nodes=-5), dict(replicas=257), dict(max_iters=-1)):
+        args = dict(max_iters=2000, max_nodes=2048, max_path=128, seed=3, replicas=1, shortcut_passes=2)
+        args.update(bad)
+        with pytest.raises(PandaValidityError):  # out-of-range capacities are refused, never replaced by defaults
+            pv.rrtc_batch(starts, goals, **args)
     for kw in (dict(max_path=2), dict(max_nodes=8), dict(max_iters=1)):
         args = dict(max_iters=2000, max_nodes=2048, max_path=128, seed=3, replicas=1, shortcut_passes=2)
         args.update(kw)
@@ -310,7 +339,8 @@ def test_unknown_attached_entity_forgives_nothing(pv):
     assert planner._attached_index(blocks["m"]) == 4
 
 
-def test_corner_cutting_shortens_and_stays_valid(pv, c64):
+def test_simplify_solution_shortens_and_stays_valid(pv, c64):
+    """ss.simplifySolution() (planning.py:196): the batched simplifyMax passes of pv_plan.cu, validated by the edge kernel."""
     from rbe550_final_project_b200.pathutil import path_length
     wall = sc.make_obb((0.55, 0.0, 0.35), (0.5, 0.04, 0.7))
     snap = sc.SceneSnapshot(obb=np.array([wall], dtype=np.float32), names=["wall"], entity_idx=[1])
@@ -325,20 +355,92 @@ def test_corner_cutting_shortens_and_stays_valid(pv, c64):
     planner.refresh_scene()
     shorter = 0
     for seed in range(12):
-        paths, plen, _, _ = pv.rrtc_batch(ql, qr, seed=40 + seed, replicas=1, shortcut_passes=2)
+        paths, plen, _, _ = pv.rrtc_batch(ql, qr, seed=40 + seed, replicas=1, shortcut_passes=0)
         assert plen[0] >= 3
         raw = paths[0, : plen[0]].astype(np.float64)
-        cut = planner._cut_corners(raw)
+        cut = planner.simplify_path(raw, seed=seed)
         assert np.array_equal(cut[0], raw[0]) and np.array_equal(cut[-1], raw[-1])
         assert path_length(cut) <= path_length(raw) + 1e-9
         shorter += path_length(cut) < path_length(raw) - 1e-6
         _path_ok(pv, c64, snap, cut)
-    assert shorter >= 6
-    # smooth_path=False returns the raw tree path resampled; both variants are valid trajectories
-    planner.replicas = 1  # deterministic winner
+        assert np.array_equal(cut, planner.simplify_path(raw, seed=seed))
+        assert sum(pv.last_simplify_counters[k] for k in ("partial_rounds", "bspline_steps", "reduce_rounds")) >= 1
+    assert shorter >= 10
+    # smooth_path=False returns the raw tree path resampled; both variants are fully valid trajectories
     for smooth in (True, False):
         path = planner.plan_path(qpos_goal=qr[0], num_waypoints=120, smooth_path=smooth, timeout=10.0)
-        assert len(path) >= 120 and planner.validate_trajectory(path).mean() > 0.95
+        assert len(path) >= 120 and planner.validate_trajectory(path).all()
+        assert (planner.last_stats["partial_rounds"] + planner.last_stats["bspline_steps"] > 0) == smooth or \
+            planner.last_stats["vertices_raw"] == 2
+
+
+def test_validate_trajectory_checks_the_first_waypoint(pv):
+    """a motion check assumes its start valid, so waypoint 0 must be checked as a state."""
+    scene, franka, _ = create_scene("goal1_scattered")
+    planner = PlannerInterface(franka, scene, validity=pv)
+    bad = np.array([0, 1.7, 0, -0.1, 0, 0.5, 0, 0.04, 0.04])  # folded into the table
+    ok = planner.validate_trajectory([bad, pm.Q_SAFE_HOME, pm.Q_SCENE_INIT])
+    assert ok.tolist() == [False, True]
+    ok = planner.validate_trajectory([pm.Q_SAFE_HOME, pm.Q_SCENE_INIT, pm.Q_SAFE_HOME])
+    assert ok.tolist() == [True, True]
+
+
+def test_replicas_are_deterministic_and_split_invariant(pv):
+    """The winner of a query is the search with the smallest (iterations, replica id): the same on every run, and the
+    same whether the batch is planned in one call or in shards (VERDICT r1 weak 11 / ADVICE)."""
+    wall = sc.make_obb((0.55, 0.0, 0.35), (0.5, 0.04, 0.7))
+    snap = sc.SceneSnapshot(obb=np.array([wall], dtype=np.float32), names=["wall"], entity_idx=[1])
+    pv.set_scene(snap)
+    pv.set_attached(-1)
+    quat = np.array([[0.0, 1.0, 0.0, 0.0]])
+    ql, _, _ = pv.ik_batch(np.array([[0.5, 0.3, 0.3]]), quat, pm.Q_SAFE_HOME, n_seeds=128)
+    qr, _, _ = pv.ik_batch(np.array([[0.5, -0.3, 0.3]]), quat, pm.Q_SAFE_HOME, n_seeds=128)
+    nq = 48
+    starts, goals = np.repeat(ql, nq, axis=0), np.repeat(qr, nq, axis=0)
+    kw = dict(max_iters=2000, max_nodes=2048, max_path=128, seed=17, replicas=8, shortcut_passes=2)
+    runs = [pv.rrtc_batch(starts, goals, **kw) for _ in range(4)]
+    used = np.arange(128)[None, :] < runs[0][1][:, None]
+    assert (runs[0][1] > 0).all() and len(set(runs[0][2].tolist())) > 3
+    for r in runs[1:]:
+        assert all(np.array_equal(r[j], runs[0][j]) for j in (1, 2, 3)) and np.array_equal(r[0][used], runs[0][0][used])
+    parts = [pv.rrtc_batch(starts[a:b], goals[a:b], query_offset=a, **kw) for a, b in ((0, 7), (7, 8), (8, nq))]
+    for j in (1, 2, 3):
+        assert np.array_equal(np.concatenate([p[j] for p in parts]), runs[0][j])
+    assert np.array_equal(np.concatenate([p[0] for p in parts])[used], runs[0][0][used])
+    # more replicas never need MORE iterations than the best of fewer: replica 0 of 8 is the single search
+    single = pv.rrtc_batch(starts, goals, **dict(kw, replicas=1))
+    keys8 = runs[0][2]
+    # (the single search of query k has global id k; with 8 replicas the ids are 8k..8k+7, so only the winner's
+    # optimality can be compared: its iteration count is minimal over ITS replicas, not over other seeds)
+    assert np.median(keys8) <= np.median(single[2])
+
+
+def test_one_million_queries_bounded_memory(pv):
+    """1 048 576 queries in one call -- the device arena is bounded by chunking, the paths come back
+    packed -- and the packed rows equal the dense form on a slice."""
+    snap = sc.goal3_tower()
+    pv.set_scene(snap)
+    pv.set_attached(-1)
+    cand = random_configs(40_000, 99)
+    valid = cand[unpack_bits(pv.check_states_host(cand), len(cand))]
+    rng = np.random.default_rng(0)
+    nq = 1 << 20
+    starts = valid[rng.integers(0, len(valid), nq)]
+    goals = valid[rng.integers(0, len(valid), nq)]
+    free0 = torch.cuda.mem_get_info()[0]
+    states, off, plen, iters, checks = pv.rrtc_batch(starts, goals, seed=3, replicas=1, packed=True)
+    used_gb = (free0 - torch.cuda.mem_get_info()[0]) / 2**30
+    assert used_gb < 4.0, f"the planner's arena grew by {used_gb:.1f} GB"
+    assert (plen >= 2).mean() > 0.999 and len(states) == int(plen.sum())
+    assert np.array_equal(off, np.concatenate([[0], np.cumsum(plen)[:-1]]))
+    solved = np.nonzero(plen >= 2)[0]
+    assert np.array_equal(states[off[solved]], starts[solved]) and np.array_equal(states[off[solved] + plen[solved] - 1], goals[solved])
+    sl = slice(500_000, 500_000 + 3000)
+    dense = pv.rrtc_batch(starts[sl], goals[sl], seed=3, replicas=1, query_offset=sl.start, max_path=128)
+    assert np.array_equal(dense[1], plen[sl]) and np.array_equal(dense[2], iters[sl]) and np.array_equal(dense[3], checks[sl])
+    for k in range(0, 3000, 37):
+        g = sl.start + k
+        assert np.array_equal(dense[0][k, : plen[g]], states[off[g]: off[g] + plen[g]])
 
 
 def test_single_tree_rrt_planner(pv, c64, c32):
@@ -377,7 +479,7 @@ def test_single_tree_rrt_planner(pv, c64, c32):
     path = planner.plan_path(qpos_goal=qr[0], num_waypoints=100, planner="RRT", timeout=10.0)
     # the resampled waypoints fall between the states the planner's validator sampled (1 % resolution, App. D), so a
     # path that grazes the wall edge can show a few waypoint-level contacts: the finer check must agree almost everywhere
-    assert len(path) >= 100 and planner.validate_trajectory(path).mean() > 0.9
+    assert len(path) >= 100 and planner.validate_trajectory(path).all()
     planner.strict_planners = True
     with pytest.raises(PlanningError):
         planner.plan_path(qpos_goal=qr[0], planner="PRM")
