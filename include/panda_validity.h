@@ -233,6 +233,11 @@ typedef struct {
 int pv_plan_path(PvHandle *h, const double *start, const double *goal, int num_waypoints, const PvPlanParams *params,
                  float *h_waypoints, int capacity, int *n_waypoints, PvPlanStats *stats);
 
+/* Scene records for pv_set_scene from what a simulator reports per box entity (entity.get_pos(), entity.get_quat() wxyz,
+ * half of entity.morph.size; scenes.py:52-83): host arithmetic only.  pos [n][3], quat [n][4] (NULL = identity),
+ * half [n][3] fp64 -> obb_out [n][16] fp32. */
+int pv_obb_from_poses(const double *pos, const double *quat, const double *half, int n, float *obb_out);
+
 /* path.interpolate(count) (planning.py:198; OMPL PathGeometric::interpolate for a RealVectorStateSpace) on its own:
  * host arithmetic only (no device, no handle).  states [n_states][9] fp64 -> out [capacity][9]; *n_out = rows. */
 int pv_interpolate_path(const double *states, int n_states, int count, double *out, int capacity, int *n_out);

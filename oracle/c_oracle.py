@@ -153,3 +153,20 @@ class COracle:
                C.c_int({"RRTConnect": 0, "RRT": 1}[planner]), self._p(path),
                C.byref(iters), C.byref(checks))
         return path[:n].copy(), iters.value, checks.value
+
+    def edge_callback(self, scene, attached=-1, flags=FLAG_SELF, base=(0.0, 0.0, 0.01), resolution=0.13037159046356686):
+        """(function pointer, context pointer, keep-alive) for pv_simplify_path_cb: this oracle as the motion validator
+        of the product's simplifier, in C on both sides (fp32 only)."""
+        assert self.np_t is np.float32
+
+        class Ctx(C.Structure):
+            _fields_ = [("m", C.c_void_p), ("obb", C.c_void_p), ("n_obb", C.c_int), ("table_z", C.c_float),
+                        ("base", C.c_void_p), ("attached", C.c_int), ("flags", C.c_int), ("resolution", C.c_float),
+                        ("motions", C.c_longlong), ("states", C.c_longlong)]
+
+        obb, n_obb, attached, flags = self._scene(scene, attached, flags)
+        b = np.ascontiguousarray(base, dtype=np.float32)
+        ctx = Ctx(C.addressof(self.model), obb.ctypes.data, n_obb, float(scene["table_z"]), b.ctypes.data, attached, flags,
+                  float(np.float32(resolution)), 0, 0)
+        fn = C.cast(self.lib.po_edge_callback_f32, C.c_void_p)
+        return fn, ctx, (obb, b)

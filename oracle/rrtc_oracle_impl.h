@@ -214,3 +214,31 @@ int po_rrtc_f32(const po_model_f32 *m, const float *obb, int n_obb, float table_
     free(par);
     return solved ? path_n : 0;
 }
+
+/* Motion validator with the callback signature of pv_simplify_path_cb (include/panda_validity.h): lets the CPU arm of
+ * bench.py and the CPU tests run the product's batched simplifier with THIS oracle answering, no Python in the loop.
+ * user = po_edge_ctx_f32. */
+typedef struct {
+    const po_model_f32 *m;
+    const float *obb;
+    int n_obb;
+    float table_z;
+    const float *base;
+    int attached, flags;
+    float resolution;
+    long long motions, states;
+} po_edge_ctx_f32;
+
+int po_edge_callback_f32(void *user, const float *a, const float *b, int n, unsigned char *ok) {
+    po_edge_ctx_f32 *c = (po_edge_ctx_f32 *)user;
+    for (int e = 0; e < n; ++e) {
+        float m;
+        long cnt = 0;
+        po_edge_margin_f32(c->m, c->obb, c->n_obb, c->table_z, c->base, c->attached, c->flags, a + 9 * e, b + 9 * e, 1, 0,
+                           c->resolution, 1, &m, &cnt, 1);
+        ok[e] = m >= 0.f ? 1 : 0;
+        c->states += cnt;
+    }
+    c->motions += n;
+    return 0;
+}

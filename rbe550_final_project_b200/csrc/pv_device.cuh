@@ -451,22 +451,194 @@ __device__ __forceinline__ void pv_fk_visit(const float* q, float bx, float by, 
 }
 
 // ---- the state check ----------------------------------------------------------------------------------
+// Everything the tests need about the robot in ONE configuration (registers: every index below is a literal).
+struct PvPlaced {
+    float3 s[PV_N_SPHERES];      // arm sphere centres
+    float3 hX, hY, hZ, hP;       // hand frame
+    float3 bc[3];                // gripper box centres (hand, left finger, right finger; axes = the hand's)
+    float grip_r;                // ball around bc[0] that contains all three gripper boxes in this configuration
+    float3 cC, cH, cX, cY, cZ;   // carried box (CARRY): centre, half extents, axes
+    float cbr;
+};
+__device__ constexpr float pv_bh[3][3] = {
+#define PV_BOX_HALF(k, link, cx, cy, cz, hx, hy, hz, br) {hx, hy, hz},
+    PV_BOXES(PV_BOX_HALF)
+#undef PV_BOX_HALF
+};
+__device__ constexpr float pv_bbr[3] = {
+#define PV_BOX_BR(k, link, cx, cy, cz, hx, hy, hz, br) br,
+    PV_BOXES(PV_BOX_BR)
+#undef PV_BOX_BR
+};
+__device__ constexpr int pv_blink[3] = {
+#define PV_BOX_LK(k, link, cx, cy, cz, hx, hy, hz, br) link,
+    PV_BOXES(PV_BOX_LK)
+#undef PV_BOX_LK
+};
+
+// FK -> sphere centres + gripper boxes (+ the carried box)
+template <bool FTRIG, bool CARRY>
+__device__ __forceinline__ void pv_place(const float* q, const PvScene& S, PvPlaced& P) {
+    pv_fk_visit<(PV_FAST_TRIG && FTRIG)>(q, S.base[0], S.base[1], S.base[2], [&](auto lc, float3 p, float3 X, float3 Y, float3 Z) {
+        constexpr int l = decltype(lc)::value;
+        if constexpr (l == 0) { PV_PLACE_LINK0(P.s, p, X, Y, Z) }
+        if constexpr (l == 1) { PV_PLACE_LINK1(P.s, p, X, Y, Z) }
+        if constexpr (l == 2) { PV_PLACE_LINK2(P.s, p, X, Y, Z) }
+        if constexpr (l == 3) { PV_PLACE_LINK3(P.s, p, X, Y, Z) }
+        if constexpr (l == 4) { PV_PLACE_LINK4(P.s, p, X, Y, Z) }
+        if constexpr (l == 5) { PV_PLACE_LINK5(P.s, p, X, Y, Z) }
+        if constexpr (l == 6) { PV_PLACE_LINK6(P.s, p, X, Y, Z) }
+        if constexpr (l == 7) { PV_PLACE_LINK7(P.s, p, X, Y, Z) }
+        if constexpr (l == 8) { P.hX = X; P.hY = Y; P.hZ = Z; P.hP = p; }
+#define PV_BOX_PLACE(k, link, cx, cy, cz, hx, hy, hz, br) \
+    if constexpr (l == link) P.bc[k] = v_fma(Z, cz, v_fma(Y, cy, v_fma(X, cx, p)));
+        PV_BOXES(PV_BOX_PLACE)
+#undef PV_BOX_PLACE
+    });
+    // radius of a ball centred on the hand box that contains all three gripper boxes for THIS configuration
+    // (with both fingers inside their travel the hand box's own bounding ball contains them -- asserted by the model
+    // generator -- so the general form only runs for out-of-limit finger values, i.e. for states that are invalid anyway)
+    P.grip_r = pv_bbr[0] + 2.0f * PV_CULL_SLACK;
+    if (!(fabsf(q[7]) <= PV_GRIP_CONST_MAXQ && fabsf(q[8]) <= PV_GRIP_CONST_MAXQ)) {
+        float3 d1 = v_sub(P.bc[1], P.bc[0]), d2 = v_sub(P.bc[2], P.bc[0]);
+        P.grip_r = fmaxf(pv_bbr[0], fmaxf(sqrtf(v_dot(d1, d1)) + pv_bbr[1], sqrtf(v_dot(d2, d2)) + pv_bbr[2])) + 2.0f * PV_CULL_SLACK;
+    }
+    P.cC = P.hP;
+    P.cH = make_float3(0.f, 0.f, 0.f);
+    P.cX = P.hX;
+    P.cY = P.hY;
+    P.cZ = P.hZ;
+    P.cbr = 0.f;
+    if constexpr (CARRY) {
+        P.cH = make_float3(S.carry_h[0], S.carry_h[1], S.carry_h[2]);
+        P.cbr = S.carry_br;
+        P.cC = v_fma(P.hZ, S.carry_t[2], v_fma(P.hY, S.carry_t[1], v_fma(P.hX, S.carry_t[0], P.hP)));
+#define PV_CARRY_AXIS(j) \
+    v_fma(P.hZ, S.carry_R[6 + j], v_fma(P.hY, S.carry_R[3 + j], make_float3(P.hX.x * S.carry_R[j], P.hX.y * S.carry_R[j], P.hX.z * S.carry_R[j])))
+        P.cX = PV_CARRY_AXIS(0);
+        P.cY = PV_CARRY_AXIS(1);
+        P.cZ = PV_CARRY_AXIS(2);
+#undef PV_CARRY_AXIS
+    }
+}
+
+#define PV_EARLY_EXIT_RET(retval)                                                          \
+    if constexpr (MODE == PV_MODE_BITS && EXIT != PV_EXIT_NONE) {                          \
+        if constexpr (PV_PACK) acc.hit |= acc.packed_hit();                                \
+        bool h_ = acc.hit;                                                                 \
+        if (EXIT == PV_EXIT_ALL ? __all_sync(0xffffffffu, h_) : __any_sync(0xffffffffu, h_)) return retval; \
+    }
+
+// ---- robot vs scene boxes (the section behind the scene-level cull) -----------------------------------------
+template <int MODE, bool CULL, int EXIT, int SYNC, bool FMAK, bool CARRY>
+__device__ __forceinline__ void pv_scene_section(PvAcc<MODE>& acc, const PvPlaced& P, const PvScene& S) {
+    const int nb = S.n_obb;
+    for (int b = 0; b < nb; ++b) {
+        if constexpr (SYNC >= 3) __syncthreads();
+        if constexpr (CARRY) {
+            if (b == S.attached) continue;  // it is where the hand is, not where the snapshot saw it
+        }
+        const float3 oc = make_float3(S.obb[b][0], S.obb[b][1], S.obb[b][2]);
+        const float3 oh = make_float3(S.obb[b][3], S.obb[b][4], S.obb[b][5]);
+        const float obr = S.obb[b][15];
+        const float3 BX = make_float3(S.obb[b][6], S.obb[b][9], S.obb[b][12]);
+        const float3 BY = make_float3(S.obb[b][7], S.obb[b][10], S.obb[b][13]);
+        const float3 BZ = make_float3(S.obb[b][8], S.obb[b][11], S.obb[b][14]);
+        const bool yaw_only = (S.yaw_only_mask >> b) & 1u;
+        float3 ok = oc;
+        if constexpr (FMAK) ok = make_float3(v_dot(oc, BX), v_dot(oc, BY), yaw_only ? oc.z : v_dot(oc, BZ));
+        const unsigned rmask = S.reach_mask[b];
+        if constexpr (CARRY) {
+            float3 d_ = v_sub(P.cC, oc);
+            float rr_ = (P.cbr + PV_CULL_SLACK) + obr;
+            if (MODE == PV_MODE_MARGIN || v_dot(d_, d_) < rr_ * rr_)
+                pv_box_box<MODE>(acc, P.cC, P.cH, P.cX, P.cY, P.cZ, oc, oh, BX, BY, BZ, PV_CODE(2, PV_LINK_CARRIED, b));
+        }
+        // one uniform yaw / general decision per GROUP keeps the hot (yaw-only) sphere tests contiguous in the code
+#define PV_ENV_SPHERE_YAW(i, link, cx, cy, cz, r)                                                         \
+    if constexpr (FMAK) pv_sphere_box_yaw_k<MODE>(acc, P.s[i], r, (r) * (r), ok, oh, BX.x, BX.y, PV_CODE(2, link, b)); \
+    else pv_sphere_box_yaw<MODE>(acc, P.s[i], r, (r) * (r), oc, oh, BX.x, BX.y, PV_CODE(2, link, b));
+#define PV_ENV_SPHERE_GEN(i, link, cx, cy, cz, r)                                                         \
+    if constexpr (FMAK) pv_sphere_box_k<MODE>(acc, P.s[i], r, (r) * (r), ok, oh, BX, BY, BZ, PV_CODE(2, link, b)); \
+    else pv_sphere_box<MODE>(acc, P.s[i], r, (r) * (r), oc, oh, BX, BY, BZ, PV_CODE(2, link, b));
+#define PV_ENV_GROUP(l, cs, br)                                 \
+    if (MODE == PV_MODE_MARGIN || (rmask & (1u << l))) {        \
+        float3 d_ = v_sub(P.s[cs], oc);                         \
+        float rr_ = (br + PV_CULL_SLACK) + obr;                 \
+        if (!CULL || v_dot(d_, d_) < rr_ * rr_) {               \
+            if (yaw_only) {                                     \
+                PV_SPHERES_LINK##l(PV_ENV_SPHERE_YAW)           \
+            } else {                                            \
+                PV_SPHERES_LINK##l(PV_ENV_SPHERE_GEN)           \
+            }                                                   \
+        }                                                       \
+    }
+        PV_LINK_GROUPS(PV_ENV_GROUP)
+#undef PV_ENV_GROUP
+#undef PV_ENV_SPHERE_YAW
+#undef PV_ENV_SPHERE_GEN
+        // one bounding ball around the whole gripper (hand + both fingers, radius from this configuration's finger
+        // openings) goes first: the three per-box culls and SATs behind it are reached by ~1 % of the lanes
+        bool near_gripper = true;
+        if constexpr (MODE != PV_MODE_MARGIN) {
+            float3 dg_ = v_sub(P.bc[0], oc);
+            float rg_ = P.grip_r + obr;
+            near_gripper = ((rmask >> 8) & 7u) && v_dot(dg_, dg_) < rg_ * rg_;
+        }
+        if (b != S.attached && near_gripper) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (MODE != PV_MODE_MARGIN && !((rmask >> (8 + k)) & 1u)) continue;
+                // bounding-ball cull in front of the 15-axis SAT: always on (exact, and the SAT is ~250 instructions)
+                float3 d_ = v_sub(P.bc[k], oc);
+                float rr_ = (pv_bbr[k] + PV_CULL_SLACK) + obr;
+                if (MODE == PV_MODE_MARGIN || v_dot(d_, d_) < rr_ * rr_) {
+                    pv_box_box<MODE>(acc, P.bc[k], make_float3(pv_bh[k][0], pv_bh[k][1], pv_bh[k][2]), P.hX, P.hY, P.hZ, oc, oh,
+                                     BX, BY, BZ, PV_CODE(2, pv_blink[k], b));
+                }
+            }
+        }
+        PV_EARLY_EXIT_RET()
+    }
+}
+
+// The scene section OUT OF LINE (verdict-bit kernels, PV_COLD_SCENE): only ~2 % of random configurations come near any
+// scene box, so the box loop -- a third of the kernel's code -- is kept out of the instruction stream every warp runs
+// through.  pv_check_config<..., DEFER = true> then only REPORTS that the section is needed and the kernel calls
+// pv_scene_cold afterwards with the configuration re-read from where it came (shared-memory staging, the edge's end
+// points): nothing stays live across the hot path for the sake of the rare call, and the function re-derives the
+// placement from q with the same code, hence the same bits (profiles/r2_notes.md).
+#ifndef PV_COLD_SCENE
+#define PV_COLD_SCENE 1
+#endif
+template <bool CULL, int EXIT, bool FMAK, bool CARRY, bool FTRIG>
+__device__ __noinline__ bool pv_scene_cold(const float* __restrict__ qp, int stride, const PvScene& S) {
+    float q[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) q[j] = qp[j * stride];
+    PvPlaced P;
+    pv_place<FTRIG, CARRY>(q, S, P);
+    PvAcc<PV_MODE_BITS> acc;
+    pv_scene_section<PV_MODE_BITS, CULL, EXIT, 0, FMAK, CARRY>(acc, P, S);
+    if constexpr (PV_PACK) acc.hit |= acc.packed_hit();
+    return acc.hit;
+}
+
 // Returns through `acc`.  All 32 lanes of a warp must call this together when EXIT != PV_EXIT_NONE.
 // SYNC: every warp of the block calls this together and block-level barriers keep the warps within one
 // code region of each other, so the (large, straight-line) instruction stream is fetched once per SM instead
 // of once per warp (ncu showed stall_no_instruction as the top stall of the free-running version).
-template <int MODE, bool CULL, int EXIT, int SYNC = 0, bool FMAK = false, bool CARRY = false, bool FTRIG = FMAK>
-__device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S, PvAcc<MODE>& acc) {
+// DEFER: do not run the scene section, return whether it is needed (see pv_scene_cold); the return value is false
+// whenever the section has been dealt with here.
+template <int MODE, bool CULL, int EXIT, int SYNC = 0, bool FMAK = false, bool CARRY = false, bool FTRIG = FMAK,
+          bool DEFER = false>
+__device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S, PvAcc<MODE>& acc) {
     static_assert(!SYNC || EXIT == PV_EXIT_NONE, "block barriers and warp-level early exit do not mix");
+    static_assert(!DEFER || (CULL && MODE == PV_MODE_BITS), "only the culling verdict-bit form defers the scene section");
     const unsigned FULL = 0xffffffffu;
 #define PV_LOCKSTEP(level) \
     if constexpr (SYNC >= level) __syncthreads();
-#define PV_EARLY_EXIT()                                                              \
-    if constexpr (MODE == PV_MODE_BITS && EXIT != PV_EXIT_NONE) {                    \
-        if constexpr (PV_PACK) acc.hit |= acc.packed_hit();                             \
-        bool h_ = acc.hit;                                                           \
-        if (EXIT == PV_EXIT_ALL ? __all_sync(FULL, h_) : __any_sync(FULL, h_)) return; \
-    }
+#define PV_EARLY_EXIT() PV_EARLY_EXIT_RET(false)
 
     {
         // Joint limits are part of the model's validity domain and are ALWAYS enforced (PV_FLAG_LIMITS is kept in the
@@ -487,40 +659,12 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
         }
     }
 
-    // FK -> sphere centres (registers) + gripper boxes
-    float3 s[PV_N_SPHERES];
-    float3 hX, hY, hZ, hP, bc[3];
-    pv_fk_visit<(PV_FAST_TRIG && FTRIG)>(q, S.base[0], S.base[1], S.base[2], [&](auto lc, float3 p, float3 X, float3 Y, float3 Z) {
-        constexpr int l = decltype(lc)::value;
-        if constexpr (l == 0) { PV_PLACE_LINK0(s, p, X, Y, Z) }
-        if constexpr (l == 1) { PV_PLACE_LINK1(s, p, X, Y, Z) }
-        if constexpr (l == 2) { PV_PLACE_LINK2(s, p, X, Y, Z) }
-        if constexpr (l == 3) { PV_PLACE_LINK3(s, p, X, Y, Z) }
-        if constexpr (l == 4) { PV_PLACE_LINK4(s, p, X, Y, Z) }
-        if constexpr (l == 5) { PV_PLACE_LINK5(s, p, X, Y, Z) }
-        if constexpr (l == 6) { PV_PLACE_LINK6(s, p, X, Y, Z) }
-        if constexpr (l == 7) { PV_PLACE_LINK7(s, p, X, Y, Z) }
-        if constexpr (l == 8) { hX = X; hY = Y; hZ = Z; hP = p; }
-#define PV_BOX_PLACE(k, link, cx, cy, cz, hx, hy, hz, br) \
-    if constexpr (l == link) bc[k] = v_fma(Z, cz, v_fma(Y, cy, v_fma(X, cx, p)));
-        PV_BOXES(PV_BOX_PLACE)
-#undef PV_BOX_PLACE
-    });
-    const float bh[3][3] = {
-#define PV_BOX_HALF(k, link, cx, cy, cz, hx, hy, hz, br) {hx, hy, hz},
-        PV_BOXES(PV_BOX_HALF)
-#undef PV_BOX_HALF
-    };
-    const float bbr[3] = {
-#define PV_BOX_BR(k, link, cx, cy, cz, hx, hy, hz, br) br,
-        PV_BOXES(PV_BOX_BR)
-#undef PV_BOX_BR
-    };
-    const int blink[3] = {
-#define PV_BOX_LK(k, link, cx, cy, cz, hx, hy, hz, br) link,
-        PV_BOXES(PV_BOX_LK)
-#undef PV_BOX_LK
-    };
+    PvPlaced P;
+    pv_place<FTRIG, CARRY>(q, S, P);
+    float3(&s)[PV_N_SPHERES] = P.s;
+    const float3 hX = P.hX, hY = P.hY, hZ = P.hZ, hP = P.hP;
+    float3(&bc)[3] = P.bc;
+    const float grip_r = P.grip_r;
 
     // ---- robot vs ground plane (link0 is fixed to the world: pair filtered) -------------
     const float tz = S.table_z;
@@ -534,26 +678,15 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float ext = fmaf(fabsf(hZ.z), bh[k][2], fmaf(fabsf(hY.z), bh[k][1], fabsf(hX.z) * bh[k][0]));
-        pv_plane<MODE>(acc, bc[k].z - ext, tz, PV_CODE(1, blink[k], 0));
+        float ext = fmaf(fabsf(hZ.z), pv_bh[k][2], fmaf(fabsf(hY.z), pv_bh[k][1], fabsf(hX.z) * pv_bh[k][0]));
+        pv_plane<MODE>(acc, bc[k].z - ext, tz, PV_CODE(1, pv_blink[k], 0));
     }
     // ---- carried box: placed by the hand, checked against the plane and the arm spheres of link0..link6 --------
-    float3 cC = hP, cH = make_float3(0.f, 0.f, 0.f), cX = hX, cY = hY, cZ = hZ;
-    float cbr = 0.f;
     if constexpr (CARRY) {
-        cH = make_float3(S.carry_h[0], S.carry_h[1], S.carry_h[2]);
-        cbr = S.carry_br;
-        cC = v_fma(hZ, S.carry_t[2], v_fma(hY, S.carry_t[1], v_fma(hX, S.carry_t[0], hP)));
-#define PV_CARRY_AXIS(j) \
-    v_fma(hZ, S.carry_R[6 + j], v_fma(hY, S.carry_R[3 + j], make_float3(hX.x * S.carry_R[j], hX.y * S.carry_R[j], hX.z * S.carry_R[j])))
-        cX = PV_CARRY_AXIS(0);
-        cY = PV_CARRY_AXIS(1);
-        cZ = PV_CARRY_AXIS(2);
-#undef PV_CARRY_AXIS
-        float ext = fmaf(fabsf(cZ.z), cH.z, fmaf(fabsf(cY.z), cH.y, fabsf(cX.z) * cH.x));
-        pv_plane<MODE>(acc, cC.z - ext, tz, PV_CODE(1, PV_LINK_CARRIED, 0));
+        float ext = fmaf(fabsf(P.cZ.z), P.cH.z, fmaf(fabsf(P.cY.z), P.cH.y, fabsf(P.cX.z) * P.cH.x));
+        pv_plane<MODE>(acc, P.cC.z - ext, tz, PV_CODE(1, PV_LINK_CARRIED, 0));
 #define PV_CARRY_SPHERE(i, link, cx, cy, cz, r) \
-    if (link <= 6) pv_sphere_box<MODE>(acc, s[i], r, (r) * (r), cC, cH, cX, cY, cZ, PV_CODE(3, link, PV_LINK_CARRIED));
+    if (link <= 6) pv_sphere_box<MODE>(acc, s[i], r, (r) * (r), P.cC, P.cH, P.cX, P.cY, P.cZ, PV_CODE(3, link, PV_LINK_CARRIED));
         PV_SPHERES(PV_CARRY_SPHERE)
 #undef PV_CARRY_SPHERE
     }
@@ -561,14 +694,6 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
     PV_LOCKSTEP(2)
 
     // ---- self collision ------------------------------------------------------------------------------
-    // radius of a ball centred on the hand box that contains all three gripper boxes for THIS configuration
-    // (with both fingers inside their travel the hand box's own bounding ball contains them -- asserted by the model
-    // generator -- so the general form only runs for out-of-limit finger values)
-    float grip_r = bbr[0] + 2.0f * PV_CULL_SLACK;
-    if (!(fabsf(q[7]) <= PV_GRIP_CONST_MAXQ && fabsf(q[8]) <= PV_GRIP_CONST_MAXQ)) {
-        float3 d1 = v_sub(bc[1], bc[0]), d2 = v_sub(bc[2], bc[0]);
-        grip_r = fmaxf(bbr[0], fmaxf(sqrtf(v_dot(d1, d1)) + bbr[1], sqrtf(v_dot(d2, d2)) + bbr[2])) + 2.0f * PV_CULL_SLACK;
-    }
     if (S.flags & PV_FLAG_SELF) {
 #define PV_SS(a, b, rr2, rr) pv_sphere_sphere<MODE>(acc, s[a], s[b], rr2, rr, PV_SELF_CODE(a, pv_sphere_link[b]));
 #define PV_SS2(a, b0, b1, n0, n1, k) pv_sphere_sphere2<k>(acc, s[a], s[b0], s[b1], n0, n1);
@@ -660,83 +785,21 @@ __device__ __forceinline__ void pv_check_config(const float* q, const PvScene& S
                           bc[0].y + grip_r > S.aabb_lo[1] && bc[0].y - grip_r < S.aabb_hi[1] &&
                           bc[0].z + grip_r > S.aabb_lo[2] && bc[0].z - grip_r < S.aabb_hi[2];
         if constexpr (CARRY) {
-            const float rc_ = cbr + PV_CULL_SLACK;
-            near_scene |= cC.x + rc_ > S.aabb_lo[0] && cC.x - rc_ < S.aabb_hi[0] && cC.y + rc_ > S.aabb_lo[1] &&
-                          cC.y - rc_ < S.aabb_hi[1] && cC.z + rc_ > S.aabb_lo[2] && cC.z - rc_ < S.aabb_hi[2];
+            const float rc_ = P.cbr + PV_CULL_SLACK;
+            near_scene |= P.cC.x + rc_ > S.aabb_lo[0] && P.cC.x - rc_ < S.aabb_hi[0] && P.cC.y + rc_ > S.aabb_lo[1] &&
+                          P.cC.y - rc_ < S.aabb_hi[1] && P.cC.z + rc_ > S.aabb_lo[2] && P.cC.z - rc_ < S.aabb_hi[2];
         }
         // kernels with warp votes inside the loop (EXIT) must take the branch as a whole warp
         if constexpr (EXIT != PV_EXIT_NONE) near_scene = __any_sync(FULL, near_scene);
     }
-    const int nb = S.n_obb;
-    if (near_scene)
-    for (int b = 0; b < nb; ++b) {
-        PV_LOCKSTEP(3)
-        if constexpr (CARRY) {
-            if (b == S.attached) continue;  // it is where the hand is, not where the snapshot saw it
-        }
-        const float3 oc = make_float3(S.obb[b][0], S.obb[b][1], S.obb[b][2]);
-        const float3 oh = make_float3(S.obb[b][3], S.obb[b][4], S.obb[b][5]);
-        const float obr = S.obb[b][15];
-        const float3 BX = make_float3(S.obb[b][6], S.obb[b][9], S.obb[b][12]);
-        const float3 BY = make_float3(S.obb[b][7], S.obb[b][10], S.obb[b][13]);
-        const float3 BZ = make_float3(S.obb[b][8], S.obb[b][11], S.obb[b][14]);
-        const bool yaw_only = (S.yaw_only_mask >> b) & 1u;
-        float3 ok = oc;
-        if constexpr (FMAK) ok = make_float3(v_dot(oc, BX), v_dot(oc, BY), yaw_only ? oc.z : v_dot(oc, BZ));
-        const unsigned rmask = S.reach_mask[b];
-        if constexpr (CARRY) {
-            float3 d_ = v_sub(cC, oc);
-            float rr_ = (cbr + PV_CULL_SLACK) + obr;
-            if (MODE == PV_MODE_MARGIN || v_dot(d_, d_) < rr_ * rr_)
-                pv_box_box<MODE>(acc, cC, cH, cX, cY, cZ, oc, oh, BX, BY, BZ, PV_CODE(2, PV_LINK_CARRIED, b));
-        }
-        // one uniform yaw / general decision per GROUP keeps the hot (yaw-only) sphere tests contiguous in the code
-#define PV_ENV_SPHERE_YAW(i, link, cx, cy, cz, r)                                                         \
-    if constexpr (FMAK) pv_sphere_box_yaw_k<MODE>(acc, s[i], r, (r) * (r), ok, oh, BX.x, BX.y, PV_CODE(2, link, b)); \
-    else pv_sphere_box_yaw<MODE>(acc, s[i], r, (r) * (r), oc, oh, BX.x, BX.y, PV_CODE(2, link, b));
-#define PV_ENV_SPHERE_GEN(i, link, cx, cy, cz, r)                                                         \
-    if constexpr (FMAK) pv_sphere_box_k<MODE>(acc, s[i], r, (r) * (r), ok, oh, BX, BY, BZ, PV_CODE(2, link, b)); \
-    else pv_sphere_box<MODE>(acc, s[i], r, (r) * (r), oc, oh, BX, BY, BZ, PV_CODE(2, link, b));
-#define PV_ENV_GROUP(l, cs, br)                                 \
-    if (MODE == PV_MODE_MARGIN || (rmask & (1u << l))) {        \
-        float3 d_ = v_sub(s[cs], oc);                           \
-        float rr_ = (br + PV_CULL_SLACK) + obr;                 \
-        if (!CULL || v_dot(d_, d_) < rr_ * rr_) {               \
-            if (yaw_only) {                                     \
-                PV_SPHERES_LINK##l(PV_ENV_SPHERE_YAW)           \
-            } else {                                            \
-                PV_SPHERES_LINK##l(PV_ENV_SPHERE_GEN)           \
-            }                                                   \
-        }                                                       \
+    if constexpr (DEFER) {
+        if constexpr (PV_PACK) acc.hit |= acc.packed_hit();
+        return near_scene;
+    } else {
+        if (near_scene) pv_scene_section<MODE, CULL, EXIT, SYNC, FMAK, CARRY>(acc, P, S);
+        if constexpr (MODE == PV_MODE_BITS && PV_PACK) acc.hit |= acc.packed_hit();
+        return false;
     }
-        PV_LINK_GROUPS(PV_ENV_GROUP)
-#undef PV_ENV_GROUP
-#undef PV_ENV_SPHERE_YAW
-#undef PV_ENV_SPHERE_GEN
-        // one bounding ball around the whole gripper (hand + both fingers, radius from this configuration's finger
-        // openings) goes first: the three per-box culls and SATs behind it are reached by ~1 % of the lanes
-        bool near_gripper = true;
-        if constexpr (MODE != PV_MODE_MARGIN) {
-            float3 dg_ = v_sub(bc[0], oc);
-            float rg_ = grip_r + obr;
-            near_gripper = ((rmask >> 8) & 7u) && v_dot(dg_, dg_) < rg_ * rg_;
-        }
-        if (b != S.attached && near_gripper) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (MODE != PV_MODE_MARGIN && !((rmask >> (8 + k)) & 1u)) continue;
-                // bounding-ball cull in front of the 15-axis SAT: always on (exact, and the SAT is ~250 instructions)
-                float3 d_ = v_sub(bc[k], oc);
-                float rr_ = (bbr[k] + PV_CULL_SLACK) + obr;
-                if (MODE == PV_MODE_MARGIN || v_dot(d_, d_) < rr_ * rr_) {
-                    pv_box_box<MODE>(acc, bc[k], make_float3(bh[k][0], bh[k][1], bh[k][2]), hX, hY, hZ, oc, oh, BX, BY,
-                                     BZ, PV_CODE(2, blink[k], b));
-                }
-            }
-        }
-        PV_EARLY_EXIT()
-    }
-    if constexpr (MODE == PV_MODE_BITS && PV_PACK) acc.hit |= acc.packed_hit();
 #undef PV_EARLY_EXIT
 #undef PV_LOCKSTEP
 }

@@ -415,6 +415,28 @@ static double now_ms() {
 
 extern "C" {
 
+int pv_obb_from_poses(const double* pos, const double* quat, const double* half, int n, float* obb_out) {
+    if (n < 0 || (n > 0 && (!pos || !half || !obb_out))) return PV_ERR_BAD_ARG;
+    for (int k = 0; k < n; ++k) {
+        double w = 1, x = 0, y = 0, z = 0;
+        if (quat) {
+            w = quat[4 * k], x = quat[4 * k + 1], y = quat[4 * k + 2], z = quat[4 * k + 3];
+            const double nq = sqrt(w * w + x * x + y * y + z * z);
+            if (!(nq > 0)) return PV_ERR_BAD_ARG;
+            w /= nq, x /= nq, y /= nq, z /= nq;
+        }
+        float* o = obb_out + 16 * k;
+        const double hx = half[3 * k], hy = half[3 * k + 1], hz = half[3 * k + 2];
+        o[0] = (float)pos[3 * k], o[1] = (float)pos[3 * k + 1], o[2] = (float)pos[3 * k + 2];
+        o[3] = (float)hx, o[4] = (float)hy, o[5] = (float)hz;
+        o[6] = (float)(1 - 2 * (y * y + z * z)), o[7] = (float)(2 * (x * y - z * w)), o[8] = (float)(2 * (x * z + y * w));
+        o[9] = (float)(2 * (x * y + z * w)), o[10] = (float)(1 - 2 * (x * x + z * z)), o[11] = (float)(2 * (y * z - x * w));
+        o[12] = (float)(2 * (x * z - y * w)), o[13] = (float)(2 * (y * z + x * w)), o[14] = (float)(1 - 2 * (x * x + y * y));
+        o[15] = (float)sqrt(hx * hx + hy * hy + hz * hz);
+    }
+    return PV_OK;
+}
+
 int pv_interpolate_path(const double* states, int n_states, int count, double* out, int capacity, int* n_out) {
     if (!states || n_states < 0 || !out || !n_out) return PV_ERR_BAD_ARG;
     Path p(n_states);
@@ -538,8 +560,9 @@ int pv_plan_path(PvHandle* h, const double* start, const double* goal, int num_w
         int iters = 0;
         long long checks = 0;
         bool spec_queued = false;
-        std::function<void(cudaStream_t)> hook = [&](cudaStream_t s) {
-            if (attempt == 0 && spec_n > 0) spec_queued = plan_queue_edges(h, spec, spec_n, base_res, s) == PV_OK;
+        // the speculative validation does not depend on the solve: it runs beside it on a second stream
+        std::function<void(cudaStream_t)> hook = [&](cudaStream_t) {
+            if (attempt == 0 && spec_n > 0) spec_queued = plan_queue_edges(h, spec, spec_n, base_res, h->streams[1]) == PV_OK;
         };
         const double t_solve = now_ms();
         rc = pv_rrtc_run(h, sg, sg + 9, 1, &rp,
@@ -551,6 +574,7 @@ int pv_plan_path(PvHandle* h, const double* start, const double* goal, int num_w
                                  for (int j = 0; j < 9; ++j) raw[k][j] = (double)rows[(size_t)(off[0] + k) * 9 + j];
                          },
                          &hook);
+        if (spec_queued && attempt == 0) PL_CUDA(cudaStreamSynchronize(h->streams[1]));
         S.ms_solve += (float)(now_ms() - t_solve);
         if (rc) return rc;
         if (iters < 0) {  // start / goal out of bounds or in collision: OMPL finds no valid start / goal -> no solution

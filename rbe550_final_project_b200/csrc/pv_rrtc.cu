@@ -84,6 +84,10 @@ struct RrtcArgs {
     float* rows;          // packed path states [sum of lengths][9]
     unsigned* cursor;     // rows handed out so far (device)
     unsigned* cursor_next;  // the other call parity's cursor: zeroed here so the next call needs no memset
+    // a single query travels in the kernel parameters themselves (constant bank): nothing is read over PCIe before the
+    // searches start
+    int use_inline;
+    float inline_q[18];
 };
 
 __device__ __forceinline__ void rrtc_sample(unsigned seed, unsigned search, unsigned it, float* q, float& extra) {
@@ -148,12 +152,21 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
     float* tq = A.tree_q + (size_t)search * 2 * 9 * M;
     int* par = A.parent + (size_t)search * 2 * M;
     float* path = A.path_tmp + (size_t)search * A.path_rows * 9;
-    const float* q_start = A.starts + (size_t)row * 9;
-    const float* q_goal = A.goals + (size_t)row * 9;
-
+    float qs_[9], qg_[9];  // warp-uniform copies of the query (registers)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        qs_[k] = A.use_inline ? A.inline_q[k] : A.starts[(size_t)row * 9 + k];
+        qg_[k] = A.use_inline ? A.inline_q[9 + k] : A.goals[(size_t)row * 9 + k];
+    }
     if (lane < 9) {
-        tq[(size_t)lane * M] = q_start[lane];
-        tq[(size_t)(9 + lane) * M] = q_goal[lane];
+        float vs = qs_[0], vg = qg_[0];
+#pragma unroll
+        for (int k = 1; k < 9; ++k) {
+            vs = (lane == k) ? qs_[k] : vs;
+            vg = (lane == k) ? qg_[k] : vg;
+        }
+        tq[(size_t)lane * M] = vs;
+        tq[(size_t)(9 + lane) * M] = vg;
     }
     if (lane == 0) {
         par[0] = -1;
@@ -171,7 +184,7 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
         // the start, the other lanes the goal (the state check itself enforces the bounds)
         float qe[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) qe[k] = (lane == 0) ? q_start[k] : q_goal[k];
+        for (int k = 0; k < 9; ++k) qe[k] = (lane == 0) ? qs_[k] : qg_[k];
         PvAcc<PV_MODE_BITS> acc0;
         pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, 0, false, CARRY>(qe, S, acc0);
         const bool bad = acc0.hit;
@@ -657,6 +670,11 @@ int pv_rrtc_run(PvHandle* h, const float* h_starts, const float* h_goals, int n,
             // zero-copy: the kernels read the queries from, and write the results to, host-mapped pinned memory
             a.starts = hm_starts;
             a.goals = hm_goals;
+            if (n == 1) {
+                a.use_inline = 1;
+                memcpy(a.inline_q, hm_starts, 9 * sizeof(float));
+                memcpy(a.inline_q + 9, hm_goals, 9 * sizeof(float));
+            }
             meta_ptrs(a, h_meta);
             a.rows = hm_rows;
         } else {

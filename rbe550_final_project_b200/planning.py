@@ -86,6 +86,20 @@ class Waypoints(collections.abc.Sequence):
         return f"Waypoints(n={len(self)})"
 
 
+_EPS = float(np.finfo(np.float64).eps)
+_LOWER = tuple(float(v) for v in pm.Q_LOWER)
+_UPPER = tuple(float(v) for v in pm.Q_UPPER)
+
+
+def _satisfies_bounds(q: np.ndarray) -> bool:
+    """ob.RealVectorBounds check of planning.py:165-173 (satisfiesBounds: eps slack on both sides); plain floats, this
+    sits inside the plan time."""
+    for v, lo, hi in zip(q.tolist(), _LOWER, _UPPER):
+        if not (v - _EPS <= hi and v + _EPS >= lo):
+            return False
+    return True
+
+
 class PlanningError(Exception):
     """Raised where the reference calls gs.raise_exception (planning.py:106,119,122,125,135)."""
 
@@ -297,12 +311,12 @@ class PlannerInterface:
         t_scene = time.perf_counter()
         self.attached_object = attached_object  # planning.py:153
         self._q_grasp = np.asarray(tensor_to_array(qpos_cur), dtype=np.float32) if attached_object is not None else None
-        self._apply_attached(attached_object, self._q_grasp)
+        if attached_object is not None:
+            self._apply_attached(attached_object, self._q_grasp)  # (refresh_scene left the handle with nothing attached)
 
         # diagnostics on start / goal (planning.py:163-183): log, keep going
-        eps = np.finfo(np.float64).eps
-        start_in = bool(np.all((qpos_start - eps <= upper) & (qpos_start + eps >= lower)))
-        goal_in = bool(np.all((qpos_goal - eps <= upper) & (qpos_goal + eps >= lower)))
+        start_in = _satisfies_bounds(qpos_start)
+        goal_in = _satisfies_bounds(qpos_goal)
         if not start_in:
             logger.warning("OMPL start state out of bounds")
             self.diagnose_bounds_violation(qpos_start, lower, upper)
@@ -337,7 +351,9 @@ class PlannerInterface:
                     waypoints = Waypoints(wp)
         finally:
             # the handle may be shared: whoever uses it next must not inherit this plan's grasp
-            self.validity.set_attached(-1)
+            if attached_object is not None:
+                stats["carried"] = self.validity.carried  # (R, t, allowance) of the carry mode, None otherwise
+                self.validity.set_attached(-1)
         if not len(waypoints):
             logger.warning("Path planning failed. Returning empty path.")
         t_end = time.perf_counter()

@@ -189,6 +189,49 @@ def _to_np(x) -> np.ndarray:
     return np.asarray(x, dtype=np.float64).reshape(-1)
 
 
+def _host_vec(x):
+    """get_pos() / get_quat() of a Genesis-like entity -> something np.array() digests cheaply (torch -> numpy)."""
+    if hasattr(x, "detach"):
+        x = x.detach()
+        if x.device.type != "cpu":
+            x = x.cpu()
+        return x.numpy()
+    return x
+
+
+_BOX_CACHE: dict = {}
+_IDENTITY_QUAT = (1.0, 0.0, 0.0, 0.0)
+
+
+def _box_entities(scene: Any, raw: Any, robot: Any):
+    """(entities, names, idxs, half extents) of the box entities of a scene -- everything about them that does not
+    change between plans, cached per scene object and entity count."""
+    ents = getattr(scene, "entities", [])
+    key = (id(scene), len(ents), id(raw))
+    hit = _BOX_CACHE.get(key)
+    if hit is not None and all(a is b for a, b in zip(hit[0], ents)):
+        return hit[1]
+    boxes, names, idxs, halves = [], [], [], []
+    for k, ent in enumerate(ents):
+        if ent is raw or ent is robot:
+            continue
+        size = getattr(getattr(ent, "morph", None), "size", None)
+        if size is None:
+            continue
+        boxes.append(ent)
+        names.append(str(getattr(ent, "name", f"entity{k}")))
+        idxs.append(int(getattr(ent, "idx", k)))
+        halves.append([0.5 * float(v) for v in size[:3]])
+    if len(boxes) > PV_MAX_OBB:
+        raise ValueError(f"scene has {len(boxes)} boxes; the validity kernels stage at most {PV_MAX_OBB}")
+    half = np.asarray(halves, dtype=np.float64).reshape(len(boxes), 3)
+    val = (boxes, names, idxs, half, np.sqrt((half * half).sum(axis=1)), [hasattr(e, "get_quat") for e in boxes])
+    if len(_BOX_CACHE) > 64:
+        _BOX_CACHE.clear()
+    _BOX_CACHE[key] = (list(ents), val)
+    return val
+
+
 def snapshot_from_sim(scene: Any, robot: Any) -> SceneSnapshot:
     """Read every box entity of a Genesis-like scene into an OBB buffer.
 
@@ -196,38 +239,28 @@ def snapshot_from_sim(scene: Any, robot: Any) -> SceneSnapshot:
     scenes.py:49-85), `entity.idx`, `entity.morph.size` for `gs.morphs.Box`, `entity.get_pos()`,
     `entity.get_quat()` (wxyz).  The robot entity (unwrapped through RobotAdapter.raw/.robot), planes
     and anything without a box size are skipped; the plane supplies table_z = 0.
+    This runs once per plan_path, i.e. inside the plan time: the per-entity facts that cannot change (which entities
+    are boxes, their sizes, names, ids) are cached, the poses are read every time and turned into rotation matrices
+    for all boxes at once.
     """
     raw = getattr(robot, "raw", None) or getattr(robot, "robot", robot)
-    recs, names, idxs = [], [], []
-    for k, ent in enumerate(getattr(scene, "entities", [])):
-        if ent is raw or ent is robot:
-            continue
-        size = getattr(getattr(ent, "morph", None), "size", None)
-        if size is None:
-            continue
-        # plain-float arithmetic: this runs once per plan_path and numpy calls on 3-4 element arrays dominate otherwise
-        px, py, pz = (float(v) for v in _to_np(ent.get_pos())[:3])
-        if hasattr(ent, "get_quat"):
-            w, x, y, z = (float(v) for v in _to_np(ent.get_quat())[:4])
-            nq = math.sqrt(w * w + x * x + y * y + z * z)
-            w, x, y, z = w / nq, x / nq, y / nq, z / nq
-        else:
-            w, x, y, z = 1.0, 0.0, 0.0, 0.0
-        hx, hy, hz = (0.5 * float(v) for v in size[:3])
-        recs.append((px, py, pz, hx, hy, hz,
-                     1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
-                     2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
-                     2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y),
-                     math.sqrt(hx * hx + hy * hy + hz * hz)))
-        names.append(str(getattr(ent, "name", f"entity{k}")))
-        idxs.append(int(getattr(ent, "idx", k)))
-    if len(recs) > PV_MAX_OBB:
-        raise ValueError(f"scene has {len(recs)} boxes; the validity kernels stage at most {PV_MAX_OBB}")
+    boxes, names, idxs, half, radius, has_quat = _box_entities(scene, raw, robot)
+    n = len(boxes)
+    obb = np.empty((n, 16), dtype=np.float32)
+    if n:
+        pos = np.array([_host_vec(e.get_pos()) for e in boxes], dtype=np.float64)
+        quat = np.array([_host_vec(e.get_quat()) if hq else _IDENTITY_QUAT for e, hq in zip(boxes, has_quat)], dtype=np.float64)
+        if pos.shape != (n, 3) or quat.shape != (n, 4):
+            pos = np.ascontiguousarray(pos.reshape(n, -1)[:, :3])
+            quat = np.ascontiguousarray(quat.reshape(n, -1)[:, :4])
+        from . import _cabi
+        if _cabi.load().pv_obb_from_poses(pos.ctypes.data, quat.ctypes.data, half.ctypes.data, n, obb.ctypes.data) != 0:
+            raise ValueError("snapshot_from_sim: an entity reports a zero or non-finite quaternion")
     base = pm.BASE_LIFT
     if hasattr(raw, "get_pos"):
         try:
-            base = tuple(float(v) for v in _to_np(raw.get_pos())[:3])
+            b = _host_vec(raw.get_pos())
+            base = (float(b[0]), float(b[1]), float(b[2]))
         except Exception:
             base = pm.BASE_LIFT
-    obb = np.array(recs, dtype=np.float32).reshape(len(recs), 16)
     return SceneSnapshot(obb=obb, table_z=0.0, base=base, names=names, entity_idx=idxs)

@@ -149,7 +149,8 @@ def test_plan_path_carrying_the_block(pv, c64):
     assert len(path) == 150 and planner.last_stats["solved"]
     arr = np.stack([w.numpy() for w in path]).astype(np.float64)
     assert np.allclose(arr[0], q_grasp, atol=1e-6) and np.allclose(arr[-1], goal, atol=1e-6)
-    R, t, shrink = pv.carried
+    R, t, shrink = planner.last_stats["carried"]  # the handle itself is left with nothing attached
+    assert pv.carried is None and pv.attached == -1
     osc = sc.goal1_scattered().as_oracle_scene()
     osc["carried"] = dict(index=0, R=R, t=t, shrink=shrink)
     wm = c64.state_margin(arr, osc)

@@ -88,6 +88,23 @@ def test_simplifier_shortens_and_stays_valid(wall_problem, c64):
     assert shorter >= len(raws) - 1
 
 
+def test_simplifier_with_the_c_validator_matches_the_python_validator(wall_problem, c32):
+    """bench.py's CPU arm runs the simplifier with the oracle's C callback (no Python in the loop): same answers."""
+    scene, raws, _ = wall_problem
+    fn, ctx, keep = c32.edge_callback(scene)
+    lib = _cabi.load()
+    for raw in raws[:3]:
+        ref, counters, _ = _simplify(raw, lambda qa, qb: c32.edge_margin(qa, qb, scene, n_steps=0) >= 0, seed=9)
+        pts = np.ascontiguousarray(raw, dtype=np.float64)
+        out = np.empty((256, 9))
+        n = C.c_int(0)
+        cnt = (C.c_int * 4)()
+        rc = lib.pv_simplify_path_cb(pts.ctypes.data, len(pts), 9, _cabi.EDGE_CALLBACK(fn.value), C.byref(ctx),
+                                     out.ctypes.data, 256, C.byref(n), cnt)
+        assert rc == 0 and np.array_equal(out[: n.value], ref) and [int(c) for c in cnt] == counters
+    assert ctx.motions > 0 and ctx.states >= ctx.motions
+
+
 def test_simplifier_smooths_corners(wall_problem):
     """With nothing in the way, a dog-leg becomes one straight motion (vertex / partial shortcuts) -- and a corner that
     must stay (validator forbids the straight motion) is rounded by the B-spline pass: more vertices, shorter path."""
