@@ -611,11 +611,11 @@ __device__ __forceinline__ void pv_scene_section(PvAcc<MODE>& acc, const PvPlace
 #ifndef PV_COLD_SCENE
 #define PV_COLD_SCENE 1
 #endif
-template <bool CULL, int EXIT, bool FMAK, bool CARRY, bool FTRIG>
-__device__ __noinline__ bool pv_scene_cold(const float* __restrict__ qp, int stride, const PvScene& S) {
+// LOAD: a small trivially-copyable callable that re-creates the configuration (load(q) fills q[9])
+template <bool CULL, int EXIT, bool FMAK, bool CARRY, bool FTRIG, class LOAD>
+__device__ __noinline__ bool pv_scene_cold(LOAD load, const PvScene& S) {
     float q[9];
-#pragma unroll
-    for (int j = 0; j < 9; ++j) q[j] = qp[j * stride];
+    load(q);
     PvPlaced P;
     pv_place<FTRIG, CARRY>(q, S, P);
     PvAcc<PV_MODE_BITS> acc;
@@ -803,6 +803,36 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
 #undef PV_EARLY_EXIT
 #undef PV_LOCKSTEP
 }
+
+// ---- re-loaders of a configuration for pv_scene_cold --------------------------------------------------------
+struct PvReloadSoa {  // two float4 (+ optional ninth value) wherever they live (global planes, shared-memory staging)
+    const float4* a;
+    const float4* b;
+    const float* c;
+    __device__ __forceinline__ void operator()(float* q) const {
+        const float4 x = *a, y = *b;
+        q[0] = x.x; q[1] = x.y; q[2] = x.z; q[3] = x.w;
+        q[4] = y.x; q[5] = y.y; q[6] = y.z; q[7] = y.w;
+        q[8] = c ? *c : y.w;
+    }
+};
+struct PvReloadStrided {  // q[j] = p[j * stride] for j < np; the rest (fingers fixed open) = 0.04
+    const float* p;
+    int stride, np;
+    __device__ __forceinline__ void operator()(float* q) const {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) q[j] = j < np ? p[j * stride] : 0.04f;
+    }
+};
+struct PvReloadLerp {  // state k of nd on the motion ea -> eb, exactly as the edge / planner kernels form it
+    float ea[9], eb[9];
+    float t;
+    bool at_end;
+    __device__ __forceinline__ void operator()(float* q) const {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) q[c] = at_end ? eb[c] : fmaf(t, eb[c] - ea[c], ea[c]);
+    }
+};
 
 // ---- config loads ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void pv_load_soa(const float4* __restrict__ qA, const float4* __restrict__ qB,

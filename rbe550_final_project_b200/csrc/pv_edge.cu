@@ -123,8 +123,23 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
 #pragma unroll
         for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, eb[c] - ea[c], ea[c]);
         PvAcc<MODE> acc;
-        pv_check_config<MODE, CULL, (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE), 0, false, CARRY,
-                        (PV_EDGE_FAST_TRIG && MODE == PV_MODE_BITS)>(q, S, acc);
+        constexpr bool COLD = PV_COLD_SCENE && CULL && MODE == PV_MODE_BITS;
+        constexpr int EX = (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE);
+        constexpr bool FT = (PV_EDGE_FAST_TRIG && MODE == PV_MODE_BITS);
+        if (pv_check_config<MODE, CULL, EX, 0, false, CARRY, FT, COLD>(q, S, acc)) {
+            // warp-uniform (the check votes before it reports): the whole warp runs the scene section out of line
+            if constexpr (COLD) {
+                PvReloadLerp rl;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    rl.ea[c] = ea[c];
+                    rl.eb[c] = eb[c];
+                }
+                rl.t = t;
+                rl.at_end = (k == nd);
+                acc.hit |= pv_scene_cold<CULL, EX, false, CARRY, FT>(rl, S);
+            }
+        }
         bool edge_done;
         bool edge_hit = false;
         if constexpr (MODE == PV_MODE_BITS) {

@@ -191,6 +191,10 @@ struct PvSortSmem {
     unsigned hist[PV_SORT_BUCKETS];
     unsigned vbits[PV_ST / 32];
     int cnt;
+    // PV_COLD_SCENE: the configurations of the super-tile whose scene section is still owed are noted by the main loop
+    // and worked off densely after it.  The list lives in `order` itself, from the front: iteration r only reads entries
+    // >= r * 512 (and prefetches those of r + 1), while at most (r + 1) * 512 configurations can owe by then
+    int n_owed;
 };
 // where the configurations come from: two float4 planes (+ optional ninth plane) or (n, 9) rows.  (The device-generated
 // sweep keeps the unsorted kernel: it has no loads to hide, and parking the generated configurations in shared memory
@@ -235,6 +239,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         const float* __restrict__ t9 = (AOS || !q9) ? nullptr : q9 + base0;
         const float* __restrict__ t_aos = AOS ? q_aos + 9 * base0 : nullptr;
         if (tid < PV_SORT_BUCKETS) hist[tid] = 0;
+        if (tid == 0) M.n_owed = 0;
         for (int w = tid; w < nc * (PV_SB_THREADS / 32); w += PV_SB_THREADS) vbits[w] = 0;
         __syncthreads();
         // pass 1: keys (kept as bytes for pass 2) and their histogram; the key loads of 8 chunks are in flight together
@@ -330,10 +335,34 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
             __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
 #endif
             PvAcc<PV_MODE_BITS> acc;
-            pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, PV_SB_SYNC, true, CARRY>(q, S, acc);
-            if (in && !acc.hit) atomicOr(&vbits[L >> 5], 1u << (L & 31));
+            constexpr bool COLD = PV_COLD_SCENE && PV_SB_SYNC < 3;
+            const bool owes = pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, PV_SB_SYNC, true, CARRY, true, COLD>(q, S, acc);
+            if (in && !acc.hit) {
+                // the few configurations that come near the scene boxes (~2 % in the goal scenes) are only NOTED here:
+                // their scene section runs after the loop, densely packed, instead of in a sparsely populated warp now
+                if (COLD && owes) order[atomicAdd(&M.n_owed, 1)] = (unsigned short)L;
+                else atomicOr(&vbits[L >> 5], 1u << (L & 31));
+            }
         }
         __syncthreads();
+        if constexpr (PV_COLD_SCENE && PV_SB_SYNC < 3) {
+            const int n_owed = M.n_owed;
+            for (int base = 0; base < n_owed; base += PV_SB_THREADS) {  // block-uniform trip count
+                const int e = base + tid;
+                const bool have = e < n_owed;
+                const int L = order[have ? e : 0];
+                const unsigned i_ = PV_OFF(L / PV_SB_THREADS, L % PV_SB_THREADS);
+                float q[9];
+                if constexpr (AOS) pv_load_aos(t_aos, (int64_t)i_, q);
+                else pv_load_soa(tA, tB, t9, (int64_t)i_, q);
+                PvPlaced P;
+                pv_place<true, CARRY>(q, S, P);
+                PvAcc<PV_MODE_BITS> acc;
+                pv_scene_section<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY>(acc, P, S);
+                if (have && !acc.hit) atomicOr(&vbits[L >> 5], 1u << (L & 31));
+            }
+            __syncthreads();
+        }
         for (int wl = tid; wl < nc * (PV_SB_THREADS / 32); wl += PV_SB_THREADS) {
             const int64_t w = (PV_GI(wl / (PV_SB_THREADS / 32), 0) >> 5) + (wl % (PV_SB_THREADS / 32));
             if (w < n_words) pv_emit_word_thread(bits, G, w, vbits[wl]);
@@ -455,6 +484,7 @@ struct PvSweepSmem {
     unsigned hist[PV_SORT_BUCKETS];
     unsigned vbits[ST_ / 32];
     int cnt;
+    int n_owed;  // see PvSortSmem: the owed list reuses the front of `order`
 };
 
 template <bool CARRY, bool OPEN>
@@ -477,6 +507,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     for (int64_t j0 = 0; j0 < my_chunks; j0 += ST_CHUNKS) {
         const int nc = (int)((my_chunks - j0 < (int64_t)ST_CHUNKS) ? (my_chunks - j0) : (int64_t)ST_CHUNKS);
         if (tid < PV_SORT_BUCKETS) M.hist[tid] = 0;
+        if (tid == 0) M.n_owed = 0;
         for (int w = tid; w < nc * (PV_SB_THREADS / 32); w += PV_SB_THREADS) M.vbits[w] = 0;
         __syncthreads();
         for (int jj = 0; jj < nc; ++jj) {  // pass 1: generate, park, key, histogram
@@ -537,10 +568,31 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
             if (OPEN) q[7] = q[8] = 0.04f;  // what pv_sweep_config sets
             __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
             PvAcc<PV_MODE_BITS> acc;
-            pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY>(q, S, acc);
-            if (in && !acc.hit) atomicOr(&M.vbits[L >> 5], 1u << (L & 31));
+            const bool owes = pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY, true, (PV_COLD_SCENE != 0)>(q, S, acc);
+            if (in && !acc.hit) {
+                if (PV_COLD_SCENE && owes) M.order[atomicAdd(&M.n_owed, 1)] = (unsigned short)L;
+                else atomicOr(&M.vbits[L >> 5], 1u << (L & 31));
+            }
         }
         __syncthreads();
+        if constexpr (PV_COLD_SCENE != 0) {  // the scene sections still owed, densely packed (see the state kernel)
+            const int n_owed = M.n_owed;
+            for (int base = 0; base < n_owed; base += PV_SB_THREADS) {
+                const int e = base + tid;
+                const bool have = e < n_owed;
+                const int L = M.order[have ? e : 0];
+                float q[9];
+#pragma unroll
+                for (int j = 0; j < NP; ++j) q[j] = M.park[j][L];
+                if (OPEN) q[7] = q[8] = 0.04f;
+                PvPlaced P;
+                pv_place<true, CARRY>(q, S, P);
+                PvAcc<PV_MODE_BITS> acc;
+                pv_scene_section<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY>(acc, P, S);
+                if (have && !acc.hit) atomicOr(&M.vbits[L >> 5], 1u << (L & 31));
+            }
+            __syncthreads();
+        }
         for (int wl = tid; wl < nc * (PV_SB_THREADS / 32); wl += PV_SB_THREADS) {
             const int64_t w = (PV_GI(wl / (PV_SB_THREADS / 32), 0) >> 5) + (wl % (PV_SB_THREADS / 32));
             if (w < n_words) {

@@ -182,17 +182,22 @@ struct Simplifier {
             if (c.saving > 1e-6 * total) cands.push_back(c);
         }
         if (cands.empty()) return false;
+        // a motion check assumes its start valid (OMPL's does too), but `a` is a NEW point: it lies on a segment that was
+        // only validated at the resolution's samples.  Every candidate is therefore two entries of the batch: the motion
+        // a -> b and the zero-length motion a -> a, which checks the state a itself
         Path A, B;
         for (auto& c : cands) {
             A.push_back(c.a);
             B.push_back(c.b);
+            A.push_back(c.a);
+            B.push_back(c.a);
         }
         std::vector<unsigned char> ok;
         if (!run_batch(A, B, ok)) return false;
         ++partial_rounds;
         std::vector<int> order;
         for (int k = 0; k < (int)cands.size(); ++k)
-            if (ok[k]) order.push_back(k);
+            if (ok[2 * k] && ok[2 * k + 1]) order.push_back(k);
         std::sort(order.begin(), order.end(), [&](int x, int y) {
             return cands[x].saving != cands[y].saving ? cands[x].saving > cands[y].saving : x < y;
         });
@@ -249,16 +254,31 @@ struct Simplifier {
             B.push_back(s[i + 1]);
         }
         if (idx.empty()) return 0;
+        // the midpoints inserted by the subdivision are new states too (on segments validated at the resolution's
+        // samples only): each is checked as a state of its own (zero-length motion); smoothBSpline asks isValid for them
+        const int n_motion = (int)A.size();
+        for (int i = 1; i < (int)s.size(); i += 2) {
+            A.push_back(s[i]);
+            B.push_back(s[i]);
+        }
         std::vector<unsigned char> ok;
         if (!run_batch(A, B, ok)) return 0;
         ++bspline_steps;
+        auto mid_ok = [&](int i) { return ok[n_motion + (i - 1) / 2] != 0; };  // i odd
         int moved = 0;
         for (size_t k = 0; k < idx.size(); ++k)
-            if (ok[2 * k] && ok[2 * k + 1]) {
+            if (ok[2 * k] && ok[2 * k + 1] && mid_ok(idx[k] - 1) && mid_ok(idx[k] + 1)) {
                 s[idx[k]] = C[k];
                 ++moved;
             }
-        if (moved) p.swap(s);  // a step that moves nothing leaves the path as it was (no growth for nothing)
+        if (!moved) return 0;  // a step that moves nothing leaves the path as it was (no growth for nothing)
+        // a midpoint that is itself in contact (its segment grazes an obstacle between the validator's samples) is not
+        // kept as a vertex: neither of its neighbours has moved (their motions through it failed), so dropping it
+        // restores the original segment
+        Path out;
+        for (int i = 0; i < (int)s.size(); ++i)
+            if ((i & 1) == 0 || mid_ok(i)) out.push_back(s[i]);
+        p.swap(out);
         return moved;
     }
 

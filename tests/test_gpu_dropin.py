@@ -46,8 +46,26 @@ def ref_primitives(tmp_path_factory):
                                            "from rbe550_final_project_b200.robot_adapter import RobotAdapter  # noqa\n")
     saved = {k: sys.modules.pop(k, None) for k in ("planning", "robot_adapter", "motion_primitives")}
     sys.path[:0] = [str(shim), STAGED]
+    # The reference targets Python 3.10 (its __pycache__ holds cpython-310 bytecode): `MotionConfig` gives a dataclass
+    # field an ndarray default (motion_primitives.py:19-21), which Python >= 3.11 rejects as a mutable default.  The file
+    # stays byte-identical; for the duration of ITS import the decorator behaves as on 3.10 (one shared default object).
+    import dataclasses
+    real_dataclass = dataclasses.dataclass
+
+    def dataclass_310(cls=None, **kw):
+        def wrap(c):
+            for name, val in list(vars(c).items()):
+                if isinstance(val, np.ndarray):
+                    setattr(c, name, dataclasses.field(default_factory=lambda v=val: v))
+            return real_dataclass(c, **kw)
+        return wrap if cls is None else wrap(cls)
+
+    dataclasses.dataclass = dataclass_310
     try:
-        mod = importlib.import_module("motion_primitives")
+        try:
+            mod = importlib.import_module("motion_primitives")
+        finally:
+            dataclasses.dataclass = real_dataclass
         assert os.path.samefile(mod.__file__, src)
         import planning
         from rbe550_final_project_b200.planning import PlannerInterface

@@ -119,7 +119,14 @@ def test_attached_object_forgiveness(pv, c64):
     path = planner.plan_path(qpos_goal=pm.Q_SAFE_HOME, qpos_start=q, attached_object=blocks["r"], timeout=10.0,
                              num_waypoints=50)
     assert len(path) == 50
+    assert pv.attached == -1  # plan_path leaves the (shared) handle with nothing attached ...
+    pv.set_attached(0)        # ... so the re-check of the path sets the grasp itself
     _path_ok(pv, c64, sc.goal1_scattered(), np.stack([w.numpy() for w in path]), attached=0)
+    pv.set_attached(-1)
+    # the planner object itself keeps attached_object (planning.py:153) and applies it per query
+    assert planner.attached_object is blocks["r"] and planner._is_ompl_state_valid(q) is True
+    planner.attached_object = None
+    assert planner._is_ompl_state_valid(q) is False
 
 
 def test_validity_callback_shape(pv):
