@@ -611,6 +611,13 @@ __device__ __forceinline__ void pv_scene_section(PvAcc<MODE>& acc, const PvPlace
 #ifndef PV_COLD_SCENE
 #define PV_COLD_SCENE 1
 #endif
+// The warp-per-edge kernels (edge validation, planner) could call the section out of line as pv_scene_cold below; measured
+// on the same box it does not pay there (config 3: 393 -> 367 M edges/s in the pentagon scene, goal-1 unchanged): their
+// warps take the section TOGETHER (the lanes are states of one edge) far more often than 2 % of the time, and every
+// call re-derives the placement.  Off.
+#ifndef PV_COLD_SCENE_WARP
+#define PV_COLD_SCENE_WARP 0
+#endif
 // LOAD: a small trivially-copyable callable that re-creates the configuration (load(q) fills q[9])
 template <bool CULL, int EXIT, bool FMAK, bool CARRY, bool FTRIG, class LOAD>
 __device__ __noinline__ bool pv_scene_cold(LOAD load, const PvScene& S) {

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
 #pragma unroll
         for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, eb[c] - ea[c], ea[c]);
         PvAcc<MODE> acc;
-        constexpr bool COLD = PV_COLD_SCENE && CULL && MODE == PV_MODE_BITS;
+        constexpr bool COLD = PV_COLD_SCENE_WARP && CULL && MODE == PV_MODE_BITS;
         constexpr int EX = (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE);
         constexpr bool FT = (PV_EDGE_FAST_TRIG && MODE == PV_MODE_BITS);
         if (pv_check_config<MODE, CULL, EX, 0, false, CARRY, FT, COLD>(q, S, acc)) {

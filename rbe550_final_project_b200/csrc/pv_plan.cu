@@ -145,7 +145,11 @@ struct Simplifier {
     }
 
     // partialShortcutPath, batched: K random pairs of points on the path (second within +-33 % of the length of the
-    // first, both snapped to a vertex when closer than 0.5 % of the length)
+    // first, both snapped to a vertex when closer than 0.5 % of the length).
+    // A candidate replaces the piece of path between its points a (on segment i1) and b (on segment i2) by the straight
+    // motion a -> b; what is left of the two segments, p[i1] -> a and b -> p[i2 + 1], are NEW motions as well (a segment
+    // that was valid at the validator's samples need not be valid at the samples of a part of it), so a candidate is
+    // three motions of the batch -- the first of which also checks the state a -- and is taken only if all three hold.
     bool partial_round(Path& p, int pass) {
         const int n = (int)p.size();
         if (n < 3) return false;
@@ -154,7 +158,7 @@ struct Simplifier {
         const double total = L[n - 1];
         if (!(total > 0)) return false;
         const int K = 24;
-        struct Cand { double s1, s2, saving; Q9 a, b; };
+        struct Cand { double s1, s2, saving; Q9 a, b; int i1, i2; bool a_vertex, b_vertex; };
         std::vector<Cand> cands;
         for (int k = 0; k < K; ++k) {
             double u[4];
@@ -162,16 +166,19 @@ struct Simplifier {
             double s1 = u[0] * total;
             double s2 = s1 + (2.0 * u[1] - 1.0) * 0.33 * total;
             s2 = std::min(total, std::max(0.0, s2));
-            for (int i = 0; i < n; ++i) {  // snap to vertices
-                if (fabs(s1 - L[i]) < 0.005 * total) s1 = L[i];
-                if (fabs(s2 - L[i]) < 0.005 * total) s2 = L[i];
-            }
             if (s1 > s2) std::swap(s1, s2);
-            if (s2 - s1 < 1e-3 * total) continue;
-            int i1, i2;
             Cand c;
-            c.a = point_at(p, L, s1, i1);
-            c.b = point_at(p, L, s2, i2);
+            c.a_vertex = c.b_vertex = false;
+            for (int i = 0; i < n; ++i) {  // snap to vertices
+                if (fabs(s1 - L[i]) < 0.005 * total) { s1 = L[i]; c.a_vertex = true; c.i1 = i; }
+                if (fabs(s2 - L[i]) < 0.005 * total) { s2 = L[i]; c.b_vertex = true; c.i2 = i - 1; }
+            }
+            if (s2 - s1 < 1e-3 * total) continue;
+            int seg;
+            c.a = point_at(p, L, s1, seg);
+            if (c.a_vertex) c.a = p[c.i1]; else c.i1 = seg;
+            c.b = point_at(p, L, s2, seg);
+            if (c.b_vertex) c.b = p[c.i2 + 1]; else c.i2 = seg;
             // both on one straight segment (or its end points): nothing to gain
             bool bend = false;
             for (int i = 1; i + 1 < n; ++i) bend |= (L[i] > s1 + 1e-12 && L[i] < s2 - 1e-12);
@@ -182,46 +189,49 @@ struct Simplifier {
             if (c.saving > 1e-6 * total) cands.push_back(c);
         }
         if (cands.empty()) return false;
-        // a motion check assumes its start valid (OMPL's does too), but `a` is a NEW point: it lies on a segment that was
-        // only validated at the resolution's samples.  Every candidate is therefore two entries of the batch: the motion
-        // a -> b and the zero-length motion a -> a, which checks the state a itself
         Path A, B;
         for (auto& c : cands) {
+            A.push_back(c.a_vertex ? c.a : p[c.i1]);  // what remains of the segment a lies on (checks the state a)
+            B.push_back(c.a);
             A.push_back(c.a);
             B.push_back(c.b);
-            A.push_back(c.a);
-            B.push_back(c.a);
+            A.push_back(c.b);                          // what remains of the segment b lies on
+            B.push_back(c.b_vertex ? c.b : p[c.i2 + 1]);
         }
         std::vector<unsigned char> ok;
         if (!run_batch(A, B, ok)) return false;
         ++partial_rounds;
         std::vector<int> order;
         for (int k = 0; k < (int)cands.size(); ++k)
-            if (ok[2 * k] && ok[2 * k + 1]) order.push_back(k);
+            if (ok[3 * k] && ok[3 * k + 1] && ok[3 * k + 2]) order.push_back(k);
         std::sort(order.begin(), order.end(), [&](int x, int y) {
             return cands[x].saving != cands[y].saving ? cands[x].saving > cands[y].saving : x < y;
         });
+        // two accepted shortcuts never share a segment (the piece between them would be one more unvalidated motion):
+        // the clash test runs on the vertex-to-vertex extents
+        auto lo_of = [&](const Cand& c) { return L[c.a_vertex ? c.i1 : c.i1]; };
+        auto hi_of = [&](const Cand& c) { return L[c.i2 + 1]; };
         std::vector<int> taken;
         for (int k : order) {
             bool clash = false;
-            for (int t : taken) clash |= !(cands[k].s2 <= cands[t].s1 || cands[k].s1 >= cands[t].s2);
+            for (int t : taken) clash |= !(hi_of(cands[k]) <= lo_of(cands[t]) || lo_of(cands[k]) >= hi_of(cands[t]));
             if (!clash) taken.push_back(k);
         }
         if (taken.empty()) return false;
         std::sort(taken.begin(), taken.end(), [&](int x, int y) { return cands[x].s1 < cands[y].s1; });
         Path out;
-        size_t t = 0;
-        for (int i = 0; i < n; ++i) {
-            while (t < taken.size() && cands[taken[t]].s1 <= L[i]) {
-                // the shortcut starts at or before this vertex: emit its end points, skip the vertices it spans
-                const Cand& c = cands[taken[t]];
-                if (out.empty() || q_dist(out.back(), c.a) > 0) out.push_back(c.a);
-                out.push_back(c.b);
-                while (i < n && L[i] <= c.s2) ++i;
-                ++t;
-            }
-            if (i < n && (out.empty() || q_dist(out.back(), p[i]) > 0)) out.push_back(p[i]);
+        auto push = [&](const Q9& q) {
+            if (out.empty() || q_dist(out.back(), q) > 0) out.push_back(q);
+        };
+        int i = 0;
+        for (int t : taken) {
+            const Cand& c = cands[t];
+            for (; i <= c.i1; ++i) push(p[i]);  // up to and including the vertex in front of (or at) a
+            push(c.a);
+            push(c.b);
+            i = c.i2 + 1;                        // the vertex behind (or at) b comes next
         }
+        for (; i < n; ++i) push(p[i]);
         if (out.size() < 2) return false;
         out.front() = p.front();
         out.back() = p.back();
@@ -229,7 +239,13 @@ struct Simplifier {
         return true;
     }
 
-    // one step of smoothBSpline; returns the number of vertices moved
+    // one step of smoothBSpline; returns the number of vertices moved.  subdivide() puts a midpoint m_i on every
+    // segment; every original interior vertex v_i then moves to c_i = 1/4 m_(i-1) + 1/2 v_i + 1/4 m_i when both new
+    // motions m_(i-1) -> c_i and c_i -> m_i are valid and it moves by more than the minimum change.  The halves
+    // v_i -> m_i and m_i -> v_(i+1) are new motions too; one batch carries them all.  A midpoint both of whose halves
+    // hold is kept (whichever neighbours move, all its motions have then been validated); a midpoint with a failing
+    // half (its segment grazes an obstacle between the validator's samples) pins its two neighbours and is dropped again,
+    // which restores the original segment.
     int bspline_step(Path& p, double min_change) {
         const int n = (int)p.size();
         if (n < 3) return 0;
@@ -240,9 +256,10 @@ struct Simplifier {
             s.push_back(q_lerp(p[i], p[i + 1], 0.5));
         }
         s.push_back(p[n - 1]);
+        const int ns = (int)s.size();
         Path A, B, C;
         std::vector<int> idx;
-        for (int i = 2; i + 1 < (int)s.size(); i += 2) {
+        for (int i = 2; i + 1 < ns; i += 2) {
             const Q9 t1 = q_lerp(s[i - 1], s[i], 0.5), t2 = q_lerp(s[i], s[i + 1], 0.5);
             const Q9 c = q_lerp(t1, t2, 0.5);
             if (!(q_dist(s[i], c) > min_change)) continue;
@@ -254,17 +271,17 @@ struct Simplifier {
             B.push_back(s[i + 1]);
         }
         if (idx.empty()) return 0;
-        // the midpoints inserted by the subdivision are new states too (on segments validated at the resolution's
-        // samples only): each is checked as a state of its own (zero-length motion); smoothBSpline asks isValid for them
         const int n_motion = (int)A.size();
-        for (int i = 1; i < (int)s.size(); i += 2) {
-            A.push_back(s[i]);
+        for (int i = 1; i < ns; i += 2) {  // the two halves of every subdivided segment
+            A.push_back(s[i - 1]);
             B.push_back(s[i]);
+            A.push_back(s[i]);
+            B.push_back(s[i + 1]);
         }
         std::vector<unsigned char> ok;
         if (!run_batch(A, B, ok)) return 0;
         ++bspline_steps;
-        auto mid_ok = [&](int i) { return ok[n_motion + (i - 1) / 2] != 0; };  // i odd
+        auto mid_ok = [&](int i) { return ok[n_motion + (i - 1)] && ok[n_motion + (i - 1) + 1]; };  // i odd
         int moved = 0;
         for (size_t k = 0; k < idx.size(); ++k)
             if (ok[2 * k] && ok[2 * k + 1] && mid_ok(idx[k] - 1) && mid_ok(idx[k] + 1)) {
@@ -272,11 +289,8 @@ struct Simplifier {
                 ++moved;
             }
         if (!moved) return 0;  // a step that moves nothing leaves the path as it was (no growth for nothing)
-        // a midpoint that is itself in contact (its segment grazes an obstacle between the validator's samples) is not
-        // kept as a vertex: neither of its neighbours has moved (their motions through it failed), so dropping it
-        // restores the original segment
         Path out;
-        for (int i = 0; i < (int)s.size(); ++i)
+        for (int i = 0; i < ns; ++i)
             if ((i & 1) == 0 || mid_ok(i)) out.push_back(s[i]);
         p.swap(out);
         return moved;

@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
 #pragma unroll
             for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, de[c], ea[c]);
             PvAcc<PV_MODE_BITS> acc;
-            if (pv_check_config<PV_MODE_BITS, true, PV_EXIT_ANY, 0, false, CARRY, false, (PV_COLD_SCENE != 0)>(q, S, acc)) {
+            if (pv_check_config<PV_MODE_BITS, true, PV_EXIT_ANY, 0, false, CARRY, false, (PV_COLD_SCENE_WARP != 0)>(q, S, acc)) {
                 PvReloadLerp rl;
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {

@@ -54,6 +54,7 @@ class StubPanda(StubEntity):
         self.q_limit = np.stack([pm.Q_LOWER, pm.Q_UPPER])
         self._q = pm.Q_SCENE_INIT.copy()
         self._target = None
+        self.ik_mode = "kinematic"
         self._validity = None
         self._scene = None
         self.set_qpos_calls = 0
@@ -82,15 +83,22 @@ class StubPanda(StubEntity):
         return _Link()
 
     def inverse_kinematics(self, link=None, pos=None, quat=None, **kw):
-        """robot.inverse_kinematics(link=hand, pos=, quat=) (motion_primitives.py:131-134) on the GPU: returns a
-        collision-free qpos (9,) near the current one, or None."""
+        """robot.inverse_kinematics(link=hand, pos=, quat=) (motion_primitives.py:131-134) on the GPU: qpos (9,) near the
+        current one, or None.
+
+        ik_mode "kinematic" (default) is what Genesis gives the reference: a solution inside the joint limits, chosen
+        with NO regard for the scene -- the reference asks for poses that only make sense that way, e.g. the place pose
+        of put_down while the "attached" block is still an obstacle at its old place.  (The candidates
+        are still filtered for SELF-collision, which no caller could use.)  ik_mode "collision_aware" filters them by the
+        full validity rule of the current world: live block poses, the held block attached (planning.py:216-230)."""
         if getattr(link, "name", "hand") != "hand":
             raise NotImplementedError("only the hand link is supported")
         v = self._validity
-        # the candidates are filtered by the validity rule of the CURRENT world: the live block poses, and -- while a
-        # block is held -- hand / finger contacts with it forgiven, as plan_path will judge the goal (planning.py:216-230)
         held = getattr(self._scene, "held", None)
-        if self._scene is not None:
+        prev_scene = v.scene
+        if self.ik_mode == "kinematic":
+            v.set_scene(sc.SceneSnapshot(obb=np.zeros((0, 16), np.float32), table_z=-10.0, base=tuple(self._pos)))
+        elif self._scene is not None:
             snap = sc.snapshot_from_sim(self._scene, self)
             v.set_scene(snap)
             if held is not None:
@@ -98,7 +106,10 @@ class StubPanda(StubEntity):
         try:
             return v.ik(np.asarray(pos, dtype=np.float64), np.asarray(quat, dtype=np.float64), self._q, **kw)
         finally:
-            v.set_attached(-1)
+            if prev_scene is not None:
+                v.set_scene(prev_scene)  # (also leaves nothing attached)
+            else:
+                v.set_attached(-1)
 
     def set_qpos(self, q):
         self.set_qpos_calls += 1
@@ -117,6 +128,8 @@ class StubPanda(StubEntity):
     def hand_pose(self):
         """(position (3,), rotation (3,3)) of the hand link from the FK kernel."""
         import torch
+        if self._validity.scene is None and self._scene is not None:  # FK places the chain on the scene's base pose
+            self._validity.set_scene(sc.snapshot_from_sim(self._scene, self))
         pose = self._validity.fk(torch.as_tensor(self._q[None], dtype=torch.float32, device=self._validity.device))
         pose = pose[0, pm.LINK_NAMES.index("hand")].double().cpu().numpy()
         return pose[:3], pose[3:].reshape(3, 3)

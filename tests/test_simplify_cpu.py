@@ -107,7 +107,8 @@ def test_simplifier_with_the_c_validator_matches_the_python_validator(wall_probl
 
 def test_simplifier_smooths_corners(wall_problem):
     """With nothing in the way, a dog-leg becomes one straight motion (vertex / partial shortcuts) -- and a corner that
-    must stay (validator forbids the straight motion) is rounded by the B-spline pass: more vertices, shorter path."""
+    must stay (validator forbids the straight motion) is cut as far as the validator allows: a shorter path all of whose
+    motions the validator accepts."""
     a = np.array(pm.Q_SAFE_HOME, dtype=np.float64)
     b, c = a.copy(), a.copy()
     b[0] += 0.8
@@ -131,8 +132,8 @@ def test_simplifier_smooths_corners(wall_problem):
         return np.array(ok)
 
     out, counters, _ = _simplify(dogleg, near_corner_only)
-    assert len(out) > 3 and counters[1] >= 1  # B-spline steps ran
-    assert path_length(out) < path_length(dogleg) - 1e-3
+    assert len(out) >= 3 and counters[0] >= 1 and counters[1] >= 1  # partial shortcuts and B-spline steps ran
+    assert path_length(out) < 0.9 * path_length(dogleg)
     assert near_corner_only(out[:-1], out[1:]).all()
 
 
