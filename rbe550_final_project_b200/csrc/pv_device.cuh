@@ -182,14 +182,18 @@ __device__ __forceinline__ void pv_sincos(float x, float& s, float& c) {
 }
 
 // FAST: the hardware approximations (MUFU.SIN / MUFU.COS, abs. error ~4e-7), see PV_FAST_TRIG
-template <bool FAST>
+// REDUCE: bring x into [-pi, pi] first (exact for |x| <= pi, where k = 0): the hardware's own reduction loses accuracy in
+// proportion to |x|.  Only joint 6 (upper limit 3.7525) can exceed pi inside the joint limits, and a state outside the
+// limits is invalid whatever its kinematics are, so the other joints go to MUFU as they are (same bits: k would be 0).
+template <bool FAST, bool REDUCE = true>
 __device__ __forceinline__ void pv_sincos_sel(float x, float& s, float& c) {
     if constexpr (FAST) {
-        // bring x into [-pi, pi] first (exact for |x| <= pi, where k = 0): the hardware's own reduction loses accuracy
-        // in proportion to |x|, and joint values outside the limits are legal input when the limit check is off
-        const float k = rintf(x * 0.15915494309189535f);
-        float r = fmaf(k, -6.2831854820251465f, x);
-        r = fmaf(k, 1.7484555e-7f, r);
+        float r = x;
+        if constexpr (REDUCE) {
+            const float k = rintf(x * 0.15915494309189535f);
+            r = fmaf(k, -6.2831854820251465f, x);
+            r = fmaf(k, 1.7484555e-7f, r);
+        }
         __sincosf(r, &s, &c);
     } else {
         pv_sincos(x, s, c);
@@ -395,14 +399,14 @@ __device__ __forceinline__ void pv_fk_visit(const float* q, float bx, float by, 
     float3 X = make_float3(1.f, 0.f, 0.f), Y = make_float3(0.f, 1.f, 0.f), Z = make_float3(0.f, 0.f, 1.f);
     on_link(std::integral_constant<int, 0>{}, p, X, Y, Z);
     // link1: pos (0,0,0.333), no pre-rotation
-    pv_sincos_sel<FAST>(q[0], s, c);
+    pv_sincos_sel<FAST, false>(q[0], s, c);
     p.z += 0.333f;
     X = make_float3(c, s, 0.f);
     Y = make_float3(-s, c, 0.f);
     on_link(std::integral_constant<int, 1>{}, p, X, Y, Z);
     float3 Xp, Yp, Zp;
     // link2: pos 0, Rx(-90): X' = X, Y' = -Z, Z' = Y
-    pv_sincos_sel<FAST>(q[1], s, c);
+    pv_sincos_sel<FAST, false>(q[1], s, c);
     {
         float3 X1 = X, Y1 = Y;
         X = make_float3(c * X1.x, c * X1.y, -s);
@@ -411,19 +415,19 @@ __device__ __forceinline__ void pv_fk_visit(const float* q, float bx, float by, 
     }
     on_link(std::integral_constant<int, 2>{}, p, X, Y, Z);
     // link3: pos (0,-0.316,0), Rx(+90): X' = X, Y' = Z, Z' = -Y
-    pv_sincos_sel<FAST>(q[2], s, c);
+    pv_sincos_sel<FAST, false>(q[2], s, c);
     p = v_fma(Y, -0.316f, p);
     Xp = X; Yp = Z; Zp = v_neg(Y);
     v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
     on_link(std::integral_constant<int, 3>{}, p, X, Y, Z);
     // link4: pos (0.0825,0,0), Rx(+90)
-    pv_sincos_sel<FAST>(q[3], s, c);
+    pv_sincos_sel<FAST, false>(q[3], s, c);
     p = v_fma(X, 0.0825f, p);
     Xp = X; Yp = Z; Zp = v_neg(Y);
     v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
     on_link(std::integral_constant<int, 4>{}, p, X, Y, Z);
     // link5: pos (-0.0825,0.384,0), Rx(-90): X' = X, Y' = -Z, Z' = Y
-    pv_sincos_sel<FAST>(q[4], s, c);
+    pv_sincos_sel<FAST, false>(q[4], s, c);
     p = v_fma(Y, 0.384f, v_fma(X, -0.0825f, p));
     Xp = X; Yp = v_neg(Z); Zp = Y;
     v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
@@ -434,7 +438,7 @@ __device__ __forceinline__ void pv_fk_visit(const float* q, float bx, float by, 
     v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;
     on_link(std::integral_constant<int, 6>{}, p, X, Y, Z);
     // link7: pos (0.088,0,0), Rx(+90)
-    pv_sincos_sel<FAST>(q[6], s, c);
+    pv_sincos_sel<FAST, false>(q[6], s, c);
     p = v_fma(X, 0.088f, p);
     Xp = X; Yp = Z; Zp = v_neg(Y);
     v_rotz(Xp, Yp, c, s, X, Y); Z = Zp;

@@ -181,11 +181,23 @@ __device__ __forceinline__ void pv_cp_async16(void* smem, const void* g) {
 }
 
 // shared memory of the sorted kernel (dynamic: above the 48 KB static limit)
+// stages of the key pass's load pipeline (one chunk each); they live in the staging area the main loop uses later
+#ifndef PV_KEY_STAGES
+#define PV_KEY_STAGES 6
+#endif
 struct PvSortSmem {
     static constexpr int ST = PV_ST;
-    float4 stA[2][PV_SB_THREADS], stB[2][PV_SB_THREADS];  // double-buffered staging of the NEXT iteration's configuration
-    float st9[2][PV_SB_THREADS];                         // (SoA inputs; AoS inputs use stq)
-    float stq[2][9][PV_SB_THREADS];
+    union {
+        struct {
+            float4 stA[2][PV_SB_THREADS], stB[2][PV_SB_THREADS];  // double-buffered staging of the NEXT iteration's configuration
+            float st9[2][PV_SB_THREADS];                         // (SoA inputs; AoS inputs use stq)
+            float stq[2][9][PV_SB_THREADS];
+        };
+        struct {  // key pass: q1..q4 and q6 of PV_KEY_STAGES chunks in flight
+            float4 kA[PV_KEY_STAGES][PV_SB_THREADS];
+            float k5[PV_KEY_STAGES][PV_SB_THREADS];
+        };
+    };
     unsigned short order[PV_ST];
     unsigned char key8[PV_ST];
     unsigned hist[PV_SORT_BUCKETS];
@@ -242,28 +254,40 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         if (tid == 0) M.n_owed = 0;
         for (int w = tid; w < nc * (PV_SB_THREADS / 32); w += PV_SB_THREADS) vbits[w] = 0;
         __syncthreads();
-        // pass 1: keys (kept as bytes for pass 2) and their histogram; the key loads of 8 chunks are in flight together
-        for (int j8 = 0; j8 < nc; j8 += PV_KEY_LOADS) {
-            float4 kq[PV_KEY_LOADS];
-            float kq5[PV_KEY_LOADS];
+        // pass 1: keys (kept as bytes for pass 2) and their histogram.  This is where the batch is first read from HBM, so
+        // the loads run PV_KEY_STAGES - 1 chunks ahead of the key computation, as cp.async into shared memory (no
+        // registers held): the ~1 us DRAM latency hides behind the ~60 instructions per key of the chunks in front (r2e
+        // profile: with 4 register loads issued and then consumed the loop spent 267 of its 499 stall samples on
+        // long_scoreboard, 13 % of the kernel).  A thread only reads back what it has copied itself: no barrier.
+        {
+            auto issue = [&](int j) {
+                const unsigned o = PV_OFF(j, tid);
+                if (j < nc && o < n_rem) {
+                    const int st_ = j % PV_KEY_STAGES;
+                    if constexpr (AOS) {
+                        float* d = reinterpret_cast<float*>(&M.kA[st_][tid]);
 #pragma unroll
-            for (int u = 0; u < PV_KEY_LOADS; ++u) {
-                const unsigned o = PV_OFF(j8 + u, tid);
-                kq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                kq5[u] = 0.f;
-                if (j8 + u < nc && o < n_rem) {
-                    kq[u] = PV_Q03_OF(o);
-                    if (PV_SORT_Q5_BINS > 1) kq5[u] = AOS ? __ldg(t_aos + 9 * o + 5) : __ldg(reinterpret_cast<const float*>(tB) + 4 * o + 1);
+                        for (int c = 0; c < 4; ++c) pv_cp_async4(d + c, t_aos + 9 * o + c);
+                        pv_cp_async4(&M.k5[st_][tid], t_aos + 9 * o + 5);
+                    } else {
+                        pv_cp_async16(&M.kA[st_][tid], tA + o);
+                        pv_cp_async4(&M.k5[st_][tid], reinterpret_cast<const float*>(tB) + 4 * o + 1);
+                    }
                 }
-            }
-#pragma unroll
-            for (int u = 0; u < PV_KEY_LOADS; ++u) {
-                if (j8 + u < nc && PV_OFF(j8 + u, tid) < n_rem) {
-                    const int key = pv_sort_key(kq[u].x, kq[u].y, kq[u].z, kq[u].w, kq5[u], S);
-                    M.key8[(j8 + u) * PV_SB_THREADS + tid] = (unsigned char)key;
+                asm volatile("cp.async.commit_group;" ::: "memory");  // (an empty group keeps the count uniform)
+            };
+            for (int j = 0; j < PV_KEY_STAGES - 1; ++j) issue(j);
+            for (int j = 0; j < nc; ++j) {
+                issue(j + PV_KEY_STAGES - 1);
+                asm volatile("cp.async.wait_group %0;" ::"n"(PV_KEY_STAGES - 1) : "memory");
+                if (PV_OFF(j, tid) < n_rem) {
+                    const float4 k = M.kA[j % PV_KEY_STAGES][tid];
+                    const int key = pv_sort_key(k.x, k.y, k.z, k.w, M.k5[j % PV_KEY_STAGES][tid], S);
+                    M.key8[j * PV_SB_THREADS + tid] = (unsigned char)key;
                     atomicAdd(&hist[key], 1u);
                 }
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
         if (tid < 32) {  // exclusive prefix sum: 8 buckets per lane + a warp scan
@@ -349,8 +373,9 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
             const int n_owed = M.n_owed;
             for (int base = 0; base < n_owed; base += PV_SB_THREADS) {  // block-uniform trip count
                 const int e = base + tid;
-                const bool have = e < n_owed;
-                const int L = order[have ? e : 0];
+                if (e >= n_owed) continue;  // (no barrier inside this loop)
+                const bool have = true;
+                const int L = order[e];
                 const unsigned i_ = PV_OFF(L / PV_SB_THREADS, L % PV_SB_THREADS);
                 float q[9];
                 if constexpr (AOS) pv_load_aos(t_aos, (int64_t)i_, q);
@@ -579,8 +604,9 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
             const int n_owed = M.n_owed;
             for (int base = 0; base < n_owed; base += PV_SB_THREADS) {
                 const int e = base + tid;
-                const bool have = e < n_owed;
-                const int L = M.order[have ? e : 0];
+                if (e >= n_owed) continue;  // (no barrier inside this loop)
+                const bool have = true;
+                const int L = M.order[e];
                 float q[9];
 #pragma unroll
                 for (int j = 0; j < NP; ++j) q[j] = M.park[j][L];

@@ -61,7 +61,7 @@ def test_fk_verdict_path(pv, c64):
     q = random_configs(50000, 12, fingers="random")
     q[0] = pm.Q_UPPER
     q[1] = pm.Q_LOWER
-    q[2] = [50.0, -40.0, 30.0, -20.0, 10.0, 25.0, -35.0, 0.02, 0.02]  # far outside the limits: still reduced exactly
+    q[2, 5] = np.float32(3.7525)  # the one joint that exceeds pi inside its limits (reduced by 2 pi before MUFU)
     out = pv.fk(_dev(q), verdict_path=True).cpu().numpy()
     R, p = c64.fk(q.astype(np.float64))
     err_p = np.abs(out[:, :, 0:3] - p).max()
