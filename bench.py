@@ -646,9 +646,12 @@ def plan_time_probe(pv, n_plans: int = 101):
         fn, cb_ctx, _keep = ora.edge_callback(oscene)
         cb = _cabi.EDGE_CALLBACK(fn.value)
         simp_out, simp_n = np.empty((256, 9)), C.c_int(0)
+        sink = io.StringIO()  # plan_path prints the waypoint count (planning.py:199); keep stdout for the JSON line
         for i in range(n_plans + 5):
             planner.rng_seed = 100 + i
-            with contextlib.redirect_stdout(io.StringIO()):
+            sink.seek(0)
+            sink.truncate()
+            with contextlib.redirect_stdout(sink):  # entered BEFORE the clock starts: the harness is not the plan
                 t = time.perf_counter()
                 path = planner.plan_path(qpos_goal=goal, num_waypoints=150, timeout=10.0)
                 dt = time.perf_counter() - t

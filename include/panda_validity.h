@@ -256,6 +256,25 @@ typedef int (*pv_edge_callback)(void *user, const float *a, const float *b, int 
 int pv_simplify_path_cb(const double *states, int n_states, uint32_t seed, pv_edge_callback cb, void *user,
                         double *out, int capacity, int *n_out, int *counters);
 
+/* Device steps of the SHARDED-TREE planner front end (distributed.ShardedTreePlanner): for trees too large
+ * for one GPU -- or simply to use the node memory and nearest-neighbour bandwidth of all of them -- every rank keeps
+ * every world-th node of every tree (global node g at slot g / world of rank g % world) and the ranks exchange, per
+ * extension, their nearest-node candidates and the motion verdicts over NCCL.  All pointers are DEVICE pointers.
+ *   pv_nn_candidates  pair t: nearest of this rank's nodes of tree d_tree_of[t] (NULL: tree t) to d_targets[t]; trees are
+ *                     [n][9][capacity] SoA, d_sizes[tree] = slots in use; d_out[t] = 11 floats: squared distance, GLOBAL
+ *                     node index (int bits; INT_MAX when the rank holds no node of the tree), the node's 9 joint values
+ *   pv_rrtc_steer     d_cand [world][n][11] (the all-gathered records): reduce by (distance, global index) and form the
+ *                     motion from the nearest node towards the target, at most `range` long (<= 0: OMPL default)
+ *   pv_rrtc_samples   sample d_it[i] of global search d_gsearch[i] of the planner's random stream
+ * With these three the front end takes the decisions of pv_rrtc_batch bit for bit (og.RRTConnect as configured at
+ * planning.py:151-156). */
+int pv_nn_candidates(PvHandle *h, const float *d_trees, const int *d_sizes, const int *d_tree_of, const float *d_targets,
+                     int n_pairs, int capacity, int rank, int world, float *d_out, void *stream);
+int pv_rrtc_steer(PvHandle *h, const float *d_cand, int world, int n, const float *d_targets, float range,
+                  int *d_from_gidx, float *d_ea, float *d_eb, int *d_reach, void *stream);
+int pv_rrtc_samples(PvHandle *h, uint32_t seed, const unsigned *d_gsearch, const int *d_it, int n, float *d_out,
+                    void *stream);
+
 /* robot.inverse_kinematics(link=hand, pos, quat) as the motion primitives call it before every plan_path
  * (motion_primitives.py:131-134), batched and collision-aware.  For each of n_targets hand poses (world
  * position, quaternion wxyz) n_seeds damped-least-squares searches run in parallel (seed 0 = h_q_init, the rest

@@ -14,7 +14,7 @@ from typing import List
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpanda_validity.so")
-SOURCES = ["pv_kernels.cu", "pv_edge.cu", "pv_rrtc.cu", "pv_ik.cu", "pv_plan.cu"]
+SOURCES = ["pv_kernels.cu", "pv_edge.cu", "pv_rrtc.cu", "pv_ik.cu", "pv_plan.cu", "pv_nn.cu"]
 HEADERS = ["pv_device.cuh", "pv_handle.h", "panda_model_gen.h", os.path.join("..", "..", "include", "panda_validity.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -28,7 +28,7 @@ EXPORTS = [
     "pv_check_edges", "pv_edge_margins", "pv_check_states_host", "pv_check_edges_host", "pv_sweep",
     "pv_rrtc_batch", "pv_rrtc_batch_packed", "pv_plan_path", "pv_interpolate_path", "pv_obb_from_poses", "pv_simplify_path",
     "pv_simplify_path_cb",
-    "pv_ik_batch", "pv_fp32_peak", "pv_launch_count",
+    "pv_nn_candidates", "pv_rrtc_steer", "pv_rrtc_samples", "pv_ik_batch", "pv_fp32_peak", "pv_launch_count",
 ]
 
 
@@ -155,6 +155,9 @@ def load() -> C.CDLL:
     lib.pv_obb_from_poses.argtypes = [vp, vp, vp, C.c_int, vp]
     lib.pv_simplify_path.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_float, vp, C.c_int, C.POINTER(C.c_int), vp]
     lib.pv_simplify_path_cb.argtypes = [vp, C.c_int, C.c_uint32, EDGE_CALLBACK, vp, vp, C.c_int, C.POINTER(C.c_int), vp]
+    lib.pv_nn_candidates.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.pv_rrtc_steer.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_float, vp, vp, vp, vp, vp]
+    lib.pv_rrtc_samples.argtypes = [vp, C.c_uint32, vp, vp, C.c_int, vp, vp]
     lib.pv_ik_batch.argtypes = [vp, fp, fp, C.c_int, fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_uint32, fp, i32p, fp]
     lib.pv_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     lib.pv_launch_count.argtypes = [vp]

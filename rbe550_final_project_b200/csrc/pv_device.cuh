@@ -871,6 +871,24 @@ __device__ __forceinline__ uint4 pv_philox(uint4 c, uint2 k) {
     return c;
 }
 
+// sample `it` of search `search` of the planner's counter-based stream (pv_rrtc.cu; also the sharded-tree front end)
+__device__ __forceinline__ void rrtc_sample(unsigned seed, unsigned search, unsigned it, float* q, float& extra) {
+    const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
+    float u[12];
+    const uint2 key = make_uint2(seed, 0x52525443u);
+#pragma unroll
+    for (int blk = 0; blk < 3; ++blk) {
+        uint4 r = pv_philox(make_uint4(it, search, blk, 1u), key);
+        u[4 * blk + 0] = (float)(r.x >> 8) * 5.9604644775390625e-08f;
+        u[4 * blk + 1] = (float)(r.y >> 8) * 5.9604644775390625e-08f;
+        u[4 * blk + 2] = (float)(r.z >> 8) * 5.9604644775390625e-08f;
+        u[4 * blk + 3] = (float)(r.w >> 8) * 5.9604644775390625e-08f;
+    }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) q[j] = __fmaf_rn(u[j], hi[j] - lo[j], lo[j]);
+    extra = u[9];  // a tenth uniform draw of the same counter: goal bias of the single-tree planner
+}
+
 __device__ __forceinline__ void pv_sweep_config(uint64_t i, unsigned seed, bool fingers_open, float* q) {
     const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
     float u[12];

@@ -79,9 +79,21 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
 
     for (;;) {
         const bool have = w < n_words;
-#if PV_E_LOCKSTEP
+#if PV_E_LOCKSTEP == 1
         if (!__syncthreads_or(have ? 1 : 0)) break;
         if (!have) continue;
+#elif PV_E_LOCKSTEP == 2
+        // lockstep only among the warps that share a scheduler -- and with it an L0 instruction cache: warp ids w, w + 4,
+        // w + 8 meet at a named barrier once per round and walk the round's code together
+        {
+            unsigned any_;
+            asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(any_)
+                         : "r"(have ? 1u : 0u), "r"(1 + ((threadIdx.x >> 5) & 3)), "n"(PV_E_THREADS / 4)
+                         : "memory");
+            if (!any_) break;
+            if (!have) continue;
+        }
 #else
         if (!have) break;
 #endif

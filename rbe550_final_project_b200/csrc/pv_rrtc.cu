@@ -90,23 +90,6 @@ struct RrtcArgs {
     float inline_q[18];
 };
 
-__device__ __forceinline__ void rrtc_sample(unsigned seed, unsigned search, unsigned it, float* q, float& extra) {
-    const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
-    float u[12];
-    const uint2 key = make_uint2(seed, 0x52525443u);
-#pragma unroll
-    for (int blk = 0; blk < 3; ++blk) {
-        uint4 r = pv_philox(make_uint4(it, search, blk, 1u), key);
-        u[4 * blk + 0] = (float)(r.x >> 8) * 5.9604644775390625e-08f;
-        u[4 * blk + 1] = (float)(r.y >> 8) * 5.9604644775390625e-08f;
-        u[4 * blk + 2] = (float)(r.z >> 8) * 5.9604644775390625e-08f;
-        u[4 * blk + 3] = (float)(r.w >> 8) * 5.9604644775390625e-08f;
-    }
-#pragma unroll
-    for (int j = 0; j < 9; ++j) q[j] = __fmaf_rn(u[j], hi[j] - lo[j], lo[j]);
-    extra = u[9];  // a tenth uniform draw of the same counter: goal bias of the single-tree planner
-}
-
 // nearest node of one tree (SoA [9][max_nodes]) to `t`: lanes stride over nodes, warp arg-min (ties -> lowest index)
 __device__ __forceinline__ int rrtc_nearest(const float* __restrict__ tq, int size, int max_nodes, const float* t,
                                             int lane, float& best_d2) {
