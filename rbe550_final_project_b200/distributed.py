@@ -216,3 +216,196 @@ class FusedVerdictGather:
 
     def close(self):
         self.deactivate()
+
+
+class ShardedTreePlanner:
+    """Batched multi-query RRT-Connect front end whose TREES are sharded over the GPUs of one box (SURVEY.md 8e,
+    BASELINE north_star: "NCCL ... only to gather verdicts and nearest-tree candidates for a batched multi-query
+    RRT-Connect front end").
+
+    og.RRTConnect as planning.py:151-156 configures it, for a batch of (start, goal) queries advanced together.  Global
+    node g of a tree lives on rank g % world at slot g // world, so the node memory and the nearest-neighbour scan of a
+    tree are spread over all ranks.  One round, for the queries still running:
+
+      1. every rank: the nearest of ITS nodes to the round's target (the sample of an EXTEND, the new node of a
+         CONNECT) -- pv_nn_candidates, one record of 44 B per query;
+      2. all-gather of the records (NCCL);
+      3. every rank: reduce by (distance, global index) and steer -- pv_rrtc_steer -- the same motion everywhere;
+      4. the motions are an independent batch: rank r validates the contiguous shard shard_range(n, r, world) with
+         pv_check_edges (OMPL's DiscreteMotionValidator) and the verdict words are all-gathered (NCCL);
+      5. the transitions of RRT-Connect (add the node on its owner rank, swap trees when trapped, ...) as tensor
+         operations on replicated control state.
+
+    Samples come from the stream of the single-GPU planner (keyed by seed, GLOBAL query id, iteration), nearest
+    neighbours and steering use its expressions, so a query takes the decisions pv_rrtc_batch(replicas=1,
+    shortcut_passes=0) takes for it, whatever the world size (the batched edge kernel evaluates sin/cos in hardware, the
+    in-kernel validator with the Cody-Waite form: a state within ~1e-6 m of contact could be judged differently).
+
+    `pv` supplies the device steps: nn_candidates, rrtc_steer, rrtc_samples, check_edges, check_states and `.device`
+    (PandaValidity; the CPU tests pass a stand-in and run this class over gloo).
+    """
+
+    EXTEND, CONNECT, DONE = 0, 1, 4
+    SOLVED, ITERCAP, NODECAP, PATHCAP, BADEND = 1, 2, 3, 4, 16
+
+    def __init__(self, pv, max_nodes: int = 2048, group=None):
+        self.pv = pv
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.max_nodes = int(max_nodes)
+        self.slots = (self.max_nodes + self.world - 1) // self.world
+        dev = getattr(pv, "device", None)
+        self.dev = dev if dev is not None else torch.device("cpu")
+        self.rounds = 0
+        self.bytes_gathered = 0
+
+    # -- collectives ------------------------------------------------------------------------------------------------
+    def _all_gather(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world == 1:
+            return t[None]
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        self.bytes_gathered += out.numel() * out.element_size()
+        return out.view((self.world,) + tuple(t.shape))
+
+    def _valid_sharded(self, ea: torch.Tensor, eb: torch.Tensor, resolution: float) -> torch.Tensor:
+        n = ea.shape[0]
+        first, count = shard_range(n, self.rank, self.world)
+        if count > 0:
+            words = self.pv.check_edges(ea[first:first + count], eb[first:first + count], n_steps=0, resolution=resolution)
+        else:
+            words = torch.zeros(0, dtype=torch.int32, device=self.dev)
+        full = gather_verdict_words(words, n, self.group)
+        if self.world > 1:
+            self.bytes_gathered += words_per_shard(n, self.world) * self.world * 4
+        i = torch.arange(n, device=self.dev)
+        return ((full[i >> 5] >> (i & 31)) & 1).bool()
+
+    # -- the planner ------------------------------------------------------------------------------------------------
+    def solve(self, starts, goals, max_iters: int = 2000, max_path: int = 128, seed: int = 1, rrt_range: float = 0.0,
+              resolution: float = 0.0, check_endpoints: bool = False, query_offset: int = 0):
+        """Returns (paths: list of (len, 9) float32 arrays -- empty when unsolved --, iters (n,) int32, status (n,) int32),
+        identical on every rank."""
+        import numpy as np
+        from . import panda_model as pm
+        rrt_range = float(rrt_range) if rrt_range > 0 else float(pm.RRTC_RANGE)
+        resolution = float(resolution) if resolution > 0 else float(pm.VALIDITY_RESOLUTION)
+        dev, rank, world, M, slots = self.dev, self.rank, self.world, self.max_nodes, self.slots
+        qs = torch.as_tensor(np.ascontiguousarray(starts, dtype=np.float32).reshape(-1, 9)).to(dev)
+        qg = torch.as_tensor(np.ascontiguousarray(goals, dtype=np.float32).reshape(-1, 9)).to(dev)
+        n = qs.shape[0]
+        i32 = dict(dtype=torch.int32, device=dev)
+        trees = torch.zeros((2 * n, 9, slots), dtype=torch.float32, device=dev)   # this rank's slots of every tree
+        gsize = torch.ones(2 * n, **i32)                                          # GLOBAL tree sizes (replicated)
+        parent = torch.full((2 * n, M), -1, **i32)                                # replicated: 4 B per node
+        if rank == 0:  # global node 0 of every tree: rank 0, slot 0
+            trees[0::2, :, 0] = qs
+            trees[1::2, :, 0] = qg
+        it = torch.zeros(n, **i32)
+        cur = torch.zeros(n, **i32)
+        phase = torch.full((n,), self.EXTEND, **i32)
+        status = torch.zeros(n, **i32)
+        target = torch.zeros((n, 9), dtype=torch.float32, device=dev)
+        added = torch.zeros(n, **i32)
+        conn = torch.full((n,), -1, **i32)
+        gsearch = (torch.arange(n, device=dev, dtype=torch.int64) + int(query_offset)).to(torch.int32)
+        qid = torch.arange(n, device=dev)
+
+        if check_endpoints and n:
+            # OMPL drops invalid / out-of-bounds start and goal states at intake (planning.py:163-187)
+            both = torch.cat([qs, qg])
+            first, count = shard_range(2 * n, rank, world)
+            w = self.pv.check_states(both[first:first + count]) if count else torch.zeros(0, **i32)
+            full = gather_verdict_words(w, 2 * n, self.group)
+            k = torch.arange(2 * n, device=dev)
+            ok = ((full[k >> 5] >> (k & 31)) & 1).bool()
+            code = (~ok[:n]).to(torch.int32) + 2 * (~ok[n:]).to(torch.int32)
+            status = torch.where(code > 0, self.BADEND + code, status)
+            phase = torch.where(code > 0, torch.full_like(phase, self.DONE), phase)
+
+        while True:
+            # caps are tested when an EXTEND begins, iteration cap first (pv_rrtc_kernel)
+            ext_all = phase == self.EXTEND
+            itcap = ext_all & (it >= max_iters)
+            ndcap = ext_all & ~itcap & ((gsize[0::2] >= M - 1) | (gsize[1::2] >= M - 1))
+            status = torch.where(itcap, torch.full_like(status, self.ITERCAP), status)
+            status = torch.where(ndcap, torch.full_like(status, self.NODECAP), status)
+            phase = torch.where(itcap | ndcap, torch.full_like(phase, self.DONE), phase)
+            a = (phase != self.DONE).nonzero().flatten()
+            if a.numel() == 0:
+                break
+            self.rounds += 1
+            ext = phase[a] == self.EXTEND
+            tsel = torch.where(ext, cur[a], cur[a] ^ 1)
+            tree_of = (2 * a).to(torch.int32) + tsel
+            smp = self.pv.rrtc_samples(seed, gsearch[a].contiguous(), it[a].contiguous())
+            aim_goal = ext & (it[a] == 0)  # the first extension aims at the goal itself
+            tg = torch.where(ext[:, None], torch.where(aim_goal[:, None], qg[a], smp), target[a]).contiguous()
+            local_sizes = torch.clamp((gsize - rank + world - 1) // world, min=0).to(torch.int32)
+            cand = self.pv.nn_candidates(trees, local_sizes, tree_of.contiguous(), tg, rank, world)
+            from_g, ea, eb, reach = self.pv.rrtc_steer(self._all_gather(cand), tg, rrt_range)
+            valid = self._valid_sharded(ea, eb, resolution)
+            reach = reach.bool()
+
+            to = tree_of.long()
+            ni = gsize[to]                       # global index the new node would get
+            v = valid
+            own = v & ((ni % world) == rank)
+            trees[to[own], :, (ni[own] // world).long()] = eb[own]
+            parent[to[v], ni[v].long()] = from_g[v]
+            gsize[to[v]] = ni[v] + 1
+            av = a[v & ext]
+            target[av] = eb[v & ext]
+            added[av] = ni[v & ext]
+            phase[av] = self.CONNECT
+            ac = a[v & ~ext & reach]
+            conn[ac] = ni[v & ~ext & reach]
+            phase[ac] = self.DONE
+            status[ac] = self.SOLVED
+            full_ = v & ~ext & ~reach & (ni + 1 >= M - 1)
+            phase[a[full_]] = self.DONE
+            status[a[full_]] = self.NODECAP
+            at = a[~v]                            # trapped: next iteration, the trees swap roles
+            phase[at] = self.EXTEND
+            cur[at] = cur[at] ^ 1
+            it[at] = it[at] + 1
+
+        # ---- path extraction: index chains from the replicated parents, states from their owner ranks -----------------
+        st = status.cpu().numpy()
+        iters = torch.where(status == self.SOLVED, it + 1, it).cpu().numpy().astype(np.int32)
+        solved = np.nonzero(st == self.SOLVED)[0]
+        par = parent.cpu().numpy()
+        cur_h, add_h, con_h = cur.cpu().numpy(), added.cpu().numpy(), conn.cpu().numpy()
+        chains, want_t, want_g = {}, [], []
+        for q in solved:
+            i_s, i_g = (add_h[q], con_h[q]) if cur_h[q] == 0 else (con_h[q], add_h[q])
+            s_chain = []
+            x = int(i_s)
+            while x >= 0:
+                s_chain.append(x)
+                x = int(par[2 * q, x])
+            g_chain = []
+            x = int(par[2 * q + 1, i_g])  # the goal tree's copy of the connecting state is skipped
+            while x >= 0:
+                g_chain.append(x)
+                x = int(par[2 * q + 1, x])
+            chain = [(2 * q, g) for g in reversed(s_chain)] + [(2 * q + 1, g) for g in g_chain]
+            if len(chain) > max_path:
+                st[q] = self.PATHCAP
+                continue
+            chains[int(q)] = (len(want_t), len(chain))
+            want_t += [c[0] for c in chain]
+            want_g += [c[1] for c in chain]
+        paths = [np.zeros((0, 9), np.float32) for _ in range(n)]
+        if want_t:
+            wt = torch.as_tensor(want_t, device=dev, dtype=torch.long)
+            wg = torch.as_tensor(want_g, device=dev, dtype=torch.long)
+            mine = (wg % world) == rank
+            rows = torch.zeros((len(want_t), 9), dtype=torch.float32, device=dev)
+            rows[mine] = trees[wt[mine], :, wg[mine] // world]
+            allr = self._all_gather(rows)                               # (world, total, 9)
+            states = allr[wg % world, torch.arange(len(want_t), device=dev)].cpu().numpy()
+            for q, (off, ln) in chains.items():
+                paths[q] = states[off:off + ln].copy()
+        return paths, iters, st.astype(np.int32)

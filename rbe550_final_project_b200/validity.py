@@ -305,6 +305,40 @@ class PandaValidity:
                  "pv_rrtc_batch")
         return paths, plen, iters, checks
 
+    # -- device steps of the sharded-tree planner front end (distributed.ShardedTreePlanner) ---------------------
+    def nn_candidates(self, trees: torch.Tensor, sizes: torch.Tensor, tree_of: Optional[torch.Tensor],
+                      targets: torch.Tensor, rank: int, world: int, stream=None) -> torch.Tensor:
+        """Nearest node of THIS rank's slots of tree tree_of[t] to targets[t]: (n, 11) = squared distance, global node
+        index (int bits), node state.  trees (T, 9, capacity) float32, sizes (T,) int32 slots in use."""
+        n = int(targets.shape[0])
+        out = torch.empty((n, 11), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.pv_nn_candidates(self._h, trees.data_ptr(), sizes.data_ptr(),
+                                           tree_of.data_ptr() if tree_of is not None else None, targets.data_ptr(), n,
+                                           int(trees.shape[2]), int(rank), int(world), out.data_ptr(),
+                                           self._stream(stream)), "pv_nn_candidates")
+        return out
+
+    def rrtc_steer(self, cand: torch.Tensor, targets: torch.Tensor, rrt_range: float = 0.0, stream=None):
+        """cand (world, n, 11): the all-gathered candidate records.  Returns (from_gidx (n,) int32, ea (n, 9), eb (n, 9),
+        reach (n,) int32): the motion og.RRTConnect would validate next (planning.py:156)."""
+        world, n = int(cand.shape[0]), int(cand.shape[1])
+        gi = torch.empty(n, dtype=torch.int32, device=self.device)
+        ea = torch.empty((n, 9), dtype=torch.float32, device=self.device)
+        eb = torch.empty((n, 9), dtype=torch.float32, device=self.device)
+        reach = torch.empty(n, dtype=torch.int32, device=self.device)
+        self._ck(self.lib.pv_rrtc_steer(self._h, cand.data_ptr(), world, n, targets.data_ptr(), float(rrt_range),
+                                        gi.data_ptr(), ea.data_ptr(), eb.data_ptr(), reach.data_ptr(),
+                                        self._stream(stream)), "pv_rrtc_steer")
+        return gi, ea, eb, reach
+
+    def rrtc_samples(self, seed: int, gsearch: torch.Tensor, it: torch.Tensor, stream=None) -> torch.Tensor:
+        """Sample it[i] of global search gsearch[i] (int32 tensors) of the planner's random stream: (n, 9)."""
+        n = int(gsearch.shape[0])
+        out = torch.empty((n, 9), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.pv_rrtc_samples(self._h, int(seed) & 0xFFFFFFFF, gsearch.data_ptr(), it.data_ptr(), n,
+                                          out.data_ptr(), self._stream(stream)), "pv_rrtc_samples")
+        return out
+
     def plan_path(self, start, goal, num_waypoints: int = 100, smooth: bool = True, planner: str = "RRTConnect",
                   seed: int = 1, replicas: int = 32, max_iters: int = 2000, max_nodes: int = 2048, validate: bool = True,
                   max_attempts: int = 4, timeout: float = 5.0, rrt_range: float = 0.0, resolution: float = 0.0):

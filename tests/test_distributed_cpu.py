@@ -183,3 +183,125 @@ def test_sharded_rrtc_packing(world, n):
         assert np.array_equal(packed[0], ref[0][used])
         for j in (1, 2, 3):
             assert np.array_equal(dense[j], ref[j]) and np.array_equal(packed[j], ref[j]), (rank, j)
+
+
+# ---- sharded-TREE planner front end (distributed.ShardedTreePlanner) over gloo ---------------------------------------
+def _fma32(a, b, c):
+    """fp32 fma: a * b is exact in fp64 (24 + 24 bits), one rounding to fp64 and one to fp32 follow."""
+    return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+class _OracleSteps:
+    """CPU stand-in for the device steps PandaValidity gives ShardedTreePlanner (pv_nn_candidates, pv_rrtc_steer,
+    pv_rrtc_samples, pv_check_edges, pv_check_states), restated with numpy fp32 and the fp32 C oracle."""
+    device = None
+
+    def __init__(self):
+        from oracle.c_oracle import COracle
+        from rbe550_final_project_b200 import panda_model as pm, scenes as sc
+        self.pm = pm
+        self.model = pm.model_arrays()
+        self.ora = COracle(self.model, "f32")
+        wall = sc.make_obb((0.55, 0.0, 0.35), (0.5, 0.04, 0.7))
+        self.scene = sc.SceneSnapshot(obb=np.array([wall], dtype=np.float32), names=["wall"], entity_idx=[1]).as_oracle_scene()
+
+    def rrtc_samples(self, seed, gsearch, it):
+        from oracle import panda_oracle as po
+        gs, itn = gsearch.numpy().astype(np.uint32), it.numpy().astype(np.uint32)
+        n = len(gs)
+        u = []
+        for blk in range(3):
+            ctr = np.stack([itn, gs, np.full(n, blk, np.uint32), np.ones(n, np.uint32)], axis=1)
+            r = po.philox4x32(ctr, (np.uint32(seed), np.uint32(0x52525443)))
+            u.append((r >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24))
+        u = np.concatenate(u, axis=1)[:, :9]
+        lo, hi = self.model["q_lower"].astype(np.float32), self.model["q_upper"].astype(np.float32)
+        return torch.from_numpy(_fma32(u, np.broadcast_to((hi - lo).astype(np.float32), u.shape), np.broadcast_to(lo, u.shape)))
+
+    def nn_candidates(self, trees, sizes, tree_of, targets, rank, world):
+        tr, sz, to, tg = trees.numpy(), sizes.numpy(), tree_of.numpy(), targets.numpy()
+        out = np.zeros((len(to), 11), np.float32)
+        for t, tree in enumerate(to):
+            size = int(sz[tree])
+            if size == 0:
+                out[t, 0] = np.float32(3.0e38)
+                out[t, 1:2] = np.array([0x7FFFFFFF], np.int32).view(np.float32)
+                continue
+            d2 = np.zeros(size, np.float32)
+            for k in range(9):
+                d = (tr[tree, k, :size] - tg[t, k]).astype(np.float32)
+                d2 = _fma32(d, d, d2)
+            i = int(np.argmin(d2))  # first minimum = lowest slot = lowest global index
+            out[t, 0] = d2[i]
+            out[t, 1:2] = np.array([i * world + rank], np.int32).view(np.float32)
+            out[t, 2:] = tr[tree, :, i]
+        return torch.from_numpy(out)
+
+    def rrtc_steer(self, cand, targets, rrt_range):
+        c, tg = cand.numpy(), targets.numpy()
+        world, n = c.shape[0], c.shape[1]
+        gi_all = np.ascontiguousarray(c[:, :, 1]).view(np.int32)
+        from_g, reach = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        ea, eb = np.zeros((n, 9), np.float32), np.zeros((n, 9), np.float32)
+        rng = np.float32(rrt_range)
+        for i in range(n):
+            r = min(range(world), key=lambda r: (c[r, i, 0], gi_all[r, i]))
+            bd = c[r, i, 0]
+            d = np.sqrt(bd, dtype=np.float32)
+            ea[i] = c[r, i, 2:]
+            from_g[i] = gi_all[r, i]
+            if d > rng:
+                f = np.float32(rng / d)
+                eb[i] = _fma32(np.full(9, f, np.float32), (tg[i] - ea[i]).astype(np.float32), ea[i])
+            else:
+                eb[i] = tg[i]
+                reach[i] = 1
+        return torch.from_numpy(from_g), torch.from_numpy(ea), torch.from_numpy(eb), torch.from_numpy(reach)
+
+    def check_edges(self, qa, qb, n_steps=0, resolution=0.0):
+        from oracle import panda_oracle as po
+        m = self.ora.edge_margin(qa.numpy(), qb.numpy(), self.scene, n_steps=n_steps, resolution=resolution)
+        return torch.from_numpy(po.pack_bits(m >= 0).view(np.int32).copy())
+
+    def check_states(self, q):
+        from oracle import panda_oracle as po
+        m = self.ora.state_margin(q.numpy(), self.scene)
+        return torch.from_numpy(po.pack_bits(m >= 0).view(np.int32).copy())
+
+
+def _tree_worker(rank, world, port, n, max_nodes, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rbe550_final_project_b200.distributed import ShardedTreePlanner
+    a, b = _rrtc_queries(n)
+    pl = ShardedTreePlanner(_OracleSteps(), max_nodes=max_nodes)
+    paths, iters, status = pl.solve(a, b, max_iters=300, max_path=64, seed=5)
+    ret[rank] = ([p.copy() for p in paths], iters.copy(), status.copy(), pl.rounds, pl.bytes_gathered)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_tree_planner_matches_the_single_tree_planner(world):
+    """Trees sharded node by node over the ranks of a gloo group (nearest-node candidates and motion verdicts gathered
+    every round): every rank returns, query by query, the path and iteration count of the C restatement of the
+    single-GPU planner (one search per query, no shortcutting), whose trees live in one memory."""
+    n, max_nodes = 13, 512
+    a, b = _rrtc_queries(n)
+    eng = _OraclePlanner()
+    ref = [eng.ora.rrtc(a[k], b[k], eng.scene, seed=5, search=k, max_path=64, max_iters=300, max_nodes=max_nodes,
+                        shortcut_passes=0) for k in range(n)]
+    assert any(r[1] > 1 for r in ref) and any(len(r[0]) > 2 for r in ref)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 35500 + (os.getpid() % 2000) + world
+    mp.spawn(_tree_worker, args=(world, port, n, max_nodes, ret), nprocs=world, join=True)
+    for rank in range(world):
+        paths, iters, status, rounds, nbytes = ret[rank]
+        assert rounds >= 2 and nbytes > 0
+        for k in range(n):
+            assert iters[k] == ref[k][1], (rank, k)
+            assert np.array_equal(paths[k], ref[k][0]), (rank, k)
+            assert (status[k] == 1) == (len(ref[k][0]) > 0)

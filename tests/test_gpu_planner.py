@@ -517,3 +517,85 @@ def test_config4_full_size(pv, c64):
     hard = np.argsort(-iters)[:40]  # the searches that had to grow trees, plus a random sample
     for k in np.concatenate([hard, rng.choice(nq, 60, replace=False)]):
         _path_ok(pv, c64, snap, paths[k, : plen[k]])
+
+
+def test_nn_candidates_of_a_sharded_tree(pv):
+    """pv_nn_candidates + pv_rrtc_steer: a tree dealt node by node to `world` ranks (emulated on one GPU), the per-rank
+    candidates stacked the way the all-gather delivers them: the reduction picks the brute-force nearest node (ties to
+    the lowest global index), and the motion is the nearest node steered towards the target by at most `range`."""
+    dev = pv.device
+    rng = np.random.default_rng(77)
+    T, cap_global, n_pairs = 5, 300, 64
+    sizes_g = np.array([1, 2, 37, 300, 129])
+    nodes = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(T, cap_global, 9)).astype(np.float32)
+    nodes[3, 17] = nodes[3, 250]  # an exact tie between two ranks' nodes: the lower global index must win
+    tree_of = rng.integers(0, T, size=n_pairs).astype(np.int32)
+    targets = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n_pairs, 9)).astype(np.float32)
+    targets[0] = nodes[3, 250]
+    tree_of[0] = 3
+    for world in (1, 2, 3, 8):
+        slots = (cap_global + world - 1) // world
+        cands = []
+        for rank in range(world):
+            loc = np.zeros((T, 9, slots), np.float32)
+            lsz = np.zeros(T, np.int32)
+            for t in range(T):
+                mine = nodes[t, rank:sizes_g[t]:world]
+                lsz[t] = len(mine)
+                loc[t, :, : len(mine)] = mine.T
+            cands.append(pv.nn_candidates(torch.from_numpy(loc).to(dev), torch.from_numpy(lsz).to(dev),
+                                          torch.from_numpy(tree_of).to(dev), torch.from_numpy(targets).to(dev), rank, world))
+        gi, ea, eb, reach = pv.rrtc_steer(torch.stack(cands).contiguous(), torch.from_numpy(targets).to(dev), 1.0)
+        gi, ea, eb, reach = gi.cpu().numpy(), ea.cpu().numpy(), eb.cpu().numpy(), reach.cpu().numpy()
+        for i in range(n_pairs):
+            t = tree_of[i]
+            d2 = ((nodes[t, : sizes_g[t]].astype(np.float64) - targets[i]) ** 2).sum(1)
+            best = int(np.argmin(d2))
+            assert d2[gi[i]] <= d2[best] * (1 + 1e-6) + 1e-12, (world, i)
+            assert np.array_equal(ea[i], nodes[t, gi[i]])
+            d = np.sqrt(d2[gi[i]])
+            if reach[i]:
+                assert d <= 1.0 + 1e-6 and np.array_equal(eb[i], targets[i])
+            else:
+                assert d > 1.0 - 1e-6 and abs(np.linalg.norm(eb[i].astype(np.float64) - ea[i]) - 1.0) < 1e-5
+        assert gi[0] == 17 and reach[0] == 1
+        if world == 1:
+            first = (gi.copy(), eb.copy(), reach.copy())
+        else:  # the decision does not depend on how the tree is dealt out
+            assert np.array_equal(gi, first[0]) and np.array_equal(eb, first[1]) and np.array_equal(reach, first[2])
+
+
+def test_sharded_tree_planner_follows_the_device_planner(pv, c64):
+    """distributed.ShardedTreePlanner (world size 1 here; worlds 2 and 3 run over gloo in the CPU suite, N GPUs in
+    tools/multi_gpu_tree.py): nearest-node candidates, steering, batched motion validation and the RRT-Connect
+    transitions as separate device steps reproduce the one-kernel planner query by query."""
+    from rbe550_final_project_b200.distributed import ShardedTreePlanner
+    wall = sc.make_obb((0.55, 0.0, 0.35), (0.5, 0.04, 0.7))
+    snap = sc.SceneSnapshot(obb=np.array([wall], dtype=np.float32), names=["wall"], entity_idx=[1])
+    pv.set_scene(snap)
+    pv.set_attached(-1)
+    pv.set_flags(True, False)
+    cand = random_configs(400, 55)
+    valid = cand[unpack_bits(pv.check_states_host(cand), len(cand))]
+    nq = 96
+    starts, goals = valid[:nq].copy(), valid[nq:2 * nq].copy()
+    starts[5] = pm.Q_LOWER - 0.1  # an out-of-bounds start: dropped at intake, like OMPL does
+    kw = dict(max_iters=400, max_path=96, seed=21)
+    ref = pv.rrtc_batch(starts, goals, max_nodes=1024, replicas=1, shortcut_passes=0, check_endpoints=True, **kw)
+    assert (ref[2] > 1).sum() > 10, "some searches must really grow trees"
+    pl = ShardedTreePlanner(pv, max_nodes=1024)
+    paths, iters, status = pl.solve(starts, goals, check_endpoints=True, **kw)
+    assert status[5] >= pl.BADEND and len(paths[5]) == 0 and ref[1][5] == 0
+    same = 0
+    for k in range(nq):
+        if len(paths[k]) == ref[1][k] and np.array_equal(paths[k], ref[0][k, : ref[1][k]]) and iters[k] == ref[2][k]:
+            same += 1
+        if len(paths[k]):
+            assert np.array_equal(paths[k][0], starts[k]) and np.array_equal(paths[k][-1], goals[k])
+            _path_ok(pv, c64, snap, paths[k])
+    # the batched edge kernel evaluates sin/cos in hardware, the in-kernel validator does not: a verdict inside the contact
+    # band may differ, everything else is decision for decision the same
+    assert same >= nq - 2, f"{same}/{nq} queries identical to pv_rrtc_batch"
+    # split invariance through query_offset, like the one-kernel planner
+    part = ShardedTreePlanner(pv, max_nodes=1024).solve(starts[40:], goals[40:], check_endpoints=True, query_offset=40, **kw)
+    assert all(np.array_equal(a, b) for a, b in zip(part[0], paths[40:])) and np.array_equal(part[1], iters[40:])
