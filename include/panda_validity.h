@@ -134,6 +134,13 @@ int pv_edge_margins(PvHandle *h, const float *d_aA, const float *d_aB, const flo
 /* Host-buffer forms of the two checks (the call a reference-side binding makes): AoS qpos rows in,
  * verdict bits out, host<->device copies pipelined inside.  h_q* may be pinned or pageable. */
 int pv_check_states_host(PvHandle *h, const float *h_q, int64_t n, uint32_t *h_bits);
+/* The same verdicts for n ARM configurations that share one gripper opening: rows of the 7 revolute joint values, the two
+ * finger joints (q8, q9 of planning.py's 9-vector) given once.  That is the shape of the reference's own batches -- the
+ * motion primitives never plan finger motion (motion_primitives.py:169-170 overwrite the finger entries of every waypoint)
+ * and BASELINE config 2 fixes q8 = q9 = 0.04 -- and the call is PCIe-bound, so 28 instead of 36 bytes per configuration
+ * cross the link.  Bit-identical to pv_check_states_host on the rows [q7, finger_left, finger_right]. */
+int pv_check_states_host_arm(PvHandle *h, const float *h_q7, int64_t n, float finger_left, float finger_right,
+                             uint32_t *h_bits);
 int pv_check_edges_host(PvHandle *h, const float *h_qa, const float *h_qb, int64_t n_edges, int n_steps,
                         float resolution, uint32_t *h_bits);
 

@@ -25,7 +25,7 @@ NVCC_FLAGS = [
 EXPORTS = [
     "pv_create", "pv_destroy", "pv_last_error", "pv_version", "pv_model_info", "pv_joint_limits",
     "pv_set_scene", "pv_set_attached", "pv_set_carried", "pv_set_flags", "pv_set_culling", "pv_set_gather", "pv_fk", "pv_fk_verdict_path", "pv_check_states", "pv_state_margins", "pv_state_contacts",
-    "pv_check_edges", "pv_edge_margins", "pv_check_states_host", "pv_check_edges_host", "pv_sweep",
+    "pv_check_edges", "pv_edge_margins", "pv_check_states_host", "pv_check_states_host_arm", "pv_check_edges_host", "pv_sweep",
     "pv_rrtc_batch", "pv_rrtc_batch_packed", "pv_plan_path", "pv_interpolate_path", "pv_obb_from_poses", "pv_simplify_path",
     "pv_simplify_path_cb",
     "pv_nn_candidates", "pv_rrtc_steer", "pv_rrtc_samples", "pv_ik_batch", "pv_fp32_peak", "pv_launch_count",
@@ -152,6 +152,7 @@ def load() -> C.CDLL:
     lib.pv_plan_path.argtypes = [vp, vp, vp, C.c_int, C.POINTER(PvPlanParams), fp, C.c_int, C.POINTER(C.c_int),
                                  C.POINTER(PvPlanStats)]
     lib.pv_interpolate_path.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
+    lib.pv_check_states_host_arm.argtypes = [vp, vp, C.c_int64, C.c_float, C.c_float, vp]
     lib.pv_obb_from_poses.argtypes = [vp, vp, vp, C.c_int, vp]
     lib.pv_simplify_path.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_float, vp, C.c_int, C.POINTER(C.c_int), vp]
     lib.pv_simplify_path_cb.argtypes = [vp, C.c_int, C.c_uint32, EDGE_CALLBACK, vp, vp, C.c_int, C.POINTER(C.c_int), vp]

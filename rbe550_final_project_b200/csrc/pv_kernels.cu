@@ -1116,6 +1116,55 @@ int pv_check_states_host(PvHandle* h, const float* h_q, int64_t n, uint32_t* h_b
     return PV_OK;
 }
 
+// rows of 7 arm joint values -> the SoA planes the validity kernels read (q8 = finger_left in B.w, q9 = finger_right)
+__global__ void __launch_bounds__(256) pv_arm_rows_to_planes_kernel(const float* __restrict__ rows, int64_t n, float f_left,
+                                                                    float f_right, float4* __restrict__ A,
+                                                                    float4* __restrict__ B, float* __restrict__ q9) {
+    // a block stages its 256 rows (1 792 consecutive floats) through shared memory: coalesced reads, float4 writes
+    __shared__ float s[256 * 7];
+    const int64_t base = (int64_t)blockIdx.x * 256;
+    const int here = (int)(n - base < 256 ? n - base : 256);
+    for (int k = threadIdx.x; k < here * 7; k += 256) s[k] = __ldg(rows + base * 7 + k);
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= here) return;
+    const float* r = s + t * 7;
+    A[base + t] = make_float4(r[0], r[1], r[2], r[3]);
+    B[base + t] = make_float4(r[4], r[5], r[6], f_left);
+    if (q9) q9[base + t] = f_right;
+}
+
+int pv_check_states_host_arm(PvHandle* h, const float* h_q7, int64_t n, float finger_left, float finger_right,
+                             uint32_t* h_bits) {
+    PV_PRECHECK(h, n);
+    if (!h_q7 || !h_bits) return PV_ERR_BAD_ARG;
+    int rc = pv_ensure_stage(h);
+    if (rc) return rc;
+    int64_t done = 0;
+    int slot = 0;
+    while (done < n) {
+        const int64_t m = (n - done < PV_HOST_CHUNK) ? (n - done) : PV_HOST_CHUNK;
+        cudaStream_t st = h->streams[slot];
+        PV_CUDA(h, cudaMemcpyAsync(h->stage_q[slot], h_q7 + done * 7, (size_t)m * 7 * sizeof(float),
+                                   cudaMemcpyHostToDevice, st));
+        // the second staging buffer (36 B per configuration) holds the planes: A | B | q9
+        float* pA = h->stage_q2[slot];
+        float* pB = pA + 4 * (size_t)PV_HOST_CHUNK;
+        float* p9 = finger_left == finger_right ? nullptr : pB + 4 * (size_t)PV_HOST_CHUNK;  // null: q9 = q8 (pv_load_soa)
+        pv_arm_rows_to_planes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(h->stage_q[slot], m, finger_left, finger_right,
+                                                                                  (float4*)pA, (float4*)pB, p9);
+        h->launches++;
+        rc = pv_launch_state_bits(h, pA, pB, p9, nullptr, m, h->stage_bits[slot], st);
+        if (rc) return rc;
+        PV_CUDA(h, cudaMemcpyAsync(h_bits + done / 32, h->stage_bits[slot], (size_t)((m + 31) / 32) * sizeof(uint32_t),
+                                   cudaMemcpyDeviceToHost, st));
+        done += m;
+        slot = (slot + 1) % PV_N_STREAMS;
+    }
+    for (int i = 0; i < PV_N_STREAMS; ++i) PV_CUDA(h, cudaStreamSynchronize(h->streams[i]));
+    return PV_OK;
+}
+
 int pv_check_edges_host(PvHandle* h, const float* h_qa, const float* h_qb, int64_t n_edges, int n_steps,
                         float resolution, uint32_t* h_bits) {
     PV_PRECHECK(h, n_edges);

@@ -244,6 +244,18 @@ class PandaValidity:
         self._ck(self.lib.pv_check_states_host(self._h, q.ctypes.data, n, out.ctypes.data), "pv_check_states_host")
         return out
 
+    def check_states_host_arm(self, q7: np.ndarray, fingers=(0.04, 0.04), out: Optional[np.ndarray] = None) -> np.ndarray:
+        """q7: (n, 7) float32 host rows of arm joint values; `fingers` = (q8, q9) shared by all of them.  Same verdict
+        words as check_states_host on the 9-column rows, 28 B per configuration over PCIe instead of 36."""
+        q7 = np.ascontiguousarray(q7, dtype=np.float32).reshape(-1, 7)
+        n = q7.shape[0]
+        if out is None:
+            out = np.empty((n + 31) // 32, dtype=np.uint32)
+        self._ck(self.lib.pv_check_states_host_arm(self._h, q7.ctypes.data, n, float(np.float32(fingers[0])),
+                                                   float(np.float32(fingers[1])), out.ctypes.data),
+                 "pv_check_states_host_arm")
+        return out
+
     def check_edges_host(self, qa: np.ndarray, qb: np.ndarray, n_steps: int = 0,
                          resolution: float = pm.VALIDITY_RESOLUTION, out: Optional[np.ndarray] = None) -> np.ndarray:
         qa = np.ascontiguousarray(qa, dtype=np.float32).reshape(-1, 9)

@@ -242,6 +242,24 @@ def test_host_entry_points_match_device(pv):
     assert (d == hh).all()
 
 
+def test_arm_rows_host_entry_point(pv, c64):
+    """pv_check_states_host_arm: rows of 7 arm joint values + one gripper opening = the 9-column call on the same
+    configurations, bit for bit (ragged sizes, several pipeline chunks, equal and unequal fingers), and the oracle."""
+    scene = sc.goal1_scattered()
+    pv.set_scene(scene)
+    for n, fingers in ((1, (0.04, 0.04)), (33, (0.0, 0.04)), (600_011, (0.04, 0.04)), (300_000, (0.013, 0.027))):
+        q = random_configs(n, 62 + n % 7)
+        q[:, 7], q[:, 8] = np.float32(fingers[0]), np.float32(fingers[1])
+        ref = pv.check_states_host(q)
+        got = pv.check_states_host_arm(np.ascontiguousarray(q[:, :7]), fingers)
+        assert np.array_equal(ref, got), (n, fingers)
+    m = c64.state_margin(q[:20000].astype(np.float64), scene.as_oracle_scene())
+    clear = np.abs(m) > 1e-4
+    assert np.array_equal(unpack_bits(got, n)[:20000][clear], (m >= 0)[clear])
+    with pytest.raises(Exception):
+        pv.check_states_host_arm(np.zeros((4, 6), np.float32))
+
+
 def test_sweep_matches_oracle_stream(pv, c64, model):
     scene = sc.goal1_scattered()
     pv.set_scene(scene)

@@ -35,7 +35,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 N_CONFIGS = 1 << 20            # one batch = BASELINE config 2
@@ -260,6 +260,18 @@ def main():
     L = PASSES * N_ROT                 # launches per step
     step_words = L * words             # verdict words one rank produces per step
 
+
+    def _e2e_dbg(tag):
+        pinned_ = [torch.from_numpy(b).pin_memory() for b in _hb[:4]]
+        o_ = torch.empty(words, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        for i in range(3): pv.check_states_host(pinned_[i % 4].numpy(), out=o_)
+        torch.cuda.synchronize()
+        ts = []
+        for i in range(40):
+            t_ = time.perf_counter(); pv.check_states_host(pinned_[i % 4].numpy(), out=o_); ts.append(time.perf_counter() - t_)
+        print(f"[dbg] {tag}: mean {np.mean(ts)*1e3:.3f} ms  median {np.median(ts)*1e3:.3f}  min {np.min(ts)*1e3:.3f}  max {np.max(ts)*1e3:.3f} -> {n/np.mean(ts)/1e9:.3f} G/s", file=sys.stderr)
+    _hb = [make_batch(SEED + r, n) for r in range(4)]
+    _e2e_dbg('A after set_scene')
     # device-resident inputs (SoA float4 planes), distinct per rank and per rotation slot
     host_batches = [make_batch(SEED + 1000 * rank + r, n) for r in range(N_ROT)]
     # two float4 planes per config (q1..q4 | q5..q8); the gripper is symmetric in this workload (q9 = q8), so no
@@ -324,7 +336,9 @@ def main():
             ms = float(t.item())
         return ms, t0, t1
 
+    _e2e_dbg('B after planes')
     fp32_peak_tflops, _ = pv.fp32_peak(8192)
+    _e2e_dbg('B2 after fp32 peak')
     sampler = ClockSampler(local)
     sampler.start()                      # NVML is up and polling before any rank reaches the pre-timing barrier
     for i in range(args.warmup):
@@ -332,7 +346,9 @@ def main():
     launches0 = pv.launch_count
     ms, t0, t1 = timed(args.steps, consume=True)
     launches = pv.launch_count - launches0
+    _e2e_dbg('C0 sampler running')
     clocks = sampler.stop(t0, t1)
+    _e2e_dbg('C after timed')
     ms_per_step = ms / args.steps
     value = world * L * n / (ms_per_step * 1e-3)
 
@@ -358,48 +374,23 @@ def main():
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------------------
     for g in (fused or []):
         g.deactivate()
-    # Two C-ABI calls, both with HOST buffers in and out: pv_check_states_host_arm takes rows of the 7 arm joints and the
-    # gripper opening once (this workload fixes q8 = q9 = 0.04, like every plan of the reference's primitives), 28 B per
-    # configuration over PCIe; pv_check_states_host takes the 9-column rows, 36 B.  The call is PCIe-bound, so the
-    # pinned-H2D rate of this box is measured beside it (`pcie`).
+    pinned = [torch.from_numpy(b).pin_memory() for b in host_batches[:4]]
     out_host = torch.empty(words, dtype=torch.int32).pin_memory()
     out_np = out_host.numpy().view(np.uint32)
+    for i in range(3):
+        pv.check_states_host(pinned[i % 4].numpy(), out=out_np)
+    barrier()
     e2e_steps = 40
-
-    def e2e_run(bufs, call):
-        for i in range(8):  # every pinned buffer is touched twice before the clock starts (the first copies out of a
-            call(bufs[i % 4].numpy())  # freshly pinned buffer take 2-3 ms instead of 0.6)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            call(bufs[i % 4].numpy())
-        s_ = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([s_], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            s_ = float(t.item())
-        return s_
-
-    pinned9 = [torch.from_numpy(b).pin_memory() for b in host_batches[:4]]
-    e2e9_s = e2e_run(pinned9, lambda q: pv.check_states_host(q, out=out_np))
-    ref_words = pv.check_states(planes[(e2e_steps - 1) % 4]).cpu().numpy().view(np.uint32)
-    assert np.array_equal(out_np, ref_words)
-    pinned7 = [torch.from_numpy(np.ascontiguousarray(b[:, :7])).pin_memory() for b in host_batches[:4]]
-    out_np[:] = 0
-    e2e_s = e2e_run(pinned7, lambda q: pv.check_states_host_arm(q, (0.04, 0.04), out=out_np))
-    assert np.array_equal(out_np, ref_words)
-    e2e_value = world * n * e2e_steps / e2e_s
-    # the PCIe roofline of that call: plain pinned H2D copies of the same buffers, same sizes
-    dst = torch.empty((n, 7), dtype=torch.float32, device="cuda")
-    for i in range(4):
-        dst.copy_(pinned7[i], non_blocking=True)
-    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for i in range(20):
-        dst.copy_(pinned7[i % 4], non_blocking=True)
-    torch.cuda.synchronize()
-    pcie_gbs = 20 * n * 28 / (time.perf_counter() - t0) / 1e9
-    del dst
+    for i in range(e2e_steps):
+        pv.check_states_host(pinned[i % 4].numpy(), out=out_np)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * n * e2e_steps / e2e_s
+    assert np.array_equal(out_np, pv.check_states(planes[(e2e_steps - 1) % 4]).cpu().numpy().view(np.uint32))
 
     # ---- BASELINE config 5 (all N): 104 857 600-config sweep, sharded, verdict words gathered on every rank ------------
     sub = {}
@@ -416,7 +407,6 @@ def main():
         return
 
     # ---- roofline ---------------------------------------------------------------------------------------------
-    per_rank_e2e_gbs = n * e2e_steps * 28 / e2e_s / 1e9
     per_gpu_rate = L * n / (ms_per_step * 1e-3)
     flops_per_check = pm.flops_per_state_check(snap.n_obb)
     peaks = {}
@@ -474,15 +464,9 @@ def main():
                         "layout": "SoA float4 x2", "parallelism": f"shard{world}" + (f"+{gather_mode}" if world > 1 else ""),
                         "timed_region_ms": ms},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": words * 4,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 36, "d2h_bytes_per_step": words * 4,
                 "steps": e2e_steps, "configs_per_step": n * world,
-                "call": "pv_check_states_host_arm (pinned host rows of the 7 arm joints + the gripper opening once in, "
-                        "verdict bits out), one batch per call, wall clock",
-                "pcie": {"bound": "pcie_h2d", "achieved": per_rank_e2e_gbs, "peak": pcie_gbs, "unit": "GB/s",
-                         "frac": per_rank_e2e_gbs / pcie_gbs,
-                         "peak_source": "pinned H2D copies of the same buffers timed in this run (per GPU)"},
-                "rows9": {"value": world * n * e2e_steps / e2e9_s, "h2d_bytes_per_step": n * 36,
-                          "call": "pv_check_states_host (the reference's 9-column qpos rows)"}},
+                "call": "pv_check_states_host (pinned AoS rows in, verdict bits out), one batch per call"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "valid_fraction_sample": n_valid / 32768.0,
