@@ -84,6 +84,12 @@ int pv_set_flags(PvHandle *h, unsigned flags);
  * reference counterpart): 0 brute force over every kept pair, 1 per-lane bounding-volume culling, 2 (default) = 1 with
  * each block's share of the batch visited in sorted order. */
 int pv_set_culling(PvHandle *h, int mode);
+/* Back-to-back pv_check_states launches on one stream (a planner validating batch after batch; no reference counterpart):
+ * with overlap on (the default) a launch may start reading its configurations while the PREVIOUS pv_check_states launch on
+ * the stream is still finishing (CUDA programmatic dependent launch), which hides the launch gap and the uneven tail of
+ * the previous launch.  Stream order is kept for everything a caller can observe: the launch never starts before any other
+ * kind of earlier work on the stream has completed, and it writes its verdict words only after ALL earlier work has. */
+int pv_set_launch_overlap(PvHandle *h, int on);
 
 /* Fused verdict gather for multi-GPU runs: after this call pv_check_states and pv_sweep also store
  * every verdict word w of this rank at word (word_offset + w) of EVERY rank's gather buffer, from inside the

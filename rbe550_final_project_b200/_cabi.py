@@ -24,7 +24,7 @@ NVCC_FLAGS = [
 # every symbol include/panda_validity.h declares
 EXPORTS = [
     "pv_create", "pv_destroy", "pv_last_error", "pv_version", "pv_model_info", "pv_joint_limits",
-    "pv_set_scene", "pv_set_attached", "pv_set_carried", "pv_set_flags", "pv_set_culling", "pv_set_gather", "pv_fk", "pv_fk_verdict_path", "pv_check_states", "pv_state_margins", "pv_state_contacts",
+    "pv_set_scene", "pv_set_attached", "pv_set_carried", "pv_set_flags", "pv_set_culling", "pv_set_launch_overlap", "pv_set_gather", "pv_fk", "pv_fk_verdict_path", "pv_check_states", "pv_state_margins", "pv_state_contacts",
     "pv_check_edges", "pv_edge_margins", "pv_check_states_host", "pv_check_states_host_arm", "pv_check_edges_host", "pv_sweep",
     "pv_rrtc_batch", "pv_rrtc_batch_packed", "pv_plan_path", "pv_interpolate_path", "pv_obb_from_poses", "pv_simplify_path",
     "pv_simplify_path_cb",
@@ -136,6 +136,7 @@ def load() -> C.CDLL:
     lib.pv_set_carried.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.c_float]
     lib.pv_set_flags.argtypes = [vp, C.c_uint]
     lib.pv_set_culling.argtypes = [vp, C.c_int]
+    lib.pv_set_launch_overlap.argtypes = [vp, C.c_int]
     lib.pv_set_gather.argtypes = [vp, vp, C.c_int, vp, C.c_longlong, C.c_longlong]
     lib.pv_fk.argtypes = [vp, fp, fp, fp, C.c_int64, fp, vp]
     lib.pv_fk_verdict_path.argtypes = [vp, fp, fp, fp, C.c_int64, fp, vp]

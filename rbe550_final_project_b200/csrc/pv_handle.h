@@ -32,6 +32,7 @@ struct PvHandle {
     int sm_count;
     int has_scene;
     int cull;
+    int launch_overlap;  // state-check launches carry the programmatic-stream-serialization attribute (pv_set_launch_overlap)
     unsigned smem_attr_mask;  // which sorted-kernel instantiations already have their dynamic shared memory opt-in
     long long launches;
     PvScene scene;

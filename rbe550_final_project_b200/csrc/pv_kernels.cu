@@ -231,6 +231,11 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     const int tid = threadIdx.x;
     const int64_t n_words = (n + 31) >> 5;
     const int64_t n_chunks = (n + PV_SB_THREADS - 1) / PV_SB_THREADS;
+    // Programmatic dependent launch (see pv_launch_state_bits): the next state-check launch on this stream may place its
+    // blocks on an SM as soon as this launch's block there has left -- its key pass, sort and checks then run in the
+    // shadow of this launch's slower blocks instead of behind a grid-wide drain.  It reads configurations (which no state
+    // kernel writes) and keeps its verdict words back until everything in front of it has completed (the wait below).
+    asm volatile("griddepcontrol.launch_dependents;");
     if ((int64_t)blockIdx.x >= n_chunks) return;
     const int64_t my_chunks = (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x;
     // local index L = jj * 512 + t of super-tile j0  <->  configuration (blockIdx.x + (j0 + jj) * gridDim.x) * 512 + t
@@ -388,6 +393,9 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
             }
             __syncthreads();
         }
+        // first global WRITE of this launch: not before every earlier operation on the stream has completed and is
+        // visible (returns at once when the launch has no programmatic dependency, and after the first super-tile)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
         for (int wl = tid; wl < nc * (PV_SB_THREADS / 32); wl += PV_SB_THREADS) {
             const int64_t w = (PV_GI(wl / (PV_SB_THREADS / 32), 0) >> 5) + (wl % (PV_SB_THREADS / 32));
             if (w < n_words) pv_emit_word_thread(bits, G, w, vbits[wl]);
@@ -725,6 +733,7 @@ int pv_create(int device, PvHandle** out) {
     h->scene.flags = PV_FLAG_SELF;
     h->scene.base[2] = 0.01f;
     h->cull = 2;
+    h->launch_overlap = 1;
     PvDeviceGuard guard(device);  // the streams are created on `device`; the caller's current device is put back
     if ((e = cudaGetLastError()) != cudaSuccess) {
         snprintf(g_create_error, sizeof(g_create_error), "cudaSetDevice: %s", cudaGetErrorString(e));
@@ -948,6 +957,14 @@ int pv_set_culling(PvHandle* h, int on) {
     return PV_OK;
 }
 
+// 1 (default): consecutive pv_check_states launches on one stream overlap (programmatic dependent launch); 0: every
+// launch waits for the previous one to drain, as plain stream order would have it.  Same verdict words either way.
+int pv_set_launch_overlap(PvHandle* h, int on) {
+    if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;
+    h->launch_overlap = on ? 1 : 0;
+    return PV_OK;
+}
+
 #define PV_PRECHECK(h, n)                                                   \
     if (pv_check_handle(h)) return PV_ERR_BAD_HANDLE;                       \
     if (!(h)->has_scene) {                                                  \
@@ -1028,9 +1045,19 @@ static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_q
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PvSortSmem))); \
             h->smem_attr_mask |= bit_;                                                                        \
         }                                                                                                     \
-        pv_state_bits_sorted_kernel<SRC_, CARRY><<<grid, PV_SB_THREADS, sizeof(PvSortSmem), st>>>(            \
-            h->scene, (const float4*)d_qA, (const float4*)d_qB, d_q9, d_aos, n, d_bits,                       \
-            d_aos ? PvGather{} : h->gather);                                                                  \
+        /* launched with programmatic stream serialization: consecutive state-check launches overlap (kernel header) */ \
+        cudaLaunchConfig_t cfg_ = {};                                                                         \
+        cfg_.gridDim = dim3((unsigned)grid);                                                                  \
+        cfg_.blockDim = dim3(PV_SB_THREADS);                                                                  \
+        cfg_.dynamicSmemBytes = sizeof(PvSortSmem);                                                           \
+        cfg_.stream = st;                                                                                     \
+        cudaLaunchAttribute at_[1];                                                                           \
+        at_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                       \
+        at_[0].val.programmaticStreamSerializationAllowed = 1;                                                \
+        cfg_.attrs = at_;                                                                                     \
+        cfg_.numAttrs = h->launch_overlap ? 1 : 0;                                                            \
+        PV_CUDA(h, cudaLaunchKernelEx(&cfg_, pv_state_bits_sorted_kernel<SRC_, CARRY>, h->scene, (const float4*)d_qA, \
+                                      (const float4*)d_qB, d_q9, d_aos, n, d_bits, d_aos ? PvGather{} : h->gather)); \
     }
     if (h->cull == 2) {  // tile-sorted + per-lane culling (the default)
         if (h->scene.carry) {

@@ -136,6 +136,10 @@ class PandaValidity:
         agree on which tests to skip; bit-identical verdicts."""
         self._ck(self.lib.pv_set_culling(self._h, int(mode)), "pv_set_culling")
 
+    def set_launch_overlap(self, on: bool):
+        """Back-to-back check_states launches overlap (programmatic dependent launch; default on).  See pv_set_launch_overlap."""
+        self._ck(self.lib.pv_set_launch_overlap(self._h, 1 if on else 0), "pv_set_launch_overlap")
+
     # -- device-buffer calls --------------------------------------------------------------------------
     def _planes(self, q) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor], int]:
         if isinstance(q, (tuple, list)) and len(q) in (2, 3) and torch.is_tensor(q[0]) and q[0].dim() == 2 \
