@@ -725,6 +725,9 @@ def plan_time_probe(pv, n_plans: int = 101):
         cb = _cabi.EDGE_CALLBACK(fn.value)
         simp_out, simp_n = np.empty((256, 9)), C.c_int(0)
         sink = io.StringIO()  # plan_path prints the waypoint count (planning.py:199); keep stdout for the JSON line
+        # GPU arm: the plans back to back (each arm runs in its own loop: the CPU arm's work between two GPU plans would
+        # leave the GPU idle for milliseconds and put a wake-up into every launch)
+        paths_ok = []
         for i in range(n_plans + 5):
             planner.rng_seed = 100 + i
             sink.seek(0)
@@ -737,6 +740,26 @@ def plan_time_probe(pv, n_plans: int = 101):
                 if len(path):
                     consume(path)
                 dcons = time.perf_counter() - t
+            if i >= 5:
+                st = planner.last_stats
+                rows.append((dt * 1e3, dcons * 1e3, st.get("ms_scene_snapshot", 0), st.get("ms_c_call", 0),
+                             st.get("ms_python_rest", 0), st.get("ms_solve", 0), st.get("ms_simplify", 0),
+                             st.get("ms_post", 0), st.get("checks", 0), st.get("launches", 0), st.get("vertices", 0),
+                             st.get("attempts", 0)))
+                ok += 1 if len(path) == 150 else 0
+        # the same plans with the GPU left idle for 2 ms in front of each (a caller that simulates between plans)
+        idle_ms = []
+        for i in range(5, 5 + min(n_plans, 51)):
+            planner.rng_seed = 100 + i
+            time.sleep(0.002)
+            sink.seek(0)
+            sink.truncate()
+            with contextlib.redirect_stdout(sink):
+                t = time.perf_counter()
+                planner.plan_path(qpos_goal=goal, num_waypoints=150, timeout=10.0)
+                idle_ms.append((time.perf_counter() - t) * 1e3)
+        # CPU arm, same seeds
+        for i in range(n_plans + 5):
             t = time.perf_counter()
             p, _, _ = ora.rrtc(start, goal, oscene, seed=100 + i, search=0, max_path=256)
             if len(p):
@@ -756,18 +779,13 @@ def plan_time_probe(pv, n_plans: int = 101):
                 ora.edge_margin(np.concatenate([w[:1], w[:-1]]), w, oscene, n_steps=0, early_exit=True, nthreads=1)
             dfull = time.perf_counter() - t
             if i >= 5:
-                st = planner.last_stats
-                rows.append((dt * 1e3, dcons * 1e3, st.get("ms_scene_snapshot", 0), st.get("ms_c_call", 0),
-                             st.get("ms_python_rest", 0), st.get("ms_solve", 0), st.get("ms_simplify", 0),
-                             st.get("ms_post", 0), st.get("checks", 0), st.get("launches", 0), st.get("vertices", 0),
-                             st.get("attempts", 0)))
                 cpu_ms.append(dc * 1e3)
                 cpu_full_ms.append(dfull * 1e3)
-                ok += 1 if len(path) == 150 else 0
         r = np.array(rows)
         med = lambda k: float(np.median(r[:, k]))  # noqa: E731
         return {"workload": what, "p50_ms": med(0), "p95_ms": float(np.percentile(r[:, 0], 95)), "success": ok / n_plans,
-                "n": n_plans, "replicas": planner.replicas,
+                "n": n_plans, "replicas": planner.replicas, "timing": "wall clock around plan_path, plans back to back",
+                "p50_ms_gpu_idle_2ms_before_each_plan": float(np.median(idle_ms)),
                 "breakdown_p50_ms": {"scene_snapshot": med(2), "c_call_pv_plan_path": med(3), "python_rest": med(4),
                                      "inside_c": {"solve": med(5), "simplify": med(6), "resample_validate": med(7)}},
                 "consume_waypoints_p50_ms": med(1),
