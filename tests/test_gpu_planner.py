@@ -231,7 +231,7 @@ def test_rrtc_batch_is_split_invariant(pv):
         assert np.array_equal(one[j], full[j])
 
 
-def test_validate_trajectory(pv):
+def test_validate_trajectory(pv, c64):
     scene, franka, blocks = create_scene("goal3_tower")
     franka.set_qpos(pm.Q_SAFE_HOME)
     planner = PlannerInterface(franka, scene, validity=pv)
@@ -244,7 +244,15 @@ def test_validate_trajectory(pv):
     low = through.copy()
     low[1] += 0.6   # shoulder forward: the hand sweeps down into the tower
     lerp = [through + t * (low - through) for t in np.linspace(0, 1, 20)]
-    assert not planner.validate_trajectory(lerp).all()
+    got = planner.validate_trajectory(lerp)
+    assert not got.all()
+    # segment by segment against the fp64 oracle (OMPL's DiscreteMotionValidator restated), outside the contact band
+    pts = np.asarray(lerp, dtype=np.float32).astype(np.float64)
+    oscene = sc.goal3_tower().as_oracle_scene()
+    m = c64.edge_margin(pts[:-1], pts[1:], oscene, n_steps=0)
+    m[0] = min(m[0], c64.state_margin(pts[:1], oscene)[0])  # segment 0 also answers for waypoint 0
+    clear = np.abs(m) > 1e-4
+    assert clear.sum() >= 15 and np.array_equal(got[clear], m[clear] >= 0)
 
 
 def test_nontrivial_planning_around_a_wall(pv, c64, c32):
