@@ -409,6 +409,11 @@ def main():
             sub["tree"] = bench_tree(torch, dist, pv, rank, world)
         except Exception as exc:  # the headline metric must still print
             sub["tree"] = {"error": repr(exc)}
+        if world > 1:  # BASELINE config 3 sharded over the ranks (N = 1: below, with its roofline)
+            try:
+                sub["edges"] = bench_edges(torch, pv, {}, 1965, dist, world)
+            except Exception as exc:
+                sub["edges"] = {"error": repr(exc)}
         pv.set_scene(snap)
     if rank != 0:
         if world > 1:
@@ -613,7 +618,7 @@ def bench_tree(torch, dist, pv, rank, world, nq=1024):
 
 
 # ---- BASELINE config 3: 10 485 760 edges x 64 interpolation states, finished-pentagon scene -----------------------------
-def bench_edges(torch, pv, counts, mhz):
+def bench_edges(torch, pv, counts, mhz, dist=None, world=1):
     from rbe550_final_project_b200 import panda_model as pm, scenes as sc
     pv.set_scene(sc.goal4_task1_pentagon())
     g = torch.Generator(device="cuda")
@@ -631,7 +636,31 @@ def bench_edges(torch, pv, counts, mhz):
     B = (qb[:, 0:4].contiguous(), qb[:, 4:8].contiguous())
     del qa, qb
     bits = torch.empty(N_EDGES // 32, dtype=torch.int32, device="cuda")
-    ms = ev_ms(torch, lambda: pv.check_edges(A, B, n_steps=64, out=bits), iters=3, warm=1)
+    if world > 1:
+        # strong scaling: contiguous shards of the same batch (every rank generates it from the same seed), verdict
+        # words all-gathered with NCCL inside the timed region; max over ranks, best of 3
+        from rbe550_final_project_b200.distributed import check_edges_sharded
+        full = check_edges_sharded(pv, A, B, n_steps=64)
+        times = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0.record()
+            full = check_edges_sharded(pv, A, B, n_steps=64)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+        ms = min(times)
+        bits = full
+        out["scaling"] = "strong"
+        out["gather"] = "nccl_allgather of the packed verdict words (1.25 MiB)"
+        out["mask_checksum"] = int(full.to(torch.int64).bitwise_and(0xFFFFFFFF).sum().item())
+    else:
+        ms = ev_ms(torch, lambda: pv.check_edges(A, B, n_steps=64, out=bits), iters=3, warm=1)
+        out["mask_checksum"] = int(bits.to(torch.int64).bitwise_and(0xFFFFFFFF).sum().item())
     valid = float(np.unpackbits(bits.cpu().numpy().view(np.uint8)).sum()) / N_EDGES
     rate = N_EDGES / (ms * 1e-3)
     out.update({"ms": ms, "value": rate, "state_checks_per_s_upper": 64 * rate, "valid_fraction": valid,

@@ -64,6 +64,27 @@ def sweep_sharded(pv, n_total: int, seed: int, fingers_open: bool = True, group=
     return full, n_valid
 
 
+def check_edges_sharded(pv, qa, qb, n_steps: int = 0, resolution: float = 0.0, group=None) -> torch.Tensor:
+    """BASELINE config 3 on N GPUs: motions are independent units, so rank r validates the contiguous shard
+    shard_range(n, r, world) of the batch (qa, qb: the same (n, 9) tensors, or SoA plane tuples, on every rank) with
+    pv.check_edges, and the verdict words (1 bit per edge) are all-gathered.  Every rank returns the words one GPU
+    computes for the whole batch."""
+    from . import panda_model as pm
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    planes = isinstance(qa, (tuple, list))
+    n = int(qa[0].shape[0] if planes else qa.shape[0])
+    first, count = shard_range(n, rank, world)
+    cut = (lambda t: tuple(x[first:first + count] for x in t)) if planes else (lambda t: t[first:first + count])
+    if count > 0:
+        words = pv.check_edges(cut(qa), cut(qb), n_steps=n_steps,
+                               resolution=resolution if resolution > 0 else pm.VALIDITY_RESOLUTION)
+    else:
+        dev = getattr(pv, "device", None) or torch.device("cpu")
+        words = torch.zeros(0, dtype=torch.int32, device=dev)
+    return gather_verdict_words(words, n, group)
+
+
 def sweep_sharded_fused(pv, gather: "FusedVerdictGather", n_total: int, seed: int, fingers_open: bool = True):
     """Same result as sweep_sharded, but the verdict words travel inside the sweep kernel (peer / multicast stores)
     and the only synchronisation is the symmetric-memory barrier.  `gather` must have words_per_rank =

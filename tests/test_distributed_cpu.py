@@ -305,3 +305,31 @@ def test_sharded_tree_planner_matches_the_single_tree_planner(world):
             assert iters[k] == ref[k][1], (rank, k)
             assert np.array_equal(paths[k], ref[k][0]), (rank, k)
             assert (status[k] == 1) == (len(ref[k][0]) > 0)
+
+
+def _edges_worker(rank, world, port, n, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from rbe550_final_project_b200.distributed import check_edges_sharded
+    a, b = _rrtc_queries(n)
+    full = check_edges_sharded(_OracleSteps(), torch.from_numpy(a), torch.from_numpy(b), n_steps=0)
+    ret[rank] = full.numpy().copy()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 100), (3, 33), (4, 7)])
+def test_sharded_edge_batches_match_single_rank(world, n):
+    """BASELINE config 3's sharding: contiguous 32-aligned shards of a motion batch per rank (ragged and empty shards
+    included), verdict words all-gathered: every rank holds the words of the unsplit call."""
+    a, b = _rrtc_queries(n)
+    ref = _OracleSteps().check_edges(torch.from_numpy(a), torch.from_numpy(b), n_steps=0, resolution=0.13037159046356686).numpy()
+    assert 0 < np.unpackbits(ref.view(np.uint8)).sum() < n
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 37500 + (os.getpid() % 2000) + world
+    mp.spawn(_edges_worker, args=(world, port, n, ret), nprocs=world, join=True)
+    for rank in range(world):
+        assert np.array_equal(ret[rank], ref), rank

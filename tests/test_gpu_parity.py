@@ -544,6 +544,22 @@ def test_edges_host_entry_point_multi_chunk(pv):
     assert np.array_equal(d, h)
 
 
+def test_sharded_edge_entry_single_rank(pv):
+    """distributed.check_edges_sharded at world size 1 (N GPUs: bench.py --gpus N `edges`, gloo tests on CPU) is the plain
+    call, for (n, 9) tensors and for SoA plane tuples."""
+    from rbe550_final_project_b200.distributed import check_edges_sharded
+    pv.set_scene(sc.goal4_task1_pentagon())
+    n = 50_017
+    q = random_configs(n, 71)
+    qb = np.clip(q + np.random.default_rng(3).normal(0, 0.3, q.shape), pm.Q_LOWER, pm.Q_UPPER).astype(np.float32)
+    qb[:, 7:] = 0.04
+    a, b = _dev(q), _dev(qb)
+    ref = pv.check_edges(a, b, n_steps=64).cpu().numpy()
+    assert np.array_equal(check_edges_sharded(pv, a, b, n_steps=64).cpu().numpy(), ref)
+    planes = lambda t: (t[:, 0:4].contiguous(), t[:, 4:8].contiguous())  # noqa: E731
+    assert np.array_equal(check_edges_sharded(pv, planes(a), planes(b), n_steps=64).cpu().numpy(), ref)
+
+
 def test_rejected_scene_keeps_the_previous_one(pv):
     from rbe550_final_project_b200.validity import PandaValidityError
     good = sc.goal1_scattered()
