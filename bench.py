@@ -843,6 +843,29 @@ def plan_time_probe(pv, n_plans: int = 101):
         case["straight_line_valid"] = straight
         out["tower"] = case
     out["p50_ms"] = out["config1"]["p50_ms"]
+    # the reference's callback shape: ONE state per call (`_is_ompl_state_valid`, planning.py:209-219) -- what an OMPL that
+    # stays on the host would pay per state through the drop-in's StateValidityChecker, beside the CPU port's cost
+    scene, franka, _ = create_scene("goal1_scattered")
+    planner = PlannerInterface(franka, scene, validity=pv)
+    cb = planner.state_validity_checker()
+    rng = np.random.default_rng(3)
+    qs = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(2100, 9))
+    qs[:, 7:] = 0.04
+    lat = []
+    for i, q in enumerate(qs):
+        t = time.perf_counter()
+        cb(q)
+        if i >= 100:
+            lat.append(time.perf_counter() - t)
+    oscene = sc.FIXTURES["goal1_scattered"]().as_oracle_scene()
+    q32 = qs.astype(np.float32)
+    t = time.perf_counter()
+    for q in q32[:500]:
+        ora.state_margin(q[None], oscene, nthreads=1)
+    cpu_us = (time.perf_counter() - t) / 500 * 1e6
+    out["callback"] = {"what": "one state per call through PlannerInterface.state_validity_checker() (host-mapped staging: one "
+                               "launch + one synchronisation)", "p50_us": float(np.median(lat)) * 1e6,
+                       "p95_us": float(np.percentile(lat, 95)) * 1e6, "cpu_port_us": cpu_us}
     return out
 
 

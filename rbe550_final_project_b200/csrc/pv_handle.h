@@ -50,6 +50,7 @@ struct PvHandle {
     int rrtc_parity;       // which of the two row cursors the next launch uses
     void* plan_host;       // host-mapped pinned staging of pv_plan_path's edge batches (end points in, verdict words out)
     size_t plan_host_bytes;
+    void* small_host;      // host-mapped pinned staging of small host-buffer calls (rows in, verdict words / bytes out)
     void* ik_buf;
     size_t ik_bytes;
     char err[512];

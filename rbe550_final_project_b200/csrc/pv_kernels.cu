@@ -764,6 +764,7 @@ void pv_destroy(PvHandle* h) {
     if (h->rrtc_host) cudaFreeHost(h->rrtc_host);
     if (h->rrtc_rows_host) cudaFreeHost(h->rrtc_rows_host);
     if (h->plan_host) cudaFreeHost(h->plan_host);
+    if (h->small_host) cudaFreeHost(h->small_host);
     if (h->ik_buf) cudaFree(h->ik_buf);
     h->magic = 0;
     delete h;
@@ -1025,7 +1026,8 @@ int pv_state_contacts(PvHandle* h, const float* d_qA, const float* d_qB, const f
 }
 
 static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9,
-                                const float* d_aos, int64_t n, uint32_t* d_bits, cudaStream_t st) {
+                                const float* d_aos, int64_t n, uint32_t* d_bits, cudaStream_t st,
+                                bool force_unsorted = false) {
     const int64_t words = (n + 31) / 32;
 #define PV_LAUNCH_SB(AOS, CULL, CARRY)                                                                        \
     {                                                                                                         \
@@ -1059,7 +1061,7 @@ static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_q
         PV_CUDA(h, cudaLaunchKernelEx(&cfg_, pv_state_bits_sorted_kernel<SRC_, CARRY>, h->scene, (const float4*)d_qA, \
                                       (const float4*)d_qB, d_q9, d_aos, n, d_bits, d_aos ? PvGather{} : h->gather)); \
     }
-    if (h->cull == 2) {  // tile-sorted + per-lane culling (the default)
+    if (h->cull == 2 && !force_unsorted) {  // tile-sorted + per-lane culling (the default)
         if (h->scene.carry) {
             if (d_aos) PV_LAUNCH_SORTED(true, true) else PV_LAUNCH_SORTED(false, true)
         } else {
@@ -1119,10 +1121,36 @@ static int pv_ensure_stage(PvHandle* h) {
     return PV_OK;
 }
 
+// Small host batches -- the reference's callback shape is ONE state per call (planning.py:209-219), a plan's waypoint
+// validation a few hundred motions -- go through host-mapped pinned memory: the kernel reads the rows and writes the verdict
+// words over PCIe itself, so a call is one launch and one synchronisation instead of copy + launch + copy (34 -> ~12 us
+// for one state).  No sort for these sizes: the unsorted kernel returns the same words.
+#ifndef PV_HOST_SMALL
+#define PV_HOST_SMALL 2048
+#endif
+static int pv_ensure_small(PvHandle* h) {
+    if (!h->small_host) {
+        const size_t bytes = (size_t)PV_HOST_SMALL * 9 * sizeof(float) * 2 + (size_t)PV_HOST_SMALL * sizeof(uint32_t);
+        PV_CUDA(h, cudaHostAlloc(&h->small_host, bytes, cudaHostAllocMapped));
+    }
+    return PV_OK;
+}
+
 int pv_check_states_host(PvHandle* h, const float* h_q, int64_t n, uint32_t* h_bits) {
     PV_PRECHECK(h, n);
     if (!h_q || !h_bits) return PV_ERR_BAD_ARG;
-    int rc = pv_ensure_stage(h);
+    int rc;
+    if (n <= PV_HOST_SMALL) {
+        if ((rc = pv_ensure_small(h))) return rc;
+        float* mq = (float*)h->small_host;
+        uint32_t* mb = (uint32_t*)(mq + (size_t)PV_HOST_SMALL * 18);
+        memcpy(mq, h_q, (size_t)n * 9 * sizeof(float));
+        if ((rc = pv_launch_state_bits(h, nullptr, nullptr, nullptr, mq, n, mb, h->streams[0], true))) return rc;
+        PV_CUDA(h, cudaStreamSynchronize(h->streams[0]));
+        memcpy(h_bits, mb, (size_t)((n + 31) / 32) * sizeof(uint32_t));
+        return PV_OK;
+    }
+    rc = pv_ensure_stage(h);
     if (rc) return rc;
     // chunk size: whole input for small batches, else PV_HOST_CHUNK (multiple of 32) so copies overlap compute
     int64_t done = 0;
@@ -1196,7 +1224,26 @@ int pv_check_edges_host(PvHandle* h, const float* h_qa, const float* h_qb, int64
                         float resolution, uint32_t* h_bits) {
     PV_PRECHECK(h, n_edges);
     if (!h_qa || !h_qb || !h_bits) return PV_ERR_BAD_ARG;
-    int rc = pv_ensure_stage(h);
+    int rc;
+    if (n_edges <= PV_HOST_SMALL) {  // host-mapped staging, one motion per warp, one verdict byte per motion
+        if ((rc = pv_ensure_small(h))) return rc;
+        float* ma = (float*)h->small_host;
+        float* mb = ma + (size_t)PV_HOST_SMALL * 9;
+        unsigned char* ok = (unsigned char*)(mb + (size_t)PV_HOST_SMALL * 9);
+        memcpy(ma, h_qa, (size_t)n_edges * 9 * sizeof(float));
+        memcpy(mb, h_qb, (size_t)n_edges * 9 * sizeof(float));
+        if ((rc = pv_launch_edges(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ma, mb, n_edges, n_steps, resolution,
+                                  nullptr, nullptr, h->streams[0], ok)))
+            return rc;
+        PV_CUDA(h, cudaStreamSynchronize(h->streams[0]));
+        for (int64_t w = 0; w < (n_edges + 31) / 32; ++w) {
+            uint32_t word = 0;
+            for (int64_t k = w * 32; k < n_edges && k < (w + 1) * 32; ++k) word |= (uint32_t)(ok[k] & 1u) << (k & 31);
+            h_bits[w] = word;
+        }
+        return PV_OK;
+    }
+    rc = pv_ensure_stage(h);
     if (rc) return rc;
     int64_t done = 0;
     int slot = 0;
