@@ -501,6 +501,19 @@ def main():
     line.update(sub)
 
     if world == 1 and not args.no_configs:
+        # SURVEY.md 8d, config 2, second set: finger joints ~ U(0, 0.04) each (three planes: 36 B per configuration)
+        try:
+            rngf = np.random.default_rng(SEED + 77)
+            bf = make_batch(SEED + 78, n)
+            bf[:, 7:] = rngf.uniform(0.0, 0.04, size=(n, 2)).astype(np.float32)
+            pf = soa_from_aos(torch.as_tensor(bf, device="cuda"))
+            of = torch.empty(words, dtype=torch.int32, device="cuda")
+            ms_f = ev_ms(torch, lambda: pv.check_states(pf, out=of), iters=24, warm=3)
+            line["config2_random_fingers"] = {"value": n / (ms_f * 1e-3), "unit": UNIT, "ms_per_launch": ms_f,
+                                              "note": "one resident batch, q8, q9 ~ U(0, 0.04) independently",
+                                              "valid_fraction": float(np.unpackbits(of.cpu().numpy().view(np.uint8)).sum()) / n}
+        except Exception as exc:
+            line["config2_random_fingers"] = {"error": repr(exc)}
         for name, fn in (("edges", bench_edges), ("rrtc", bench_rrtc)):
             try:
                 line[name] = fn(torch, pv, counts, mhz)
@@ -663,6 +676,17 @@ def bench_edges(torch, pv, counts, mhz, dist=None, world=1):
         out["mask_checksum"] = int(bits.to(torch.int64).bitwise_and(0xFFFFFFFF).sum().item())
     valid = float(np.unpackbits(bits.cpu().numpy().view(np.uint8)).sum()) / N_EDGES
     rate = N_EDGES / (ms * 1e-3)
+    if world == 1:
+        # SURVEY.md 8d also asks for the uniform-pair variant: both end points uniform in the joint limits (long motions)
+        del B
+        qb = lo + (hi - lo) * torch.rand((N_EDGES, 9), generator=g, device="cuda")
+        qb[:, 7:] = 0.04
+        B = (qb[:, 0:4].contiguous(), qb[:, 4:8].contiguous())
+        del qb
+        bits_u = torch.empty(N_EDGES // 32, dtype=torch.int32, device="cuda")
+        ms_u = ev_ms(torch, lambda: pv.check_edges(A, B, n_steps=64, out=bits_u), iters=3, warm=1)
+        out["uniform_pairs"] = {"ms": ms_u, "value": N_EDGES / (ms_u * 1e-3),
+                                "valid_fraction": float(np.unpackbits(bits_u.cpu().numpy().view(np.uint8)).sum()) / N_EDGES}
     out.update({"ms": ms, "value": rate, "state_checks_per_s_upper": 64 * rate, "valid_fraction": valid,
                 "bytes_per_edge": 64.125, "hbm_gbs": 64.125 * rate / 1e9})
     ec = counts.get("edges", {})
