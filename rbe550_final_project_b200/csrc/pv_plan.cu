@@ -573,6 +573,37 @@ int pv_plan_path(PvHandle* h, const double* start, const double* goal, int num_w
 
     std::vector<float> out_rows;
     bool delivered = false;
+    // Fast path: ONE launch answers the questions the common plan consists of -- is the straight motion start -> goal
+    // valid at the planner's resolution (the first extension of the solve aims at the goal itself, so this IS its first
+    // decision), and is every waypoint of its resampling valid (w0 -> w0 covers the start state, the last waypoint is the
+    // goal)?  Most plans of the reference's primitives are such lines (approach, descend, lift); they cost one launch and
+    // one synchronisation.  Any failure falls through to the full pipeline, which also reports WHY an end point is bad.
+    bool spec_ready = false;
+    if (spec_n > 0 && spec_n + 1 <= PLAN_EDGE_CAP) {
+        memcpy(spec.a + (size_t)spec_n * 9, sg, 9 * sizeof(float));
+        memcpy(spec.b + (size_t)spec_n * 9, sg + 9, 9 * sizeof(float));
+        const double t_fast = now_ms();
+        rc = plan_queue_edges(h, spec, spec_n + 1, base_res, h->streams[0]);
+        if (rc) return rc;
+        PL_CUDA(cudaStreamSynchronize(h->streams[0]));
+        spec_ready = true;
+        bool all_ok = true;
+        for (int k = 0; k <= spec_n; ++k) all_ok &= spec.ok[k] != 0;
+        S.ms_solve += (float)(now_ms() - t_fast);
+        if (all_ok) {
+            float d2 = 0.f;
+            for (int j = 0; j < 9; ++j) d2 = fmaf(sg[9 + j] - sg[j], sg[9 + j] - sg[j], d2);
+            const int nd = std::max(1, (int)ceilf(sqrtf(d2) / base_res));
+            out_rows = spec_rows;
+            delivered = true;
+            S.attempts = 1;
+            S.iters = 1;
+            S.checks = nd;
+            S.vertices_raw = S.vertices = 2;
+            S.validated = 1;
+            S.speculative_hit = 1;
+        }
+    }
     for (int attempt = 0; attempt < max_attempts && !delivered; ++attempt) {
         if (attempt > 0 && prm->timeout_s > 0 && (now_ms() - t0) * 1e-3 > prm->timeout_s) break;
         S.attempts = attempt + 1;
@@ -596,7 +627,8 @@ int pv_plan_path(PvHandle* h, const double* start, const double* goal, int num_w
         bool spec_queued = false;
         // the speculative validation does not depend on the solve: it runs beside it on a second stream
         std::function<void(cudaStream_t)> hook = [&](cudaStream_t) {
-            if (attempt == 0 && spec_n > 0) spec_queued = plan_queue_edges(h, spec, spec_n, base_res, h->streams[1]) == PV_OK;
+            if (attempt == 0 && spec_n > 0)
+                spec_queued = spec_ready || plan_queue_edges(h, spec, spec_n, base_res, h->streams[1]) == PV_OK;
         };
         const double t_solve = now_ms();
         rc = pv_rrtc_run(h, sg, sg + 9, 1, &rp,
@@ -608,7 +640,7 @@ int pv_plan_path(PvHandle* h, const double* start, const double* goal, int num_w
                                  for (int j = 0; j < 9; ++j) raw[k][j] = (double)rows[(size_t)(off[0] + k) * 9 + j];
                          },
                          &hook);
-        if (spec_queued && attempt == 0) PL_CUDA(cudaStreamSynchronize(h->streams[1]));
+        if (spec_queued && !spec_ready && attempt == 0) PL_CUDA(cudaStreamSynchronize(h->streams[1]));
         S.ms_solve += (float)(now_ms() - t_solve);
         if (rc) return rc;
         if (iters < 0) {  // start / goal out of bounds or in collision: OMPL finds no valid start / goal -> no solution

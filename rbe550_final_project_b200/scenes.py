@@ -200,6 +200,7 @@ def _host_vec(x):
 
 
 _BOX_CACHE: dict = {}
+_LAST_SNAPSHOT: dict = {}  # id(scene) -> (box list, positions, quaternions, base, snapshot) of the previous call
 _IDENTITY_QUAT = (1.0, 0.0, 0.0, 0.0)
 
 
@@ -246,16 +247,13 @@ def snapshot_from_sim(scene: Any, robot: Any) -> SceneSnapshot:
     raw = getattr(robot, "raw", None) or getattr(robot, "robot", robot)
     boxes, names, idxs, half, radius, has_quat = _box_entities(scene, raw, robot)
     n = len(boxes)
-    obb = np.empty((n, 16), dtype=np.float32)
+    pos = quat = None
     if n:
         pos = np.array([_host_vec(e.get_pos()) for e in boxes], dtype=np.float64)
         quat = np.array([_host_vec(e.get_quat()) if hq else _IDENTITY_QUAT for e, hq in zip(boxes, has_quat)], dtype=np.float64)
         if pos.shape != (n, 3) or quat.shape != (n, 4):
             pos = np.ascontiguousarray(pos.reshape(n, -1)[:, :3])
             quat = np.ascontiguousarray(quat.reshape(n, -1)[:, :4])
-        from . import _cabi
-        if _cabi.load().pv_obb_from_poses(pos.ctypes.data, quat.ctypes.data, half.ctypes.data, n, obb.ctypes.data) != 0:
-            raise ValueError("snapshot_from_sim: an entity reports a zero or non-finite quaternion")
     base = pm.BASE_LIFT
     if hasattr(raw, "get_pos"):
         try:
@@ -263,4 +261,20 @@ def snapshot_from_sim(scene: Any, robot: Any) -> SceneSnapshot:
             base = (float(b[0]), float(b[1]), float(b[2]))
         except Exception:
             base = pm.BASE_LIFT
-    return SceneSnapshot(obb=obb, table_z=0.0, base=base, names=names, entity_idx=idxs)
+    # the poses are READ on every call (blocks move between plans); when they are what the previous call saw -- plan after
+    # plan of one primitive -- the previous snapshot object is handed back and nothing is converted again
+    last = _LAST_SNAPSHOT.get(id(scene))
+    if last is not None and last[0] is boxes and last[3] == base and (n == 0 or (np.array_equal(last[1], pos) and
+                                                                               np.array_equal(last[2], quat))):
+        return last[4]
+    obb = np.empty((n, 16), dtype=np.float32)
+    if n:
+        from . import _cabi
+        if _cabi.load().pv_obb_from_poses(pos.ctypes.data, quat.ctypes.data, half.ctypes.data, n, obb.ctypes.data) != 0:
+            raise ValueError("snapshot_from_sim: an entity reports a zero or non-finite quaternion")
+    obb.flags.writeable = False  # a snapshot that may be handed out again must not be edited in place
+    snap = SceneSnapshot(obb=obb, table_z=0.0, base=base, names=names, entity_idx=idxs)
+    if len(_LAST_SNAPSHOT) > 64:
+        _LAST_SNAPSHOT.clear()
+    _LAST_SNAPSHOT[id(scene)] = (boxes, pos, quat, base, snap)
+    return snap

@@ -42,9 +42,12 @@ class PandaValidity:
         self.device = torch.device("cuda", int(device))
         self.scene: Optional[SceneSnapshot] = None
         self._scene_key = None
+        self._scene_obj_key = None
         self.attached = -1
         self.carried = None
         self.flags = FLAG_SELF
+        self._plan_key = None
+        self._plan_prm = None
 
     # -- plumbing -------------------------------------------------------------------------------------
     def close(self):
@@ -73,10 +76,19 @@ class PandaValidity:
 
     # -- configuration --------------------------------------------------------------------------------
     def set_scene(self, scene: SceneSnapshot):
+        if scene is self.scene and not scene.obb.flags.writeable and \
+                self._scene_obj_key == (id(scene.obb), scene.table_z, scene.base):
+            # the very snapshot object the handle already holds, read-only (scenes.snapshot_from_sim hands the previous
+            # one back when no pose has changed): nothing to compare
+            if self.attached != -1 or self.carried is not None:
+                self._ck(self.lib.pv_set_attached(self._h, -1), "pv_set_attached")
+                self.attached, self.carried = -1, None
+            return
         obb = np.ascontiguousarray(scene.obb, dtype=np.float32).reshape(-1, 16)
         # plan_path snapshots the scene on every call (planning.py reads the live poses each time); the handle only
         # re-derives its tables (reach masks, scene bounds) when the bytes differ from what it already holds
         key = (obb.tobytes(), float(scene.table_z), tuple(float(v) for v in scene.base))
+        self._scene_obj_key = (id(scene.obb), scene.table_z, scene.base)
         if key != self._scene_key:
             base = (C.c_float * 3)(*key[2])
             self._ck(self.lib.pv_set_scene(self._h, obb.ctypes.data_as(C.POINTER(C.c_float)), obb.shape[0],
@@ -363,10 +375,16 @@ class PandaValidity:
         Returns (waypoints (n, 9) float32 -- n = 0 when no path was found --, stats dict)."""
         qs = np.ascontiguousarray(start, dtype=np.float64).reshape(9)
         qg = np.ascontiguousarray(goal, dtype=np.float64).reshape(9)
-        prm = _cabi.PvPlanParams(float(rrt_range), float(resolution), int(max_iters), int(max_nodes),
-                                 int(seed) & 0xFFFFFFFF, int(replicas), 1 if smooth else 0,
-                                 {"RRTConnect": 0, "RRT": 1}[planner], 1 if validate else 0, int(max_attempts),
-                                 float(timeout))
+        # the parameter block is kept between calls (this wrapper is inside every plan's wall time): only what changed
+        # since the last call is rewritten
+        key = (rrt_range, resolution, max_iters, max_nodes, replicas, smooth, planner, validate, max_attempts, timeout)
+        if key != self._plan_key:
+            self._plan_prm = _cabi.PvPlanParams(float(rrt_range), float(resolution), int(max_iters), int(max_nodes), 0,
+                                                int(replicas), 1 if smooth else 0, {"RRTConnect": 0, "RRT": 1}[planner],
+                                                1 if validate else 0, int(max_attempts), float(timeout))
+            self._plan_key = key
+        prm = self._plan_prm
+        prm.seed = int(seed) & 0xFFFFFFFF
         cap = max(int(num_waypoints) if num_waypoints else 0, 256)
         out = np.empty((cap, 9), dtype=np.float32)
         n = C.c_int(0)
