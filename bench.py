@@ -603,8 +603,9 @@ def bench_tree(torch, dist, pv, rank, world, nq=1024):
     valid = cand[ok]
     starts, goals = valid[:nq], valid[nq:2 * nq]
     kw = dict(max_iters=2000, max_path=128, seed=7)
-    ShardedTreePlanner(pv, max_nodes=2048).solve(starts[:64], goals[:64], **kw)  # warm-up (allocator, NCCL channels)
     pl = ShardedTreePlanner(pv, max_nodes=2048)
+    pl.solve(starts, goals, max_iters=1, max_path=128, seed=7)  # warm-up: allocator, NCCL channels, the symmetric buffer
+    pl.rounds, pl.bytes_gathered = 0, 0
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -624,7 +625,8 @@ def bench_tree(torch, dist, pv, rank, world, nq=1024):
                         "round pv_nn_candidates -> all-gather of 44 B records -> pv_rrtc_steer -> the round's motions validated "
                         "in shards (pv_check_edges) -> all-gather of verdict words (distributed.ShardedTreePlanner)",
             "ms": float(dt.item()) * 1e3, "value": nq / float(dt.item()), "unit": "queries/s", "rounds": pl.rounds,
-            "gathered_bytes": pl.bytes_gathered, "success": float((status == pl.SOLVED).mean()),
+            "gathered_bytes": pl.bytes_gathered, "candidate_exchange": pl.candidate_exchange,
+            "success": float((status == pl.SOLVED).mean()),
             "identical_to_pv_rrtc_batch": int(agree.item()), "of": nq,
             "timing": "wall clock around solve(), max over ranks (host-orchestrated rounds: latency-bound by design, the "
                       "one-kernel planner of `rrtc` is the throughput path)"}

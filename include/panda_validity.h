@@ -283,6 +283,13 @@ int pv_simplify_path_cb(const double *states, int n_states, uint32_t seed, pv_ed
  * planning.py:151-156). */
 int pv_nn_candidates(PvHandle *h, const float *d_trees, const int *d_sizes, const int *d_tree_of, const float *d_targets,
                      int n_pairs, int capacity, int rank, int world, float *d_out, void *stream);
+/* pv_nn_candidates with the all-gather fused into it: record t of this rank goes, word by word, into EVERY rank's
+ * symmetric buffer at [rank][t][11] (buffers of world * n_pairs * 11 32-bit words; d_peer_ptrs = device array of the
+ * n_peers buffer base pointers, d_multicast = the NVSwitch multicast address of the same buffer or NULL), so that after the
+ * symmetric-memory barrier every rank holds what the all-gather would have delivered -- pv_rrtc_steer's input. */
+int pv_nn_candidates_gather(PvHandle *h, const float *d_trees, const int *d_sizes, const int *d_tree_of,
+                            const float *d_targets, int n_pairs, int capacity, int rank, int world, const void *d_peer_ptrs,
+                            int n_peers, void *d_multicast, void *stream);
 int pv_rrtc_steer(PvHandle *h, const float *d_cand, int world, int n, const float *d_targets, float range,
                   int *d_from_gidx, float *d_ea, float *d_eb, int *d_reach, void *stream);
 int pv_rrtc_samples(PvHandle *h, uint32_t seed, const unsigned *d_gsearch, const int *d_it, int n, float *d_out,

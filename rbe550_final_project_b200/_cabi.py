@@ -29,7 +29,7 @@ EXPORTS = [
     "pv_check_edges", "pv_edge_margins", "pv_check_states_host", "pv_check_states_host_arm", "pv_check_edges_host", "pv_sweep",
     "pv_rrtc_batch", "pv_rrtc_batch_packed", "pv_plan_path", "pv_interpolate_path", "pv_obb_from_poses", "pv_simplify_path",
     "pv_simplify_path_cb",
-    "pv_nn_candidates", "pv_rrtc_steer", "pv_rrtc_samples", "pv_ik_batch", "pv_fp32_peak", "pv_launch_count",
+    "pv_nn_candidates", "pv_nn_candidates_gather", "pv_rrtc_steer", "pv_rrtc_samples", "pv_ik_batch", "pv_fp32_peak", "pv_launch_count",
 ]
 
 
@@ -163,6 +163,7 @@ def load() -> C.CDLL:
     lib.pv_simplify_path.argtypes = [vp, vp, C.c_int, C.c_uint32, C.c_float, vp, C.c_int, C.POINTER(C.c_int), vp]
     lib.pv_simplify_path_cb.argtypes = [vp, C.c_int, C.c_uint32, EDGE_CALLBACK, vp, vp, C.c_int, C.POINTER(C.c_int), vp]
     lib.pv_nn_candidates.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.pv_nn_candidates_gather.argtypes = [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp]
     lib.pv_rrtc_steer.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_float, vp, vp, vp, vp, vp]
     lib.pv_rrtc_samples.argtypes = [vp, C.c_uint32, vp, vp, C.c_int, vp, vp]
     lib.pv_ik_batch.argtypes = [vp, fp, fp, C.c_int, fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_uint32, fp, i32p, fp]

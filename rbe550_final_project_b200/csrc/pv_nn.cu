@@ -17,10 +17,16 @@
 // trees: [n_trees][9][capacity] SoA (this rank's slots); sizes[t] = slots in use; targets [n_trees][9];
 // out [n_trees][11] = squared distance, GLOBAL node index (int bits), node state -- the record that is all-gathered.
 // Pair t searches tree tree_of[t] (null: tree t), so a batch can address any subset of the trees.
+// Fused gather (peers / mc non-null): the record is ALSO stored into every rank's symmetric buffer, at rank-major
+// position [rank][pair][11] -- one multimem.st per word through the NVSwitch multicast address, or one peer store per rank
+// -- so the all-gather of the candidates happens inside the kernel that finds them (no collective launch; the ranks meet at
+// the symmetric-memory barrier that follows).
 __global__ void __launch_bounds__(NN_THREADS) pv_nn_kernel(const float* __restrict__ trees, const int* __restrict__ sizes,
                                                            const int* __restrict__ tree_of,
                                                            const float* __restrict__ targets, int capacity, int rank,
-                                                           int world, float* __restrict__ out /* [n_pairs][11] */) {
+                                                           int world, float* __restrict__ out /* [n_pairs][11] or null */,
+                                                           uint32_t* const* __restrict__ peers, uint32_t* __restrict__ mc,
+                                                           int n_peers) {
     const int t = blockIdx.x;
     const int tree = tree_of ? tree_of[t] : t;
     const float* tq = trees + (size_t)tree * 9 * capacity;
@@ -58,34 +64,47 @@ __global__ void __launch_bounds__(NN_THREADS) pv_nn_kernel(const float* __restri
         s_i[threadIdx.x >> 5] = bi;
     }
     __syncthreads();
+    __shared__ float s_rec[11];
     if (threadIdx.x == 0) {
         for (int w = 1; w < NN_THREADS / 32; ++w)
             if (s_d[w] < bd || (s_d[w] == bd && s_i[w] < bi)) {
                 bd = s_d[w];
                 bi = s_i[w];
             }
-        out[(size_t)t * 11] = bd;
-        out[(size_t)t * 11 + 1] = __int_as_float(size > 0 ? bi * world + rank : 0x7fffffff);
+        s_rec[0] = bd;
+        s_rec[1] = __int_as_float(size > 0 ? bi * world + rank : 0x7fffffff);
         s_i[0] = bi;
     }
     __syncthreads();
     const int slot = s_i[0];
-    if (threadIdx.x < 9) out[(size_t)t * 11 + 2 + threadIdx.x] = size > 0 ? tq[(size_t)threadIdx.x * capacity + slot] : 0.f;
+    if (threadIdx.x < 9) s_rec[2 + threadIdx.x] = size > 0 ? tq[(size_t)threadIdx.x * capacity + slot] : 0.f;
+    __syncthreads();
+    if (threadIdx.x < 11) {
+        const float v = s_rec[threadIdx.x];
+        if (out) out[(size_t)t * 11 + threadIdx.x] = v;
+        const size_t W = ((size_t)rank * gridDim.x + t) * 11 + threadIdx.x;
+        if (mc) {
+            asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(mc + W), "r"(__float_as_uint(v)) : "memory");
+        } else if (peers) {
+            for (int p = 0; p < n_peers; ++p) peers[p][W] = __float_as_uint(v);
+        }
+    }
 }
 
-extern "C" int pv_nn_candidates(PvHandle* h, const float* d_trees, const int* d_sizes, const int* d_tree_of,
-                                const float* d_targets, int n_trees, int capacity, int rank, int world, float* d_out,
-                                void* stream) {
+static int nn_launch(PvHandle* h, const float* d_trees, const int* d_sizes, const int* d_tree_of, const float* d_targets,
+                     int n_trees, int capacity, int rank, int world, float* d_out, const void* d_peer_ptrs, int n_peers,
+                     void* d_multicast, void* stream, const char* who) {
     if (!h || h->magic != PV_HANDLE_MAGIC) return PV_ERR_BAD_HANDLE;
-    if (n_trees < 0 || capacity < 1 || world < 1 || rank < 0 || rank >= world ||
-        (n_trees > 0 && (!d_trees || !d_sizes || !d_targets || !d_out))) {
-        snprintf(h->err, sizeof(h->err), "pv_nn_candidates: bad arguments");
+    if (n_trees < 0 || capacity < 1 || world < 1 || rank < 0 || rank >= world || n_peers < 0 || n_peers > 32 ||
+        (n_trees > 0 && (!d_trees || !d_sizes || !d_targets || (!d_out && !d_peer_ptrs && !d_multicast)))) {
+        snprintf(h->err, sizeof(h->err), "%s: bad arguments", who);
         return PV_ERR_BAD_ARG;
     }
     if (n_trees == 0) return PV_OK;
     PvDeviceGuard guard(h->device);
     pv_nn_kernel<<<n_trees, NN_THREADS, 0, (cudaStream_t)stream>>>(d_trees, d_sizes, d_tree_of, d_targets, capacity, rank, world,
-                                                                   d_out);
+                                                                   d_out, (uint32_t* const*)d_peer_ptrs, (uint32_t*)d_multicast,
+                                                                   n_peers);
     h->launches++;
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -93,6 +112,22 @@ extern "C" int pv_nn_candidates(PvHandle* h, const float* d_trees, const int* d_
         return PV_ERR_CUDA;
     }
     return PV_OK;
+}
+
+extern "C" int pv_nn_candidates(PvHandle* h, const float* d_trees, const int* d_sizes, const int* d_tree_of,
+                                const float* d_targets, int n_trees, int capacity, int rank, int world, float* d_out,
+                                void* stream) {
+    if (n_trees > 0 && !d_out) return PV_ERR_BAD_ARG;
+    return nn_launch(h, d_trees, d_sizes, d_tree_of, d_targets, n_trees, capacity, rank, world, d_out, nullptr, 0, nullptr,
+                     stream, "pv_nn_candidates");
+}
+
+extern "C" int pv_nn_candidates_gather(PvHandle* h, const float* d_trees, const int* d_sizes, const int* d_tree_of,
+                                       const float* d_targets, int n_pairs, int capacity, int rank, int world,
+                                       const void* d_peer_ptrs, int n_peers, void* d_multicast, void* stream) {
+    if (n_pairs > 0 && !d_peer_ptrs && !d_multicast) return PV_ERR_BAD_ARG;
+    return nn_launch(h, d_trees, d_sizes, d_tree_of, d_targets, n_pairs, capacity, rank, world, nullptr, d_peer_ptrs, n_peers,
+                     d_multicast, stream, "pv_nn_candidates_gather");
 }
 
 // ---- the two other device steps of the sharded-tree front end (distributed.ShardedTreePlanner) --------------------

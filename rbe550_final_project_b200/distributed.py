@@ -239,6 +239,40 @@ class FusedVerdictGather:
         self.deactivate()
 
 
+class FusedCandidateGather:
+    """All-gather of the nearest-node candidate records fused into the kernel that finds them (pv_nn_candidates_gather):
+    a symmetric-memory buffer of world x capacity x 11 32-bit words on every rank; each rank's kernel stores its records
+    into every rank's copy (NVSwitch multicast when the fabric offers it, else peer stores), and `finish(n)` -- a
+    symmetric-memory barrier -- returns the (world, n, 11) float view pv_rrtc_steer reads.  No NCCL launch is involved."""
+
+    def __init__(self, pv, capacity: int, group=None, use_multicast: bool = True):
+        import torch.distributed._symmetric_memory as symm
+        self.pv = pv
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.capacity = int(capacity)
+        self.buf = symm.empty(self.world * self.capacity * 11, dtype=torch.float32, device=pv.device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        self.buf.zero_()
+        mc = 0
+        if use_multicast and getattr(self.hdl, "has_multicast_support", False):
+            mc = int(self.hdl.multicast_ptr or 0)
+        self._mc = mc
+        self.multicast = bool(mc)
+        self.hdl.barrier()
+
+    def launch(self, trees, local_sizes, tree_of, targets):
+        if int(targets.shape[0]) > self.capacity:
+            raise ValueError("more (tree, target) pairs than the candidate buffer holds")
+        self.pv.nn_candidates_gather(trees, local_sizes, tree_of, targets, self.rank, self.world,
+                                     int(self.hdl.buffer_ptrs_dev), self._mc)
+
+    def finish(self, n: int) -> torch.Tensor:
+        self.hdl.barrier()  # every rank's kernel has completed and its stores are visible
+        return self.buf[: self.world * n * 11].view(self.world, n, 11)
+
+
 class ShardedTreePlanner:
     """Batched multi-query RRT-Connect front end whose TREES are sharded over the GPUs of one box (SURVEY.md 8e,
     BASELINE north_star: "NCCL ... only to gather verdicts and nearest-tree candidates for a batched multi-query
@@ -269,9 +303,12 @@ class ShardedTreePlanner:
     EXTEND, CONNECT, DONE = 0, 1, 4
     SOLVED, ITERCAP, NODECAP, PATHCAP, BADEND = 1, 2, 3, 4, 16
 
-    def __init__(self, pv, max_nodes: int = 2048, group=None):
+    def __init__(self, pv, max_nodes: int = 2048, group=None, fused_candidates: bool = True):
         self.pv = pv
         self.group = group
+        self.fused_candidates = bool(fused_candidates)
+        self._cand_gather = None
+        self.candidate_exchange = "none"
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.max_nodes = int(max_nodes)
@@ -333,6 +370,21 @@ class ShardedTreePlanner:
         gsearch = (torch.arange(n, device=dev, dtype=torch.int64) + int(query_offset)).to(torch.int32)
         qid = torch.arange(n, device=dev)
 
+        # candidate exchange: fused into pv_nn_candidates over NVLink peer memory when symmetric memory is available (GPUs,
+        # world > 1), else an NCCL / gloo all-gather of the records.  (A round's later verdict all-gather orders round k's
+        # readers before round k + 1's writers, so one buffer suffices.)
+        fused = None
+        if self.fused_candidates and world > 1 and dev.type == "cuda" and hasattr(self.pv, "nn_candidates_gather"):
+            try:
+                if self._cand_gather is None or self._cand_gather.capacity < n:
+                    self._cand_gather = FusedCandidateGather(self.pv, max(n, 1), self.group)
+                fused = self._cand_gather
+            except Exception:  # no symmetric memory on this fabric: keep the collective
+                fused = None
+        self.candidate_exchange = ("none" if world == 1 else
+                                   ("fused_multicast" if fused is not None and fused.multicast else
+                                    "fused_peer_stores" if fused is not None else "all_gather"))
+
         if check_endpoints and n:
             # OMPL drops invalid / out-of-bounds start and goal states at intake (planning.py:163-187)
             both = torch.cat([qs, qg])
@@ -364,8 +416,13 @@ class ShardedTreePlanner:
             aim_goal = ext & (it[a] == 0)  # the first extension aims at the goal itself
             tg = torch.where(ext[:, None], torch.where(aim_goal[:, None], qg[a], smp), target[a]).contiguous()
             local_sizes = torch.clamp((gsize - rank + world - 1) // world, min=0).to(torch.int32)
-            cand = self.pv.nn_candidates(trees, local_sizes, tree_of.contiguous(), tg, rank, world)
-            from_g, ea, eb, reach = self.pv.rrtc_steer(self._all_gather(cand), tg, rrt_range)
+            if fused is not None:
+                fused.launch(trees, local_sizes, tree_of.contiguous(), tg)
+                all_cand = fused.finish(int(a.numel()))
+                self.bytes_gathered += all_cand.numel() * 4
+            else:
+                all_cand = self._all_gather(self.pv.nn_candidates(trees, local_sizes, tree_of.contiguous(), tg, rank, world))
+            from_g, ea, eb, reach = self.pv.rrtc_steer(all_cand, tg, rrt_range)
             valid = self._valid_sharded(ea, eb, resolution)
             reach = reach.bool()
 

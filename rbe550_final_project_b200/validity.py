@@ -346,6 +346,18 @@ class PandaValidity:
                                            self._stream(stream)), "pv_nn_candidates")
         return out
 
+    def nn_candidates_gather(self, trees: torch.Tensor, sizes: torch.Tensor, tree_of: Optional[torch.Tensor],
+                             targets: torch.Tensor, rank: int, world: int, peer_ptrs_dev: int, multicast_ptr: int,
+                             n_peers: Optional[int] = None, stream=None):
+        """nn_candidates whose records land in every rank's symmetric buffer at [rank][pair][11] (pv_nn_candidates_gather)."""
+        n = int(targets.shape[0])
+        self._ck(self.lib.pv_nn_candidates_gather(self._h, trees.data_ptr(), sizes.data_ptr(),
+                                                  tree_of.data_ptr() if tree_of is not None else None, targets.data_ptr(), n,
+                                                  int(trees.shape[2]), int(rank), int(world),
+                                                  C.c_void_p(peer_ptrs_dev or None), int(world if n_peers is None else n_peers),
+                                                  C.c_void_p(multicast_ptr or None), self._stream(stream)),
+                 "pv_nn_candidates_gather")
+
     def rrtc_steer(self, cand: torch.Tensor, targets: torch.Tensor, rrt_range: float = 0.0, stream=None):
         """cand (world, n, 11): the all-gathered candidate records.  Returns (from_gidx (n,) int32, ea (n, 9), eb (n, 9),
         reach (n,) int32): the motion og.RRTConnect would validate next (planning.py:156)."""

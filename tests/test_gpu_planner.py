@@ -553,7 +553,22 @@ def test_nn_candidates_of_a_sharded_tree(pv):
                 loc[t, :, : len(mine)] = mine.T
             cands.append(pv.nn_candidates(torch.from_numpy(loc).to(dev), torch.from_numpy(lsz).to(dev),
                                           torch.from_numpy(tree_of).to(dev), torch.from_numpy(targets).to(dev), rank, world))
-        gi, ea, eb, reach = pv.rrtc_steer(torch.stack(cands).contiguous(), torch.from_numpy(targets).to(dev), 1.0)
+        # the fused form stores the same records rank-major into a "peer" buffer (here: one local buffer as the only peer)
+        gathered = torch.zeros((world, n_pairs, 11), dtype=torch.float32, device=dev)
+        peer_tab = torch.tensor([gathered.data_ptr()], dtype=torch.int64, device=dev)
+        for rank in range(world):
+            loc = np.zeros((T, 9, slots), np.float32)
+            lsz = np.zeros(T, np.int32)
+            for t in range(T):
+                mine = nodes[t, rank:sizes_g[t]:world]
+                lsz[t] = len(mine)
+                loc[t, :, : len(mine)] = mine.T
+            pv.nn_candidates_gather(torch.from_numpy(loc).to(dev), torch.from_numpy(lsz).to(dev),
+                                    torch.from_numpy(tree_of).to(dev), torch.from_numpy(targets).to(dev), rank, world,
+                                    peer_tab.data_ptr(), 0, n_peers=1)
+        torch.cuda.synchronize()
+        assert torch.equal(gathered.view(torch.int32), torch.stack(cands).contiguous().view(torch.int32)), world
+        gi, ea, eb, reach = pv.rrtc_steer(gathered, torch.from_numpy(targets).to(dev), 1.0)
         gi, ea, eb, reach = gi.cpu().numpy(), ea.cpu().numpy(), eb.cpu().numpy(), reach.cpu().numpy()
         for i in range(n_pairs):
             t = tree_of[i]
