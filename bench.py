@@ -654,8 +654,20 @@ def bench_edges(torch, pv, counts, mhz, dist=None, world=1):
     if world > 1:
         # strong scaling: contiguous shards of the same batch (every rank generates it from the same seed), verdict
         # words all-gathered with NCCL inside the timed region; max over ranks, best of 3
-        from rbe550_final_project_b200.distributed import check_edges_sharded
+        from rbe550_final_project_b200.distributed import FusedVerdictGather, check_edges_sharded as ces, words_per_shard
+        eg = None
+        try:
+            eg = FusedVerdictGather(pv, words_per_shard(N_EDGES, world))
+            eg.deactivate()
+        except Exception:
+            eg = None
+
+        def check_edges_sharded(pv_, a_, b_, n_steps):
+            return ces(pv_, a_, b_, n_steps=n_steps, gather=eg)
+
         full = check_edges_sharded(pv, A, B, n_steps=64)
+        nccl_full = ces(pv, A, B, n_steps=64)  # the NCCL gather of the same shards: the reference for the fused words
+        out["gather_verified"] = bool(torch.equal(full[: N_EDGES // 32], nccl_full[: N_EDGES // 32]))
         times = []
         for _ in range(3):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -671,7 +683,8 @@ def bench_edges(torch, pv, counts, mhz, dist=None, world=1):
         ms = min(times)
         bits = full
         out["scaling"] = "strong"
-        out["gather"] = "nccl_allgather of the packed verdict words (1.25 MiB)"
+        out["gather"] = ("nccl_allgather" if eg is None else "fused_multicast" if eg.multicast else "fused_peer_stores") + \
+            " of the packed verdict words (1.25 MiB)"
         out["mask_checksum"] = int(full.to(torch.int64).bitwise_and(0xFFFFFFFF).sum().item())
     else:
         ms = ev_ms(torch, lambda: pv.check_edges(A, B, n_steps=64, out=bits), iters=3, warm=1)

@@ -91,13 +91,14 @@ int pv_set_culling(PvHandle *h, int mode);
  * kind of earlier work on the stream has completed, and it writes its verdict words only after ALL earlier work has. */
 int pv_set_launch_overlap(PvHandle *h, int on);
 
-/* Fused verdict gather for multi-GPU runs: after this call pv_check_states and pv_sweep also store
+/* Fused verdict gather for multi-GPU runs: after this call pv_check_states, pv_sweep and pv_check_edges
+ * (batches above 16 384 motions, which are written as whole verdict words) also store
  * every verdict word w of this rank at word (word_offset + w) of EVERY rank's gather buffer, from inside the
  * kernel, over peer memory: d_peer_ptrs is a device array of n_peers buffer base pointers (symmetric memory, one per
  * rank, this rank included); d_multicast, if not NULL, is the NVSwitch multicast address of the same buffer and is
  * used instead (one store, replicated by the switch).  The caller synchronises the ranks (e.g. the symmetric-memory
  * barrier) before reading.  Words at or beyond word_capacity (this rank's slot size) are not forwarded.  n_peers = 0
- * switches the gather off.  d_bits of those calls may then be NULL. */
+ * switches the gather off.  d_bits of pv_check_states / pv_sweep may then be NULL. */
 int pv_set_gather(PvHandle *h, const void *d_peer_ptrs, int n_peers, void *d_multicast, long long word_offset,
                   long long word_capacity);
 

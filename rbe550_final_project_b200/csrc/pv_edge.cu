@@ -54,14 +54,25 @@
 #ifndef PV_E_LOCKSTEP
 #define PV_E_LOCKSTEP 0
 #endif
+// Verdict words of large batches also go to the handle's fused-gather target (pv_set_gather), like the state kernels' --
+// from a SEPARATE instantiation that is only launched while a gather is configured: with the epilogue compiled into the
+// one kernel the single-GPU rate fell by 3-4.5 % (402 -> 384 M edges/s on the pentagon scene; the layout of this
+// fetch-bound kernel is that sensitive), so the default instantiation carries neither the parameter nor the code.
+template <bool ON>
+struct PvGatherOpt {};
+template <>
+struct PvGatherOpt<true> {
+    PvGather g;
+};
 
-template <bool CULL, int MODE, bool CARRY>
+template <bool CULL, int MODE, bool CARRY, bool GATHER = false>
 __global__ void __launch_bounds__(PV_E_THREADS, 1)
     pv_edge_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ aA, const float4* __restrict__ aB,
                    const float* __restrict__ a9, const float4* __restrict__ bA, const float4* __restrict__ bB,
                    const float* __restrict__ b9, const float* __restrict__ a_aos, const float* __restrict__ b_aos,
                    int64_t n_edges, int n_steps, float resolution, uint32_t* __restrict__ bits,
-                   float* __restrict__ margin, int epw, unsigned char* __restrict__ ok_bytes) {
+                   float* __restrict__ margin, int epw, unsigned char* __restrict__ ok_bytes,
+                   const __grid_constant__ PvGatherOpt<GATHER> GO) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t n_words = (n_edges + epw - 1) / epw;
@@ -177,9 +188,13 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
         need_edge = true;
         if (j >= n_here) {
             if constexpr (MODE == PV_MODE_BITS) {
+                if constexpr (GATHER) {
+                    if (epw == 32) pv_emit_word(bits, GO.g, w, word, lane);  // local word + peer / multicast stores
+                }
                 if (lane == 0) {
-                    if (epw == 32) bits[w] = word;
-                    else if (ok_bytes) ok_bytes[w] = (unsigned char)(word & 1u);  // epw == 1
+                    if (epw == 32) {
+                        if constexpr (!GATHER) bits[w] = word;
+                    } else if (ok_bytes) ok_bytes[w] = (unsigned char)(word & 1u);  // epw == 1
                     else if (word & 1u) atomicOr(bits + (w >> 5), 1u << (w & 31));  // epw == 1, bits zeroed by the launcher
                 }
             }
@@ -205,17 +220,24 @@ int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* 
     const int epw = (d_ok_bytes || (d_bits && n <= PV_E_SMALL_BATCH)) ? 1 : 32;
     const int64_t words = (n + epw - 1) / epw;
     if (epw == 1 && d_bits && !d_ok_bytes) PV_CUDA(h, cudaMemsetAsync(d_bits, 0, (size_t)((n + 31) / 32) * sizeof(uint32_t), st));
-#define PV_LAUNCH_E(CULL, MODE, CARRY)                                                                         \
-    {                                                                                                          \
-        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE, CARRY>, PV_E_THREADS, words);        \
-        pv_edge_kernel<CULL, MODE, CARRY><<<grid, PV_E_THREADS, 0, st>>>(                                      \
-            h->scene, (const float4*)aA, (const float4*)aB, a9, (const float4*)bA, (const float4*)bB, b9, a_aos, \
-            b_aos, n, n_steps, resolution, d_bits, d_margin, epw, d_ok_bytes);                                 \
+    // the fused-gather target applies to whole verdict words only (large batches); small batches and margins never gather
+    const bool gather_on = epw == 32 && d_bits && h->gather.n_peers > 0;
+#define PV_LAUNCH_E(CULL, MODE, CARRY, GATHER, GARG)                                                              \
+    {                                                                                                             \
+        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE, CARRY, GATHER>, PV_E_THREADS, words);   \
+        pv_edge_kernel<CULL, MODE, CARRY, GATHER><<<grid, PV_E_THREADS, 0, st>>>(                                 \
+            h->scene, (const float4*)aA, (const float4*)aB, a9, (const float4*)bA, (const float4*)bB, b9, a_aos,  \
+            b_aos, n, n_steps, resolution, d_bits, d_margin, epw, d_ok_bytes, GARG);                              \
     }
-    if (d_bits || d_ok_bytes) {
-        if (h->scene.carry) PV_LAUNCH_E(true, PV_MODE_BITS, true) else PV_LAUNCH_E(true, PV_MODE_BITS, false)
+    if (gather_on) {
+        const PvGatherOpt<true> go = {h->gather};
+        if (h->scene.carry) PV_LAUNCH_E(true, PV_MODE_BITS, true, true, go) else PV_LAUNCH_E(true, PV_MODE_BITS, false, true, go)
+    } else if (d_bits || d_ok_bytes) {
+        if (h->scene.carry) PV_LAUNCH_E(true, PV_MODE_BITS, true, false, PvGatherOpt<false>{})
+        else PV_LAUNCH_E(true, PV_MODE_BITS, false, false, PvGatherOpt<false>{})
     } else {  // margins: always brute force
-        if (h->scene.carry) PV_LAUNCH_E(false, PV_MODE_MARGIN, true) else PV_LAUNCH_E(false, PV_MODE_MARGIN, false)
+        if (h->scene.carry) PV_LAUNCH_E(false, PV_MODE_MARGIN, true, false, PvGatherOpt<false>{})
+        else PV_LAUNCH_E(false, PV_MODE_MARGIN, false, false, PvGatherOpt<false>{})
     }
 #undef PV_LAUNCH_E
     h->launches++;

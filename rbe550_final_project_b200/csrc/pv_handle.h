@@ -26,6 +26,24 @@ struct PvGather {
     long long word_cap;      // words this rank may write there (stores beyond it are dropped)
 };
 
+// Epilogue shared by the verdict-producing kernels: one word per warp to the local buffer and, when a gather is
+// configured, straight into every rank's gather buffer -- through the NVSwitch multicast address when there is one
+// (a single store, replicated by the switch), else one peer store per rank issued by lanes 0..n_peers-1.  This fuses
+// the verdict all-gather into the kernel that produces the verdicts: no collective launch, no SMs taken from the
+// compute kernel.  Visibility on the peers is guaranteed at kernel completion + the symmetric-memory barrier.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pv_emit_word(uint32_t* __restrict__ bits, const PvGather& G, int64_t w, unsigned word, int lane) {
+    if (lane == 0 && bits) bits[w] = word;
+    if (w >= G.word_cap) return;
+    if (G.mc) {
+        if (lane == 0) asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(G.mc + G.word_off + w), "r"(word) : "memory");
+    } else if (G.peers) {
+        if (lane < G.n_peers) G.peers[lane][G.word_off + w] = word;
+    }
+}
+
+#endif
+
 struct PvHandle {
     uint32_t magic;
     int device;

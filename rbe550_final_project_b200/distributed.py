@@ -64,12 +64,35 @@ def sweep_sharded(pv, n_total: int, seed: int, fingers_open: bool = True, group=
     return full, n_valid
 
 
-def check_edges_sharded(pv, qa, qb, n_steps: int = 0, resolution: float = 0.0, group=None) -> torch.Tensor:
+def check_edges_sharded(pv, qa, qb, n_steps: int = 0, resolution: float = 0.0, group=None,
+                        gather: Optional["FusedVerdictGather"] = None) -> torch.Tensor:
     """BASELINE config 3 on N GPUs: motions are independent units, so rank r validates the contiguous shard
     shard_range(n, r, world) of the batch (qa, qb: the same (n, 9) tensors, or SoA plane tuples, on every rank) with
     pv.check_edges, and the verdict words (1 bit per edge) are all-gathered.  Every rank returns the words one GPU
-    computes for the whole batch."""
+    computes for the whole batch.  With `gather` (a FusedVerdictGather of words_per_shard(n, world) words per rank) the
+    words travel inside the edge kernel -- peer / multicast stores from its epilogue -- and the only synchronisation is
+    the symmetric-memory barrier; the returned mask is then a view of the symmetric buffer (valid until the next use)."""
     from . import panda_model as pm
+    if gather is not None:
+        n_ = int(qa[0].shape[0] if isinstance(qa, (tuple, list)) else qa.shape[0])
+        if gather.words_per_rank != words_per_shard(n_, gather.world):
+            raise ValueError("gather slot size does not match words_per_shard(n, world)")
+        first, count = shard_range(n_, gather.rank, gather.world)
+        if count <= 16384:
+            raise ValueError("the fused edge gather applies to shards above 16 384 motions (whole verdict words per warp)")
+        cut_ = (lambda t: tuple(x[first:first + count] for x in t)) if isinstance(qa, (tuple, list)) else \
+            (lambda t: t[first:first + count])
+        gather.hdl.barrier()  # every rank has finished reading the previous mask
+        used = (count + 31) // 32
+        if used < gather.words_per_rank:
+            gather.zero_own_slot_tail(used)
+        gather.activate()
+        try:
+            pv.check_edges(cut_(qa), cut_(qb), n_steps=n_steps,
+                           resolution=resolution if resolution > 0 else pm.VALIDITY_RESOLUTION)
+        finally:
+            gather.deactivate()
+        return gather.finish()[: (n_ + 31) // 32]
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     planes = isinstance(qa, (tuple, list))
