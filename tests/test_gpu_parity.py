@@ -560,6 +560,42 @@ def test_sharded_edge_entry_single_rank(pv):
     assert np.array_equal(check_edges_sharded(pv, planes(a), planes(b), n_steps=64).cpu().numpy(), ref)
 
 
+def test_fused_gather_epilogues_with_a_local_peer(pv):
+    """pv_set_gather with ONE peer that is a local buffer (the N-GPU form runs in bench.py --gpus N and
+    tools/multi_gpu_sweep.py): the state, sweep and edge kernels store their verdict words at the configured offset of the
+    'peer' as well as locally, words beyond the slot's capacity are dropped, and small edge batches never gather."""
+    pv.set_scene(sc.goal1_scattered())
+    dev = pv.device
+    n = 70_000
+    words = (n + 31) // 32
+    q = random_configs(n, 81)
+    qb = np.clip(q + np.random.default_rng(4).normal(0, 0.3, q.shape), pm.Q_LOWER, pm.Q_UPPER).astype(np.float32)
+    qb[:, 7:] = 0.04
+    off, cap = 100, words - 7  # the last 7 words fall outside the slot
+    peer = torch.full((off + words + 50,), 0x5A5A5A5A, dtype=torch.int32, device=dev)
+    table = torch.tensor([peer.data_ptr()], dtype=torch.int64, device=dev)
+    try:
+        for name, run in (("states", lambda: pv.check_states(_dev(q))),
+                          ("edges", lambda: pv.check_edges(_dev(q), _dev(qb), n_steps=8)),
+                          ("sweep", lambda: pv.sweep(0, n, 5)[0])):
+            pv.set_gather(0, 0, 0, 0, 0)
+            ref = run().cpu().numpy()
+            peer.fill_(0x5A5A5A5A)
+            pv.set_gather(table.data_ptr(), 1, 0, off, cap)
+            got = run().cpu().numpy()
+            torch.cuda.synchronize()
+            g = peer.cpu().numpy()
+            assert np.array_equal(got, ref), name
+            assert np.array_equal(g[off:off + cap], ref[:cap]), name
+            assert (g[:off] == 0x5A5A5A5A).all() and (g[off + cap:] == 0x5A5A5A5A).all(), name
+        peer.fill_(0x5A5A5A5A)
+        pv.check_edges(_dev(q[:5000]), _dev(qb[:5000]), n_steps=8)  # one edge per warp: no whole words, no gather
+        torch.cuda.synchronize()
+        assert (peer.cpu().numpy() == 0x5A5A5A5A).all()
+    finally:
+        pv.set_gather(0, 0, 0, 0, 0)
+
+
 def test_rejected_scene_keeps_the_previous_one(pv):
     from rbe550_final_project_b200.validity import PandaValidityError
     good = sc.goal1_scattered()
