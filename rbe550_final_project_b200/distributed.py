@@ -377,12 +377,17 @@ class ShardedTreePlanner:
         qg = torch.as_tensor(np.ascontiguousarray(goals, dtype=np.float32).reshape(-1, 9)).to(dev)
         n = qs.shape[0]
         i32 = dict(dtype=torch.int32, device=dev)
-        trees = torch.zeros((2 * n, 9, slots), dtype=torch.float32, device=dev)   # this rank's slots of every tree
-        gsize = torch.ones(2 * n, **i32)                                          # GLOBAL tree sizes (replicated)
-        parent = torch.full((2 * n, M), -1, **i32)                                # replicated: 4 B per node
+        # (row 2n of `trees` / `parent` is a dump for the writes of rows that have nothing to store, see the transitions)
+        trees = torch.zeros((2 * n + 1, 9, slots), dtype=torch.float32, device=dev)  # this rank's slots of every tree
+        gsize = torch.ones(2 * n, **i32)                                             # GLOBAL tree sizes (replicated)
+        parent = torch.full((2 * n + 1, M), -1, **i32)                               # replicated: 4 B per node
+        dump = torch.tensor(2 * n, dtype=torch.long, device=dev)
+        zero_l = torch.tensor(0, dtype=torch.long, device=dev)
+        c_extend, c_connect, c_done = (torch.tensor(x, **i32) for x in (self.EXTEND, self.CONNECT, self.DONE))
+        c_solved, c_nodecap = (torch.tensor(x, **i32) for x in (self.SOLVED, self.NODECAP))
         if rank == 0:  # global node 0 of every tree: rank 0, slot 0
-            trees[0::2, :, 0] = qs
-            trees[1::2, :, 0] = qg
+            trees[0:2 * n:2, :, 0] = qs
+            trees[1:2 * n:2, :, 0] = qg
         it = torch.zeros(n, **i32)
         cur = torch.zeros(n, **i32)
         phase = torch.full((n,), self.EXTEND, **i32)
@@ -449,28 +454,33 @@ class ShardedTreePlanner:
             valid = self._valid_sharded(ea, eb, resolution)
             reach = reach.bool()
 
+            # ---- transitions of RRT-Connect, as whole-array selects on the active rows (no boolean-mask indexing: every
+            # masked gather / scatter would be a device synchronisation) ---------------------------------------------------
             to = tree_of.long()
             ni = gsize[to]                       # global index the new node would get
             v = valid
+            ext_v, con_v = v & ext, v & ~ext
+            # the new node is stored by its owner rank only; everybody else (and invalid motions) writes to a dump tree
             own = v & ((ni % world) == rank)
-            trees[to[own], :, (ni[own] // world).long()] = eb[own]
-            parent[to[v], ni[v].long()] = from_g[v]
-            gsize[to[v]] = ni[v] + 1
-            av = a[v & ext]
-            target[av] = eb[v & ext]
-            added[av] = ni[v & ext]
-            phase[av] = self.CONNECT
-            ac = a[v & ~ext & reach]
-            conn[ac] = ni[v & ~ext & reach]
-            phase[ac] = self.DONE
-            status[ac] = self.SOLVED
-            full_ = v & ~ext & ~reach & (ni + 1 >= M - 1)
-            phase[a[full_]] = self.DONE
-            status[a[full_]] = self.NODECAP
-            at = a[~v]                            # trapped: next iteration, the trees swap roles
-            phase[at] = self.EXTEND
-            cur[at] = cur[at] ^ 1
-            it[at] = it[at] + 1
+            trees[torch.where(own, to, dump), :, torch.where(own, (ni // world).long(), zero_l)] = eb
+            parent[torch.where(v, to, dump), torch.where(v, ni.long(), zero_l)] = from_g
+            gsize[to] = ni + v.to(torch.int32)   # (one tree per active query: no duplicate indices)
+            target[a] = torch.where(ext_v[:, None], eb, target[a])
+            added[a] = torch.where(ext_v, ni, added[a])
+            solved = con_v & reach
+            conn[a] = torch.where(solved, ni, conn[a])
+            full_ = con_v & ~reach & (ni + 1 >= M - 1)
+            ph = phase[a]
+            ph = torch.where(ext_v, c_connect, ph)
+            ph = torch.where(solved | full_, c_done, ph)
+            ph = torch.where(~v, c_extend, ph)       # trapped: next iteration, the trees swap roles
+            phase[a] = ph
+            st_a = status[a]
+            st_a = torch.where(solved, c_solved, st_a)
+            status[a] = torch.where(full_, c_nodecap, st_a)
+            cur_a = cur[a]
+            cur[a] = torch.where(v, cur_a, cur_a ^ 1)
+            it[a] = it[a] + (~v).to(torch.int32)
 
         # ---- path extraction: index chains from the replicated parents, states from their owner ranks -----------------
         st = status.cpu().numpy()
