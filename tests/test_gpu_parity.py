@@ -242,6 +242,23 @@ def test_host_entry_points_match_device(pv):
     assert (d == hh).all()
 
 
+def test_host_entry_points_around_the_small_batch_threshold(pv):
+    """Host batches up to 2 048 rows take the host-mapped path (one launch, no copies, unsorted kernel / one motion per
+    warp), larger ones the chunked copy pipeline: same words on both sides of the threshold, ragged sizes included."""
+    pv.set_scene(sc.goal3_tower())
+    q = random_configs(5000, 91)
+    q[7] = np.nan  # a non-finite joint value is an invalid state on every path
+    qb = np.clip(q + np.random.default_rng(9).normal(0, 0.3, q.shape), pm.Q_LOWER, pm.Q_UPPER).astype(np.float32)
+    qb[:, 7:] = 0.04
+    dev_s = unpack_bits(pv.check_states(_dev(q)).cpu().numpy().view(np.uint32), len(q))
+    dev_e = unpack_bits(pv.check_edges(_dev(q), _dev(qb), n_steps=0).cpu().numpy().view(np.uint32), len(q))
+    assert not dev_s[7] and not dev_e[7]
+    for n in (1, 31, 32, 33, 1000, 2047, 2048, 2049, 4097):
+        assert np.array_equal(unpack_bits(pv.check_states_host(q[:n]), n), dev_s[:n]), n
+        assert np.array_equal(unpack_bits(pv.check_edges_host(q[:n], qb[:n], n_steps=0), n), dev_e[:n]), n
+        assert np.array_equal(unpack_bits(pv.check_states_host_arm(np.ascontiguousarray(q[:n, :7])), n), dev_s[:n]), n
+
+
 def test_arm_rows_host_entry_point(pv, c64):
     """pv_check_states_host_arm: rows of 7 arm joint values + one gripper opening = the 9-column call on the same
     configurations, bit for bit (ragged sizes, several pipeline chunks, equal and unequal fingers), and the oracle."""
