@@ -743,8 +743,10 @@ def bench_rrtc(torch, pv, counts, mhz):
     # a large batch: the arena is bounded, the paths come back packed
     big = 1 << 18
     idx = rng.integers(0, len(valid), (2, big))
+    big_a, big_b = valid[idx[0]], valid[idx[1]]
+    pv.rrtc_batch(big_a[:4096], big_b[:4096], **kw)
     t = time.perf_counter()
-    _, _, plen_b, _, _ = pv.rrtc_batch(valid[idx[0]], valid[idx[1]], **kw)
+    _, _, plen_b, _, _ = pv.rrtc_batch(big_a, big_b, **kw)
     big_ms = (time.perf_counter() - t) * 1e3
     return {"workload": f"{N_QUERIES} (start, goal) pairs of valid configurations with the hand above 0.15 m, tall-tower scene "
                         "(goal3: 8-high tower + 2 loose blocks), RRT-Connect range 2.607, resolution 0.13037, 2000 iterations "

@@ -38,7 +38,7 @@
 #define RRTC_T1_NODES 64
 #endif
 #ifndef RRTC_CHUNK_SEARCHES
-#define RRTC_CHUNK_SEARCHES 32768
+#define RRTC_CHUNK_SEARCHES 131072  // 32 768: 7.1 M queries/s on 2^18..2^20 queries, 131 072: 8.8-8.9 (arena 1.3 GB + rows <= 1 GB)
 #endif
 #ifndef RRTC_T2_ARENA_BYTES
 #define RRTC_T2_ARENA_BYTES ((size_t)2 << 30)
