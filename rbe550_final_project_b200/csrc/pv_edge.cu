@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
 int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* a9, const float* bA,
                            const float* bB, const float* b9, const float* a_aos, const float* b_aos, int64_t n,
                            int n_steps, float resolution, uint32_t* d_bits, float* d_margin, cudaStream_t st,
-                           unsigned char* d_ok_bytes) {
+                           unsigned char* d_ok_bytes, bool allow_gather) {
     if (n_steps < 0 || (n_steps == 0 && !(resolution > 0.f))) {
         snprintf(h->err, sizeof(h->err), "edge check needs n_steps > 0 or resolution > 0");
         return PV_ERR_BAD_ARG;
@@ -221,7 +221,8 @@ int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* 
     const int64_t words = (n + epw - 1) / epw;
     if (epw == 1 && d_bits && !d_ok_bytes) PV_CUDA(h, cudaMemsetAsync(d_bits, 0, (size_t)((n + 31) / 32) * sizeof(uint32_t), st));
     // the fused-gather target applies to whole verdict words only (large batches); small batches and margins never gather
-    const bool gather_on = epw == 32 && d_bits && h->gather.n_peers > 0;
+    // (and device-buffer calls only: a host-buffer call numbers its words per chunk, see pv_launch_state_bits)
+    const bool gather_on = allow_gather && epw == 32 && d_bits && h->gather.n_peers > 0;
 #define PV_LAUNCH_E(CULL, MODE, CARRY, GATHER, GARG)                                                              \
     {                                                                                                             \
         int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE, CARRY, GATHER>, PV_E_THREADS, words);   \
@@ -251,7 +252,7 @@ extern "C" int pv_check_edges(PvHandle* h, const float* d_aA, const float* d_aB,
     PV_PRECHECK(h, n_edges);
     if (!d_aA || !d_aB || !d_bA || !d_bB || !d_bits) return PV_ERR_BAD_ARG;
     return pv_launch_edges(h, d_aA, d_aB, d_a9, d_bA, d_bB, d_b9, nullptr, nullptr, n_edges, n_steps, resolution,
-                           d_bits, nullptr, (cudaStream_t)stream, nullptr);
+                           d_bits, nullptr, (cudaStream_t)stream, nullptr, true);
 }
 
 extern "C" int pv_edge_margins(PvHandle* h, const float* d_aA, const float* d_aB, const float* d_a9, const float* d_bA,

@@ -100,4 +100,4 @@ int pv_grid_for(PvHandle* h, const void* kernel, int threads, int64_t warps_need
 int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* a9, const float* bA,
                     const float* bB, const float* b9, const float* a_aos, const float* b_aos, int64_t n,
                     int n_steps, float resolution, uint32_t* d_bits, float* d_margin, cudaStream_t st,
-                    unsigned char* d_ok_bytes);
+                    unsigned char* d_ok_bytes, bool allow_gather = false);

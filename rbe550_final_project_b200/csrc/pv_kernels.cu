@@ -1014,14 +1014,17 @@ int pv_state_contacts(PvHandle* h, const float* d_qA, const float* d_qB, const f
 
 static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_qB, const float* d_q9,
                                 const float* d_aos, int64_t n, uint32_t* d_bits, cudaStream_t st,
-                                bool force_unsorted = false) {
+                                bool force_unsorted = false, bool host_call = false) {
+    // the fused gather forwards the words of DEVICE-buffer calls only: a host-buffer call (whatever staging layout it uses
+    // internally) numbers its words per chunk and must never write into the ranks' gather buffers
+    const PvGather gather_ = (d_aos || host_call) ? PvGather{} : h->gather;
     const int64_t words = (n + 31) / 32;
 #define PV_LAUNCH_SB(AOS, CULL, CARRY)                                                                        \
     {                                                                                                         \
         int grid = pv_grid_for(h, (const void*)pv_state_bits_kernel<AOS, CULL, CARRY>, PV_SB_THREADS, words); \
         pv_state_bits_kernel<AOS, CULL, CARRY><<<grid, PV_SB_THREADS, 0, st>>>(                               \
             h->scene, (const float4*)d_qA, (const float4*)d_qB, d_q9, d_aos, n, d_bits,                       \
-            d_aos ? PvGather{} : h->gather);                                                                  \
+            gather_);                                                                  \
     }
 #define PV_LAUNCH_SORTED(AOS_, CARRY)                                                                         \
     {                                                                                                         \
@@ -1046,7 +1049,7 @@ static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_q
         cfg_.attrs = at_;                                                                                     \
         cfg_.numAttrs = h->launch_overlap ? 1 : 0;                                                            \
         PV_CUDA(h, cudaLaunchKernelEx(&cfg_, pv_state_bits_sorted_kernel<SRC_, CARRY>, h->scene, (const float4*)d_qA, \
-                                      (const float4*)d_qB, d_q9, d_aos, n, d_bits, d_aos ? PvGather{} : h->gather)); \
+                                      (const float4*)d_qB, d_q9, d_aos, n, d_bits, gather_)); \
     }
     if (h->cull == 2 && !force_unsorted) {  // tile-sorted + per-lane culling (the default)
         if (h->scene.carry) {
@@ -1196,7 +1199,7 @@ int pv_check_states_host_arm(PvHandle* h, const float* h_q7, int64_t n, float fi
         pv_arm_rows_to_planes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(h->stage_q[slot], m, finger_left, finger_right,
                                                                                   (float4*)pA, (float4*)pB, p9);
         h->launches++;
-        rc = pv_launch_state_bits(h, pA, pB, p9, nullptr, m, h->stage_bits[slot], st);
+        rc = pv_launch_state_bits(h, pA, pB, p9, nullptr, m, h->stage_bits[slot], st, false, true);
         if (rc) return rc;
         PV_CUDA(h, cudaMemcpyAsync(h_bits + done / 32, h->stage_bits[slot], (size_t)((m + 31) / 32) * sizeof(uint32_t),
                                    cudaMemcpyDeviceToHost, st));

@@ -607,6 +607,10 @@ def test_fused_gather_epilogues_with_a_local_peer(pv):
             assert (g[:off] == 0x5A5A5A5A).all() and (g[off + cap:] == 0x5A5A5A5A).all(), name
         peer.fill_(0x5A5A5A5A)
         pv.check_edges(_dev(q[:5000]), _dev(qb[:5000]), n_steps=8)  # one edge per warp: no whole words, no gather
+        # host-buffer calls number their words per chunk: they never forward, whatever layout they stage internally
+        pv.check_states_host(q)
+        pv.check_states_host_arm(np.ascontiguousarray(q[:, :7]))
+        pv.check_edges_host(q, qb, n_steps=8)
         torch.cuda.synchronize()
         assert (peer.cpu().numpy() == 0x5A5A5A5A).all()
     finally:
