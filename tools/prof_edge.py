@@ -2,7 +2,10 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from rbe550_final_project_b200 import panda_model as pm, scenes as sc
+from rbe550_final_project_b200 import _cabi, panda_model as pm, scenes as sc
+if os.environ.get("PV_LIB"):  # a variant build (tools/build_variant.py)
+    _cabi.LIB_PATH = os.path.join(_cabi.CSRC, os.environ["PV_LIB"])
+STEPS = int(os.environ.get("PV_STEPS", "64"))
 from rbe550_final_project_b200.validity import PandaValidity, soa_from_aos
 pv = PandaValidity(0)
 pv.set_scene(sc.goal4_task1_pentagon())
@@ -13,6 +16,6 @@ qb = np.clip(qa + rng.normal(0, 0.3, qa.shape), pm.Q_LOWER, pm.Q_UPPER).astype(n
 A = soa_from_aos(torch.as_tensor(qa, device="cuda")); B = soa_from_aos(torch.as_tensor(qb, device="cuda"))
 out = torch.empty(n // 32, dtype=torch.int32, device="cuda")
 for _ in range(3):
-    pv.check_edges(A, B, n_steps=64, out=out)
+    pv.check_edges(A, B, n_steps=STEPS, out=out)
 torch.cuda.synchronize()
 print("ok")
