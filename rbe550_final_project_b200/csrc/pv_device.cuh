@@ -16,18 +16,6 @@
 #ifndef PV_MAX_OBB
 #define PV_MAX_OBB 32
 #endif
-// layout experiments (profiles/r2_notes.md)
-#ifndef PV_X_YAWONLY
-#define PV_X_YAWONLY 0
-#endif
-#ifndef PV_X_EXPECT
-#define PV_X_EXPECT 0
-#endif
-#if PV_X_EXPECT
-#define PV_X_UNLIKELY(c) __builtin_expect(!!(c), 0)
-#else
-#define PV_X_UNLIKELY(c) (c)
-#endif
 #define PV_FLAG_SELF 1u
 #define PV_FLAG_LIMITS 2u
 
@@ -88,10 +76,6 @@ struct PvAcc;
 template <>
 struct PvAcc<PV_MODE_BITS> {
     bool hit = false;
-    // motion certificates (SLK instantiations of pv_check_config): dl = slack sought in metres (0 = none); unc comes back
-    // false only when the state is free AND every culling test and the ground-plane test cleared by more than dl
-    bool unc = true;
-    float dl = 0.f;
     // packed tests accumulate min(d^2 - r^2) here (one FMNMX3 per two tests); hit |= min(m) < 0 at the end.  PV_PACK_ACC
     // independent accumulators keep the FMNMX3 chain from serialising the tests.
     float m[4] = {1e30f, 1e30f, 1e30f, 1e30f};
@@ -550,7 +534,12 @@ __device__ __forceinline__ void pv_place(const float* q, const PvScene& S, PvPla
     }
 
 // ---- robot vs scene boxes (the section behind the scene-level cull) -----------------------------------------
-template <int MODE, bool CULL, int EXIT, int SYNC, bool FMAK, bool CARRY>
+// YAW: every box of the scene is rotated about the world's z axis only (true of every reference scene: blocks resting on
+// the table or on each other); the kernels then come in an instantiation WITHOUT the general sphere-vs-box tests.  That
+// code never ran for such scenes anyway, but it sat in the middle of the box loop: these kernels are bound by instruction
+// fetch (a third of the loop body was dead weight between the culls: 23.6 -> 11.9 KB), and without it the edge kernel
+// gains 5.7 % and the state kernel 3.4 % on the same box (profiles/r2_notes.md).  pv_set_scene decides (PvHandle::all_yaw).
+template <int MODE, bool CULL, int EXIT, int SYNC, bool FMAK, bool CARRY, bool YAW = false>
 __device__ __forceinline__ void pv_scene_section(PvAcc<MODE>& acc, const PvPlaced& P, const PvScene& S) {
     const int nb = S.n_obb;
     for (int b = 0; b < nb; ++b) {
@@ -564,11 +553,7 @@ __device__ __forceinline__ void pv_scene_section(PvAcc<MODE>& acc, const PvPlace
         const float3 BX = make_float3(S.obb[b][6], S.obb[b][9], S.obb[b][12]);
         const float3 BY = make_float3(S.obb[b][7], S.obb[b][10], S.obb[b][13]);
         const float3 BZ = make_float3(S.obb[b][8], S.obb[b][11], S.obb[b][14]);
-#if PV_X_YAWONLY
-        const bool yaw_only = true;
-#else
-        const bool yaw_only = (S.yaw_only_mask >> b) & 1u;
-#endif
+        const bool yaw_only = YAW ? true : (bool)((S.yaw_only_mask >> b) & 1u);
         float3 ok = oc;
         if constexpr (FMAK) ok = make_float3(v_dot(oc, BX), v_dot(oc, BY), yaw_only ? oc.z : v_dot(oc, BZ));
         const unsigned rmask = S.reach_mask[b];
@@ -589,7 +574,7 @@ __device__ __forceinline__ void pv_scene_section(PvAcc<MODE>& acc, const PvPlace
     if (MODE == PV_MODE_MARGIN || (rmask & (1u << l))) {        \
         float3 d_ = v_sub(P.s[cs], oc);                         \
         float rr_ = (br + PV_CULL_SLACK) + obr;                 \
-        if (!CULL || PV_X_UNLIKELY(v_dot(d_, d_) < rr_ * rr_)) { \
+        if (!CULL || v_dot(d_, d_) < rr_ * rr_) {               \
             if (yaw_only) {                                     \
                 PV_SPHERES_LINK##l(PV_ENV_SPHERE_YAW)           \
             } else {                                            \
@@ -661,29 +646,9 @@ __device__ __noinline__ bool pv_scene_cold(LOAD load, const PvScene& S) {
 // of once per warp (ncu showed stall_no_instruction as the top stall of the free-running version).
 // DEFER: do not run the scene section, return whether it is needed (see pv_scene_cold); the return value is false
 // whenever the section has been dealt with here.
-// CULLS-FIRST layout (the warp-per-motion kernels: EXIT == PV_EXIT_ANY, verdict bits, culling): their lanes are
-// neighbouring states of ONE motion, so most warps pass every cull -- 57 % of the config-3 motions never enter a block of
-// tests.  Those kernels are instruction-fetch bound (profiles/r2_notes.md), so the code they always run is laid out as
-// one straight line: FK, placement, ground plane, ALL self-collision culls (a bit mask) and the scene-level test; then
-// one warp vote jumps over the whole region of test blocks (22 KB) and a second one over the scene section.  The order
-// of the tests does not matter for the verdict (it is the OR of all of them).
-// SLK (culls-first only): the motion validator's certificate.  When acc.dl > 0 and the whole warp passed every cull, the
-// culls, the scene-level test and the ground-plane test are evaluated once more with their reach inflated by acc.dl,
-// in a block of code of their own behind the hot path; acc.unc = false reports that this state cleared all of them.
-// Every configuration whose robot points lie within dl of this state's (in the world, and relative to any proximal
-// link) then passes every cull too, and stays above the plane: it is free of contact without being tested.
-#ifndef PV_CULLS_FIRST
-#define PV_CULLS_FIRST 0
-#endif
-
-// (r + dl)^2 <= r^2 + (2 r + PV_MOTION_CERT_MAX_SLACK) dl for 0 <= dl <= PV_MOTION_CERT_MAX_SLACK; r2 is a literal, so
-// the factor folds to a constant (the 1.001 covers the rounding of the fold and of the FFMA)
-#define PV_SLK_THR(r2, dl) fmaf((2.0f * sqrtf(r2) + PV_MOTION_CERT_MAX_SLACK) * 1.001f, dl, r2)
 template <int MODE, bool CULL, int EXIT, int SYNC = 0, bool FMAK = false, bool CARRY = false, bool FTRIG = FMAK,
-          bool DEFER = false, bool SLK = false>
+          bool DEFER = false, bool YAW = false>
 __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S, PvAcc<MODE>& acc) {
-    constexpr bool CF = PV_CULLS_FIRST && CULL && MODE == PV_MODE_BITS && EXIT == PV_EXIT_ANY && !DEFER && !PV_PACK;
-    static_assert(!SLK || (CF && !CARRY), "the slack form belongs to the culls-first layout without a carried box");
     static_assert(!SYNC || EXIT == PV_EXIT_NONE, "block barriers and warp-level early exit do not mix");
     static_assert(!DEFER || (CULL && MODE == PV_MODE_BITS), "only the culling verdict-bit form defers the scene section");
     const unsigned FULL = 0xffffffffu;
@@ -719,11 +684,8 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
 
     // ---- robot vs ground plane (link0 is fixed to the world: pair filtered) -------------
     const float tz = S.table_z;
-    float low_ = 1e30f;  // lowest point of the robot above the plane (SLK)
     if constexpr (MODE == PV_MODE_BITS && PV_TABLE_MIN) {
-        const float l_ = PV_TABLE_LOWEST(s);
-        pv_plane<MODE>(acc, l_, tz, 0);
-        if constexpr (SLK) low_ = l_ - tz;
+        pv_plane<MODE>(acc, PV_TABLE_LOWEST(s), tz, 0);
     } else {
 #define PV_TABLE_SPHERE(i, link, cx, cy, cz, r) \
     if (link != 0) pv_plane<MODE>(acc, s[i].z - r, tz, PV_CODE(1, link, 0));
@@ -734,7 +696,6 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
     for (int k = 0; k < 3; ++k) {
         float ext = fmaf(fabsf(hZ.z), pv_bh[k][2], fmaf(fabsf(hY.z), pv_bh[k][1], fabsf(hX.z) * pv_bh[k][0]));
         pv_plane<MODE>(acc, bc[k].z - ext, tz, PV_CODE(1, pv_blink[k], 0));
-        if constexpr (SLK) low_ = fminf(low_, (bc[k].z - ext) - tz);
     }
     // ---- carried box: placed by the hand, checked against the plane and the arm spheres of link0..link6 --------
     if constexpr (CARRY) {
@@ -749,120 +710,13 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
     PV_LOCKSTEP(2)
 
     // ---- self collision ------------------------------------------------------------------------------
-    unsigned cm = 0;  // CF: bit i = cull i fired (link-pair culls first, then the sphere-vs-gripper ones)
-    bool run_blocks = (S.flags & PV_FLAG_SELF) != 0u;
-    if constexpr (CF) {
-        if (S.flags & PV_FLAG_SELF) {
-            int bit_ = 0;
-#define PV_LPC(la, lb, ca, cb, cull2)                             \
-    {                                                             \
-        float3 d_ = v_sub(s[ca], s[cb]);                          \
-        cm |= (v_dot(d_, d_) < cull2 ? 1u : 0u) << bit_;          \
-        ++bit_;                                                   \
-    }
-            PV_SS_LINKPAIRS(PV_LPC)
-#undef PV_LPC
-#define PV_LBC(la, ca, c0, c1, c2, rla)                                                   \
-    {                                                                                     \
-        bool near_;                                                                       \
-        if ((c0) > 0.f) {                                                                 \
-            float3 d0_ = v_sub(s[ca], bc[0]);                                             \
-            float rr_ = (rla) + grip_r;                                                   \
-            near_ = v_dot(d0_, d0_) < rr_ * rr_;                                          \
-        } else {                                                                          \
-            float3 d1_ = v_sub(s[ca], bc[1]), d2_ = v_sub(s[ca], bc[2]);                  \
-            near_ = v_dot(d1_, d1_) < c1 || v_dot(d2_, d2_) < c2;                         \
-        }                                                                                 \
-        cm |= (near_ ? 1u : 0u) << bit_;                                                  \
-        ++bit_;                                                                           \
-    }
-            PV_SBH_LINKS(PV_LBC)
-#undef PV_LBC
-        }
-    }
-    // CF: the scene-level test belongs to the straight line too (the same expressions as below, where the other layouts
-    // evaluate it)
-    bool near_scene_cf = false;
-    if constexpr (CF) {
-#define PV_SCENE_GROUP(l, cs, br)                                                                                  \
-    if (S.group_any & (1u << l))                                                                                   \
-        near_scene_cf |= s[cs].x > S.gpad[l][0] && s[cs].x < S.gpad[l][3] && s[cs].y > S.gpad[l][1] &&             \
-                         s[cs].y < S.gpad[l][4] && s[cs].z > S.gpad[l][2] && s[cs].z < S.gpad[l][5];
-        PV_LINK_GROUPS(PV_SCENE_GROUP)
-#undef PV_SCENE_GROUP
-        if (S.group_any & 0x100u)
-            near_scene_cf |= bc[0].x + grip_r > S.aabb_lo[0] && bc[0].x - grip_r < S.aabb_hi[0] &&
-                             bc[0].y + grip_r > S.aabb_lo[1] && bc[0].y - grip_r < S.aabb_hi[1] &&
-                             bc[0].z + grip_r > S.aabb_lo[2] && bc[0].z - grip_r < S.aabb_hi[2];
-        if constexpr (CARRY) {
-            const float rc_ = P.cbr + PV_CULL_SLACK;
-            near_scene_cf |= P.cC.x + rc_ > S.aabb_lo[0] && P.cC.x - rc_ < S.aabb_hi[0] && P.cC.y + rc_ > S.aabb_lo[1] &&
-                             P.cC.y - rc_ < S.aabb_hi[1] && P.cC.z + rc_ > S.aabb_lo[2] && P.cC.z - rc_ < S.aabb_hi[2];
-        }
-        // one vote for both regions: bit 31 = the scene section is needed by some lane
-        cm |= near_scene_cf ? 0x80000000u : 0u;
-        const unsigned any_ = __reduce_or_sync(FULL, cm);
-        near_scene_cf = (any_ & 0x80000000u) != 0;
-        if constexpr (SLK) {
-            acc.unc = true;
-            if (acc.dl > 0.f && any_ == 0u) {  // warp-uniform: nobody is near anything at the plain reach
-                const float dl = acc.dl;
-                bool u_ = acc.hit || low_ < dl;
-                if (S.flags & PV_FLAG_SELF) {
-#define PV_LPS(la, lb, ca, cb, cull2)                             \
-    {                                                             \
-        float3 d_ = v_sub(s[ca], s[cb]);                          \
-        u_ |= v_dot(d_, d_) < PV_SLK_THR(cull2, dl);              \
-    }
-                    PV_SS_LINKPAIRS(PV_LPS)
-#undef PV_LPS
-#define PV_LBS(la, ca, c0, c1, c2, rla)                                                   \
-    {                                                                                     \
-        if ((c0) > 0.f) {                                                                 \
-            float3 d0_ = v_sub(s[ca], bc[0]);                                             \
-            float rr_ = ((rla) + grip_r) + dl;                                            \
-            u_ |= v_dot(d0_, d0_) < rr_ * rr_;                                            \
-        } else {                                                                          \
-            float3 d1_ = v_sub(s[ca], bc[1]), d2_ = v_sub(s[ca], bc[2]);                  \
-            u_ |= v_dot(d1_, d1_) < PV_SLK_THR(c1, dl) || v_dot(d2_, d2_) < PV_SLK_THR(c2, dl); \
-        }                                                                                 \
-    }
-                    PV_SBH_LINKS(PV_LBS)
-#undef PV_LBS
-                }
-#define PV_SCENE_GROUP(l, cs, br)                                                                                  \
-    if (S.group_any & (1u << l))                                                                                   \
-        u_ |= s[cs].x + dl > S.gpad[l][0] && s[cs].x - dl < S.gpad[l][3] && s[cs].y + dl > S.gpad[l][1] &&         \
-              s[cs].y - dl < S.gpad[l][4] && s[cs].z + dl > S.gpad[l][2] && s[cs].z - dl < S.gpad[l][5];
-                PV_LINK_GROUPS(PV_SCENE_GROUP)
-#undef PV_SCENE_GROUP
-                const float grs_ = grip_r + dl;
-                if (S.group_any & 0x100u)
-                    u_ |= bc[0].x + grs_ > S.aabb_lo[0] && bc[0].x - grs_ < S.aabb_hi[0] &&
-                          bc[0].y + grs_ > S.aabb_lo[1] && bc[0].y - grs_ < S.aabb_hi[1] &&
-                          bc[0].z + grs_ > S.aabb_lo[2] && bc[0].z - grs_ < S.aabb_hi[2];
-                acc.unc = u_;
-                return false;  // nothing else to run: no cull fired for any lane
-            }
-        }
-        run_blocks = (any_ & 0x7fffffffu) != 0u;  // warp-uniform: the whole region of test blocks is one jump
-    }
-    if (run_blocks) {
-        int bit_ = 0;
-        (void)bit_;
+    if (S.flags & PV_FLAG_SELF) {
 #define PV_SS(a, b, rr2, rr) pv_sphere_sphere<MODE>(acc, s[a], s[b], rr2, rr, PV_SELF_CODE(a, pv_sphere_link[b]));
 #define PV_SS2(a, b0, b1, n0, n1, k) pv_sphere_sphere2<k>(acc, s[a], s[b0], s[b1], n0, n1);
 #define PV_LP(la, lb, ca, cb, cull2)                         \
     {                                                        \
-        bool run_;                                           \
-        if constexpr (CF) {                                  \
-            run_ = (cm >> bit_) & 1u;                        \
-            ++bit_;                                          \
-        } else {                                             \
-            float3 d_ = v_sub(s[ca], s[cb]);                 \
-            run_ = !CULL || v_dot(d_, d_) < cull2;           \
-        }                                                    \
-        if (PV_X_UNLIKELY(run_)) {                           \
+        float3 d_ = v_sub(s[ca], s[cb]);                     \
+        if (!CULL || v_dot(d_, d_) < cull2) {                \
             if constexpr (MODE == PV_MODE_BITS && PV_PACK) { \
                 PV_SS2_PAIRS_##la##_##lb(PV_SS2)             \
             } else {                                         \
@@ -907,10 +761,7 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
 #define PV_LB(la, ca, c0, c1, c2, rla)                                                                  \
     {                                                                                                   \
         bool near_;                                                                                     \
-        if constexpr (CF) {                                                                             \
-            near_ = (cm >> bit_) & 1u;                                                                  \
-            ++bit_;                                                                                     \
-        } else if ((c0) > 0.f) {                                                                        \
+        if ((c0) > 0.f) {                                                                               \
             float3 d0_ = v_sub(s[ca], bc[0]);                                                           \
             float rr_ = (rla) + grip_r;                                                                 \
             near_ = v_dot(d0_, d0_) < rr_ * rr_;                                                        \
@@ -918,7 +769,7 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
             float3 d1_ = v_sub(s[ca], bc[1]), d2_ = v_sub(s[ca], bc[2]);                                \
             near_ = v_dot(d1_, d1_) < c1 || v_dot(d2_, d2_) < c2;                                       \
         }                                                                                               \
-        if (!CULL || PV_X_UNLIKELY(near_)) {                                                            \
+        if (!CULL || near_) {                                                                           \
             PV_SBH_##la(PV_SBH_S, PV_SBH_B)                                                             \
         }                                                                                               \
     }
@@ -937,9 +788,7 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
     // per-box cull (profiles/r1_notes.md: a third of the instructions of the check); the sorted kernel orders its
     // configurations so that whole warps agree (pv_sort_key).
     bool near_scene = true;
-    if constexpr (CF) {
-        near_scene = near_scene_cf;
-    } else if constexpr (CULL && MODE == PV_MODE_BITS) {
+    if constexpr (CULL && MODE == PV_MODE_BITS) {
         near_scene = false;
 #define PV_SCENE_GROUP(l, cs, br)                                                                                  \
     if (S.group_any & (1u << l))                                                                                   \
@@ -963,7 +812,7 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
         if constexpr (PV_PACK) acc.hit |= acc.packed_hit();
         return near_scene;
     } else {
-        if (PV_X_UNLIKELY(near_scene)) pv_scene_section<MODE, CULL, EXIT, SYNC, FMAK, CARRY>(acc, P, S);
+        if (near_scene) pv_scene_section<MODE, CULL, EXIT, SYNC, FMAK, CARRY, YAW>(acc, P, S);
         if constexpr (MODE == PV_MODE_BITS && PV_PACK) acc.hit |= acc.packed_hit();
         return false;
     }

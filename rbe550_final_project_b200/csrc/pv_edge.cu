@@ -54,9 +54,6 @@
 #ifndef PV_E_LOCKSTEP
 #define PV_E_LOCKSTEP 0
 #endif
-#ifndef PV_EDGE_CERT
-#define PV_EDGE_CERT 0
-#endif
 // Verdict words of large batches also go to the handle's fused-gather target (pv_set_gather), like the state kernels' --
 // from a SEPARATE instantiation that is only launched while a gather is configured: with the epilogue compiled into the
 // one kernel the single-GPU rate fell by 3-4.5 % (402 -> 384 M edges/s on the pentagon scene; the layout of this
@@ -68,22 +65,14 @@ struct PvGatherOpt<true> {
     PvGather g;
 };
 
-template <bool CULL, int MODE, bool CARRY, bool GATHER = false>
+template <bool CULL, int MODE, bool CARRY, bool GATHER = false, bool YAW = false>
 __global__ void __launch_bounds__(PV_E_THREADS, 1)
     pv_edge_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ aA, const float4* __restrict__ aB,
                    const float* __restrict__ a9, const float4* __restrict__ bA, const float4* __restrict__ bB,
                    const float* __restrict__ b9, const float* __restrict__ a_aos, const float* __restrict__ b_aos,
                    int64_t n_edges, int n_steps, float resolution, uint32_t* __restrict__ bits,
                    float* __restrict__ margin, int epw, unsigned char* __restrict__ ok_bytes,
-                   const __grid_constant__ PvGatherOpt<GATHER> GO, int cert) {
-    // Motion certificates (cert != 0; verdict bits, no carried box): a motion of more than 32 states is validated coarse
-    // to fine, and its first round -- every `rounds`-th state -- runs the slack form of the check (pv_check_config<SLK>)
-    // with dl = the farthest any robot point can travel within rounds - 1 interpolation steps (sum_j |dq_j| R_j per step,
-    // panda_model.motion_reach_bounds).  If no state of the round is in contact and none of its culling tests came within
-    // dl, every skipped state is proven free (each lies within rounds - 1 steps of a tested one, its joints stay inside
-    // the limits because both neighbours do), and the motion is done after ONE round.  Exact: the verdict words are
-    // those of cert == 0 (tests/test_gpu_parity.py::test_motion_certificates_do_not_change_verdicts).
-    constexpr bool SLK = PV_EDGE_CERT && PV_CULLS_FIRST && CULL && MODE == PV_MODE_BITS && !CARRY;
+                   const __grid_constant__ PvGatherOpt<GATHER> GO) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t n_words = (n_edges + epw - 1) / epw;
@@ -95,7 +84,7 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
     // from 95 to 132 M edges/s at 384 threads (512-thread blocks spill and are slower; block sizes swept 384..512).
     float ea[9], eb[9];
     int j = 0, r = 0, n_here = 0, nd = 1, rounds = 1;
-    float inv_nd = 1.f, edge_m = 1e30f, dl = 0.f;
+    float inv_nd = 1.f, edge_m = 1e30f;
     unsigned word = 0;
     bool need_word = true, need_edge = true;
 
@@ -148,22 +137,6 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
             r = 0;
             edge_m = 1e30f;
             need_edge = false;
-            if constexpr (SLK) {
-                dl = 0.f;
-                if (cert && rounds > 1) {
-                    const float reach[7] = PV_MOTION_REACH, lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
-                    float trav = fabsf(eb[7] - ea[7]) + fabsf(eb[8] - ea[8]);
-                    bool a_in = true;  // the start state is never tested: its joints must be inside the limits for the
-                                       // states next to it to be (the tested ones are, or the round reports a hit)
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) {
-                        if (c < 7) trav = fmaf(fabsf(eb[c] - ea[c]), reach[c], trav);
-                        a_in = a_in && ea[c] >= lo[c] && ea[c] <= hi[c];
-                    }
-                    const float d_ = fmaf(trav * inv_nd, (float)(rounds - 1) * 1.0002f, 2e-5f);
-                    if (a_in && d_ <= PV_MOTION_CERT_MAX_SLACK) dl = d_;
-                }
-            }
         }
         // one round: lane -> state k (coarse to fine; idle lanes re-check the end point)
         int k = nd - (lane * rounds + r);
@@ -173,11 +146,10 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
 #pragma unroll
         for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, eb[c] - ea[c], ea[c]);
         PvAcc<MODE> acc;
-        if constexpr (SLK) acc.dl = (r == 0) ? dl : 0.f;
         constexpr bool COLD = PV_COLD_SCENE_WARP && CULL && MODE == PV_MODE_BITS;
         constexpr int EX = (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE);
         constexpr bool FT = (PV_EDGE_FAST_TRIG && MODE == PV_MODE_BITS);
-        if (pv_check_config<MODE, CULL, EX, 0, false, CARRY, FT, COLD, SLK>(q, S, acc)) {
+        if (pv_check_config<MODE, CULL, EX, 0, false, CARRY, FT, COLD, YAW>(q, S, acc)) {
             // warp-uniform (the check votes before it reports): the whole warp runs the scene section out of line
             if constexpr (COLD) {
                 PvReloadLerp rl;
@@ -196,9 +168,6 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
         if constexpr (MODE == PV_MODE_BITS) {
             edge_hit = __any_sync(FULL, acc.hit);
             edge_done = edge_hit || (r + 1 >= rounds);
-            if constexpr (SLK) {
-                if (!edge_done && r == 0 && dl > 0.f) edge_done = !__any_sync(FULL, acc.unc);
-            }
         } else {
             edge_m = fminf(edge_m, acc.m);
             edge_done = (r + 1 >= rounds);
@@ -254,22 +223,25 @@ int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* 
     // the fused-gather target applies to whole verdict words only (large batches); small batches and margins never gather
     // (and device-buffer calls only: a host-buffer call numbers its words per chunk, see pv_launch_state_bits)
     const bool gather_on = allow_gather && epw == 32 && d_bits && h->gather.n_peers > 0;
-#define PV_LAUNCH_E(CULL, MODE, CARRY, GATHER, GARG)                                                              \
+#define PV_LAUNCH_E(CULL, MODE, CARRY, GATHER, GARG, YAW_)                                                        \
     {                                                                                                             \
-        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE, CARRY, GATHER>, PV_E_THREADS, words);   \
-        pv_edge_kernel<CULL, MODE, CARRY, GATHER><<<grid, PV_E_THREADS, 0, st>>>(                                 \
+        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE, CARRY, GATHER, YAW_>, PV_E_THREADS, words); \
+        pv_edge_kernel<CULL, MODE, CARRY, GATHER, YAW_><<<grid, PV_E_THREADS, 0, st>>>(                           \
             h->scene, (const float4*)aA, (const float4*)aB, a9, (const float4*)bA, (const float4*)bB, b9, a_aos,  \
-            b_aos, n, n_steps, resolution, d_bits, d_margin, epw, d_ok_bytes, GARG, h->cull == 2 ? 1 : 0);        \
+            b_aos, n, n_steps, resolution, d_bits, d_margin, epw, d_ok_bytes, GARG);                              \
     }
     if (gather_on) {
         const PvGatherOpt<true> go = {h->gather};
-        if (h->scene.carry) PV_LAUNCH_E(true, PV_MODE_BITS, true, true, go) else PV_LAUNCH_E(true, PV_MODE_BITS, false, true, go)
+        if (h->scene.carry) PV_LAUNCH_E(true, PV_MODE_BITS, true, true, go, false)
+        else if (h->all_yaw) PV_LAUNCH_E(true, PV_MODE_BITS, false, true, go, true)
+        else PV_LAUNCH_E(true, PV_MODE_BITS, false, true, go, false)
     } else if (d_bits || d_ok_bytes) {
-        if (h->scene.carry) PV_LAUNCH_E(true, PV_MODE_BITS, true, false, PvGatherOpt<false>{})
-        else PV_LAUNCH_E(true, PV_MODE_BITS, false, false, PvGatherOpt<false>{})
+        if (h->scene.carry) PV_LAUNCH_E(true, PV_MODE_BITS, true, false, PvGatherOpt<false>{}, false)
+        else if (h->all_yaw) PV_LAUNCH_E(true, PV_MODE_BITS, false, false, PvGatherOpt<false>{}, true)
+        else PV_LAUNCH_E(true, PV_MODE_BITS, false, false, PvGatherOpt<false>{}, false)
     } else {  // margins: always brute force
-        if (h->scene.carry) PV_LAUNCH_E(false, PV_MODE_MARGIN, true, false, PvGatherOpt<false>{})
-        else PV_LAUNCH_E(false, PV_MODE_MARGIN, false, false, PvGatherOpt<false>{})
+        if (h->scene.carry) PV_LAUNCH_E(false, PV_MODE_MARGIN, true, false, PvGatherOpt<false>{}, false)
+        else PV_LAUNCH_E(false, PV_MODE_MARGIN, false, false, PvGatherOpt<false>{}, false)
     }
 #undef PV_LAUNCH_E
     h->launches++;

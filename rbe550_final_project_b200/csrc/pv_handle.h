@@ -49,6 +49,7 @@ struct PvHandle {
     int device;
     int sm_count;
     int has_scene;
+    int all_yaw;  // every scene box is rotated about world z only: the kernels' YAW instantiations apply (pv_device.cuh)
     int cull;
     int launch_overlap;  // state-check launches carry the programmatic-stream-serialization attribute (pv_set_launch_overlap)
     unsigned smem_attr_mask;  // which sorted-kernel instantiations already have their dynamic shared memory opt-in

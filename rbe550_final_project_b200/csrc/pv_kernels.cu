@@ -200,7 +200,7 @@ struct PvSortSmem {
 // for the sort cost as much as the sort saved -- 8.87 vs 8.91 G checks/s, profiles/r1_notes.md.)
 enum { PV_SRC_SOA = 0, PV_SRC_AOS = 1 };
 
-template <int SRC, bool CARRY>
+template <int SRC, bool CARRY, bool YAW = false>
 __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     pv_state_bits_sorted_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ qA,
                                 const float4* __restrict__ qB, const float* __restrict__ q9,
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
 #endif
             PvAcc<PV_MODE_BITS> acc;
             constexpr bool COLD = PV_COLD_SCENE && PV_SB_SYNC < 3;
-            const bool owes = pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, PV_SB_SYNC, true, CARRY, true, COLD>(q, S, acc);
+            const bool owes = pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, PV_SB_SYNC, true, CARRY, true, COLD, YAW>(q, S, acc);
             if (in && !acc.hit) {
                 // the few configurations that come near the scene boxes (~2 % in the goal scenes) are only NOTED here:
                 // their scene section runs after the loop, densely packed, instead of in a sparsely populated warp now
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
                 PvPlaced P;
                 pv_place<true, CARRY>(q, S, P);
                 PvAcc<PV_MODE_BITS> acc;
-                pv_scene_section<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY>(acc, P, S);
+                pv_scene_section<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY, YAW>(acc, P, S);
                 if (have && !acc.hit) atomicOr(&vbits[L >> 5], 1u << (L & 31));
             }
             __syncthreads();
@@ -507,7 +507,7 @@ struct PvSweepSmem {
     int n_owed;  // see PvSortSmem: the owed list reuses the front of `order`
 };
 
-template <bool CARRY, bool OPEN>
+template <bool CARRY, bool OPEN, bool YAW = false>
 __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
     pv_sweep_sorted_kernel(const __grid_constant__ PvScene S, uint64_t first, int64_t n, unsigned seed,
                            uint32_t* __restrict__ bits, unsigned long long* __restrict__ n_valid,
@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
             if (OPEN) q[7] = q[8] = 0.04f;  // what pv_sweep_config sets
             __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches
             PvAcc<PV_MODE_BITS> acc;
-            const bool owes = pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY, true, (PV_COLD_SCENE != 0)>(q, S, acc);
+            const bool owes = pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY, true, (PV_COLD_SCENE != 0), YAW>(q, S, acc);
             if (in && !acc.hit) {
                 if (PV_COLD_SCENE && owes) M.order[atomicAdd(&M.n_owed, 1)] = (unsigned short)L;
                 else atomicOr(&M.vbits[L >> 5], 1u << (L & 31));
@@ -609,7 +609,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
                 PvPlaced P;
                 pv_place<true, CARRY>(q, S, P);
                 PvAcc<PV_MODE_BITS> acc;
-                pv_scene_section<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY>(acc, P, S);
+                pv_scene_section<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY, YAW>(acc, P, S);
                 if (have && !acc.hit) atomicOr(&M.vbits[L >> 5], 1u << (L & 31));
             }
             __syncthreads();
@@ -857,6 +857,7 @@ int pv_set_scene(PvHandle* h, const float* h_obb, int n_obb, float table_z, cons
     }
     h->scene = S;
     h->has_scene = 1;
+    h->all_yaw = S.yaw_only_mask == (S.n_obb >= 32 ? 0xffffffffu : ((1u << S.n_obb) - 1u));
     return PV_OK;
 }
 
@@ -1026,14 +1027,14 @@ static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_q
             h->scene, (const float4*)d_qA, (const float4*)d_qB, d_q9, d_aos, n, d_bits,                       \
             gather_);                                                                  \
     }
-#define PV_LAUNCH_SORTED(AOS_, CARRY)                                                                         \
+#define PV_LAUNCH_SORTED(AOS_, CARRY, YAW_)                                                                   \
     {                                                                                                         \
         int64_t chunks = (n + PV_SB_THREADS - 1) / PV_SB_THREADS;                                             \
         int grid = (int)(chunks < (int64_t)h->sm_count ? chunks : (int64_t)h->sm_count);                      \
         constexpr int SRC_ = (AOS_) ? PV_SRC_AOS : PV_SRC_SOA;                                                \
-        const unsigned bit_ = 1u << (2 * SRC_ + (CARRY ? 1 : 0));                                             \
+        const unsigned bit_ = 1u << (2 * SRC_ + (CARRY ? 1 : 0) + (YAW_ ? 16 : 0));                           \
         if (!(h->smem_attr_mask & bit_)) {                                                                    \
-            PV_CUDA(h, cudaFuncSetAttribute(pv_state_bits_sorted_kernel<SRC_, CARRY>,                         \
+            PV_CUDA(h, cudaFuncSetAttribute(pv_state_bits_sorted_kernel<SRC_, CARRY, YAW_>,                   \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PvSortSmem))); \
             h->smem_attr_mask |= bit_;                                                                        \
         }                                                                                                     \
@@ -1048,14 +1049,16 @@ static int pv_launch_state_bits(PvHandle* h, const float* d_qA, const float* d_q
         at_[0].val.programmaticStreamSerializationAllowed = 1;                                                \
         cfg_.attrs = at_;                                                                                     \
         cfg_.numAttrs = h->launch_overlap ? 1 : 0;                                                            \
-        PV_CUDA(h, cudaLaunchKernelEx(&cfg_, pv_state_bits_sorted_kernel<SRC_, CARRY>, h->scene, (const float4*)d_qA, \
+        PV_CUDA(h, cudaLaunchKernelEx(&cfg_, pv_state_bits_sorted_kernel<SRC_, CARRY, YAW_>, h->scene, (const float4*)d_qA, \
                                       (const float4*)d_qB, d_q9, d_aos, n, d_bits, gather_)); \
     }
     if (h->cull == 2 && !force_unsorted) {  // tile-sorted + per-lane culling (the default)
         if (h->scene.carry) {
-            if (d_aos) PV_LAUNCH_SORTED(true, true) else PV_LAUNCH_SORTED(false, true)
+            if (d_aos) PV_LAUNCH_SORTED(true, true, false) else PV_LAUNCH_SORTED(false, true, false)
+        } else if (h->all_yaw) {
+            if (d_aos) PV_LAUNCH_SORTED(true, false, true) else PV_LAUNCH_SORTED(false, false, true)
         } else {
-            if (d_aos) PV_LAUNCH_SORTED(true, false) else PV_LAUNCH_SORTED(false, false)
+            if (d_aos) PV_LAUNCH_SORTED(true, false, false) else PV_LAUNCH_SORTED(false, false, false)
         }
     } else if (h->scene.carry) {  // carry mode always culls (the brute-force variant exists for the A/B identity test)
         if (d_aos) PV_LAUNCH_SB(true, true, true) else PV_LAUNCH_SB(false, true, true)
@@ -1268,22 +1271,24 @@ int pv_sweep(PvHandle* h, uint64_t first, int64_t n, uint32_t seed, int fingers_
     if (h->cull == 2) {  // tile-sorted (the default)
         const int64_t chunks = (n + PV_SB_THREADS - 1) / PV_SB_THREADS;
         const int grid = (int)(chunks < (int64_t)h->sm_count ? chunks : (int64_t)h->sm_count);
-#define PV_LAUNCH_SWEEP_SORTED(CARRY, OPEN)                                                                      \
+#define PV_LAUNCH_SWEEP_SORTED(CARRY, OPEN, YAW_)                                                                \
     {                                                                                                            \
         typedef PvSweepSmem<(OPEN ? 7 : 9), (OPEN ? PV_SWEEP_ST7 : PV_SWEEP_ST9)> Smem_;                         \
-        const unsigned bit_ = 1u << (8 + (CARRY ? 1 : 0) + (OPEN ? 2 : 0));                                      \
+        const unsigned bit_ = 1u << (8 + (CARRY ? 1 : 0) + (OPEN ? 2 : 0) + (YAW_ ? 4 : 0));                     \
         if (!(h->smem_attr_mask & bit_)) {                                                                       \
-            PV_CUDA(h, cudaFuncSetAttribute(pv_sweep_sorted_kernel<CARRY, OPEN>,                                 \
+            PV_CUDA(h, cudaFuncSetAttribute(pv_sweep_sorted_kernel<CARRY, OPEN, YAW_>,                           \
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem_)));   \
             h->smem_attr_mask |= bit_;                                                                           \
         }                                                                                                        \
-        pv_sweep_sorted_kernel<CARRY, OPEN><<<grid, PV_SB_THREADS, sizeof(Smem_), st>>>(                         \
+        pv_sweep_sorted_kernel<CARRY, OPEN, YAW_><<<grid, PV_SB_THREADS, sizeof(Smem_), st>>>(                   \
             h->scene, first, n, seed, d_bits, d_n_valid, d_q_out, h->gather);                                    \
     }
         if (h->scene.carry) {
-            if (fingers_open) PV_LAUNCH_SWEEP_SORTED(true, true) else PV_LAUNCH_SWEEP_SORTED(true, false)
+            if (fingers_open) PV_LAUNCH_SWEEP_SORTED(true, true, false) else PV_LAUNCH_SWEEP_SORTED(true, false, false)
+        } else if (h->all_yaw) {
+            if (fingers_open) PV_LAUNCH_SWEEP_SORTED(false, true, true) else PV_LAUNCH_SWEEP_SORTED(false, false, true)
         } else {
-            if (fingers_open) PV_LAUNCH_SWEEP_SORTED(false, true) else PV_LAUNCH_SWEEP_SORTED(false, false)
+            if (fingers_open) PV_LAUNCH_SWEEP_SORTED(false, true, false) else PV_LAUNCH_SWEEP_SORTED(false, false, false)
         }
 #undef PV_LAUNCH_SWEEP_SORTED
     } else {

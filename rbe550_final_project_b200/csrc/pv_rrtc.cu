@@ -120,7 +120,7 @@ __device__ __forceinline__ int rrtc_nearest(const float* __restrict__ tq, int si
     return bi;
 }
 
-template <bool CARRY>
+template <bool CARRY, bool YAW = false>
 __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_constant__ PvScene S,
                                                                    const __grid_constant__ RrtcArgs A) {
     const unsigned FULL = 0xffffffffu;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
 #pragma unroll
         for (int k = 0; k < 9; ++k) qe[k] = (lane == 0) ? qs_[k] : qg_[k];
         PvAcc<PV_MODE_BITS> acc0;
-        pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, 0, false, CARRY>(qe, S, acc0);
+        pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, 0, false, CARRY, false, false, YAW>(qe, S, acc0);
         const bool bad = acc0.hit;
         const int code = (__shfl_sync(FULL, bad ? 1 : 0, 0) ? 1 : 0) | (__shfl_sync(FULL, bad ? 1 : 0, 1) ? 2 : 0);
         if (code) status = ST_BADEND + code;
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(RRTC_THREADS, 3) pv_rrtc_kernel(const __grid_c
 #pragma unroll
             for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, de[c], ea[c]);
             PvAcc<PV_MODE_BITS> acc;
-            if (pv_check_config<PV_MODE_BITS, true, PV_EXIT_ANY, 0, false, CARRY, false, (PV_COLD_SCENE_WARP != 0)>(q, S, acc)) {
+            if (pv_check_config<PV_MODE_BITS, true, PV_EXIT_ANY, 0, false, CARRY, false, (PV_COLD_SCENE_WARP != 0), YAW>(q, S, acc)) {
                 PvReloadLerp rl;
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
@@ -640,6 +640,7 @@ int pv_rrtc_run(PvHandle* h, const float* h_starts, const float* h_goals, int n,
         const int wpb = RRTC_THREADS / 32;
         const int grid = (int)((n_search + wpb - 1) / wpb);
         if (h->scene.carry) pv_rrtc_kernel<true><<<grid, RRTC_THREADS, 0, st>>>(h->scene, a);
+        else if (h->all_yaw) pv_rrtc_kernel<false, true><<<grid, RRTC_THREADS, 0, st>>>(h->scene, a);
         else pv_rrtc_kernel<false><<<grid, RRTC_THREADS, 0, st>>>(h->scene, a);
         pv_rrtc_collect_kernel<<<(a.n_queries + 3) / 4, 128, 0, st>>>(a);
         h->launches += 2;
