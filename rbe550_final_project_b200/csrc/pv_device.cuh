@@ -647,8 +647,13 @@ __device__ __noinline__ bool pv_scene_cold(LOAD load, const PvScene& S) {
 // DEFER: do not run the scene section, return whether it is needed (see pv_scene_cold); the return value is false
 // whenever the section has been dealt with here.
 template <int MODE, bool CULL, int EXIT, int SYNC = 0, bool FMAK = false, bool CARRY = false, bool FTRIG = FMAK,
-          bool DEFER = false, bool YAW = false>
+          bool DEFER = false, bool YAW = false, int SECT = 3>
 __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S, PvAcc<MODE>& acc) {
+    // SECT: which sections exist at all in this instantiation -- bit 0 the self-collision section, bit 1 the scene-level
+    // test and the scene section.  The motion validator routes motions that provably never need one of them (their
+    // coarse states clear all of its culls with slack: pv_cull_status) to a kernel compiled without it: 30 KB of code
+    // instead of 53 KB, which is what these instruction-fetch-bound kernels respond to.
+    static_assert(SECT == 3 || (CULL && MODE == PV_MODE_BITS && !CARRY && !DEFER), "section-less forms: culling verdict bits");
     static_assert(!SYNC || EXIT == PV_EXIT_NONE, "block barriers and warp-level early exit do not mix");
     static_assert(!DEFER || (CULL && MODE == PV_MODE_BITS), "only the culling verdict-bit form defers the scene section");
     const unsigned FULL = 0xffffffffu;
@@ -710,7 +715,7 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
     PV_LOCKSTEP(2)
 
     // ---- self collision ------------------------------------------------------------------------------
-    if (S.flags & PV_FLAG_SELF) {
+    if ((SECT & 1) && (S.flags & PV_FLAG_SELF)) {
 #define PV_SS(a, b, rr2, rr) pv_sphere_sphere<MODE>(acc, s[a], s[b], rr2, rr, PV_SELF_CODE(a, pv_sphere_link[b]));
 #define PV_SS2(a, b0, b1, n0, n1, k) pv_sphere_sphere2<k>(acc, s[a], s[b0], s[b1], n0, n1);
 #define PV_LP(la, lb, ca, cb, cull2)                         \
@@ -788,7 +793,9 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
     // per-box cull (profiles/r1_notes.md: a third of the instructions of the check); the sorted kernel orders its
     // configurations so that whole warps agree (pv_sort_key).
     bool near_scene = true;
-    if constexpr (CULL && MODE == PV_MODE_BITS) {
+    if constexpr (!(SECT & 2)) {
+        near_scene = false;
+    } else if constexpr (CULL && MODE == PV_MODE_BITS) {
         near_scene = false;
 #define PV_SCENE_GROUP(l, cs, br)                                                                                  \
     if (S.group_any & (1u << l))                                                                                   \
@@ -818,6 +825,74 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
     }
 #undef PV_EARLY_EXIT
 #undef PV_LOCKSTEP
+}
+
+// ---- motion certificates: the culls with slack ------------------------------------------------------------------
+// Nothing is flagged when the configuration is inside the joint limits and EVERY culling test of pv_check_config -- the link-pair and
+// gripper balls of the self-collision section, the scene-level test -- as well as the ground-plane test clears by more
+// than dl metres.  Every configuration whose robot points lie within dl of this one's (in the world, and relative to
+// any link proximal to them) then skips all of its culls too and stays above the plane: it is free of contact without
+// being tested (pv_edge_cert_kernel, csrc/pv_edge.cu; panda_model.motion_reach_bounds bounds the travel).  The
+// comparisons are written so that a non-finite value never certifies.  The placement is pv_place's: only the handful of
+// centres the culls look at and the z coordinates survive dead-code elimination (~520 instructions, 10 KB of code).
+// (r + dl)^2 <= r^2 + (2 r + PV_MOTION_CERT_MAX_SLACK) dl for 0 <= dl <= PV_MOTION_CERT_MAX_SLACK; r2 is a literal, so
+// the factor folds to a constant (the 1.001 covers the rounding of the fold and of the FFMA)
+#define PV_SLK_THR(r2, dl) fmaf((2.0f * sqrtf(r2) + PV_MOTION_CERT_MAX_SLACK) * 1.001f, dl, r2)
+// Returns 0 when everything is clear; bit 0: limits, ground plane or a self-collision cull within dl; bit 1: the
+// scene-level test within dl.
+template <bool FTRIG>
+__device__ __forceinline__ unsigned pv_cull_status(const float* q, const PvScene& S, float dl) {
+    const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) ok = ok && q[j] >= lo[j] && q[j] <= hi[j];
+    PvPlaced P;
+    pv_place<FTRIG, false>(q, S, P);
+    float3(&s)[PV_N_SPHERES] = P.s;
+    float3(&bc)[3] = P.bc;
+    const float grip_r = P.grip_r, tz = S.table_z;
+    ok = ok && (PV_TABLE_LOWEST(s) - tz) >= dl;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float ext = fmaf(fabsf(P.hZ.z), pv_bh[k][2], fmaf(fabsf(P.hY.z), pv_bh[k][1], fabsf(P.hX.z) * pv_bh[k][0]));
+        ok = ok && ((bc[k].z - ext) - tz) >= dl;
+    }
+    if (S.flags & PV_FLAG_SELF) {
+#define PV_LPS(la, lb, ca, cb, cull2)                          \
+    {                                                          \
+        float3 d_ = v_sub(s[ca], s[cb]);                       \
+        ok = ok && v_dot(d_, d_) >= PV_SLK_THR(cull2, dl);     \
+    }
+        PV_SS_LINKPAIRS(PV_LPS)
+#undef PV_LPS
+#define PV_LBS(la, ca, c0, c1, c2, rla)                                                                \
+    {                                                                                                  \
+        if ((c0) > 0.f) {                                                                              \
+            float3 d0_ = v_sub(s[ca], bc[0]);                                                          \
+            float rr_ = ((rla) + grip_r) + dl;                                                         \
+            ok = ok && v_dot(d0_, d0_) >= rr_ * rr_;                                                   \
+        } else {                                                                                       \
+            float3 d1_ = v_sub(s[ca], bc[1]), d2_ = v_sub(s[ca], bc[2]);                               \
+            ok = ok && v_dot(d1_, d1_) >= PV_SLK_THR(c1, dl) && v_dot(d2_, d2_) >= PV_SLK_THR(c2, dl); \
+        }                                                                                              \
+    }
+        PV_SBH_LINKS(PV_LBS)
+#undef PV_LBS
+    }
+    // scene-level test, reach inflated by dl: outside the padded bounds along at least one axis
+    const bool ok_self = ok;
+    ok = true;
+#define PV_SCENE_GROUP(l, cs, br)                                                                                  \
+    if (S.group_any & (1u << l))                                                                                   \
+        ok = ok && (s[cs].x + dl <= S.gpad[l][0] || s[cs].x - dl >= S.gpad[l][3] || s[cs].y + dl <= S.gpad[l][1] || \
+                    s[cs].y - dl >= S.gpad[l][4] || s[cs].z + dl <= S.gpad[l][2] || s[cs].z - dl >= S.gpad[l][5]);
+    PV_LINK_GROUPS(PV_SCENE_GROUP)
+#undef PV_SCENE_GROUP
+    const float grs_ = grip_r + dl;
+    if (S.group_any & 0x100u)
+        ok = ok && (bc[0].x + grs_ <= S.aabb_lo[0] || bc[0].x - grs_ >= S.aabb_hi[0] || bc[0].y + grs_ <= S.aabb_lo[1] ||
+                    bc[0].y - grs_ >= S.aabb_hi[1] || bc[0].z + grs_ <= S.aabb_lo[2] || bc[0].z - grs_ >= S.aabb_hi[2]);
+    return (ok_self ? 0u : 1u) | (ok ? 0u : 2u);
 }
 
 // ---- re-loaders of a configuration for pv_scene_cold --------------------------------------------------------

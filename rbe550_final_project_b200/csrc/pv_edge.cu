@@ -65,19 +65,33 @@ struct PvGatherOpt<true> {
     PvGather g;
 };
 
-template <bool CULL, int MODE, bool CARRY, bool GATHER = false, bool YAW = false>
+// LIST: the motions to validate are the entries of `list` (their count is read from *n_list: the certificate pass
+// below wrote both), and a valid motion sets its own bit in the zero-initialised word with an atomic.
+// SECT (LIST only): the sections of the check this instantiation contains (pv_check_config; 3 = all).
+template <bool CULL, int MODE, bool CARRY, bool GATHER = false, bool YAW = false, bool LIST = false, int SECT = 3>
 __global__ void __launch_bounds__(PV_E_THREADS, 1)
     pv_edge_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ aA, const float4* __restrict__ aB,
                    const float* __restrict__ a9, const float4* __restrict__ bA, const float4* __restrict__ bB,
                    const float* __restrict__ b9, const float* __restrict__ a_aos, const float* __restrict__ b_aos,
                    int64_t n_edges, int n_steps, float resolution, uint32_t* __restrict__ bits,
                    float* __restrict__ margin, int epw, unsigned char* __restrict__ ok_bytes,
-                   const __grid_constant__ PvGatherOpt<GATHER> GO) {
+                   const __grid_constant__ PvGatherOpt<GATHER> GO, const unsigned* __restrict__ list = nullptr,
+                   const unsigned* __restrict__ n_list = nullptr, unsigned* __restrict__ next_group = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    if constexpr (LIST) n_edges = (int64_t)__ldg(n_list);
+    unsigned my_e = 0;  // LIST: lane i holds the i-th motion of the group of 32 this warp works on
     const int64_t n_words = (n_edges + epw - 1) / epw;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // LIST: the listed motions are the expensive ones and their cost varies, so the warps draw small groups (epw = 4)
+    // from a counter instead of striding over the list: no warp is left with a long tail
+    auto next_w = [&]() -> int64_t {
+        unsigned g_ = 0;
+        if (lane == 0) g_ = atomicAdd(next_group, 1u);
+        return (int64_t)__shfl_sync(0xffffffffu, g_, 0);
+    };
+    if constexpr (LIST) w = next_w();
 
     // warp state machine: word w, edge j of the word, round r of the edge.  Only the end points of the edge being
     // validated are kept in registers (warp-uniform, fetched with broadcast loads that hit L1), which took the kernel
@@ -114,9 +128,11 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
             j = 0;
             need_word = false;
             need_edge = true;
+            if constexpr (LIST) my_e = lane < n_here ? __ldg(list + w * epw + lane) : 0u;
         }
         if (need_edge) {
-            const int64_t e = w * epw + j;
+            int64_t e = w * epw + j;
+            if constexpr (LIST) e = (int64_t)__shfl_sync(FULL, my_e, j);
             if (a_aos) {
                 pv_load_aos(a_aos, e, ea);
                 pv_load_aos(b_aos, e, eb);
@@ -149,7 +165,7 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
         constexpr bool COLD = PV_COLD_SCENE_WARP && CULL && MODE == PV_MODE_BITS;
         constexpr int EX = (MODE == PV_MODE_BITS ? PV_EXIT_ANY : PV_EXIT_NONE);
         constexpr bool FT = (PV_EDGE_FAST_TRIG && MODE == PV_MODE_BITS);
-        if (pv_check_config<MODE, CULL, EX, 0, false, CARRY, FT, COLD, YAW>(q, S, acc)) {
+        if (pv_check_config<MODE, CULL, EX, 0, false, CARRY, FT, COLD, YAW, SECT>(q, S, acc)) {
             // warp-uniform (the check votes before it reports): the whole warp runs the scene section out of line
             if constexpr (COLD) {
                 PvReloadLerp rl;
@@ -191,15 +207,111 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
                 if constexpr (GATHER) {
                     if (epw == 32) pv_emit_word(bits, GO.g, w, word, lane);  // local word + peer / multicast stores
                 }
-                if (lane == 0) {
+                if constexpr (LIST) {  // epw == 32: lane i owns the i-th entry of this group
+                    if (lane < n_here && ((word >> lane) & 1u)) atomicOr(bits + (my_e >> 5), 1u << (my_e & 31u));
+                } else if (lane == 0) {
                     if (epw == 32) {
                         if constexpr (!GATHER) bits[w] = word;
                     } else if (ok_bytes) ok_bytes[w] = (unsigned char)(word & 1u);  // epw == 1
                     else if (word & 1u) atomicOr(bits + (w >> 5), 1u << (w & 31));  // epw == 1, bits zeroed by the launcher
                 }
             }
-            w += n_warps;
+            if constexpr (LIST) w = next_w();
+            else w += n_warps;
             need_word = true;
+        }
+    }
+}
+
+// ---- motion certificates (pv_set_culling(2), the default; large batches of motions without a carried box) ----------
+// A motion of nd > 32 interpolation states is first looked at COARSELY by this small kernel: half a warp per motion, 16
+// states t_i = nd - floor((s - 1) / 2) - i s with s = ceil(nd / 16), so that every state 1..nd lies within h = floor(s / 2)
+// interpolation steps of a tested one.  Between two configurations dq apart no robot point moves farther than
+// sum_j |dq_j| R_j + |dq_8| + |dq_9| (panda_model.motion_reach_bounds; tests/test_model_pruning.py), so with
+// dl = h steps of that travel: if all 16 tested states are inside the joint limits and clear every culling test and the
+// ground plane by more than dl (pv_cull_clear), every state of the motion passes all of its culls -- none of them is in
+// contact, the start state's joints being inside the limits too -- and the motion is VALID without a single primitive
+// test.  52 % of the config-3 motions (gaussian steps, sigma 0.3 rad, 64 states) finish here at a quarter of the states
+// and a fraction of the instructions; the others go, as a compacted list, through pv_edge_kernel<LIST> unchanged.
+// Exact, not a heuristic: the verdict words are those of the exhaustive validator (pv_set_culling(1); tests/
+// test_gpu_parity.py::test_motion_certificates_do_not_change_verdicts).  The kernel is 10 KB of code at <= 80 registers:
+// none of the instruction-fetch trouble of the full check (profiles/r2_notes.md).
+#ifndef PV_EDGE_CERT
+#define PV_EDGE_CERT 1
+#endif
+#ifndef PV_CERT_MIN_ND
+#define PV_CERT_MIN_ND 33
+#endif
+#ifndef PV_CERT_THREADS
+#define PV_CERT_THREADS 256
+#endif
+__global__ void __launch_bounds__(PV_CERT_THREADS)
+    pv_edge_cert_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ aA, const float4* __restrict__ aB,
+                        const float* __restrict__ a9, const float4* __restrict__ bA, const float4* __restrict__ bB,
+                        const float* __restrict__ b9, int64_t n_edges, int n_steps, float resolution,
+                        uint32_t* __restrict__ bits, unsigned* __restrict__ lists, unsigned* __restrict__ n_list) {
+    // lists: two arrays of n_edges entries each -- the motions that provably never come near the scene boxes and need
+    // the self-collision section only (class 1), and the others (class 2: the whole check); n_list[c - 1] = their lengths
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+    const int64_t n_words = (n_edges + 31) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += n_warps) {
+        unsigned word = 0;   // bit j: motion 32 w + j is certified valid
+        unsigned cls0 = 0, cls1 = 0;  // bit j of (cls0, cls1): class of motion 32 w + j (low, high bit)
+        for (int it = 0; it < 16; ++it) {
+            const int64_t e = w * 32 + 2 * it + half;
+            unsigned st = 3;  // not certifiable: the whole check
+            if (e < n_edges) {
+                float ea[9], eb[9];
+                pv_load_soa(aA, aB, a9, e, ea);
+                pv_load_soa(bA, bB, b9, e, eb);
+                const float reach[7] = PV_MOTION_REACH, lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
+                float d2 = 0.f, trav = fabsf(eb[7] - ea[7]) + fabsf(eb[8] - ea[8]);
+                bool a_in = true;  // the start state is never tested, but its joints must be inside the limits
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    const float de = eb[c] - ea[c];
+                    d2 = fmaf(de, de, d2);
+                    if (c < 7) trav = fmaf(fabsf(de), reach[c], trav);
+                    a_in = a_in && ea[c] >= lo[c] && ea[c] <= hi[c];
+                }
+                int nd = n_steps;
+                if (nd <= 0) nd = max(1, (int)ceilf(sqrtf(d2) / resolution));  // as pv_edge_kernel counts them
+                const int s = (nd + 15) >> 4, h = s >> 1;
+                const float inv_nd = 1.0f / (float)nd;
+                const float dl = fmaf(trav * inv_nd, (float)h * 1.0002f, 2e-5f);
+                if (nd >= PV_CERT_MIN_ND && a_in && dl <= PV_MOTION_CERT_MAX_SLACK) {
+                    int k = nd - ((s - 1) >> 1) - sub * s;
+                    if (k < 1) k = 1;
+                    const float t = (float)k * inv_nd;
+                    float q[9];
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, eb[c] - ea[c], ea[c]);
+                    st = pv_cull_status<(PV_EDGE_FAST_TRIG != 0)>(q, S, dl);
+                }
+            }
+            // class of a motion = OR over its 16 states
+            const unsigned m0 = __ballot_sync(FULL, st & 1u), m1 = __ballot_sync(FULL, st & 2u);
+            const unsigned a0 = (m0 & 0xffffu) ? 1u : 0u, a1 = (m1 & 0xffffu) ? 1u : 0u;
+            const unsigned b0 = (m0 >> 16) ? 1u : 0u, b1 = (m1 >> 16) ? 1u : 0u;
+            cls0 |= (a0 << (2 * it)) | (b0 << (2 * it + 1));
+            cls1 |= (a1 << (2 * it)) | (b1 << (2 * it + 1));
+        }
+        word = ~(cls0 | cls1);
+        const int64_t mine = w * 32 + lane;
+        if (mine + 32 > n_edges) word &= (n_edges - w * 32 >= 32) ? 0xffffffffu : ((1u << (unsigned)(n_edges - w * 32)) - 1u);
+        if (lane == 0) bits[w] = word;
+        // the rest goes to the validators: append to the list of its class (one atomic per warp and class)
+        const unsigned c = mine < n_edges ? (((cls1 >> lane) & 1u) ? 2u : ((cls0 >> lane) & 1u)) : 0u;
+#pragma unroll
+        for (unsigned k = 1; k <= 2; ++k) {
+            const unsigned tm = __ballot_sync(FULL, c == k);
+            if (!tm) continue;
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(n_list + (k - 1), (unsigned)__popc(tm));
+            base = __shfl_sync(FULL, base, 0);
+            if (c == k) lists[(size_t)(k - 1) * (size_t)n_edges + base + __popc(tm & ((1u << lane) - 1u))] = (unsigned)mine;
         }
     }
 }
@@ -223,6 +335,51 @@ int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* 
     // the fused-gather target applies to whole verdict words only (large batches); small batches and margins never gather
     // (and device-buffer calls only: a host-buffer call numbers its words per chunk, see pv_launch_state_bits)
     const bool gather_on = allow_gather && epw == 32 && d_bits && h->gather.n_peers > 0;
+#if PV_EDGE_CERT
+    // certificate pass + full validation of the rest (see pv_edge_cert_kernel), for motions cut into a fixed number of
+    // more than 32 states.  (Under the resolution rule the planners' motions are a handful of states long -- nothing to
+    // skip -- and the pass would only cost its loads, so n_steps == 0 keeps the single kernel.)  Scratch comes from the
+    // stream-ordered allocator, so any number of streams and handles may be in flight.
+    if (h->cull == 2 && epw == 32 && d_bits && !gather_on && !h->scene.carry && !a_aos && n < ((int64_t)1 << 32) &&
+        n_steps >= PV_CERT_MIN_ND) {
+        unsigned* scratch = nullptr;
+        if (!h->pool) {  // a pool of the handle's own that keeps its memory between calls
+            cudaMemPoolProps pp = {};
+            pp.allocType = cudaMemAllocationTypePinned;
+            pp.location.type = cudaMemLocationTypeDevice;
+            pp.location.id = h->device;
+            PV_CUDA(h, cudaMemPoolCreate(&h->pool, &pp));
+            uint64_t keep = ~0ull;
+            PV_CUDA(h, cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        PV_CUDA(h, cudaMallocFromPoolAsync((void**)&scratch, (2 * (size_t)n + 64) * sizeof(unsigned), h->pool, st));
+        unsigned* d_list = scratch + 64;  // scratch[0..1] = lengths of the two lists, scratch[2..3] = their group counters
+        PV_CUDA(h, cudaMemsetAsync(scratch, 0, 8 * sizeof(unsigned), st));
+        const int cgrid = pv_grid_for(h, (const void*)pv_edge_cert_kernel, PV_CERT_THREADS, words);
+        pv_edge_cert_kernel<<<cgrid, PV_CERT_THREADS, 0, st>>>(h->scene, (const float4*)aA, (const float4*)aB, a9,
+                                                              (const float4*)bA, (const float4*)bB, b9, n, n_steps,
+                                                              resolution, d_bits, d_list, scratch);
+#define PV_LAUNCH_EL(YAW_, SECT_, CLS_)                                                                             \
+    {                                                                                                               \
+        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<true, PV_MODE_BITS, false, false, YAW_, true, SECT_>, \
+                               PV_E_THREADS, words * 8);                                                            \
+        pv_edge_kernel<true, PV_MODE_BITS, false, false, YAW_, true, SECT_><<<grid, PV_E_THREADS, 0, st>>>(         \
+            h->scene, (const float4*)aA, (const float4*)aB, a9, (const float4*)bA, (const float4*)bB, b9, nullptr,  \
+            nullptr, n, n_steps, resolution, d_bits, nullptr, 4, nullptr, PvGatherOpt<false>{},                     \
+            d_list + (size_t)(CLS_ - 1) * (size_t)n, scratch + (CLS_ - 1), scratch + 2 + (CLS_ - 1));               \
+    }
+        if (h->all_yaw) {
+            PV_LAUNCH_EL(true, 3, 2) PV_LAUNCH_EL(true, 1, 1)
+        } else {
+            PV_LAUNCH_EL(false, 3, 2) PV_LAUNCH_EL(false, 1, 1)
+        }
+#undef PV_LAUNCH_EL
+        PV_CUDA(h, cudaGetLastError());
+        PV_CUDA(h, cudaFreeAsync(scratch, st));
+        h->launches += 3;
+        return PV_OK;
+    }
+#endif
 #define PV_LAUNCH_E(CULL, MODE, CARRY, GATHER, GARG, YAW_)                                                        \
     {                                                                                                             \
         int grid = pv_grid_for(h, (const void*)pv_edge_kernel<CULL, MODE, CARRY, GATHER, YAW_>, PV_E_THREADS, words); \

@@ -72,6 +72,7 @@ struct PvHandle {
     void* small_host;      // host-mapped pinned staging of small host-buffer calls (rows in, verdict words / bytes out)
     void* ik_buf;
     size_t ik_bytes;
+    cudaMemPool_t pool;  // stream-ordered scratch of the motion validator's certificate pass (created on first use)
     char err[512];
 };
 

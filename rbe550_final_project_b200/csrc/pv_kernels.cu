@@ -753,6 +753,7 @@ void pv_destroy(PvHandle* h) {
     if (h->plan_host) cudaFreeHost(h->plan_host);
     if (h->small_host) cudaFreeHost(h->small_host);
     if (h->ik_buf) cudaFree(h->ik_buf);
+    if (h->pool) cudaMemPoolDestroy(h->pool);
     h->magic = 0;
     delete h;
 }

@@ -344,6 +344,36 @@ def static_reach():
     return link_reach, box_reach
 
 
+def motion_reach_bounds():
+    """R_j for the seven revolute joints: no point the validity tests look at (arm sphere centres, gripper box centres
+    and corners) is ever farther than R_j from joint j's axis, whatever the configuration (triangle inequality over the
+    body offsets from the joint's own origin, which lies on its axis, plus the finger travel).  When the joints move by
+    dq, every such point therefore moves by at most sum_j |dq_j| R_j + |dq_8| + |dq_9| -- in the world and, for a point
+    distal to link a, relative to link a's frame (joints up to a move both rigidly).  The motion validator turns that
+    into a certificate: a state whose culling tests clear by more than this displacement proves its neighbours on the
+    motion valid without testing them (pv_edge_kernel, csrc/pv_edge.cu)."""
+    loc = np.zeros(N_LINKS)
+    for i in range(N_SPHERES):
+        l = int(SPHERE_LINK[i])
+        loc[l] = max(loc[l], float(np.linalg.norm(SPHERE_CENTER[i])))
+    for k in range(N_BOXES):
+        l = int(BOX_LINK[k])
+        loc[l] = max(loc[l], float(np.linalg.norm(np.abs(BOX_CENTER[k]) + BOX_HALF[k])))
+    out = np.zeros(7)
+    for j in range(1, 8):  # joint j turns body j about the z axis through body j's origin
+        for b in range(j, N_LINKS):
+            chain, l = 0.0, b
+            while l != j and l >= 0:
+                chain += float(np.linalg.norm(BODY_POS[l])) + (FINGER_SLIDE_MAX if l in (LINK_LF, LINK_RF) else 0.0)
+                l = PARENT[l]
+            if l == j:
+                out[j - 1] = max(out[j - 1], chain + loc[b])
+    return out
+
+
+MOTION_CERT_MAX_SLACK = 0.05  # metres: motions whose per-round displacement bound exceeds this seek no certificate
+
+
 def _place_expr(c, axis):
     """p.axis + X.axis*cx + Y.axis*cy + Z.axis*cz with zero terms dropped (fmaf chain)."""
     e = f"p.{axis}"
@@ -379,6 +409,9 @@ def header_text() -> str:
     a("#define PV_LINK_REACH {" + ", ".join(_f(v) for v in lr) + "}")
     a("#define PV_BOX_REACH {" + ", ".join(_f(v) for v in br_) + "}")
     a("#define PV_SPHERE_LINK {" + ", ".join(str(int(v)) for v in SPHERE_LINK) + "}")
+    a("// motion certificates (motion_reach_bounds): R_j of the seven revolute joints, and the largest slack ever sought")
+    a("#define PV_MOTION_REACH {" + ", ".join(_f(v * 1.0001) for v in motion_reach_bounds()) + "}")
+    a(f"#define PV_MOTION_CERT_MAX_SLACK {_f(MOTION_CERT_MAX_SLACK)}")
     a("// joint limits")
     a("#define PV_Q_LOWER {" + ", ".join(_f(v) for v in Q_LOWER) + "}")
     a("#define PV_Q_UPPER {" + ", ".join(_f(v) for v in Q_UPPER) + "}")

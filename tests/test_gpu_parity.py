@@ -223,6 +223,45 @@ def test_edge_long_edges_resolution_mode(pv, c64):
     _assert_verdicts(gpu, ref, "long edges")
 
 
+def test_motion_certificates_do_not_change_verdicts(pv, c64):
+    """pv_edge_kernel finishes a motion of more than 32 states after its coarse round when that round's culling tests
+    clear by more than the robot can travel between tested states.  The verdict words must be those of
+    the exhaustive validator (pv_set_culling(1) switches the certificates off), whatever the scene, the attached box,
+    the motion length or the step rule -- including motions that start outside the joint limits."""
+    rng = np.random.default_rng(97)
+    n = 200_003
+    qa = random_configs(n, 95)
+    cases = []
+    for sigma in (0.05, 0.3, 1.0):
+        qb = np.clip(qa + rng.normal(0, sigma, qa.shape), pm.Q_LOWER, pm.Q_UPPER).astype(np.float32)
+        qb[:, 7:] = rng.uniform(0, 0.04, (n, 2)).astype(np.float32)
+        cases.append((qa, qb))
+    qo = qa.copy()
+    qo[::3, 1] = np.float32(pm.Q_LOWER[1]) - rng.uniform(0, 0.05, qo[::3, 1].shape).astype(np.float32)  # start outside
+    cases.append((qo, cases[1][1]))
+    for name in SCENES:
+        pv.set_scene(sc.FIXTURES[name]())
+        for att in (-1, 2):
+            pv.set_attached(att)
+            for a, b in cases:
+                for n_steps in (64, 40, 200, 0):
+                    A, B = _dev(a), _dev(b)
+                    pv.set_culling(1)
+                    ref = pv.check_edges(A, B, n_steps=n_steps).cpu().numpy()
+                    pv.set_culling(2)
+                    got = pv.check_edges(A, B, n_steps=n_steps).cpu().numpy()
+                    assert (ref == got).all(), (name, att, n_steps)
+    pv.set_attached(-1)
+    # against the fp64 oracle on long motions cut finely (every certificate skips 3 of 4 states)
+    scene = sc.goal4_task1_pentagon()
+    pv.set_scene(scene)
+    k = 6000
+    a, b = cases[1][0][:k], cases[1][1][:k]
+    gpu = unpack_bits(pv.check_edges(_dev(a), _dev(b), n_steps=128), k)
+    ref = c64.edge_margin(a.astype(np.float64), b.astype(np.float64), scene.as_oracle_scene(), n_steps=128)
+    _assert_verdicts(gpu, ref, "certified motions, 128 steps")
+
+
 def test_host_entry_points_match_device(pv):
     scene = sc.goal1_scattered()
     pv.set_scene(scene)

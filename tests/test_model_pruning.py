@@ -96,3 +96,44 @@ def test_generated_cull_constants_are_conservative():
             assert (c > 0) == has
             if has:
                 assert np.sqrt(c) >= need + pm.BOX_BOUND_RADIUS[k] + 0.5 * pm.CULL_SLACK
+
+
+def test_motion_reach_bounds_hold():
+    """The displacement bound behind the motion certificates (panda_model.motion_reach_bounds; pv_edge_kernel): when the
+    joints move by dq, no tested point of the robot -- sphere centres, gripper box centres and corners -- moves farther
+    than sum_j |dq_j| R_j + |dq_8| + |dq_9|, in the world and relative to every link proximal to it."""
+    from oracle import panda_oracle as po
+    rng = np.random.default_rng(5)
+    n = 40_000
+    Rj = pm.motion_reach_bounds()
+    qa = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n, 9))
+    step = rng.choice([1e-3, 0.02, 0.3], size=(n, 1)) * rng.standard_normal((n, 9))
+    step[n // 2:, :] *= (rng.random((n - n // 2, 9)) < 0.3)  # sparse moves: single joints, where the bound is tightest
+    step[:, 7:] *= 0.05
+    qb = np.clip(qa + step, pm.Q_LOWER, pm.Q_UPPER)
+    bound = (np.abs(qb - qa)[:, :7] * Rj[None]).sum(1) + np.abs(qb - qa)[:, 7:].sum(1)
+
+    def points(q):
+        R, p = po.fk(q)
+        sl = pm.SPHERE_LINK
+        cen = p[:, sl] + np.einsum("nsij,sj->nsi", R[:, sl], pm.SPHERE_CENTER)
+        sg = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 0, 1)], float)  # corners + centres
+        loc = pm.BOX_CENTER[:, None, :] + sg[None] * pm.BOX_HALF[:, None, :]
+        box = p[:, pm.BOX_LINK, None, :] + np.einsum("nkij,kcj->nkci", R[:, pm.BOX_LINK], loc)
+        link = np.concatenate([sl, np.repeat(pm.BOX_LINK, sg.shape[0])])
+        return np.concatenate([cen, box.reshape(n, -1, 3)], 1), link, R, p
+
+    Pa, link, Ra, pa = points(qa)
+    Pb, _, Rb, pb = points(qb)
+    world = np.linalg.norm(Pb - Pa, axis=2).max(1)
+    assert (world <= bound * (1 + 1e-9) + 1e-12).all()
+    # the chord of a straight joint-space motion is what the validator needs: sampled states of the SAME motion
+    # relative to a proximal link frame a: x_a = R_a^T (x - p_a)
+    for a in (1, 2, 3, 4):
+        la = np.einsum("nji,npj->npi", Ra[:, a], Pa - pa[:, a, None, :])
+        lb = np.einsum("nji,npj->npi", Rb[:, a], Pb - pb[:, a, None, :])
+        distal = link > a
+        rel = np.linalg.norm(lb - la, axis=2)[:, distal].max(1)
+        assert (rel <= bound * (1 + 1e-9) + 1e-12).all(), a
+    # and the bound is not vacuous: some single-joint moves come within 25 % of it
+    assert (world / np.maximum(bound, 1e-12)).max() > 0.75

@@ -16,10 +16,10 @@ src = open(os.path.join(ROOT, "rbe550_final_project_b200/csrc/pv_device.cuh")).r
 def find(t): return [i + 1 for i, l in enumerate(src) if t in l][0]
 marks = [("limits", find("Joint limits are part of the model")), ("place-call", find("PvPlaced P;\n") if False else find("    PvPlaced P;")),
          ("plane", find("robot vs ground plane")), ("carry", find("carried box: placed by the hand, checked")),
-         ("self:culls-first", find("unsigned cm = 0;")), ("self:ss-blocks", find("#define PV_SS(a, b, rr2, rr)")),
+         ("self:ss-blocks", find("#define PV_SS(a, b, rr2, rr)")),
          ("self:sbh-blocks", find("sphere-vs-gripper pairs: the three")), ("scene-level", find("// ---- robot vs scene boxes ----")),
          ("end", find("#undef PV_EARLY_EXIT\n") if False else find("#undef PV_LOCKSTEP"))]
-sec_lo, sec_hi = find("template <int MODE, bool CULL, int EXIT, int SYNC, bool FMAK, bool CARRY>"), find("// The scene section OUT OF LINE")
+sec_lo, sec_hi = find("__device__ __forceinline__ void pv_scene_section("), find("// The scene section OUT OF LINE")
 fk_lo, fk_hi = find("template <bool FAST = false, class F>"), find("// ---- the state check")
 pl_lo, pl_hi = find("// FK -> sphere centres + gripper boxes"), find("#define PV_EARLY_EXIT_RET")
 def cat(fr):

@@ -8,7 +8,7 @@ if os.environ.get("PV_LIB"):  # a variant build (tools/build_variant.py)
 STEPS = int(os.environ.get("PV_STEPS", "64"))
 from rbe550_final_project_b200.validity import PandaValidity, soa_from_aos
 pv = PandaValidity(0)
-pv.set_scene(sc.goal4_task1_pentagon())
+pv.set_scene(sc.FIXTURES[os.environ.get("PV_SCENE", "goal4_task1_pentagon")]())
 n = 1 << 20
 rng = np.random.default_rng(20251212)
 qa = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n, 9)).astype(np.float32); qa[:, 7:] = 0.04
