@@ -708,7 +708,7 @@ def bench_edges(torch, pv, counts, mhz, dist=None, world=1):
     if ec.get("warp_inst_per_edge"):
         peak_issue = 148 * 4 * mhz * 1e6
         ach = ec["warp_inst_per_edge"] * rate
-        out["roofline"] = {"bound": "warp-instruction issue", "kernel": "pv_edge_kernel", "achieved": ach, "peak": peak_issue,
+        out["roofline"] = {"bound": "warp-instruction issue", "kernel": ec.get("kernel", "pv_edge_kernel"), "achieved": ach, "peak": peak_issue,
                            "unit": "warp-inst/s", "frac": ach / peak_issue, "counts": ec,
                            "executed_counts_stale": counts.get("source_hash") != source_hash()}
     return out

@@ -840,12 +840,15 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
 #define PV_SLK_THR(r2, dl) fmaf((2.0f * sqrtf(r2) + PV_MOTION_CERT_MAX_SLACK) * 1.001f, dl, r2)
 // Returns 0 when everything is clear; bit 0: limits, ground plane or a self-collision cull within dl; bit 1: the
 // scene-level test within dl.
-template <bool FTRIG>
+// LIMITS = false: the caller vouches for the joint limits (both ends of a motion inside them: so is every state between).
+template <bool FTRIG, bool LIMITS = true>
 __device__ __forceinline__ unsigned pv_cull_status(const float* q, const PvScene& S, float dl) {
     const float lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
     bool ok = true;
+    if constexpr (LIMITS) {
 #pragma unroll
-    for (int j = 0; j < 9; ++j) ok = ok && q[j] >= lo[j] && q[j] <= hi[j];
+        for (int j = 0; j < 9; ++j) ok = ok && q[j] >= lo[j] && q[j] <= hi[j];
+    }
     PvPlaced P;
     pv_place<FTRIG, false>(q, S, P);
     float3(&s)[PV_N_SPHERES] = P.s;

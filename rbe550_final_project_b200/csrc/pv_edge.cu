@@ -91,7 +91,21 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
         if (lane == 0) g_ = atomicAdd(next_group, 1u);
         return (int64_t)__shfl_sync(0xffffffffu, g_, 0);
     };
-    if constexpr (LIST) w = next_w();
+    // ... and stay ONE group ahead: the counter draw and the group's list entries (two dependent global accesses) are
+    // issued while the previous group is being validated, and the end points of the next motion are prefetched into
+    // L2 / L1 when the current one starts (with 12 warps per SM nothing else hides those latencies)
+    int64_t w_nx = 0;
+    unsigned e_nx = 0;
+    auto load_group = [&](int64_t g_) -> unsigned {
+        const int64_t i_ = g_ * epw + lane;
+        return (lane < epw && i_ < n_edges) ? __ldg(list + i_) : 0u;
+    };
+    if constexpr (LIST) {
+        w = next_w();
+        my_e = load_group(w);
+        w_nx = next_w();
+        e_nx = load_group(w_nx);
+    }
 
     // warp state machine: word w, edge j of the word, round r of the edge.  Only the end points of the edge being
     // validated are kept in registers (warp-uniform, fetched with broadcast loads that hit L1), which took the kernel
@@ -128,11 +142,18 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
             j = 0;
             need_word = false;
             need_edge = true;
-            if constexpr (LIST) my_e = lane < n_here ? __ldg(list + w * epw + lane) : 0u;
         }
         if (need_edge) {
             int64_t e = w * epw + j;
-            if constexpr (LIST) e = (int64_t)__shfl_sync(FULL, my_e, j);
+            if constexpr (LIST) {
+                e = (int64_t)__shfl_sync(FULL, my_e, j);
+                // the motion after this one (next entry of the group, else the first one of the next group)
+                const unsigned en_ = (j + 1 < n_here) ? __shfl_sync(FULL, my_e, (j + 1) & 31) : __shfl_sync(FULL, e_nx, 0);
+                if (lane < 4) {
+                    const float4* p_ = (lane == 0 ? aA : lane == 1 ? aB : lane == 2 ? bA : bB) + en_;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p_));
+                }
+            }
             if (a_aos) {
                 pv_load_aos(a_aos, e, ea);
                 pv_load_aos(b_aos, e, eb);
@@ -216,8 +237,14 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
                     else if (word & 1u) atomicOr(bits + (w >> 5), 1u << (w & 31));  // epw == 1, bits zeroed by the launcher
                 }
             }
-            if constexpr (LIST) w = next_w();
-            else w += n_warps;
+            if constexpr (LIST) {
+                w = w_nx;
+                my_e = e_nx;
+                w_nx = next_w();
+                e_nx = load_group(w_nx);
+            } else {
+                w += n_warps;
+            }
             need_word = true;
         }
     }
@@ -268,13 +295,13 @@ __global__ void __launch_bounds__(PV_CERT_THREADS)
                 pv_load_soa(bA, bB, b9, e, eb);
                 const float reach[7] = PV_MOTION_REACH, lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
                 float d2 = 0.f, trav = fabsf(eb[7] - ea[7]) + fabsf(eb[8] - ea[8]);
-                bool a_in = true;  // the start state is never tested, but its joints must be inside the limits
+                bool a_in = true;  // both ends inside the joint limits: so is every state between them
 #pragma unroll
                 for (int c = 0; c < 9; ++c) {
                     const float de = eb[c] - ea[c];
                     d2 = fmaf(de, de, d2);
                     if (c < 7) trav = fmaf(fabsf(de), reach[c], trav);
-                    a_in = a_in && ea[c] >= lo[c] && ea[c] <= hi[c];
+                    a_in = a_in && ea[c] >= lo[c] && ea[c] <= hi[c] && eb[c] >= lo[c] && eb[c] <= hi[c];
                 }
                 int nd = n_steps;
                 if (nd <= 0) nd = max(1, (int)ceilf(sqrtf(d2) / resolution));  // as pv_edge_kernel counts them
@@ -288,7 +315,7 @@ __global__ void __launch_bounds__(PV_CERT_THREADS)
                     float q[9];
 #pragma unroll
                     for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, eb[c] - ea[c], ea[c]);
-                    st = pv_cull_status<(PV_EDGE_FAST_TRIG != 0)>(q, S, dl);
+                    st = pv_cull_status<(PV_EDGE_FAST_TRIG != 0), false>(q, S, dl);
                 }
             }
             // class of a motion = OR over its 16 states
@@ -312,6 +339,22 @@ __global__ void __launch_bounds__(PV_CERT_THREADS)
             if (lane == 0) base = atomicAdd(n_list + (k - 1), (unsigned)__popc(tm));
             base = __shfl_sync(FULL, base, 0);
             if (c == k) lists[(size_t)(k - 1) * (size_t)n_edges + base + __popc(tm & ((1u << lane) - 1u))] = (unsigned)mine;
+        }
+    }
+}
+
+// Fused verdict gather behind the certificate pipeline: its verdict words are complete only after the last list kernel,
+// so a small kernel then stores them into every rank's gather buffer (one multimem.st per word through the NVSwitch
+// multicast address, or one peer store per rank) -- still no collective launch and no host round trip.
+__global__ void __launch_bounds__(256) pv_edge_emit_kernel(const uint32_t* __restrict__ bits, const __grid_constant__ PvGather G,
+                                                           int64_t n_words) {
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words && w < G.word_cap;
+         w += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned word = bits[w];
+        if (G.mc) {
+            asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(G.mc + G.word_off + w), "r"(word) : "memory");
+        } else if (G.peers) {
+            for (int p = 0; p < G.n_peers; ++p) G.peers[p][G.word_off + w] = word;
         }
     }
 }
@@ -340,7 +383,7 @@ int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* 
     // more than 32 states.  (Under the resolution rule the planners' motions are a handful of states long -- nothing to
     // skip -- and the pass would only cost its loads, so n_steps == 0 keeps the single kernel.)  Scratch comes from the
     // stream-ordered allocator, so any number of streams and handles may be in flight.
-    if (h->cull == 2 && epw == 32 && d_bits && !gather_on && !h->scene.carry && !a_aos && n < ((int64_t)1 << 32) &&
+    if (h->cull == 2 && epw == 32 && d_bits && !h->scene.carry && !a_aos && n < ((int64_t)1 << 32) &&
         n_steps >= PV_CERT_MIN_ND) {
         unsigned* scratch = nullptr;
         if (!h->pool) {  // a pool of the handle's own that keeps its memory between calls
@@ -374,6 +417,12 @@ int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* 
             PV_LAUNCH_EL(false, 3, 2) PV_LAUNCH_EL(false, 1, 1)
         }
 #undef PV_LAUNCH_EL
+        if (gather_on) {
+            int egrid = (int)((words + 255) / 256);
+            if (egrid > h->sm_count * 8) egrid = h->sm_count * 8;
+            pv_edge_emit_kernel<<<egrid, 256, 0, st>>>(d_bits, h->gather, words);
+            h->launches++;
+        }
         PV_CUDA(h, cudaGetLastError());
         PV_CUDA(h, cudaFreeAsync(scratch, st));
         h->launches += 3;

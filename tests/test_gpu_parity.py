@@ -633,6 +633,8 @@ def test_fused_gather_epilogues_with_a_local_peer(pv):
     try:
         for name, run in (("states", lambda: pv.check_states(_dev(q))),
                           ("edges", lambda: pv.check_edges(_dev(q), _dev(qb), n_steps=8)),
+                          # more than 32 states: certificate pass + list kernels, the words forwarded by pv_edge_emit_kernel
+                          ("edges64", lambda: pv.check_edges(_dev(q), _dev(qb), n_steps=64)),
                           ("sweep", lambda: pv.sweep(0, n, 5)[0])):
             pv.set_gather(0, 0, 0, 0, 0)
             ref = run().cpu().numpy()

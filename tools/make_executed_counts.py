@@ -6,7 +6,9 @@ One gpurun call produces the inputs (see profiles/README or DESIGN.md section 4)
 smsp__sass_thread_inst_executed_op_fmul_pred_on.sum,smsp__thread_inst_executed.sum,smsp__inst_executed.sum,\
 dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum
     ncu --metrics $M --clock-control none -k regex:pv_state_bits_sorted -s 2 -c 1 --csv --log-file gpurun_out/state_counts.csv python tools/prof_state.py
-    ncu --metrics $M --clock-control none -k regex:pv_edge_kernel -s 1 -c 1 --csv --log-file gpurun_out/edge_counts.csv python tools/prof_edge.py
+    ncu --metrics $M --clock-control none -k regex:pv_edge -s 6 -c 3 --csv --log-file gpurun_out/edge_counts.csv python tools/prof_edge.py
+(one pv_check_edges call of the config-3 workload = three launches: pv_edge_cert_kernel, pv_edge_kernel<list, whole check>,
+pv_edge_kernel<list, self-collision only>; their counts are summed and kept per kernel)
 then here:
     python tools/make_executed_counts.py gpurun_out/state_counts.csv gpurun_out/edge_counts.csv [--tag r2a]
 (prof_state.py checks 1 048 576 configurations, prof_edge.py 1 048 576 edges x 64 states: the bench workloads.)
@@ -28,6 +30,17 @@ def metrics(path):
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "usecond": 1e3, "msecond": 1e6, "nsecond": 1.0}.get(row[13], 1.0)
             vals[row[12]] = float(row[14].replace(",", "")) * scale
     return vals
+
+
+def metrics_per_launch(path):
+    """[(kernel name, {metric: value})] per profiled launch, in launch order"""
+    launches = {}
+    for row in csv.reader(open(path)):
+        if len(row) > 14 and row[0].isdigit() and row[12].startswith(("smsp__", "gpu__", "dram__")):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "usecond": 1e3, "msecond": 1e6, "nsecond": 1.0}.get(row[13], 1.0)
+            name = row[4].split("(")[0].replace("void ", "")
+            launches.setdefault(int(row[0]), (name, {}))[1][row[12]] = float(row[14].replace(",", "")) * scale
+    return [launches[k] for k in sorted(launches)]
 
 
 def fp(v, n):
@@ -58,10 +71,16 @@ out["state"] = {
     "algorithmic_bytes_per_launch": n * (32 + 0.125), "source": os.path.basename(args[0]),
 }
 if len(args) > 1:
-    v = metrics(args[1])
+    per = metrics_per_launch(args[1])
+    v = {}
+    for _, m in per:
+        for k, x in m.items():
+            v[k] = v.get(k, 0.0) + x
     f = fp(v, n)
     out["edges"] = {
-        "kernel": "pv_edge_kernel<cull, bits, no carry>", "workload": f"{n} edges x 64 states vs goal4_task1_pentagon (gaussian 0.3 pairs)",
+        "kernel": " + ".join(name for name, _ in per), "workload": f"{n} edges x 64 states vs goal4_task1_pentagon (gaussian 0.3 pairs)",
+        "per_kernel": [{"kernel": name, "warp_inst": m["smsp__inst_executed.sum"], "ncu_duration_us": m.get("gpu__time_duration.sum", 0) / 1e3}
+                       for name, m in per],
         "warp_inst_per_edge": v["smsp__inst_executed.sum"] / n, "thread_inst_per_edge": v["smsp__thread_inst_executed.sum"] / n,
         "fp32_flops_per_edge": f["fp32_flops"], "ncu_duration_us": v.get("gpu__time_duration.sum", 0) / 1e3,
         "dram_bytes_per_launch": v.get("dram__bytes_read.sum", 0) + v.get("dram__bytes_write.sum", 0),

@@ -96,3 +96,30 @@ def main():
                   f"cull-free at zero slack {np.mean((pl > 0) & (se > 0) & (scn > 0)):.3f}")
 
 main()
+
+
+def cells():
+    """per uncertified motion: how many of the 16 coarse cells are unclear (self/plane vs scene)"""
+    scene = sys.argv[1] if len(sys.argv) > 1 else "goal4_task1_pentagon"
+    n_e = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
+    rng = np.random.default_rng(1)
+    qa = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n_e, 9)); qa[:, 7:] = 0.04
+    qb = np.clip(qa + 0.3 * rng.standard_normal((n_e, 9)), pm.Q_LOWER, pm.Q_UPPER)
+    Rj = reach_bounds(); nd = 64; s = 4; h = 2
+    dstep = (np.abs(qb - qa)[:, :7] * Rj[None]).sum(1) / nd + np.abs(qb - qa)[:, 7:].sum(1) / nd
+    ks = nd - 1 - s * np.arange(16)
+    q = qa[:, None, :] + (ks / nd)[None, :, None] * (qb - qa)[:, None, :]
+    pl, se, scn = (x.reshape(n_e, 16) for x in clearances(q.reshape(-1, 9), scene))
+    d = (dstep * h)[:, None]
+    ok_d = (d[:, 0] <= float(os.environ.get("MAXDL", "0.05")))
+    u_self = (pl <= d) | (se <= d); u_scene = scn <= d
+    u_self[~ok_d] = True; u_scene[~ok_d] = True
+    cert = ~(u_self | u_scene).any(1)
+    cls1 = ~cert & ~u_scene.any(1); cls2 = ~cert & u_scene.any(1)
+    print(f"certified {cert.mean():.3f}  class 1 {cls1.mean():.3f}  class 2 {cls2.mean():.3f}  (no certificate sought {np.mean(~ok_d):.3f})")
+    print(f"class 1: unclear cells per motion {u_self[cls1].sum(1).mean():.2f} of 16 -> states {4 * u_self[cls1].sum(1).mean():.1f} of 64; "
+          f"P(<= 8 cells, one round) {np.mean(u_self[cls1].sum(1) <= 8):.3f}")
+    u = (u_self | u_scene)[cls2]
+    print(f"class 2: unclear cells per motion {u.sum(1).mean():.2f} of 16; P(<= 8 cells) {np.mean(u.sum(1) <= 8):.3f}")
+
+cells()
