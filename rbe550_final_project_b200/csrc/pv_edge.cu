@@ -68,7 +68,10 @@ struct PvGatherOpt<true> {
 // LIST: the motions to validate are the entries of `list` (their count is read from *n_list: the certificate pass
 // below wrote both), and a valid motion sets its own bit in the zero-initialised word with an atomic.
 // SECT (LIST only): the sections of the check this instantiation contains (pv_check_config; 3 = all).
-template <bool CULL, int MODE, bool CARRY, bool GATHER = false, bool YAW = false, bool LIST = false, int SECT = 3>
+// APPEND (LIST only): a motion found valid is not final yet -- it is appended to out_list (length *out_n) for the kernel
+// that holds the other section, instead of setting its bit.
+template <bool CULL, int MODE, bool CARRY, bool GATHER = false, bool YAW = false, bool LIST = false, int SECT = 3,
+          bool APPEND = false>
 __global__ void __launch_bounds__(PV_E_THREADS, 1)
     pv_edge_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ aA, const float4* __restrict__ aB,
                    const float* __restrict__ a9, const float4* __restrict__ bA, const float4* __restrict__ bB,
@@ -76,7 +79,8 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
                    int64_t n_edges, int n_steps, float resolution, uint32_t* __restrict__ bits,
                    float* __restrict__ margin, int epw, unsigned char* __restrict__ ok_bytes,
                    const __grid_constant__ PvGatherOpt<GATHER> GO, const unsigned* __restrict__ list = nullptr,
-                   const unsigned* __restrict__ n_list = nullptr, unsigned* __restrict__ next_group = nullptr) {
+                   const unsigned* __restrict__ n_list = nullptr, unsigned* __restrict__ next_group = nullptr,
+                   unsigned* __restrict__ out_list = nullptr, unsigned* __restrict__ out_n = nullptr) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     if constexpr (LIST) n_edges = (int64_t)__ldg(n_list);
@@ -229,7 +233,18 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
                     if (epw == 32) pv_emit_word(bits, GO.g, w, word, lane);  // local word + peer / multicast stores
                 }
                 if constexpr (LIST) {  // epw == 32: lane i owns the i-th entry of this group
-                    if (lane < n_here && ((word >> lane) & 1u)) atomicOr(bits + (my_e >> 5), 1u << (my_e & 31u));
+                    const bool ok_ = lane < n_here && ((word >> lane) & 1u);
+                    if constexpr (APPEND) {
+                        const unsigned om_ = __ballot_sync(FULL, ok_);
+                        if (om_) {
+                            unsigned base_ = 0;
+                            if (lane == 0) base_ = atomicAdd(out_n, (unsigned)__popc(om_));
+                            base_ = __shfl_sync(FULL, base_, 0);
+                            if (ok_) out_list[base_ + __popc(om_ & ((1u << lane) - 1u))] = my_e;
+                        }
+                    } else if (ok_) {
+                        atomicOr(bits + (my_e >> 5), 1u << (my_e & 31u));
+                    }
                 } else if (lane == 0) {
                     if (epw == 32) {
                         if constexpr (!GATHER) bits[w] = word;
@@ -272,7 +287,7 @@ __global__ void __launch_bounds__(PV_E_THREADS, 1)
 #ifndef PV_CERT_THREADS
 #define PV_CERT_THREADS 256
 #endif
-__global__ void __launch_bounds__(PV_CERT_THREADS)
+__global__ void __launch_bounds__(PV_CERT_THREADS, 3)
     pv_edge_cert_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ aA, const float4* __restrict__ aB,
                         const float* __restrict__ a9, const float4* __restrict__ bA, const float4* __restrict__ bB,
                         const float* __restrict__ b9, int64_t n_edges, int n_steps, float resolution,
@@ -281,42 +296,58 @@ __global__ void __launch_bounds__(PV_CERT_THREADS)
     // the self-collision section only (class 1), and the others (class 2: the whole check); n_list[c - 1] = their lengths
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
-    const int64_t n_words = (n_edges + 31) >> 5;
+    const int64_t n_words = (n_edges + 31) >> 5;  // (n_edges < 2^32: the launcher checks)
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += n_warps) {
         unsigned word = 0;   // bit j: motion 32 w + j is certified valid
-        unsigned cls0 = 0, cls1 = 0;  // bit j of (cls0, cls1): class of motion 32 w + j (low, high bit)
+        // lane-parallel setup: lane L looks at motion 32 w + L -- its number of states, whether a certificate is sought
+        // (more than 32 states, both ends inside the joint limits, slack within the cap) and with which slack
+        const int64_t mine = w * 32 + lane;
+        float dl_m = 0.f;
+        int nd_m = 1;
+        if (mine < n_edges) {
+            float ea[9], eb[9];
+            pv_load_soa(aA, aB, a9, mine, ea);
+            pv_load_soa(bA, bB, b9, mine, eb);
+            const float reach[7] = PV_MOTION_REACH, lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
+            float d2 = 0.f, trav = fabsf(eb[7] - ea[7]) + fabsf(eb[8] - ea[8]);
+            bool in_ = true;  // both ends inside the joint limits: so is every state between them
+#pragma unroll
+            for (int c = 0; c < 9; ++c) {
+                const float de = eb[c] - ea[c];
+                d2 = fmaf(de, de, d2);
+                if (c < 7) trav = fmaf(fabsf(de), reach[c], trav);
+                in_ = in_ && ea[c] >= lo[c] && ea[c] <= hi[c] && eb[c] >= lo[c] && eb[c] <= hi[c];
+            }
+            int nd = n_steps;
+            if (nd <= 0) nd = max(1, (int)ceilf(sqrtf(d2) / resolution));  // as pv_edge_kernel counts them
+            const int h = ((nd + 15) >> 4) >> 1;
+            const float dl = fmaf(trav / (float)nd, (float)h * 1.0002f, 2e-5f);
+            nd_m = nd;
+            if (nd >= PV_CERT_MIN_ND && in_ && dl <= PV_MOTION_CERT_MAX_SLACK) dl_m = dl;
+        }
+        const unsigned seek = __ballot_sync(FULL, dl_m > 0.f);
+        // (cls0, cls1): bit j = class of motion 32 w + j, low and high bit; no certificate sought = the whole check
+        unsigned cls0 = 0, cls1 = ~seek;
         for (int it = 0; it < 16; ++it) {
-            const int64_t e = w * 32 + 2 * it + half;
-            unsigned st = 3;  // not certifiable: the whole check
-            if (e < n_edges) {
+            if (!((seek >> (2 * it)) & 3u)) continue;  // warp-uniform: neither motion of this pair seeks one
+            const int src = 2 * it + half;
+            const float dl = __shfl_sync(FULL, dl_m, src);
+            const int nd = __shfl_sync(FULL, nd_m, src);
+            unsigned st = 0;
+            if (dl > 0.f) {
+                const int64_t e = w * 32 + src;
                 float ea[9], eb[9];
-                pv_load_soa(aA, aB, a9, e, ea);
+                pv_load_soa(aA, aB, a9, e, ea);  // (L1 hits: the owner lane has just read them)
                 pv_load_soa(bA, bB, b9, e, eb);
-                const float reach[7] = PV_MOTION_REACH, lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
-                float d2 = 0.f, trav = fabsf(eb[7] - ea[7]) + fabsf(eb[8] - ea[8]);
-                bool a_in = true;  // both ends inside the joint limits: so is every state between them
+                const int s = (nd + 15) >> 4;
+                int k = nd - ((s - 1) >> 1) - sub * s;
+                if (k < 1) k = 1;
+                const float t = (float)k / (float)nd;
+                float q[9];
 #pragma unroll
-                for (int c = 0; c < 9; ++c) {
-                    const float de = eb[c] - ea[c];
-                    d2 = fmaf(de, de, d2);
-                    if (c < 7) trav = fmaf(fabsf(de), reach[c], trav);
-                    a_in = a_in && ea[c] >= lo[c] && ea[c] <= hi[c] && eb[c] >= lo[c] && eb[c] <= hi[c];
-                }
-                int nd = n_steps;
-                if (nd <= 0) nd = max(1, (int)ceilf(sqrtf(d2) / resolution));  // as pv_edge_kernel counts them
-                const int s = (nd + 15) >> 4, h = s >> 1;
-                const float inv_nd = 1.0f / (float)nd;
-                const float dl = fmaf(trav * inv_nd, (float)h * 1.0002f, 2e-5f);
-                if (nd >= PV_CERT_MIN_ND && a_in && dl <= PV_MOTION_CERT_MAX_SLACK) {
-                    int k = nd - ((s - 1) >> 1) - sub * s;
-                    if (k < 1) k = 1;
-                    const float t = (float)k * inv_nd;
-                    float q[9];
-#pragma unroll
-                    for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, eb[c] - ea[c], ea[c]);
-                    st = pv_cull_status<(PV_EDGE_FAST_TRIG != 0), false>(q, S, dl);
-                }
+                for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, eb[c] - ea[c], ea[c]);
+                st = pv_cull_status<(PV_EDGE_FAST_TRIG != 0), false>(q, S, dl);
             }
             // class of a motion = OR over its 16 states
             const unsigned m0 = __ballot_sync(FULL, st & 1u), m1 = __ballot_sync(FULL, st & 2u);
@@ -326,7 +357,6 @@ __global__ void __launch_bounds__(PV_CERT_THREADS)
             cls1 |= (a1 << (2 * it)) | (b1 << (2 * it + 1));
         }
         word = ~(cls0 | cls1);
-        const int64_t mine = w * 32 + lane;
         if (mine + 32 > n_edges) word &= (n_edges - w * 32 >= 32) ? 0xffffffffu : ((1u << (unsigned)(n_edges - w * 32)) - 1u);
         if (lane == 0) bits[w] = word;
         // the rest goes to the validators: append to the list of its class (one atomic per warp and class)
@@ -402,19 +432,21 @@ int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* 
         pv_edge_cert_kernel<<<cgrid, PV_CERT_THREADS, 0, st>>>(h->scene, (const float4*)aA, (const float4*)aB, a9,
                                                               (const float4*)bA, (const float4*)bB, b9, n, n_steps,
                                                               resolution, d_bits, d_list, scratch);
-#define PV_LAUNCH_EL(YAW_, SECT_, CLS_)                                                                             \
+        // class 2 first, through the instantiation that holds the scene section only: the motions it finds free of
+        // the scene (and above the plane) join list 1, and the self-collision-only instantiation finishes both classes
+#define PV_LAUNCH_EL(YAW_, SECT_, CLS_, APPEND_)                                                                    \
     {                                                                                                               \
-        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<true, PV_MODE_BITS, false, false, YAW_, true, SECT_>, \
+        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<true, PV_MODE_BITS, false, false, YAW_, true, SECT_, APPEND_>, \
                                PV_E_THREADS, words * 8);                                                            \
-        pv_edge_kernel<true, PV_MODE_BITS, false, false, YAW_, true, SECT_><<<grid, PV_E_THREADS, 0, st>>>(         \
+        pv_edge_kernel<true, PV_MODE_BITS, false, false, YAW_, true, SECT_, APPEND_><<<grid, PV_E_THREADS, 0, st>>>( \
             h->scene, (const float4*)aA, (const float4*)aB, a9, (const float4*)bA, (const float4*)bB, b9, nullptr,  \
             nullptr, n, n_steps, resolution, d_bits, nullptr, 4, nullptr, PvGatherOpt<false>{},                     \
-            d_list + (size_t)(CLS_ - 1) * (size_t)n, scratch + (CLS_ - 1), scratch + 2 + (CLS_ - 1));               \
+            d_list + (size_t)(CLS_ - 1) * (size_t)n, scratch + (CLS_ - 1), scratch + 2 + (CLS_ - 1), d_list, scratch); \
     }
         if (h->all_yaw) {
-            PV_LAUNCH_EL(true, 3, 2) PV_LAUNCH_EL(true, 1, 1)
+            PV_LAUNCH_EL(true, 2, 2, true) PV_LAUNCH_EL(true, 1, 1, false)
         } else {
-            PV_LAUNCH_EL(false, 3, 2) PV_LAUNCH_EL(false, 1, 1)
+            PV_LAUNCH_EL(false, 2, 2, true) PV_LAUNCH_EL(false, 1, 1, false)
         }
 #undef PV_LAUNCH_EL
         if (gather_on) {

@@ -345,7 +345,9 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
                 q[8] = q9 ? M.st9[r & 1][tid] : b.w;
             }
             if (r + 1 < nc) PV_PREFETCH(r + 1)
-#if PV_SB_BAR_GROUPS > 1  // experiment: lockstep inside groups of warps only (named barriers)
+#if PV_SB_BAR_GROUPS == 0  // experiment: free-running warps
+            __syncwarp();
+#elif PV_SB_BAR_GROUPS > 1  // experiment: lockstep inside groups of warps only (named barriers)
             asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / (PV_SB_THREADS / PV_SB_BAR_GROUPS)), "n"(PV_SB_THREADS / PV_SB_BAR_GROUPS) : "memory");
 #else
             __syncthreads();  // lockstep: the 16 warps of the block share instruction fetches

@@ -13,6 +13,10 @@ n = 1 << 20
 rng = np.random.default_rng(20251212)
 qa = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n, 9)).astype(np.float32); qa[:, 7:] = 0.04
 qb = np.clip(qa + rng.normal(0, 0.3, qa.shape), pm.Q_LOWER, pm.Q_UPPER).astype(np.float32); qb[:, 7:] = 0.04
+if os.environ.get("PV_PAIRS") == "uniform":
+    qb = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n, 9)).astype(np.float32); qb[:, 7:] = 0.04
+if os.environ.get("PV_CULL"):
+    pv.set_culling(int(os.environ["PV_CULL"]))
 A = soa_from_aos(torch.as_tensor(qa, device="cuda")); B = soa_from_aos(torch.as_tensor(qb, device="cuda"))
 out = torch.empty(n // 32, dtype=torch.int32, device="cuda")
 for _ in range(3):
