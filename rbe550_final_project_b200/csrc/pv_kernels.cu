@@ -46,8 +46,14 @@ static char g_create_error[512] = "";
 #ifndef PV_SB_SYNC
 #define PV_SB_SYNC 0
 #endif
+// Lockstep of the sorted kernel's main loop: 1 = one block barrier per iteration (what made the 60 KB loop of round 1
+// share its instruction fetches), n > 1 = named barriers inside n groups of warps, 0 = none.  Since the scene section left
+// the loop (PV_COLD_SCENE) and the general sphere-vs-box tests left the kernel (YAW), the loop is 27 KB and fits the
+// instruction cache: free-running warps no longer miss, and the barrier -- the top stall, 1.39 warp-cycles per issue -- only
+// made every warp wait for the slowest.  Same box, resident 2 Mi batch: goal 1 22.6 -> 23.8, tower 16.4 -> 16.9, pentagon
+// 21.3 -> 22.1 G checks/s (groups of 4 warps: 23.1 / 16.4 / 21.5).
 #ifndef PV_SB_BAR_GROUPS
-#define PV_SB_BAR_GROUPS 1
+#define PV_SB_BAR_GROUPS 0
 #endif
 #ifndef PV_SB_MINB
 #define PV_SB_MINB 1
@@ -191,8 +197,10 @@ struct PvSortSmem {
     unsigned vbits[PV_ST / 32];
     int cnt;
     // PV_COLD_SCENE: the configurations of the super-tile whose scene section is still owed are noted by the main loop
-    // and worked off densely after it.  The list lives in `order` itself, from the front: iteration r only reads entries
-    // >= r * 512 (and prefetches those of r + 1), while at most (r + 1) * 512 configurations can owe by then
+    // and worked off densely after it.  The list has an array of its own: the warps of the main loop run free (no
+    // lockstep barrier any more, see the loop), so a fast warp may note configurations while a slow one still reads the
+    // early entries of `order`.
+    unsigned short owed[PV_ST];
     int n_owed;
 };
 // where the configurations come from: two float4 planes (+ optional ninth plane) or (n, 9) rows.  (The device-generated
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
                 q[8] = q9 ? M.st9[r & 1][tid] : b.w;
             }
             if (r + 1 < nc) PV_PREFETCH(r + 1)
-#if PV_SB_BAR_GROUPS == 0  // experiment: free-running warps
+#if PV_SB_BAR_GROUPS == 0  // free-running warps (the default)
             __syncwarp();
 #elif PV_SB_BAR_GROUPS > 1  // experiment: lockstep inside groups of warps only (named barriers)
             asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / (PV_SB_THREADS / PV_SB_BAR_GROUPS)), "n"(PV_SB_THREADS / PV_SB_BAR_GROUPS) : "memory");
@@ -358,7 +366,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
             if (in && !acc.hit) {
                 // the few configurations that come near the scene boxes (~2 % in the goal scenes) are only NOTED here:
                 // their scene section runs after the loop, densely packed, instead of in a sparsely populated warp now
-                if (COLD && owes) order[atomicAdd(&M.n_owed, 1)] = (unsigned short)L;
+                if (COLD && owes) M.owed[atomicAdd(&M.n_owed, 1)] = (unsigned short)L;
                 else atomicOr(&vbits[L >> 5], 1u << (L & 31));
             }
         }
@@ -369,7 +377,7 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
                 const int e = base + tid;
                 if (e >= n_owed) continue;  // (no barrier inside this loop)
                 const bool have = true;
-                const int L = order[e];
+                const int L = M.owed[e];
                 const unsigned i_ = PV_OFF(L / PV_SB_THREADS, L % PV_SB_THREADS);
                 float q[9];
                 if constexpr (AOS) pv_load_aos(t_aos, (int64_t)i_, q);

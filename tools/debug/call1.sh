@@ -1,0 +1,11 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/s4_gputest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s4_gputest.log
+timeout 400 python bench.py > gpurun_out/s4_bench.json 2> gpurun_out/s4_bench.err; echo "bench rc=$?" >> gpurun_out/s4_bench.err
+M=smsp__sass_thread_inst_executed_op_ffma_pred_on.sum,smsp__sass_thread_inst_executed_op_fadd_pred_on.sum,smsp__sass_thread_inst_executed_op_fmul_pred_on.sum,smsp__thread_inst_executed.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum
+timeout 300 ncu --metrics $M --clock-control none -k regex:pv_state_bits_sorted -s 2 -c 1 --csv --log-file gpurun_out/s4_state_counts.csv python tools/prof_state.py > gpurun_out/s4_ncu1.log 2>&1
+timeout 300 ncu --metrics $M --clock-control none -k regex:pv_edge -s 6 -c 3 --csv --log-file gpurun_out/s4_edge_counts.csv python tools/prof_edge.py > gpurun_out/s4_ncu2.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:pv_state_bits_sorted -s 2 -c 1 -o gpurun_out/s4_state python tools/prof_state.py > gpurun_out/s4_ncu3.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:pv_edge -s 6 -c 3 -o gpurun_out/s4_edge python tools/prof_edge.py > gpurun_out/s4_ncu4.log 2>&1
+tail -3 gpurun_out/s4_gputest.log; cat gpurun_out/s4_bench.json | cut -c1-1500
