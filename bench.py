@@ -247,7 +247,14 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the validity path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = None
     if world > 1:
+        # one process per GPU: this rank onto the CPUs (and memory) of its GPU's socket before anything is pinned, so that
+        # eight ranks do not feed eight PCIe links out of one socket's memory (hostmem.py).  N = 1 stays unbound: the CPU
+        # baseline of that run uses every host thread.
+        from rbe550_final_project_b200.hostmem import bind_to_gpu_numa
+        numa = bind_to_gpu_numa(local) if os.environ.get("PV_BENCH_NO_NUMA") != "1" else {"bound": False, "why": "PV_BENCH_NO_NUMA"}
+        print(f"[bench] rank {rank}: host placement {numa}", file=sys.stderr)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -479,7 +486,7 @@ def main():
                         "layout": "SoA float4 x2", "parallelism": f"shard{world}" + (f"+{gather_mode}" if world > 1 else ""),
                         "timed_region_ms": ms},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": words * 4,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": words * 4, "numa_rank0": numa,
                 "steps": e2e_steps, "configs_per_step": n * world,
                 "call": "pv_check_states_host_arm (pinned host rows of the 7 arm joints + the gripper opening once in, "
                         "verdict bits out), one batch per call, wall clock",
