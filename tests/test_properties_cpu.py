@@ -74,3 +74,15 @@ def test_oracle_monotone_under_inflation_and_edge_is_and_of_states(seed, scale):
     states = q[:6, None, :] + t * (qb[:6, None, :] - q[:6, None, :])
     sm = po.state_margin(states.reshape(-1, 9), s, model).reshape(6, 8).min(1)
     assert np.allclose(e, sm, atol=1e-12)
+
+
+def test_host_placement_never_raises_and_keeps_the_affinity_without_a_gpu():
+    """hostmem.bind_to_gpu_numa is an optimisation for multi-socket hosts: without NVML / a GPU it must change nothing."""
+    import os
+
+    from rbe550_final_project_b200.hostmem import bind_to_gpu_numa
+
+    before = os.sched_getaffinity(0)
+    info = bind_to_gpu_numa(0)
+    assert info["bound"] is False and "why" in info
+    assert os.sched_getaffinity(0) == before
