@@ -76,6 +76,12 @@ struct PvAcc;
 template <>
 struct PvAcc<PV_MODE_BITS> {
     bool hit = false;
+    // SLK instantiations of pv_check_config (second-tier motion certificates, pv_edge_cert2_kernel): the self-collision
+    // tests accumulate min(d^2 - r^2) in mslk instead of setting hit -- a contact is mslk < 0, exactly the comparison the
+    // other instantiations make, and a test that clears by less than dl metres is mslk < (2 PV_SELF_R_MAX + cap) dl; the
+    // culls in front of them and the plane tests compare with dl of slack (nearp: the plane is within dl)
+    float mslk = 1e30f, dl = 0.f;
+    bool nearp = false;
     // packed tests accumulate min(d^2 - r^2) here (one FMNMX3 per two tests); hit |= min(m) < 0 at the end.  PV_PACK_ACC
     // independent accumulators keep the FMNMX3 chain from serialising the tests.
     float m[4] = {1e30f, 1e30f, 1e30f, 1e30f};
@@ -274,7 +280,7 @@ __device__ __forceinline__ void pv_sphere_box_yaw_k(PvAcc<MODE>& acc, float3 c, 
 }
 
 // sphere already expressed in the box's frame (loc = R^T (c - origin)) vs a box with centre bcl in that frame
-template <int MODE>
+template <int MODE, bool SLK = false>
 __device__ __forceinline__ void pv_sphere_box_local(PvAcc<MODE>& acc, float3 loc, float r, float r2, float3 bcl, float3 oh,
                                                     int code) {
     float ex = fabsf(loc.x - bcl.x) - oh.x;
@@ -282,7 +288,9 @@ __device__ __forceinline__ void pv_sphere_box_local(PvAcc<MODE>& acc, float3 loc
     float ez = fabsf(loc.z - bcl.z) - oh.z;
     float px = fmaxf(ex, 0.f), py = fmaxf(ey, 0.f), pz = fmaxf(ez, 0.f);
     float s2 = fmaf(pz, pz, fmaf(py, py, px * px));
-    if constexpr (MODE == PV_MODE_BITS) {
+    if constexpr (MODE == PV_MODE_BITS && SLK) {
+        acc.mslk = fminf(acc.mslk, s2 - r2);  // (s2 - r2 < 0 exactly when s2 < r2)
+    } else if constexpr (MODE == PV_MODE_BITS) {
         acc.hit |= (s2 < r2);
     } else {
         float g = (s2 > 0.f ? sqrtf(s2) : fmaxf(ex, fmaxf(ey, ez))) - r;
@@ -290,22 +298,25 @@ __device__ __forceinline__ void pv_sphere_box_local(PvAcc<MODE>& acc, float3 loc
     }
 }
 
-template <int MODE>
+template <int MODE, bool SLK = false>
 __device__ __forceinline__ void pv_sphere_sphere(PvAcc<MODE>& acc, float3 a, float3 b, float rr2, float rr, int code) {
     float3 d = v_sub(a, b);
     float d2 = v_dot(d, d);
-    if constexpr (MODE == PV_MODE_BITS) {
+    if constexpr (MODE == PV_MODE_BITS && SLK) {
+        acc.mslk = fminf(acc.mslk, d2 - rr2);  // (d2 - rr2 < 0 exactly when d2 < rr2)
+    } else if constexpr (MODE == PV_MODE_BITS) {
         acc.hit |= (d2 < rr2);
     } else {
         acc.take(sqrtf(d2) - rr, code);
     }
 }
 
-template <int MODE>
+template <int MODE, bool SLK = false>
 __device__ __forceinline__ void pv_plane(PvAcc<MODE>& acc, float lowest, float table_z, int code) {
     float g = lowest - table_z;
     if constexpr (MODE == PV_MODE_BITS) {
         acc.hit |= (g < 0.f);
+        if constexpr (SLK) acc.nearp |= !(g >= acc.dl);
     } else {
         acc.take(g, code);
     }
@@ -640,6 +651,16 @@ __device__ __noinline__ bool pv_scene_cold(LOAD load, const PvScene& S) {
     return acc.hit;
 }
 
+// slack thresholds of the motion certificates (pv_cull_status and the SLK form of pv_check_config):
+template <bool SLK, class ACC>
+__device__ __forceinline__ float pv_slk_dl(const ACC& a) {
+    if constexpr (SLK) return a.dl;
+    else return 0.f;
+}
+// (r + dl)^2 <= r^2 + (2 r + PV_MOTION_CERT_MAX_SLACK) dl for 0 <= dl <= PV_MOTION_CERT_MAX_SLACK; r2 is a literal, so
+// the factor folds to a constant (the 1.001 covers the rounding of the fold and of the FFMA)
+#define PV_SLK_THR(r2, dl) fmaf((2.0f * sqrtf(r2) + PV_MOTION_CERT_MAX_SLACK) * 1.001f, dl, r2)
+
 // Returns through `acc`.  All 32 lanes of a warp must call this together when EXIT != PV_EXIT_NONE.
 // SYNC: every warp of the block calls this together and block-level barriers keep the warps within one
 // code region of each other, so the (large, straight-line) instruction stream is fetched once per SM instead
@@ -647,8 +668,12 @@ __device__ __noinline__ bool pv_scene_cold(LOAD load, const PvScene& S) {
 // DEFER: do not run the scene section, return whether it is needed (see pv_scene_cold); the return value is false
 // whenever the section has been dealt with here.
 template <int MODE, bool CULL, int EXIT, int SYNC = 0, bool FMAK = false, bool CARRY = false, bool FTRIG = FMAK,
-          bool DEFER = false, bool YAW = false, int SECT = 3>
+          bool DEFER = false, bool YAW = false, int SECT = 3, bool SLK = false>
 __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S, PvAcc<MODE>& acc) {
+    // SLK (self-collision-only verdict bits, no early exit): the check ALSO says whether the configuration clears every
+    // test by acc.dl metres -- see PvAcc<PV_MODE_BITS>::mslk.  The caller reads acc.hit | (acc.mslk < 0) for the verdict
+    // (bit-identical to the other instantiations') and acc.nearp | (acc.mslk < slack threshold) for the clearance.
+    static_assert(!SLK || (SECT == 1 && MODE == PV_MODE_BITS && EXIT == PV_EXIT_NONE && !PV_PACK), "slack form: self-collision section, bits");
     // SECT: which sections exist at all in this instantiation -- bit 0 the self-collision section, bit 1 the scene-level
     // test and the scene section.  The motion validator routes motions that provably never need one of them (their
     // coarse states clear all of its culls with slack: pv_cull_status) to a kernel compiled without it: 30 KB of code
@@ -690,7 +715,7 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
     // ---- robot vs ground plane (link0 is fixed to the world: pair filtered) -------------
     const float tz = S.table_z;
     if constexpr (MODE == PV_MODE_BITS && PV_TABLE_MIN) {
-        pv_plane<MODE>(acc, PV_TABLE_LOWEST(s), tz, 0);
+        pv_plane<MODE, SLK>(acc, PV_TABLE_LOWEST(s), tz, 0);
     } else {
 #define PV_TABLE_SPHERE(i, link, cx, cy, cz, r) \
     if (link != 0) pv_plane<MODE>(acc, s[i].z - r, tz, PV_CODE(1, link, 0));
@@ -700,7 +725,7 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float ext = fmaf(fabsf(hZ.z), pv_bh[k][2], fmaf(fabsf(hY.z), pv_bh[k][1], fabsf(hX.z) * pv_bh[k][0]));
-        pv_plane<MODE>(acc, bc[k].z - ext, tz, PV_CODE(1, pv_blink[k], 0));
+        pv_plane<MODE, SLK>(acc, bc[k].z - ext, tz, PV_CODE(1, pv_blink[k], 0));
     }
     // ---- carried box: placed by the hand, checked against the plane and the arm spheres of link0..link6 --------
     if constexpr (CARRY) {
@@ -716,12 +741,12 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
 
     // ---- self collision ------------------------------------------------------------------------------
     if ((SECT & 1) && (S.flags & PV_FLAG_SELF)) {
-#define PV_SS(a, b, rr2, rr) pv_sphere_sphere<MODE>(acc, s[a], s[b], rr2, rr, PV_SELF_CODE(a, pv_sphere_link[b]));
+#define PV_SS(a, b, rr2, rr) pv_sphere_sphere<MODE, SLK>(acc, s[a], s[b], rr2, rr, PV_SELF_CODE(a, pv_sphere_link[b]));
 #define PV_SS2(a, b0, b1, n0, n1, k) pv_sphere_sphere2<k>(acc, s[a], s[b0], s[b1], n0, n1);
 #define PV_LP(la, lb, ca, cb, cull2)                         \
     {                                                        \
         float3 d_ = v_sub(s[ca], s[cb]);                     \
-        if (!CULL || v_dot(d_, d_) < cull2) {                \
+        if (!CULL || v_dot(d_, d_) < (SLK ? PV_SLK_THR(cull2, pv_slk_dl<SLK>(acc)) : cull2)) { \
             if constexpr (MODE == PV_MODE_BITS && PV_PACK) { \
                 PV_SS2_PAIRS_##la##_##lb(PV_SS2)             \
             } else {                                         \
@@ -760,7 +785,7 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
         lr_ = r;                                                                                        \
         lr2_ = r2;                                                                                      \
     }
-#define PV_SBH_B(a, k) pv_sphere_box_local<MODE>(acc, loc_, lr_, lr2_, bcl[k], bhl[k], PV_SELF_CODE(a, 8 + k));
+#define PV_SBH_B(a, k) pv_sphere_box_local<MODE, SLK>(acc, loc_, lr_, lr2_, bcl[k], bhl[k], PV_SELF_CODE(a, 8 + k));
         // links that pair with all three gripper boxes are culled against the one gripper ball, the others against
         // the bounding balls of the boxes they pair with
 #define PV_LB(la, ca, c0, c1, c2, rla)                                                                  \
@@ -769,10 +794,12 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
         if ((c0) > 0.f) {                                                                               \
             float3 d0_ = v_sub(s[ca], bc[0]);                                                           \
             float rr_ = (rla) + grip_r;                                                                 \
+            if constexpr (SLK) rr_ += pv_slk_dl<SLK>(acc);                                                      \
             near_ = v_dot(d0_, d0_) < rr_ * rr_;                                                        \
         } else {                                                                                        \
             float3 d1_ = v_sub(s[ca], bc[1]), d2_ = v_sub(s[ca], bc[2]);                                \
-            near_ = v_dot(d1_, d1_) < c1 || v_dot(d2_, d2_) < c2;                                       \
+            near_ = v_dot(d1_, d1_) < (SLK ? PV_SLK_THR(c1, pv_slk_dl<SLK>(acc)) : c1) ||                            \
+                    v_dot(d2_, d2_) < (SLK ? PV_SLK_THR(c2, pv_slk_dl<SLK>(acc)) : c2);                              \
         }                                                                                               \
         if (!CULL || near_) {                                                                           \
             PV_SBH_##la(PV_SBH_S, PV_SBH_B)                                                             \
@@ -835,9 +862,6 @@ __device__ __forceinline__ bool pv_check_config(const float* q, const PvScene& S
 // being tested (pv_edge_cert_kernel, csrc/pv_edge.cu; panda_model.motion_reach_bounds bounds the travel).  The
 // comparisons are written so that a non-finite value never certifies.  The placement is pv_place's: only the handful of
 // centres the culls look at and the z coordinates survive dead-code elimination (~520 instructions, 10 KB of code).
-// (r + dl)^2 <= r^2 + (2 r + PV_MOTION_CERT_MAX_SLACK) dl for 0 <= dl <= PV_MOTION_CERT_MAX_SLACK; r2 is a literal, so
-// the factor folds to a constant (the 1.001 covers the rounding of the fold and of the FFMA)
-#define PV_SLK_THR(r2, dl) fmaf((2.0f * sqrtf(r2) + PV_MOTION_CERT_MAX_SLACK) * 1.001f, dl, r2)
 // Returns 0 when everything is clear; bit 0: limits, ground plane or a self-collision cull within dl; bit 1: the
 // scene-level test within dl.
 // LIMITS = false: the caller vouches for the joint limits (both ends of a motion inside them: so is every state between).

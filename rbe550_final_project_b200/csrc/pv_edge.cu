@@ -373,6 +373,110 @@ __global__ void __launch_bounds__(PV_CERT_THREADS, 3)
     }
 }
 
+// Second-tier certificate (self-collision section): the motions the first pass could not finish but proved free of the
+// scene (list 1: class 1 and the survivors of the scene-only validator) keep some self-collision cull busy along the whole
+// motion -- 14 of their 16 coarse cells on average -- yet most of the valid ones are valid COMFORTABLY.  This kernel runs the
+// self-collision section itself at the same 16 coarse states, two motions per warp, with `dl` metres of slack on every cull
+// and every test (the SLK form of pv_check_config; dl = the travel bound over the half-spacing of the coarse states, as
+// in pv_edge_cert_kernel):
+//   * a contact at a coarse state -- the very comparison the validator makes at that state (same interpolation
+//     formula, same instantiation flags) -- makes the motion invalid: done, its bit stays 0;
+//   * every coarse state clears everything by dl: every state of the motion is free of contact: done, bit set;
+//   * otherwise the motion goes on to the exhaustive self-collision-only validator (out_list).
+// Offline (tools/probes/edge_round_cert_model.py, config 3): 41 % of list 1 certifies and most of its 41 % invalid motions
+// show their contact at a coarse state, so about a quarter is left for the 64-state validator.
+#ifndef PV_EDGE_CERT2
+#define PV_EDGE_CERT2 1
+#endif
+#ifndef PV_CERT2_THREADS
+#define PV_CERT2_THREADS 512  // 123 registers, no spills (384: 153 registers, -1.3 %; 640: 96 registers with 36 B of spills, same)
+#endif
+template <bool YAW>
+__global__ void __launch_bounds__(PV_CERT2_THREADS, 1)
+    pv_edge_cert2_kernel(const __grid_constant__ PvScene S, const float4* __restrict__ aA, const float4* __restrict__ aB,
+                         const float* __restrict__ a9, const float4* __restrict__ bA, const float4* __restrict__ bB,
+                         const float* __restrict__ b9, int n_steps, float resolution, uint32_t* __restrict__ bits,
+                         const unsigned* __restrict__ list, const unsigned* __restrict__ n_list,
+                         unsigned* __restrict__ next_group, unsigned* __restrict__ out_list, unsigned* __restrict__ out_n) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+    const unsigned n = __ldg(n_list), n_groups = (n + 31u) >> 5;
+    // a test of radius (sum) r clears by dl when d^2 - r^2 >= (2 r + dl) dl; r <= PV_SELF_R_MAX, dl <= the cap
+    const float slk_k = (2.0f * PV_SELF_R_MAX + PV_MOTION_CERT_MAX_SLACK) * 1.001f;
+    for (;;) {
+        unsigned g = 0;
+        if (lane == 0) g = atomicAdd(next_group, 1u);
+        g = __shfl_sync(FULL, g, 0);
+        if (g >= n_groups) break;
+        const unsigned at = g * 32u + (unsigned)lane;
+        const bool have = at < n;
+        const unsigned mine = have ? __ldg(list + at) : 0u;
+        // lane-parallel setup, as in pv_edge_cert_kernel
+        float dl_m = 0.f;
+        int nd_m = 1;
+        if (have) {
+            float ea[9], eb[9];
+            pv_load_soa(aA, aB, a9, (int64_t)mine, ea);
+            pv_load_soa(bA, bB, b9, (int64_t)mine, eb);
+            const float reach[7] = PV_MOTION_REACH, lo[9] = PV_Q_LOWER, hi[9] = PV_Q_UPPER;
+            float d2 = 0.f, trav = fabsf(eb[7] - ea[7]) + fabsf(eb[8] - ea[8]);
+            bool in_ = true;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) {
+                const float de = eb[c] - ea[c];
+                d2 = fmaf(de, de, d2);
+                if (c < 7) trav = fmaf(fabsf(de), reach[c], trav);
+                in_ = in_ && ea[c] >= lo[c] && ea[c] <= hi[c] && eb[c] >= lo[c] && eb[c] <= hi[c];
+            }
+            int nd = n_steps;
+            if (nd <= 0) nd = max(1, (int)ceilf(sqrtf(d2) / resolution));
+            const int h = ((nd + 15) >> 4) >> 1;
+            const float dl = fmaf(trav / (float)nd, (float)h * 1.0002f, 2e-5f);
+            nd_m = nd;
+            if (nd >= PV_CERT_MIN_ND && in_ && dl <= PV_MOTION_CERT_MAX_SLACK) dl_m = dl;
+        }
+        const unsigned seek = __ballot_sync(FULL, dl_m > 0.f);
+        unsigned hit_m = 0, near_m = ~seek;  // bit j: the motion of lane j has a contact / is not cleared (or seeks nothing)
+        for (int it = 0; it < 16; ++it) {
+            if (!((seek >> (2 * it)) & 3u)) continue;  // warp-uniform
+            const int src = 2 * it + half;
+            const float dl = __shfl_sync(FULL, dl_m, src);
+            const int nd = __shfl_sync(FULL, nd_m, src);
+            const unsigned e = __shfl_sync(FULL, mine, src);
+            bool hit = false, near = false;
+            if (dl > 0.f) {
+                float ea[9], eb[9];
+                pv_load_soa(aA, aB, a9, (int64_t)e, ea);  // (L1 hits: the owner lane has just read them)
+                pv_load_soa(bA, bB, b9, (int64_t)e, eb);
+                const int s = (nd + 15) >> 4;
+                int k = nd - ((s - 1) >> 1) - sub * s;
+                if (k < 1) k = 1;
+                const float t = (float)k * (1.0f / (float)nd);  // the validator's expression: state k bit for bit
+                float q[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) q[c] = (k == nd) ? eb[c] : fmaf(t, eb[c] - ea[c], ea[c]);
+                PvAcc<PV_MODE_BITS> acc;
+                acc.dl = dl;
+                pv_check_config<PV_MODE_BITS, true, PV_EXIT_NONE, 0, false, false, (PV_EDGE_FAST_TRIG != 0), false, YAW, 1, true>(q, S, acc);
+                hit = acc.hit || acc.mslk < 0.f;
+                near = acc.nearp || !(acc.mslk >= slk_k * dl);
+            }
+            const unsigned hb = __ballot_sync(FULL, hit), nb = __ballot_sync(FULL, near);
+            hit_m |= (((hb & 0xffffu) ? 1u : 0u) << (2 * it)) | (((hb >> 16) ? 1u : 0u) << (2 * it + 1));
+            near_m |= (((nb & 0xffffu) ? 1u : 0u) << (2 * it)) | (((nb >> 16) ? 1u : 0u) << (2 * it + 1));
+        }
+        const bool my_hit = (hit_m >> lane) & 1u, my_near = (near_m >> lane) & 1u;
+        if (have && !my_hit && !my_near) atomicOr(bits + (mine >> 5), 1u << (mine & 31u));
+        const unsigned fwd = __ballot_sync(FULL, have && !my_hit && my_near);
+        if (fwd) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(out_n, (unsigned)__popc(fwd));
+            base = __shfl_sync(FULL, base, 0);
+            if ((fwd >> lane) & 1u) out_list[base + __popc(fwd & ((1u << lane) - 1u))] = mine;
+        }
+    }
+}
+
 // Fused verdict gather behind the certificate pipeline: its verdict words are complete only after the last list kernel,
 // so a small kernel then stores them into every rank's gather buffer (one multimem.st per word through the NVSwitch
 // multicast address, or one peer store per rank) -- still no collective launch and no host round trip.
@@ -425,29 +529,48 @@ int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* 
             uint64_t keep = ~0ull;
             PV_CUDA(h, cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep));
         }
-        PV_CUDA(h, cudaMallocFromPoolAsync((void**)&scratch, (2 * (size_t)n + 64) * sizeof(unsigned), h->pool, st));
-        unsigned* d_list = scratch + 64;  // scratch[0..1] = lengths of the two lists, scratch[2..3] = their group counters
+        PV_CUDA(h, cudaMallocFromPoolAsync((void**)&scratch, (3 * (size_t)n + 64) * sizeof(unsigned), h->pool, st));
+        // scratch[0], [1], [4] = lengths of lists 1, 2, 3; [2], [3], [5] = their group counters, [6] = the group counter of
+        // the second-tier certificate pass over list 1; then the three lists of n entries each
+        unsigned* d_list = scratch + 64;
         PV_CUDA(h, cudaMemsetAsync(scratch, 0, 8 * sizeof(unsigned), st));
         const int cgrid = pv_grid_for(h, (const void*)pv_edge_cert_kernel, PV_CERT_THREADS, words);
         pv_edge_cert_kernel<<<cgrid, PV_CERT_THREADS, 0, st>>>(h->scene, (const float4*)aA, (const float4*)aB, a9,
                                                               (const float4*)bA, (const float4*)bB, b9, n, n_steps,
                                                               resolution, d_bits, d_list, scratch);
         // class 2 first, through the instantiation that holds the scene section only: the motions it finds free of
-        // the scene (and above the plane) join list 1, and the self-collision-only instantiation finishes both classes
-#define PV_LAUNCH_EL(YAW_, SECT_, CLS_, APPEND_)                                                                    \
+        // the scene (and above the plane) join list 1; the second-tier certificate finishes most of list 1 at 16 states
+        // a motion and passes the rest on (list 3) to the self-collision-only instantiation
+#define PV_LAUNCH_EL(YAW_, SECT_, APPEND_, LIST_, NLIST_, GROUP_)                                                   \
     {                                                                                                               \
-        int grid = pv_grid_for(h, (const void*)pv_edge_kernel<true, PV_MODE_BITS, false, false, YAW_, true, SECT_, APPEND_>, \
-                               PV_E_THREADS, words * 8);                                                            \
-        pv_edge_kernel<true, PV_MODE_BITS, false, false, YAW_, true, SECT_, APPEND_><<<grid, PV_E_THREADS, 0, st>>>( \
+        auto kern_ = pv_edge_kernel<true, PV_MODE_BITS, false, false, YAW_, true, SECT_, APPEND_>;                  \
+        int grid = pv_grid_for(h, (const void*)kern_, PV_E_THREADS, words * 8);                                     \
+        kern_<<<grid, PV_E_THREADS, 0, st>>>(                                                                       \
             h->scene, (const float4*)aA, (const float4*)aB, a9, (const float4*)bA, (const float4*)bB, b9, nullptr,  \
-            nullptr, n, n_steps, resolution, d_bits, nullptr, 4, nullptr, PvGatherOpt<false>{},                     \
-            d_list + (size_t)(CLS_ - 1) * (size_t)n, scratch + (CLS_ - 1), scratch + 2 + (CLS_ - 1), d_list, scratch); \
+            nullptr, n, n_steps, resolution, d_bits, nullptr, 4, nullptr, PvGatherOpt<false>{}, LIST_, NLIST_,      \
+            GROUP_, d_list, scratch);                                                                               \
     }
+#define PV_LAUNCH_C2(YAW_)                                                                                          \
+    {                                                                                                               \
+        int grid = pv_grid_for(h, (const void*)pv_edge_cert2_kernel<YAW_>, PV_CERT2_THREADS, words * 8);            \
+        pv_edge_cert2_kernel<YAW_><<<grid, PV_CERT2_THREADS, 0, st>>>(                                              \
+            h->scene, (const float4*)aA, (const float4*)aB, a9, (const float4*)bA, (const float4*)bB, b9, n_steps,  \
+            resolution, d_bits, d_list, scratch, scratch + 6, d_list + 2 * (size_t)n, scratch + 4);                 \
+    }
+        const bool tier2 = PV_EDGE_CERT2 && h->edge_cert2;
+        unsigned* l1 = tier2 ? d_list + 2 * (size_t)n : d_list;  // what the self-collision-only validator works off
+        unsigned* l1n = tier2 ? scratch + 4 : scratch;
+        unsigned* l1g = tier2 ? scratch + 5 : scratch + 2;
         if (h->all_yaw) {
-            PV_LAUNCH_EL(true, 2, 2, true) PV_LAUNCH_EL(true, 1, 1, false)
+            PV_LAUNCH_EL(true, 2, true, d_list + (size_t)n, scratch + 1, scratch + 3)
+            if (tier2) PV_LAUNCH_C2(true)
+            PV_LAUNCH_EL(true, 1, false, l1, l1n, l1g)
         } else {
-            PV_LAUNCH_EL(false, 2, 2, true) PV_LAUNCH_EL(false, 1, 1, false)
+            PV_LAUNCH_EL(false, 2, true, d_list + (size_t)n, scratch + 1, scratch + 3)
+            if (tier2) PV_LAUNCH_C2(false)
+            PV_LAUNCH_EL(false, 1, false, l1, l1n, l1g)
         }
+#undef PV_LAUNCH_C2
 #undef PV_LAUNCH_EL
         if (gather_on) {
             int egrid = (int)((words + 255) / 256);
@@ -457,7 +580,7 @@ int pv_launch_edges(PvHandle* h, const float* aA, const float* aB, const float* 
         }
         PV_CUDA(h, cudaGetLastError());
         PV_CUDA(h, cudaFreeAsync(scratch, st));
-        h->launches += 3;
+        h->launches += tier2 ? 4 : 3;
         return PV_OK;
     }
 #endif

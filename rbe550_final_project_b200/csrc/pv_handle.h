@@ -51,6 +51,7 @@ struct PvHandle {
     int has_scene;
     int all_yaw;  // every scene box is rotated about world z only: the kernels' YAW instantiations apply (pv_device.cuh)
     int cull;
+    int edge_cert2;      // second-tier motion certificates (pv_edge_cert2_kernel); on unless the environment says PV_EDGE_CERT2=0 at pv_create
     int launch_overlap;  // state-check launches carry the programmatic-stream-serialization attribute (pv_set_launch_overlap)
     unsigned smem_attr_mask;  // which sorted-kernel instantiations already have their dynamic shared memory opt-in
     long long launches;

@@ -731,6 +731,10 @@ int pv_create(int device, PvHandle** out) {
     h->scene.base[2] = 0.01f;
     h->cull = 2;
     h->launch_overlap = 1;
+    {
+        const char* e2 = getenv("PV_EDGE_CERT2");  // developer switch for same-box A/B runs
+        h->edge_cert2 = !(e2 && e2[0] == '0');
+    }
     PvDeviceGuard guard(device);  // the streams are created on `device`; the caller's current device is put back
     if ((e = cudaGetLastError()) != cudaSuccess) {
         snprintf(g_create_error, sizeof(g_create_error), "cudaSetDevice: %s", cudaGetErrorString(e));

@@ -412,6 +412,9 @@ def header_text() -> str:
     a("// motion certificates (motion_reach_bounds): R_j of the seven revolute joints, and the largest slack ever sought")
     a("#define PV_MOTION_REACH {" + ", ".join(_f(v * 1.0001) for v in motion_reach_bounds()) + "}")
     a(f"#define PV_MOTION_CERT_MAX_SLACK {_f(MOTION_CERT_MAX_SLACK)}")
+    a("// the largest radius (sum) any self-collision test compares a distance with: sphere pairs, sphere vs gripper box")
+    rs_ = max([float(SPHERE_RADIUS[a_] + SPHERE_RADIUS[b_]) for a_, b_ in SS_PAIRS] + [float(SPHERE_RADIUS[a_]) for a_, _ in SB_PAIRS])
+    a(f"#define PV_SELF_R_MAX {_f(rs_ * 1.0001)}")
     a("// joint limits")
     a("#define PV_Q_LOWER {" + ", ".join(_f(v) for v in Q_LOWER) + "}")
     a("#define PV_Q_UPPER {" + ", ".join(_f(v) for v in Q_UPPER) + "}")

@@ -11,7 +11,7 @@ from conftest import random_configs
 from oracle import panda_oracle as po
 from rbe550_final_project_b200 import panda_model as pm
 from rbe550_final_project_b200 import scenes as sc
-from rbe550_final_project_b200.validity import unpack_bits
+from rbe550_final_project_b200.validity import PandaValidity, unpack_bits
 
 pytestmark = pytest.mark.gpu
 
@@ -260,6 +260,32 @@ def test_motion_certificates_do_not_change_verdicts(pv, c64):
     gpu = unpack_bits(pv.check_edges(_dev(a), _dev(b), n_steps=128), k)
     ref = c64.edge_margin(a.astype(np.float64), b.astype(np.float64), scene.as_oracle_scene(), n_steps=128)
     _assert_verdicts(gpu, ref, "certified motions, 128 steps")
+
+
+def test_second_tier_certificates_run_and_change_nothing(pv, monkeypatch):
+    """pv_edge_cert2_kernel (the self-collision section with slack at the 16 coarse states) sits between the
+    scene-only and the self-collision-only list validators: a handle created with PV_EDGE_CERT2=0 leaves it out.  Same
+    verdict words either way, one launch more with it."""
+    monkeypatch.setenv("PV_EDGE_CERT2", "0")
+    pv0 = PandaValidity(0)
+    monkeypatch.delenv("PV_EDGE_CERT2")
+    rng = np.random.default_rng(5)
+    n = 150_017
+    qa = random_configs(n, 96)
+    for name, sigma in (("goal4_task1_pentagon", 0.3), ("goal3_tower", 0.15)):
+        qb = np.clip(qa + rng.normal(0, sigma, qa.shape), pm.Q_LOWER, pm.Q_UPPER).astype(np.float32)
+        qb[:, 7:] = 0.04
+        snap = sc.FIXTURES[name]()
+        pv.set_scene(snap)
+        pv0.set_scene(snap)
+        A, B = _dev(qa), _dev(qb)
+        for n_steps in (64, 100, 33):
+            l0, l1 = pv0.launch_count, pv.launch_count
+            w0 = pv0.check_edges(A, B, n_steps=n_steps).cpu().numpy()
+            w1 = pv.check_edges(A, B, n_steps=n_steps).cpu().numpy()
+            assert (w0 == w1).all(), (name, n_steps)
+            assert pv0.launch_count - l0 == 3 and pv.launch_count - l1 == 4
+    del pv0
 
 
 def test_host_entry_points_match_device(pv):

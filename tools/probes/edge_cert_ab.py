@@ -1,11 +1,18 @@
-"""Same-box A/B of the motion certificates: pv_set_culling(2) (certificates) vs pv_set_culling(1) (exhaustive).  Developer probe."""
+"""Same-box A/B of the motion certificates: pv_set_culling(1) (exhaustive) vs pv_set_culling(2) with the first-tier
+certificates only (a handle created under PV_EDGE_CERT2=0) vs both tiers (the default).  Developer probe."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from rbe550_final_project_b200 import panda_model as pm, scenes as sc
 from rbe550_final_project_b200.validity import PandaValidity
 
-pv = PandaValidity(0)
+def handle(mode):  # PV_EDGE_CERT2: bit 0 = pv_edge_cert2_kernel, bit 1 = slack round inside the list validator
+    os.environ["PV_EDGE_CERT2"] = str(mode)
+    h = PandaValidity(0)
+    os.environ.pop("PV_EDGE_CERT2")
+    return h
+pvs = {m: handle(m) for m in (0, 1, 2, 3)}
+pv = pvs[0]
 n = 1 << 20
 g = torch.Generator(device="cuda"); g.manual_seed(20251212)
 lo = torch.tensor(pm.Q_LOWER, dtype=torch.float32, device="cuda"); hi = torch.tensor(pm.Q_UPPER, dtype=torch.float32, device="cuda")
@@ -24,7 +31,8 @@ def ev(fn, iters=5, warm=2):
     return e0.elapsed_time(e1) / iters
 
 for scene in ("goal4_task1_pentagon", "goal1_scattered", "goal3_tower"):
-    pv.set_scene(sc.FIXTURES[scene]())
+    for h in pvs.values():
+        h.set_scene(sc.FIXTURES[scene]())
     for what, b_, ns in (("gauss 64", qb, 64), ("gauss 128", qb, 128), ("gauss res", qb, 0), ("uniform 64", qu, 64), ("uniform res", qu, 0)):
         out = {}
         for mode in (1, 2):
@@ -32,5 +40,10 @@ for scene in ("goal4_task1_pentagon", "goal1_scattered", "goal3_tower"):
             ms = ev(lambda: pv.check_edges(qa, b_, n_steps=ns, out=bits))
             out[mode] = (ms, bits.clone())
         same = bool((out[1][1] == out[2][1]).all())
-        print(f"{scene:22s} {what:12s} exhaustive {n / out[1][0] / 1e3:7.1f} M edges/s   certificates {n / out[2][0] / 1e3:7.1f} M edges/s   x{out[1][0] / out[2][0]:.3f}  identical {same}", flush=True)
+        rates = []
+        for m in (1, 2, 3):
+            ms_ = ev(lambda: pvs[m].check_edges(qa, b_, n_steps=ns, out=bits))
+            same = same and bool((out[1][1] == bits).all())
+            rates.append(n / ms_ / 1e3)
+        print(f"{scene:22s} {what:12s} exhaustive {n / out[1][0] / 1e3:7.1f}   tier 1 {n / out[2][0] / 1e3:7.1f}   +cert2 kernel {rates[0]:7.1f}   +slack round {rates[1]:7.1f}   +both {rates[2]:7.1f} M edges/s   identical {same}", flush=True)
 pv.set_culling(2)

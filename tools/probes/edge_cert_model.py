@@ -73,7 +73,7 @@ def reach_bounds():
     return np.array(Rj)
 
 def main():
-    scene = sys.argv[1] if len(sys.argv) > 1 else "goal2_pentagon_done"
+    scene = sys.argv[1] if len(sys.argv) > 1 else "goal4_task1_pentagon"
     n_e = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
     rng = np.random.default_rng(1)
     qa = rng.uniform(pm.Q_LOWER, pm.Q_UPPER, size=(n_e, 9)); qa[:, 7:] = 0.04
@@ -95,7 +95,6 @@ def main():
             print(f"stride {stride} {name}: certified {cert.mean():.3f}  (plane {np.mean(pl > d):.3f} self {np.mean(se > d):.3f} scene {np.mean(scn > d):.3f}); "
                   f"cull-free at zero slack {np.mean((pl > 0) & (se > 0) & (scn > 0)):.3f}")
 
-main()
 
 
 def cells():
@@ -122,4 +121,7 @@ def cells():
     u = (u_self | u_scene)[cls2]
     print(f"class 2: unclear cells per motion {u.sum(1).mean():.2f} of 16; P(<= 8 cells) {np.mean(u.sum(1) <= 8):.3f}")
 
-cells()
+
+if __name__ == "__main__":
+    main()
+    cells()
