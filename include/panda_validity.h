@@ -50,7 +50,8 @@ typedef struct PvHandle PvHandle;
 
 /* Library/handle life cycle.  Replaces PlannerInterface.__init__ (planning.py:24-30): binds the frozen
  * Panda model to one CUDA device.  Fails with PV_ERR_NO_DEVICE when no sm_100 device is visible --
- * there is no CPU fallback. */
+ * there is no CPU fallback.  (Developer switch, read here: the environment variable PV_EDGE_CERT2=0 creates a handle
+ * whose motion validator leaves out the second-tier certificate pass -- same verdict words, for A/B timing.) */
 int pv_create(int device, PvHandle **out);
 void pv_destroy(PvHandle *h);
 const char *pv_last_error(const PvHandle *h); /* h may be NULL: last pv_create error */
