@@ -551,9 +551,12 @@ __device__ __forceinline__ void pv_place(const float* q, const PvScene& S, PvPla
 // fetch (a third of the loop body was dead weight between the culls: 23.6 -> 11.9 KB), and without it the edge kernel
 // gains 5.7 % and the state kernel 3.4 % on the same box (profiles/r2_notes.md).  pv_set_scene decides (PvHandle::all_yaw).
 template <int MODE, bool CULL, int EXIT, int SYNC, bool FMAK, bool CARRY, bool YAW = false>
-__device__ __forceinline__ void pv_scene_section(PvAcc<MODE>& acc, const PvPlaced& P, const PvScene& S) {
+__device__ __forceinline__ void pv_scene_section(PvAcc<MODE>& acc, const PvPlaced& P, const PvScene& S, int b0 = 0,
+                                                 int bstep = 1) {
+    // (b0, bstep): the boxes b0, b0 + bstep, ... only -- the dense owed-section passes of the sorted kernels deal one
+    // configuration's boxes out to several lanes when they have lanes to spare (everything below is per box)
     const int nb = S.n_obb;
-    for (int b = 0; b < nb; ++b) {
+    for (int b = b0; b < nb; b += bstep) {
         if constexpr (SYNC >= 3) __syncthreads();
         if constexpr (CARRY) {
             if (b == S.attached) continue;  // it is where the hand is, not where the snapshot saw it

@@ -55,6 +55,9 @@ static char g_create_error[512] = "";
 #ifndef PV_SB_BAR_GROUPS
 #define PV_SB_BAR_GROUPS 0
 #endif
+#ifndef PV_OWED_SPLIT
+#define PV_OWED_SPLIT 1  // owed scene sections dealt out box-wise to idle lanes (sorted state kernel)
+#endif
 #ifndef PV_SB_MINB
 #define PV_SB_MINB 1
 #endif
@@ -373,11 +376,16 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         __syncthreads();
         if constexpr (PV_COLD_SCENE && PV_SB_SYNC < 3) {
             const int n_owed = M.n_owed;
-            for (int base = 0; base < n_owed; base += PV_SB_THREADS) {  // block-uniform trip count
-                const int e = base + tid;
-                if (e >= n_owed) continue;  // (no barrier inside this loop)
-                const bool have = true;
-                const int L = M.owed[e];
+            // ~2 % of a super-tile owes: a few hundred configurations for 512 threads.  While there are lanes to spare a
+            // configuration goes to 2 or 4 neighbouring lanes, each taking every 2nd / 4th box of the scene (the placement
+            // is repeated per lane; the lanes were idle): the pass is the serial tail of the block, nothing overlaps it
+            const int sh = (PV_OWED_SPLIT && n_owed * 4 <= PV_SB_THREADS) ? 2 : (PV_OWED_SPLIT && n_owed * 2 <= PV_SB_THREADS) ? 1 : 0;
+            const int part = tid & ((1 << sh) - 1);
+            for (int base = 0; base < n_owed; base += PV_SB_THREADS >> sh) {  // block-uniform trip count
+                const int e = base + (tid >> sh);
+                const bool have = e < n_owed;
+                if (!__any_sync(0xffffffffu, have)) continue;  // (warp-uniform; no barrier inside this loop)
+                const int L = M.owed[have ? e : n_owed - 1];
                 const unsigned i_ = PV_OFF(L / PV_SB_THREADS, L % PV_SB_THREADS);
                 float q[9];
                 if constexpr (AOS) pv_load_aos(t_aos, (int64_t)i_, q);
@@ -385,8 +393,12 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
                 PvPlaced P;
                 pv_place<true, CARRY>(q, S, P);
                 PvAcc<PV_MODE_BITS> acc;
-                pv_scene_section<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY, YAW>(acc, P, S);
-                if (have && !acc.hit) atomicOr(&vbits[L >> 5], 1u << (L & 31));
+                if (sh == 0) pv_scene_section<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY, YAW>(acc, P, S);  // (block-uniform)
+                else pv_scene_section<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY, YAW>(acc, P, S, part, 1 << sh);
+                // a configuration is valid when none of its lanes found a contact
+                const unsigned hb = __ballot_sync(0xffffffffu, acc.hit);
+                const unsigned mine = (hb >> ((tid & 31) & ~((1 << sh) - 1))) & ((1u << (1 << sh)) - 1u);
+                if (have && part == 0 && !mine) atomicOr(&vbits[L >> 5], 1u << (L & 31));
             }
             __syncthreads();
         }
@@ -607,11 +619,14 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
         __syncthreads();
         if constexpr (PV_COLD_SCENE != 0) {  // the scene sections still owed, densely packed (see the state kernel)
             const int n_owed = M.n_owed;
-            for (int base = 0; base < n_owed; base += PV_SB_THREADS) {
-                const int e = base + tid;
-                if (e >= n_owed) continue;  // (no barrier inside this loop)
-                const bool have = true;
-                const int L = M.order[e];
+            // (lanes to spare: a configuration's boxes dealt out to 2 or 4 neighbouring lanes, see the state kernel)
+            const int sh = (PV_OWED_SPLIT && n_owed * 4 <= PV_SB_THREADS) ? 2 : (PV_OWED_SPLIT && n_owed * 2 <= PV_SB_THREADS) ? 1 : 0;
+            const int part = tid & ((1 << sh) - 1);
+            for (int base = 0; base < n_owed; base += PV_SB_THREADS >> sh) {
+                const int e = base + (tid >> sh);
+                const bool have = e < n_owed;
+                if (!__any_sync(0xffffffffu, have)) continue;  // (warp-uniform; no barrier inside this loop)
+                const int L = M.order[have ? e : n_owed - 1];
                 float q[9];
 #pragma unroll
                 for (int j = 0; j < NP; ++j) q[j] = M.park[j][L];
@@ -619,8 +634,11 @@ __global__ void __launch_bounds__(PV_SB_THREADS, PV_SB_MINB)
                 PvPlaced P;
                 pv_place<true, CARRY>(q, S, P);
                 PvAcc<PV_MODE_BITS> acc;
-                pv_scene_section<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY, YAW>(acc, P, S);
-                if (have && !acc.hit) atomicOr(&M.vbits[L >> 5], 1u << (L & 31));
+                if (sh == 0) pv_scene_section<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY, YAW>(acc, P, S);
+                else pv_scene_section<PV_MODE_BITS, true, PV_EXIT_NONE, 0, true, CARRY, YAW>(acc, P, S, part, 1 << sh);
+                const unsigned hb = __ballot_sync(0xffffffffu, acc.hit);
+                const unsigned mine = (hb >> ((tid & 31) & ~((1 << sh) - 1))) & ((1u << (1 << sh)) - 1u);
+                if (have && part == 0 && !mine) atomicOr(&M.vbits[L >> 5], 1u << (L & 31));
             }
             __syncthreads();
         }
