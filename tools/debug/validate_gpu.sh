@@ -1,3 +1,6 @@
+# One gpurun call that validates a build: GPU tests, smoke(), bench.py, metric counts for tools/make_executed_counts.py,
+# one ncu --set full capture of the state kernel and the launch list of bench.py (outputs under gpurun_out/s7_*).
+#   gpurun --timeout 2400 -- bash tools/debug/validate_gpu.sh
 cd $GRAFT_REPO_ROOT
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/s7_gputest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/s7_gputest.log
 timeout 100 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/s7_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/s7_smoke.log
