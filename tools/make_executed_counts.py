@@ -6,9 +6,10 @@ One gpurun call produces the inputs (see profiles/README or DESIGN.md section 4)
 smsp__sass_thread_inst_executed_op_fmul_pred_on.sum,smsp__thread_inst_executed.sum,smsp__inst_executed.sum,\
 dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum
     ncu --metrics $M --clock-control none -k regex:pv_state_bits_sorted -s 2 -c 1 --csv --log-file gpurun_out/state_counts.csv python tools/prof_state.py
-    ncu --metrics $M --clock-control none -k regex:pv_edge -s 6 -c 3 --csv --log-file gpurun_out/edge_counts.csv python tools/prof_edge.py
-(one pv_check_edges call of the config-3 workload = three launches: pv_edge_cert_kernel, pv_edge_kernel<list, whole check>,
-pv_edge_kernel<list, self-collision only>; their counts are summed and kept per kernel)
+    ncu --metrics $M --clock-control none -k regex:pv_edge -s 8 -c 4 --csv --log-file gpurun_out/edge_counts.csv python tools/prof_edge.py
+(one pv_check_edges call of the config-3 workload = four launches: pv_edge_cert_kernel, pv_edge_kernel<list, scene only>,
+pv_edge_cert2_kernel, pv_edge_kernel<list, self-collision only>; their counts are summed and kept per kernel;
+tools/debug/validate_gpu.sh runs both commands)
 then here:
     python tools/make_executed_counts.py gpurun_out/state_counts.csv gpurun_out/edge_counts.csv [--tag r2a]
 (prof_state.py checks 1 048 576 configurations, prof_edge.py 1 048 576 edges x 64 states: the bench workloads.)

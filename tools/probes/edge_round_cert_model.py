@@ -52,3 +52,9 @@ for mult in (1.0, 1.5, 2.0):
 for fixed in (0.02, 0.025, 0.03):
     ok = (even > fixed).all(1) & (dstep <= fixed)
     print(f"class-1: fixed slack {fixed}: {ok[cls1].mean():.3f} (eligible {np.mean(dstep[cls1] <= fixed):.3f})")
+# class 2: how many of the 16 coarse cells are unclear for the SCENE-level test (and the plane) alone?
+c2 = ~cert & ~cls1 & seek
+us = (scn <= d) | (pl <= d)
+k = us[c2].sum(1)
+print(f"class 2 (certificate sought): scene/plane-unclear cells per motion: mean {k.mean():.2f} of 16; "
+      f"P(<= 4) {np.mean(k <= 4):.3f}  P(<= 8) {np.mean(k <= 8):.3f}; scene alone: mean {(scn <= d)[c2].sum(1).mean():.2f}")
