@@ -376,12 +376,30 @@ def main():
     e2e_blocks = {}
 
     def e2e_run(bufs, call, tag):
-        for i in range(8):  # every pinned buffer is touched twice before the clock starts (the first copies out of a
-            call(bufs[i % 4].numpy())  # freshly pinned buffer take 2-3 ms instead of 0.6)
-        # three blocks of e2e_steps calls each, the MEDIAN block is reported (all three are in the line): the call is a
-        # 0.6 ms host-driven pipeline and single blocks vary by +-10 % with whatever else the host is doing
+        # Warm-up to the steady state: the first copies out of a freshly pinned buffer take 2-3 ms instead of 0.6, and after
+        # seconds of device-only work the host side of the link ramps up slowly on some boxes (blocks of 40 calls measured
+        # at 1.32, 1.45, 1.51, 1.59, 1.66 G checks/s in a row).  Untimed blocks run until two in a row agree within 2 %
+        # (at most 40 blocks, ~1 s); their count is in the line.
+        prev, n_warm = None, 0
+        while n_warm < 40:
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                call(bufs[i % 4].numpy())
+            cur = time.perf_counter() - t0
+            n_warm += 1
+            stable = prev is not None and abs(cur - prev) <= 0.02 * cur
+            if world > 1:  # every rank leaves the loop in the same iteration
+                t = torch.tensor([0.0 if stable else 1.0], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                stable = float(t.item()) == 0.0
+            prev = cur
+            if stable and n_warm >= 2:
+                break
+        e2e_blocks[tag + "_warm_blocks"] = n_warm
+        # five blocks of e2e_steps calls each, the MEDIAN block is reported (all five are in the line): the call is a
+        # 0.6 ms host-driven pipeline and single blocks vary by +-5 % with whatever else the host is doing
         blocks = []
-        for _ in range(3):
+        for _ in range(5):
             barrier()
             t0 = time.perf_counter()
             for i in range(e2e_steps):
@@ -393,7 +411,7 @@ def main():
                 s_ = float(t.item())
             blocks.append(s_)
         e2e_blocks[tag] = [world * n * e2e_steps / b for b in blocks]
-        return sorted(blocks)[1]
+        return sorted(blocks)[2]
 
     pinned9 = [torch.from_numpy(b).pin_memory() for b in host_batches[:4]]
     e2e9_s = e2e_run(pinned9, lambda q: pv.check_states_host(q, out=out_np), "rows9")
@@ -495,7 +513,8 @@ def main():
                         "timed_region_ms": ms},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 28, "d2h_bytes_per_step": words * 4, "numa_rank0": numa,
-                "steps": e2e_steps, "blocks": e2e_blocks.get("arm"), "value_is": "median of 3 blocks of `steps` calls", "configs_per_step": n * world,
+                "steps": e2e_steps, "blocks": e2e_blocks.get("arm"), "warm_blocks": e2e_blocks.get("arm_warm_blocks"),
+                "value_is": "median of 5 blocks of `steps` calls after an untimed warm-up to the steady state", "configs_per_step": n * world,
                 "call": "pv_check_states_host_arm (pinned host rows of the 7 arm joints + the gripper opening once in, "
                         "verdict bits out), one batch per call, wall clock",
                 "pcie": {"bound": "pcie_h2d", "achieved": per_rank_e2e_gbs, "peak": pcie_gbs, "unit": "GB/s",

@@ -1147,6 +1147,17 @@ static int pv_ensure_stage(PvHandle* h) {
     return PV_OK;
 }
 
+// Chunk schedule of the pipelined state calls: full chunks, then a SHORT last one.  The copies run back to back on the one
+// host-to-device engine, so the call ends one kernel + one D2H after the last copy has landed: that kernel should be small.
+#ifndef PV_HOST_TAIL
+#define PV_HOST_TAIL 32768  // configurations in the last chunk of a multi-chunk call (multiple of 32; 0: equal chunks)
+#endif
+static inline int64_t pv_host_chunk(int64_t left) {
+    if (left > (int64_t)PV_HOST_CHUNK + PV_HOST_TAIL) return PV_HOST_CHUNK;
+    if (PV_HOST_TAIL > 0 && left > 2 * (int64_t)PV_HOST_TAIL) return (left - PV_HOST_TAIL) & ~(int64_t)31;
+    return left < PV_HOST_CHUNK ? left : PV_HOST_CHUNK;
+}
+
 // Small host batches -- the reference's callback shape is ONE state per call (planning.py:209-219), a plan's waypoint
 // validation a few hundred motions -- go through host-mapped pinned memory: the kernel reads the rows and writes the verdict
 // words over PCIe itself, so a call is one launch and one synchronisation instead of copy + launch + copy (34 -> ~12 us
@@ -1182,7 +1193,7 @@ int pv_check_states_host(PvHandle* h, const float* h_q, int64_t n, uint32_t* h_b
     int64_t done = 0;
     int slot = 0;
     while (done < n) {
-        const int64_t m = (n - done < PV_HOST_CHUNK) ? (n - done) : PV_HOST_CHUNK;
+        const int64_t m = pv_host_chunk(n - done);
         cudaStream_t st = h->streams[slot];
         PV_CUDA(h, cudaMemcpyAsync(h->stage_q[slot], h_q + done * 9, (size_t)m * 9 * sizeof(float),
                                    cudaMemcpyHostToDevice, st));
@@ -1224,7 +1235,7 @@ int pv_check_states_host_arm(PvHandle* h, const float* h_q7, int64_t n, float fi
     int64_t done = 0;
     int slot = 0;
     while (done < n) {
-        const int64_t m = (n - done < PV_HOST_CHUNK) ? (n - done) : PV_HOST_CHUNK;
+        const int64_t m = pv_host_chunk(n - done);
         cudaStream_t st = h->streams[slot];
         PV_CUDA(h, cudaMemcpyAsync(h->stage_q[slot], h_q7 + done * 7, (size_t)m * 7 * sizeof(float),
                                    cudaMemcpyHostToDevice, st));
